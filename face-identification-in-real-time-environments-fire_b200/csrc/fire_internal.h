@@ -1,0 +1,42 @@
+// fire_internal.h - host-side helpers shared by the translation units of libfire_b200.so.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/fire_b200.h"
+
+namespace fire {
+
+// Thread-local error message returned by fire_last_error().
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+
+#define FIRE_CUDA(expr)                                                                              \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      return ::fire::fail(FIRE_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define FIRE_LAUNCH_CHECK(what)                                                                      \
+  do {                                                                                               \
+    cudaError_t _e = cudaGetLastError();                                                             \
+    if (_e != cudaSuccess)                                                                           \
+      return ::fire::fail(FIRE_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(_e));    \
+  } while (0)
+
+// 2-D row-major fp16 matrix [rows, cols] with `row_stride_bytes`; box = (64 cols, box_rows), 128-byte swizzle.
+// Returns 0 or a FIRE_ERR_* code.  cuTensorMapEncodeTiled is resolved through the runtime
+// (cudaGetDriverEntryPoint), so the library does not link libcuda and loads on GPU-less hosts.
+int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                     uint32_t box_rows);
+
+int device_sm_count();
+
+// Launch counter (every kernel launch of this library bumps it; bench.py reports it as gpu_launches).
+void count_launch(int n = 1);
+
+}  // namespace fire

@@ -1,0 +1,887 @@
+// knn.cu - exact cosine top-k over the enrolled gallery (K3 of DESIGN.md).
+//
+// Replaces hnswlib's Index.add_items / knn_query as used by modules/hnsw_manager.py:127,137,147,237
+// with a brute-force search whose ids equal hnswlib BFIndex's:
+//
+//   knn_add_kernel      rows -> x * 1/(||x||+1e-30)  -> fp32 master copy + fp16 operand copy
+//   knn_prep_kernel     same normalisation for the query batch
+//   knn_scan_kernel     tcgen05 GEMM  S = Q16 . G16^T  (fp16 operands, fp32 accumulate in TMEM);
+//                       the epilogue warps read S out of TMEM and keep a per-query sorted list of the
+//                       KP best (score, row) in REGISTERS - the score matrix is never written anywhere.
+//   knn_rerank_kernel   merges the per-split lists, recomputes the KP survivors exactly in fp32 from
+//                       the master copy, orders by (distance asc, id asc) and PROVES the fp16 filter
+//                       could not have dropped a true top-k row (|fp16 score - exact| <= eps); queries
+//                       for which that proof fails are queued for
+//   knn_exact_*         a plain fp32 scan of the whole shard (rare; correctness backstop).
+//   knn_merge_kernel    multi-GPU: merge G per-shard top-k lists after the all-gather.
+#include <algorithm>
+#include <cfloat>
+#include <cstring>
+#include <new>
+
+#include "fire_common.cuh"
+#include "fire_internal.h"
+
+namespace fire {
+
+constexpr int KNN_BM = 128;                  // queries per CTA  (UMMA M)
+constexpr int KNN_BN = 256;                  // gallery rows per accumulator tile (UMMA N)
+constexpr int KNN_THREADS = 192;             // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int KNN_A_KB_BYTES = KNN_BM * 128; // one 64-wide K block of the query tile
+constexpr int KNN_B_STAGE_BYTES = KNN_BN * 128;
+constexpr int KNN_MAX_LISTS_PER_LANE = 10;   // merge routines handle up to 320 sorted lists
+constexpr float KNN_DEFAULT_EPS = 1.1e-3f;   // >= 2^-10 (two fp16 roundings, Cauchy-Schwarz) + accumulation slack
+constexpr size_t KNN_SMEM_BUDGET = 232448 - 2048;
+
+struct KnnScanParams {
+  int nkb;              // D / 64
+  int n_rows;           // rows in this shard
+  int S;                // gallery splits
+  int rows_per_split;   // multiple of KNN_BN
+  int QB;               // query blocks of 128
+  int stages;
+  float* cand_score;    // [QB*128][S][KP]
+  uint32_t* cand_idx;
+};
+
+// ------------------------------------------------------------------------------------------------
+// normalise rows like hnswlib's cosine space: x * (1 / (sqrt(sum x^2) + 1e-30))
+// one warp per row; writes the fp32 normalised row and its fp16 rounding.
+__global__ void knn_normalize_kernel(const float* __restrict__ in, size_t n, int D, float* __restrict__ out32,
+                                     __half* __restrict__ out16, size_t n_pad16) {
+  size_t row = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= n_pad16) return;
+  if (row >= n) {   // zero padding rows of the fp16 operand (query tile padding)
+    for (int c = lane * 2; c < D; c += 64) *reinterpret_cast<uint32_t*>(out16 + row * D + c) = 0u;
+    return;
+  }
+  const float* x = in + row * D;
+  float s = 0.f;
+  for (int c = lane * 4; c < D; c += 128) {
+    float4 v = *reinterpret_cast<const float4*>(x + c);
+    s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float inv = 1.0f / (sqrtf(s) + 1e-30f);
+  for (int c = lane * 4; c < D; c += 128) {
+    float4 v = *reinterpret_cast<const float4*>(x + c);
+    v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+    *reinterpret_cast<float4*>(out32 + row * D + c) = v;
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    *reinterpret_cast<uint2*>(out16 + row * D + c) = pk;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sorted (descending score) candidate list held in registers.
+template <int KP>
+struct RegList {
+  float s[KP];
+  uint32_t ix[KP];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int j = 0; j < KP; ++j) { s[j] = -FLT_MAX; ix[j] = 0xFFFFFFFFu; }
+  }
+  __device__ __forceinline__ float worst() const { return s[KP - 1]; }
+  // precondition: v > s[KP-1].  Bubble the new entry up from the bottom.
+  __device__ __forceinline__ void insert(float v, uint32_t id) {
+    s[KP - 1] = v; ix[KP - 1] = id;
+#pragma unroll
+    for (int j = KP - 1; j > 0; --j) {
+      bool sw = s[j] > s[j - 1];
+      float ts = sw ? s[j - 1] : s[j];   uint32_t ti = sw ? ix[j - 1] : ix[j];
+      s[j - 1] = sw ? s[j] : s[j - 1];   ix[j - 1] = sw ? ix[j] : ix[j - 1];
+      s[j] = ts; ix[j] = ti;
+    }
+  }
+};
+
+// r[j] with a run-time j, as a 5-level select tree (keeps r[] in registers).
+__device__ __forceinline__ float pick32(const uint32_t (&r)[32], int j) {
+  uint32_t a[16], b[8], c[4], d[2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? r[2 * i + 1] : r[2 * i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) d[i] = (j & 8) ? c[2 * i + 1] : c[2 * i];
+  return __uint_as_float((j & 16) ? d[1] : d[0]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// One CTA = one (query block, gallery split).  The 128 x D query tile stays resident in shared
+// memory; gallery K-blocks stream through a TMA ring; two 256-column accumulators alternate in TMEM
+// so the top-k epilogue of tile t overlaps the MMAs of tile t+1.
+template <int KP>
+__global__ void __launch_bounds__(KNN_THREADS, 1)
+knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
+                const KnnScanParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + static_cast<size_t>(p.nkb) * KNN_A_KB_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + static_cast<size_t>(p.stages) * KNN_B_STAGE_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* full = bars + 1;
+  uint64_t* empty = full + p.stages;
+  uint64_t* tfull = empty + p.stages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = blockIdx.x % p.QB, split = blockIdx.x / p.QB;
+  const int row0 = split * p.rows_per_split;
+  const int row1 = min(row0 + p.rows_per_split, p.n_rows);
+  const int n_tiles = row1 > row0 ? (row1 - row0 + KNN_BN - 1) / KNN_BN : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_g);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(a_full, 1);
+      for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 128); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(a_full, static_cast<uint32_t>(p.nkb) * KNN_A_KB_BYTES);
+      for (int kb = 0; kb < p.nkb; ++kb)
+        tma_load_2d_hint(sA + static_cast<size_t>(kb) * KNN_A_KB_BYTES, &tmap_q, a_full, kb * 64, qb * KNN_BM, kEvictLast);
+      int it = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&empty[s], ph ^ 1, 1);
+          mbar_arrive_expect_tx(&full[s], KNN_B_STAGE_BYTES);
+          tma_load_2d(sB + static_cast<size_t>(s) * KNN_B_STAGE_BYTES, &tmap_g, &full[s], kb * 64, row0 + t * KNN_BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(KNN_BM, KNN_BN);
+      mbar_wait(a_full, 0, 2);
+      tc_fence_after();
+      int it = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int buf = t & 1;
+        mbar_wait(&tempty[buf], ((t >> 1) & 1) ^ 1, 3);
+        tc_fence_after();
+        const uint32_t d = tmem_base + static_cast<uint32_t>(buf * KNN_BN);
+        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&full[s], ph, 4);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA + static_cast<size_t>(kb) * KNN_A_KB_BYTES);
+          const uint32_t b0 = smem_u32(sB + static_cast<size_t>(s) * KNN_B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[s]);      // frees the smem stage once these MMAs have read it
+        }
+        umma_commit(&tfull[buf]);      // accumulator tile complete
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ top-k epilogue (4 warps)
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
+    const int qrow = quarter * 32 + lane;         // query row inside the block
+    RegList<KP> list;
+    list.init();
+    float thr = -FLT_MAX;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int buf = t & 1;
+      mbar_wait(&tfull[buf], (t >> 1) & 1, 5);
+      tc_fence_after();
+      const int col0 = row0 + t * KNN_BN;
+      const int nvalid = min(KNN_BN, row1 - col0);
+#pragma unroll 1
+      for (int c = 0; c < KNN_BN / 32; ++c) {
+        if (c * 32 >= nvalid) break;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * KNN_BN + c * 32), r);
+        tmem_ld_wait();
+        const int lim = nvalid - c * 32;          // >= 32 for full chunks
+        if (lim < 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j >= lim) r[j] = __float_as_uint(-FLT_MAX);
+        }
+        float m = __uint_as_float(r[0]);
+#pragma unroll
+        for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+        if (m > thr) {                             // rare once the list has warmed up
+          uint32_t mask = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) > thr) ? (1u << j) : 0u;
+          while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float v = pick32(r, j);
+            if (v > thr) {
+              list.insert(v, static_cast<uint32_t>(col0 + c * 32 + j));
+              thr = list.worst();
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[buf]);
+    }
+    const size_t q = static_cast<size_t>(qb) * KNN_BM + qrow;
+    float* os = p.cand_score + (q * p.S + split) * KP;
+    uint32_t* oi = p.cand_idx + (q * p.S + split) * KP;
+#pragma unroll
+    for (int j = 0; j < KP; j += 4) {
+      *reinterpret_cast<float4*>(os + j) = make_float4(list.s[j], list.s[j + 1], list.s[j + 2], list.s[j + 3]);
+      *reinterpret_cast<uint4*>(oi + j) = make_uint4(list.ix[j], list.ix[j + 1], list.ix[j + 2], list.ix[j + 3]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-cooperative k-way merge of G lists, each sorted ascending by (key, id).  Lane l owns lists
+// l, l+32, ...  `get(list, pos, &key, &id)` reads one entry.  Emits the n_out smallest entries in
+// order through `emit(rank, key, id)` (called by all lanes with identical arguments).
+struct KeyId {
+  float key;
+  unsigned long long id;
+};
+__device__ __forceinline__ bool keyid_less(float ka, unsigned long long ia, float kb, unsigned long long ib) {
+  return ka < kb || (ka == kb && ia < ib);
+}
+
+template <class Get, class Emit>
+__device__ __forceinline__ void warp_merge_lists(int G, int len, int n_out, Get get, Emit emit) {
+  const int lane = threadIdx.x & 31;
+  int head[KNN_MAX_LISTS_PER_LANE];
+  float hk[KNN_MAX_LISTS_PER_LANE];
+  unsigned long long hid[KNN_MAX_LISTS_PER_LANE];
+#pragma unroll
+  for (int i = 0; i < KNN_MAX_LISTS_PER_LANE; ++i) {
+    head[i] = 0;
+    const int l = lane + 32 * i;
+    hk[i] = FLT_MAX; hid[i] = ~0ull;
+    if (l < G && len > 0) get(l, 0, hk[i], hid[i]);
+  }
+  for (int r = 0; r < n_out; ++r) {
+    float bk = FLT_MAX; unsigned long long bid = ~0ull; int bi = -1;
+#pragma unroll
+    for (int i = 0; i < KNN_MAX_LISTS_PER_LANE; ++i) {
+      if (lane + 32 * i < G && head[i] < len && (bi < 0 || keyid_less(hk[i], hid[i], bk, bid))) {
+        bk = hk[i]; bid = hid[i]; bi = i;
+      }
+    }
+    // warp arg-min over (key, id); lanes with bi < 0 carry (FLT_MAX, ~0) and lose every comparison
+    float wk = bk; unsigned long long wid = bid; int wl = bi >= 0 ? lane : 64;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ok = __shfl_xor_sync(0xffffffffu, wk, o);
+      unsigned long long oid = __shfl_xor_sync(0xffffffffu, wid, o);
+      int ol = __shfl_xor_sync(0xffffffffu, wl, o);
+      bool take = (ol < 64) && (wl >= 64 || keyid_less(ok, oid, wk, wid) || (ok == wk && oid == wid && ol < wl));
+      if (take) { wk = ok; wid = oid; wl = ol; }
+    }
+    emit(r, wk, wid, wl < 64);
+    if (wl == lane && bi >= 0) {
+#pragma unroll
+      for (int i = 0; i < KNN_MAX_LISTS_PER_LANE; ++i) {
+        if (i == bi) {
+          head[i]++;
+          hk[i] = FLT_MAX; hid[i] = ~0ull;
+          if (head[i] < len) get(lane + 32 * i, head[i], hk[i], hid[i]);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One warp per query: merge split lists by fp16 score, exact fp32 re-rank, order, prove or flag.
+template <int KP>
+__global__ void knn_rerank_kernel(const float* __restrict__ qn, const float* __restrict__ g32,
+                                  const float* __restrict__ cand_score, const uint32_t* __restrict__ cand_idx, int S,
+                                  int D, int Q, int k, int64_t id_offset, float eps, float* __restrict__ out_dist,
+                                  long long* __restrict__ out_ids, uint32_t* __restrict__ flagged,
+                                  uint32_t* __restrict__ flagged_count) {
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= Q) return;
+  constexpr int EPL = (KP + 31) / 32;   // entries per lane
+  float sel_score[EPL];
+  uint32_t sel_idx[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) { sel_score[e] = -FLT_MAX; sel_idx[e] = 0xFFFFFFFFu; }
+
+  const float* cs = cand_score + static_cast<size_t>(q) * S * KP;
+  const uint32_t* ci = cand_idx + static_cast<size_t>(q) * S * KP;
+  auto get = [&](int l, int pos, float& key, unsigned long long& id) {
+    key = -cs[l * KP + pos];                       // descending score == ascending -score
+    id = ci[l * KP + pos];
+  };
+  auto emit = [&](int r, float key, unsigned long long id, bool valid) {
+    if ((r & 31) == lane) {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e)
+        if (e == (r >> 5)) { sel_score[e] = valid ? -key : -FLT_MAX; sel_idx[e] = valid ? static_cast<uint32_t>(id) : 0xFFFFFFFFu; }
+    }
+  };
+  warp_merge_lists(S, KP, KP, get, emit);
+
+  // exact fp32 distances of the survivors
+  const float* qv = qn + static_cast<size_t>(q) * D;
+  float dist[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) dist[e] = FLT_MAX;
+  for (int r = 0; r < KP; ++r) {
+    uint32_t idx = 0;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e)
+      if (e == (r >> 5)) idx = __shfl_sync(0xffffffffu, sel_idx[e], r & 31);
+    if (idx == 0xFFFFFFFFu) continue;             // warp-uniform
+    const float* gv = g32 + static_cast<size_t>(idx) * D;
+    float acc = 0.f;
+    for (int c = lane * 4; c < D; c += 128) {
+      float4 a = *reinterpret_cast<const float4*>(qv + c);
+      float4 b = __ldg(reinterpret_cast<const float4*>(gv + c));
+      acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((r & 31) == lane) {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e)
+        if (e == (r >> 5)) dist[e] = 1.0f - acc;
+    }
+  }
+
+  // rank by (distance asc, id asc); invalid entries (FLT_MAX, ~0) sort last
+  int rank[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) rank[e] = 0;
+  for (int r = 0; r < KP; ++r) {
+    float od = 0.f; uint32_t oi = 0;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e)
+      if (e == (r >> 5)) { od = __shfl_sync(0xffffffffu, dist[e], r & 31); oi = __shfl_sync(0xffffffffu, sel_idx[e], r & 31); }
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const int me = e * 32 + lane;
+      if (me < KP && me != r && keyid_less(od, oi, dist[e], sel_idx[e])) rank[e]++;
+    }
+  }
+  float kth_dist = -FLT_MAX;   // distance of rank k-1
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const int me = e * 32 + lane;
+    if (me < KP && rank[e] < k) {
+      out_dist[static_cast<size_t>(q) * k + rank[e]] = dist[e];
+      out_ids[static_cast<size_t>(q) * k + rank[e]] =
+          sel_idx[e] == 0xFFFFFFFFu ? -1ll : static_cast<long long>(sel_idx[e]) + id_offset;
+      if (rank[e] == k - 1) kth_dist = dist[e];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kth_dist = fmaxf(kth_dist, __shfl_xor_sync(0xffffffffu, kth_dist, o));
+  // worst surviving fp16 score: entry KP-1 (valid only if the merged list is full)
+  float cmin = __shfl_sync(0xffffffffu, sel_score[EPL - 1], (KP - 1) & 31);
+  uint32_t last_idx = __shfl_sync(0xffffffffu, sel_idx[EPL - 1], (KP - 1) & 31);
+  const bool list_full = last_idx != 0xFFFFFFFFu;
+  // rows outside the list have fp16 score <= cmin, hence exact cosine <= cmin + eps.  They cannot
+  // enter the top-k iff cmin + eps < (1 - kth_dist).
+  if (lane == 0 && list_full && (cmin + eps >= 1.0f - kth_dist)) {
+    uint32_t slot = atomicAdd(flagged_count, 1u);
+    flagged[slot] = static_cast<uint32_t>(q);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact fp32 fallback for flagged queries.  The kernels read the flagged count on the device and
+// return at once when it is zero, so they are enqueued unconditionally (no host round trip).
+//   pass A (<= EXACT_CAP flagged queries): rows split over the blocks -> per-block partial top-k
+//           -> knn_exact_merge_kernel merges the partials and overwrites the query's output row;
+//   pass B (overflow beyond EXACT_CAP, pathological galleries): one block scans the whole shard
+//           for one query, blocks stride over the overflow queries.
+constexpr int EXACT_WARPS = 8;
+constexpr int EXACT_CAP = 256;
+
+struct ExactSmem {
+  float q[512];
+  float d[EXACT_WARPS][64];
+  uint32_t i[EXACT_WARPS][64];
+};
+
+// every warp scans rows r0+warp, r0+warp+8, ... < r1 and keeps its k best in sm.d/sm.i[warp]
+__device__ __forceinline__ void exact_block_scan(ExactSmem& sm, const float* __restrict__ qn,
+                                                 const float* __restrict__ g32, uint32_t q, int D, int k, int r0,
+                                                 int r1) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) sm.q[c] = qn[static_cast<size_t>(q) * D + c];
+  for (int j = lane; j < 64; j += 32) { sm.d[warp][j] = FLT_MAX; sm.i[warp][j] = 0xFFFFFFFFu; }
+  __syncthreads();
+  for (int r = r0 + warp; r < r1; r += EXACT_WARPS) {
+    const float* gv = g32 + static_cast<size_t>(r) * D;
+    float acc = 0.f;
+    for (int c = lane * 4; c < D; c += 128) {
+      float4 b = __ldg(reinterpret_cast<const float4*>(gv + c));
+      acc = fmaf(sm.q[c], b.x, acc); acc = fmaf(sm.q[c + 1], b.y, acc);
+      acc = fmaf(sm.q[c + 2], b.z, acc); acc = fmaf(sm.q[c + 3], b.w, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const float d = 1.0f - acc;
+    if (lane == 0 && keyid_less(d, static_cast<unsigned long long>(r), sm.d[warp][k - 1], sm.i[warp][k - 1])) {
+      int j = k - 1;
+      while (j > 0 && keyid_less(d, static_cast<unsigned long long>(r), sm.d[warp][j - 1], sm.i[warp][j - 1])) {
+        sm.d[warp][j] = sm.d[warp][j - 1]; sm.i[warp][j] = sm.i[warp][j - 1]; --j;
+      }
+      sm.d[warp][j] = d; sm.i[warp][j] = static_cast<uint32_t>(r);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(EXACT_WARPS * 32)
+knn_exact_scan_kernel(const float* __restrict__ qn, const float* __restrict__ g32, int n_rows, int D, int k,
+                      const uint32_t* __restrict__ flagged, const uint32_t* __restrict__ flagged_count,
+                      float* __restrict__ part_dist, uint32_t* __restrict__ part_idx) {
+  __shared__ ExactSmem sm;
+  const int lane = threadIdx.x & 31;
+  const uint32_t nf = min(*flagged_count, static_cast<uint32_t>(EXACT_CAP));
+  const int rows_per_block = (n_rows + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(n_rows, r0 + rows_per_block);
+  for (uint32_t f = 0; f < nf; ++f) {
+    exact_block_scan(sm, qn, g32, flagged[f], D, k, r0, r1);
+    if (threadIdx.x < 32) {
+      float* od = part_dist + (static_cast<size_t>(f) * gridDim.x + blockIdx.x) * k;
+      uint32_t* oi = part_idx + (static_cast<size_t>(f) * gridDim.x + blockIdx.x) * k;
+      auto get = [&](int l, int pos, float& key, unsigned long long& id) { key = sm.d[l][pos]; id = sm.i[l][pos]; };
+      auto emit = [&](int r, float key, unsigned long long id, bool valid) {
+        if (lane == 0) { od[r] = valid ? key : FLT_MAX; oi[r] = valid ? static_cast<uint32_t>(id) : 0xFFFFFFFFu; }
+      };
+      warp_merge_lists(EXACT_WARPS, k, k, get, emit);
+    }
+  }
+}
+
+// merge the per-block partial lists of every pass-A query and overwrite its output row;
+// block 0 also folds this search into the handle's counters.
+__global__ void knn_exact_merge_kernel(const float* __restrict__ part_dist, const uint32_t* __restrict__ part_idx,
+                                       int nblk, int k, int64_t id_offset, const uint32_t* __restrict__ flagged,
+                                       const uint32_t* __restrict__ flagged_count, float* __restrict__ out_dist,
+                                       long long* __restrict__ out_ids, unsigned long long* __restrict__ stats, int Q) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    stats[0] += static_cast<unsigned long long>(Q);
+    stats[1] += static_cast<unsigned long long>(*flagged_count);
+  }
+  const uint32_t nf = min(*flagged_count, static_cast<uint32_t>(EXACT_CAP));
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (uint32_t f = blockIdx.x * wpb + (threadIdx.x >> 5); f < nf; f += gridDim.x * wpb) {
+    const uint32_t q = flagged[f];
+    const float* pd = part_dist + static_cast<size_t>(f) * nblk * k;
+    const uint32_t* pi = part_idx + static_cast<size_t>(f) * nblk * k;
+    auto get = [&](int l, int pos, float& key, unsigned long long& id) { key = pd[l * k + pos]; id = pi[l * k + pos]; };
+    auto emit = [&](int r, float key, unsigned long long id, bool valid) {
+      if (lane == 0) {
+        out_dist[static_cast<size_t>(q) * k + r] = key;
+        out_ids[static_cast<size_t>(q) * k + r] = valid && id != 0xFFFFFFFFull ? static_cast<long long>(id) + id_offset : -1ll;
+      }
+    };
+    warp_merge_lists(nblk, k, k, get, emit);
+  }
+}
+
+__global__ void __launch_bounds__(EXACT_WARPS * 32)
+knn_exact_overflow_kernel(const float* __restrict__ qn, const float* __restrict__ g32, int n_rows, int D, int k,
+                          int64_t id_offset, const uint32_t* __restrict__ flagged,
+                          const uint32_t* __restrict__ flagged_count, float* __restrict__ out_dist,
+                          long long* __restrict__ out_ids) {
+  __shared__ ExactSmem sm;
+  const int lane = threadIdx.x & 31;
+  const uint32_t total = *flagged_count;
+  for (uint32_t f = EXACT_CAP + blockIdx.x; f < total; f += gridDim.x) {
+    const uint32_t q = flagged[f];
+    exact_block_scan(sm, qn, g32, q, D, k, 0, n_rows);
+    if (threadIdx.x < 32) {
+      auto get = [&](int l, int pos, float& key, unsigned long long& id) { key = sm.d[l][pos]; id = sm.i[l][pos]; };
+      auto emit = [&](int r, float key, unsigned long long id, bool valid) {
+        if (lane == 0) {
+          out_dist[static_cast<size_t>(q) * k + r] = key;
+          out_ids[static_cast<size_t>(q) * k + r] = valid && id != 0xFFFFFFFFull ? static_cast<long long>(id) + id_offset : -1ll;
+        }
+      };
+      warp_merge_lists(EXACT_WARPS, k, k, get, emit);
+    }
+  }
+}
+
+// multi-GPU merge: dists/ids [G][Q][k] ascending per row -> global top-k per query
+__global__ void knn_merge_kernel(const float* __restrict__ dists, const long long* __restrict__ ids, int Q, int k, int G,
+                                 float* __restrict__ out_dist, long long* __restrict__ out_ids) {
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= Q) return;
+  auto get = [&](int l, int pos, float& key, unsigned long long& id) {
+    const size_t o = (static_cast<size_t>(l) * Q + q) * k + pos;
+    key = dists[o];
+    id = static_cast<unsigned long long>(ids[o]);
+  };
+  auto emit = [&](int r, float key, unsigned long long id, bool valid) {
+    if (lane == 0) {
+      out_dist[static_cast<size_t>(q) * k + r] = key;
+      out_ids[static_cast<size_t>(q) * k + r] = valid ? static_cast<long long>(id) : -1ll;
+    }
+  };
+  warp_merge_lists(G, k, k, get, emit);
+}
+
+}  // namespace fire
+
+// ================================================================================================
+// host side
+// ================================================================================================
+using namespace fire;
+
+struct fire_knn {
+  int D = 0;
+  int device = 0;
+  size_t capacity = 0, count = 0;
+  float* g32 = nullptr;       // [capacity][D] normalised fp32 master
+  __half* g16 = nullptr;      // [capacity][D] fp16 operand copy
+  // search scratch (grow-only)
+  int q_cap = 0;              // queries the scratch can hold (multiple of 128)
+  int s_cap = 0, kp_cap = 0;
+  float* qn32 = nullptr;
+  __half* q16 = nullptr;
+  float* cand_score = nullptr;
+  uint32_t* cand_idx = nullptr;
+  uint32_t* flagged = nullptr;       // [q_cap]
+  uint32_t* flagged_count = nullptr; // [1] + stats [2] (uint64 each, separate alloc below)
+  unsigned long long* stats = nullptr;   // device: {queries_total, queries_fallback}
+  float* part_dist = nullptr;
+  uint32_t* part_idx = nullptr;
+  int exact_blocks = 0;
+  float eps = KNN_DEFAULT_EPS;
+  // staging for *_host calls
+  float* stage_q = nullptr; float* stage_d = nullptr; long long* stage_i = nullptr;
+  size_t stage_q_cap = 0, stage_o_cap = 0;
+  float* stage_rows = nullptr; size_t stage_rows_cap = 0;
+  float* dev_q = nullptr; float* dev_d = nullptr; long long* dev_i = nullptr;
+  size_t dev_q_cap = 0, dev_o_cap = 0;
+};
+
+static int knn_ensure_scratch(fire_knn* h, int Q, int S, int KP, int k) {
+  const int q_pad = (Q + KNN_BM - 1) / KNN_BM * KNN_BM;
+  if (q_pad > h->q_cap || S > h->s_cap || KP > h->kp_cap) {
+    const int nq = std::max(q_pad, h->q_cap), ns = std::max(S, h->s_cap), nkp = std::max(KP, h->kp_cap);
+    FIRE_CUDA(cudaDeviceSynchronize());
+    cudaFree(h->qn32); cudaFree(h->q16); cudaFree(h->cand_score); cudaFree(h->cand_idx); cudaFree(h->flagged);
+    h->qn32 = nullptr; h->q16 = nullptr; h->cand_score = nullptr; h->cand_idx = nullptr; h->flagged = nullptr;
+    FIRE_CUDA(cudaMalloc(&h->qn32, sizeof(float) * nq * h->D));
+    FIRE_CUDA(cudaMalloc(&h->q16, sizeof(__half) * nq * h->D));
+    FIRE_CUDA(cudaMalloc(&h->cand_score, sizeof(float) * static_cast<size_t>(nq) * ns * nkp));
+    FIRE_CUDA(cudaMalloc(&h->cand_idx, sizeof(uint32_t) * static_cast<size_t>(nq) * ns * nkp));
+    FIRE_CUDA(cudaMalloc(&h->flagged, sizeof(uint32_t) * nq));
+    h->q_cap = nq; h->s_cap = ns; h->kp_cap = nkp;
+  }
+  if (!h->flagged_count) {
+    FIRE_CUDA(cudaMalloc(&h->flagged_count, sizeof(uint32_t) * 4));
+    FIRE_CUDA(cudaMalloc(&h->stats, sizeof(unsigned long long) * 2));
+    FIRE_CUDA(cudaMemset(h->stats, 0, sizeof(unsigned long long) * 2));
+    h->exact_blocks = std::min(320, 2 * device_sm_count());
+  }
+  if (!h->part_dist) {
+    FIRE_CUDA(cudaMalloc(&h->part_dist, sizeof(float) * EXACT_CAP * h->exact_blocks * 64));
+    FIRE_CUDA(cudaMalloc(&h->part_idx, sizeof(uint32_t) * EXACT_CAP * h->exact_blocks * 64));
+  }
+  (void)k;
+  return FIRE_OK;
+}
+
+template <int KP>
+static int knn_launch_scan(fire_knn* h, const CUtensorMap& tq, const CUtensorMap& tg, const KnnScanParams& p,
+                           size_t smem_bytes, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    FIRE_CUDA(cudaFuncSetAttribute(knn_scan_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(KNN_SMEM_BUDGET + 1024)));
+    attr_done = true;
+  }
+  (void)h;
+  knn_scan_kernel<KP><<<p.QB * p.S, KNN_THREADS, smem_bytes, st>>>(tq, tg, p);
+  FIRE_LAUNCH_CHECK("knn_scan_kernel");
+  count_launch();
+  return FIRE_OK;
+}
+
+extern "C" {
+
+int fire_knn_create(int D, size_t capacity, fire_knn_t** out) {
+  if (!out) return fail(FIRE_ERR_ARG, "fire_knn_create: out is NULL");
+  if (D <= 0 || D % 64 != 0 || D > 512) return fail(FIRE_ERR_UNSUPPORTED, "fire_knn_create: D=%d must be a multiple of 64 in [64,512]", D);
+  if (capacity == 0 || capacity > 0x7FFFFFF0ull) return fail(FIRE_ERR_ARG, "fire_knn_create: capacity %zu out of range", capacity);
+  fire_knn* h = new (std::nothrow) fire_knn();
+  if (!h) return fail(FIRE_ERR_STATE, "out of host memory");
+  h->D = D;
+  h->capacity = capacity;
+  if (cudaGetDevice(&h->device) != cudaSuccess) { delete h; return fail(FIRE_ERR_CUDA, "no current CUDA device (no CPU fallback)"); }
+  cudaError_t e1 = cudaMalloc(&h->g32, sizeof(float) * capacity * D);
+  cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(&h->g16, sizeof(__half) * capacity * D) : e1;
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    cudaFree(h->g32); cudaFree(h->g16);
+    delete h;
+    return fail(FIRE_ERR_CUDA, "fire_knn_create: cudaMalloc of %zu x %d gallery failed: %s", capacity, D,
+                cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  }
+  *out = h;
+  return FIRE_OK;
+}
+
+int fire_knn_destroy(fire_knn_t* h) {
+  if (!h) return FIRE_OK;
+  cudaFree(h->g32); cudaFree(h->g16); cudaFree(h->qn32); cudaFree(h->q16); cudaFree(h->cand_score);
+  cudaFree(h->cand_idx); cudaFree(h->flagged); cudaFree(h->flagged_count); cudaFree(h->stats);
+  cudaFree(h->part_dist); cudaFree(h->part_idx);
+  if (h->stage_q) cudaFreeHost(h->stage_q);
+  if (h->stage_d) cudaFreeHost(h->stage_d);
+  if (h->stage_i) cudaFreeHost(h->stage_i);
+  if (h->stage_rows) cudaFree(h->stage_rows);
+  cudaFree(h->dev_q); cudaFree(h->dev_d); cudaFree(h->dev_i);
+  delete h;
+  return FIRE_OK;
+}
+
+int fire_knn_reset(fire_knn_t* h) {
+  if (!h) return fail(FIRE_ERR_ARG, "NULL handle");
+  h->count = 0;
+  return FIRE_OK;
+}
+size_t fire_knn_count(const fire_knn_t* h) { return h ? h->count : 0; }
+size_t fire_knn_capacity(const fire_knn_t* h) { return h ? h->capacity : 0; }
+int fire_knn_dim(const fire_knn_t* h) { return h ? h->D : 0; }
+
+int fire_knn_add(fire_knn_t* h, const float* rows, size_t n, fire_stream_t stream) {
+  if (!h || (!rows && n)) return fail(FIRE_ERR_ARG, "fire_knn_add: NULL argument");
+  if (n == 0) return FIRE_OK;
+  if (h->count + n > h->capacity)
+    return fail(FIRE_ERR_STATE, "fire_knn_add: %zu + %zu rows exceed capacity %zu", h->count, n, h->capacity);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t warps_per_block = 8;
+  const size_t blocks = (n + warps_per_block - 1) / warps_per_block;
+  knn_normalize_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(rows, n, h->D, h->g32 + h->count * h->D,
+                                                                       h->g16 + h->count * h->D, n);
+  FIRE_LAUNCH_CHECK("knn_normalize_kernel(add)");
+  count_launch();
+  h->count += n;
+  return FIRE_OK;
+}
+
+int fire_knn_add_host(fire_knn_t* h, const float* host_rows, size_t n) {
+  if (!h || (!host_rows && n)) return fail(FIRE_ERR_ARG, "fire_knn_add_host: NULL argument");
+  if (n == 0) return FIRE_OK;
+  if (h->count + n > h->capacity)
+    return fail(FIRE_ERR_STATE, "fire_knn_add_host: %zu + %zu rows exceed capacity %zu", h->count, n, h->capacity);
+  const size_t chunk_rows = std::max<size_t>(1, (64u << 20) / (sizeof(float) * h->D));
+  if (h->stage_rows_cap < std::min(n, chunk_rows)) {
+    if (h->stage_rows) cudaFree(h->stage_rows);
+  cudaFree(h->dev_q); cudaFree(h->dev_d); cudaFree(h->dev_i);
+    h->stage_rows = nullptr;
+    h->stage_rows_cap = std::min(n, chunk_rows);
+    FIRE_CUDA(cudaMalloc(&h->stage_rows, sizeof(float) * h->stage_rows_cap * h->D));
+  }
+  for (size_t off = 0; off < n; off += h->stage_rows_cap) {
+    const size_t m = std::min(h->stage_rows_cap, n - off);
+    FIRE_CUDA(cudaMemcpy(h->stage_rows, host_rows + off * h->D, sizeof(float) * m * h->D, cudaMemcpyHostToDevice));
+    int rc = fire_knn_add(h, h->stage_rows, m, nullptr);
+    if (rc != FIRE_OK) return rc;
+    FIRE_CUDA(cudaStreamSynchronize(nullptr));
+  }
+  return FIRE_OK;
+}
+
+int fire_knn_get_rows_host(fire_knn_t* h, size_t first, size_t n, float* host_out) {
+  if (!h || (!host_out && n)) return fail(FIRE_ERR_ARG, "fire_knn_get_rows_host: NULL argument");
+  if (first + n > h->count) return fail(FIRE_ERR_ARG, "fire_knn_get_rows_host: rows [%zu,%zu) beyond count %zu", first, first + n, h->count);
+  if (n == 0) return FIRE_OK;
+  FIRE_CUDA(cudaMemcpy(host_out, h->g32 + first * h->D, sizeof(float) * n * h->D, cudaMemcpyDeviceToHost));
+  return FIRE_OK;
+}
+
+int fire_knn_set_margin(fire_knn_t* h, float eps) {
+  if (!h) return fail(FIRE_ERR_ARG, "NULL handle");
+  h->eps = eps > 0.f ? eps : KNN_DEFAULT_EPS;
+  return FIRE_OK;
+}
+
+int fire_knn_stats(fire_knn_t* h, uint64_t* host_queries_total, uint64_t* host_queries_fallback) {
+  if (!h) return fail(FIRE_ERR_ARG, "NULL handle");
+  unsigned long long v[2] = {0, 0};
+  if (h->stats) FIRE_CUDA(cudaMemcpy(v, h->stats, sizeof(v), cudaMemcpyDeviceToHost));
+  if (host_queries_total) *host_queries_total = v[0];
+  if (host_queries_fallback) *host_queries_fallback = v[1];
+  return FIRE_OK;
+}
+
+int fire_knn_search(fire_knn_t* h, const float* queries, int Q, int k, int64_t id_offset, float* out_dist,
+                    int64_t* out_ids, fire_stream_t stream) {
+  if (!h || !queries || !out_dist || !out_ids) return fail(FIRE_ERR_ARG, "fire_knn_search: NULL argument");
+  if (Q <= 0) return fail(FIRE_ERR_ARG, "fire_knn_search: Q=%d", Q);
+  if (k < 1 || k > 64) return fail(FIRE_ERR_UNSUPPORTED, "fire_knn_search: k=%d outside [1,64]", k);
+  if (static_cast<size_t>(k) > h->count)
+    return fail(FIRE_ERR_STATE, "fire_knn_search: k=%d exceeds the %zu stored rows", k, h->count);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int D = h->D, nkb = D / 64;
+  const int KP = k <= 10 ? 16 : 64;
+  const int n_rows = static_cast<int>(h->count);
+  const int QB = (Q + KNN_BM - 1) / KNN_BM;
+  const int tiles_total = (n_rows + KNN_BN - 1) / KNN_BN;
+  const int sms = device_sm_count();
+  // work decomposition: QB x S CTAs, about W waves over the SMs, >= ~200 tiles per CTA when possible
+  long long w = (static_cast<long long>(tiles_total) * QB) / (static_cast<long long>(sms) * 200);
+  const int W = static_cast<int>(std::max<long long>(1, std::min<long long>(8, w)));
+  int S = std::max(1, (W * sms) / QB);
+  S = std::min(S, std::min(tiles_total, 32 * KNN_MAX_LISTS_PER_LANE));
+  const int tiles_per_split = (tiles_total + S - 1) / S;
+  S = (tiles_total + tiles_per_split - 1) / tiles_per_split;
+
+  int rc = knn_ensure_scratch(h, Q, S, KP, k);
+  if (rc != FIRE_OK) return rc;
+
+  // normalised queries (fp32 for the exact re-rank, fp16 tile-padded for the tensor cores)
+  {
+    const size_t q_pad = static_cast<size_t>(QB) * KNN_BM;
+    const size_t blocks = (q_pad + 7) / 8;
+    knn_normalize_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(queries, static_cast<size_t>(Q), D, h->qn32,
+                                                                         h->q16, q_pad);
+    FIRE_LAUNCH_CHECK("knn_normalize_kernel(query)");
+    count_launch();
+  }
+  CUtensorMap tq, tg;
+  rc = make_tmap_f16_2d(&tq, h->q16, static_cast<uint64_t>(QB) * KNN_BM, D, static_cast<uint64_t>(D) * 2, KNN_BM);
+  if (rc != FIRE_OK) return rc;
+  rc = make_tmap_f16_2d(&tg, h->g16, static_cast<uint64_t>(n_rows), D, static_cast<uint64_t>(D) * 2, KNN_BN);
+  if (rc != FIRE_OK) return rc;
+
+  KnnScanParams p;
+  p.nkb = nkb; p.n_rows = n_rows; p.S = S; p.rows_per_split = tiles_per_split * KNN_BN; p.QB = QB;
+  const size_t a_bytes = static_cast<size_t>(nkb) * KNN_A_KB_BYTES;
+  const size_t bar_bytes = 256;
+  int stages = static_cast<int>((KNN_SMEM_BUDGET - a_bytes - bar_bytes) / KNN_B_STAGE_BYTES);
+  stages = std::max(2, std::min(stages, 6));
+  p.stages = stages;
+  p.cand_score = h->cand_score; p.cand_idx = h->cand_idx;
+  const size_t smem_bytes = 1024 + a_bytes + static_cast<size_t>(stages) * KNN_B_STAGE_BYTES + bar_bytes;
+
+  FIRE_CUDA(cudaMemsetAsync(h->flagged_count, 0, sizeof(uint32_t) * 4, st));
+  rc = KP == 16 ? knn_launch_scan<16>(h, tq, tg, p, smem_bytes, st) : knn_launch_scan<64>(h, tq, tg, p, smem_bytes, st);
+  if (rc != FIRE_OK) return rc;
+
+  {
+    const int blocks = (Q + 7) / 8;
+    if (KP == 16)
+      knn_rerank_kernel<16><<<blocks, 256, 0, st>>>(h->qn32, h->g32, h->cand_score, h->cand_idx, S, D, Q, k, id_offset, h->eps,
+                                                    out_dist, reinterpret_cast<long long*>(out_ids), h->flagged, h->flagged_count);
+    else
+      knn_rerank_kernel<64><<<blocks, 256, 0, st>>>(h->qn32, h->g32, h->cand_score, h->cand_idx, S, D, Q, k, id_offset, h->eps,
+                                                    out_dist, reinterpret_cast<long long*>(out_ids), h->flagged, h->flagged_count);
+    FIRE_LAUNCH_CHECK("knn_rerank_kernel");
+    count_launch();
+  }
+  knn_exact_scan_kernel<<<h->exact_blocks, EXACT_WARPS * 32, 0, st>>>(h->qn32, h->g32, n_rows, D, k, h->flagged,
+                                                                      h->flagged_count, h->part_dist, h->part_idx);
+  knn_exact_merge_kernel<<<32, 256, 0, st>>>(h->part_dist, h->part_idx, h->exact_blocks, k, id_offset, h->flagged,
+                                             h->flagged_count, out_dist, reinterpret_cast<long long*>(out_ids), h->stats, Q);
+  knn_exact_overflow_kernel<<<h->exact_blocks, EXACT_WARPS * 32, 0, st>>>(h->qn32, h->g32, n_rows, D, k, id_offset, h->flagged,
+                                                                          h->flagged_count, out_dist,
+                                                                          reinterpret_cast<long long*>(out_ids));
+  FIRE_LAUNCH_CHECK("knn exact fallback");
+  count_launch(3);
+  return FIRE_OK;
+}
+
+int fire_knn_search_host(fire_knn_t* h, const float* host_queries, int Q, int k, int64_t id_offset,
+                         float* host_out_dist, int64_t* host_out_ids) {
+  if (!h || !host_queries || !host_out_dist || !host_out_ids) return fail(FIRE_ERR_ARG, "fire_knn_search_host: NULL argument");
+  if (Q <= 0 || k < 1) return fail(FIRE_ERR_ARG, "fire_knn_search_host: Q=%d k=%d", Q, k);
+  const size_t qn = static_cast<size_t>(Q) * h->D, on = static_cast<size_t>(Q) * k;
+  if (qn > h->stage_q_cap) {
+    if (h->stage_q) cudaFreeHost(h->stage_q);
+    h->stage_q = nullptr;
+    FIRE_CUDA(cudaMallocHost(&h->stage_q, sizeof(float) * qn));
+    h->stage_q_cap = qn;
+  }
+  if (on > h->stage_o_cap) {
+    if (h->stage_d) cudaFreeHost(h->stage_d);
+    if (h->stage_i) cudaFreeHost(h->stage_i);
+    h->stage_d = nullptr; h->stage_i = nullptr;
+    FIRE_CUDA(cudaMallocHost(&h->stage_d, sizeof(float) * on));
+    FIRE_CUDA(cudaMallocHost(&h->stage_i, sizeof(long long) * on));
+    h->stage_o_cap = on;
+  }
+  if (qn > h->dev_q_cap) {
+    cudaFree(h->dev_q); h->dev_q = nullptr;
+    FIRE_CUDA(cudaMalloc(&h->dev_q, sizeof(float) * qn));
+    h->dev_q_cap = qn;
+  }
+  if (on > h->dev_o_cap) {
+    cudaFree(h->dev_d); cudaFree(h->dev_i); h->dev_d = nullptr; h->dev_i = nullptr;
+    FIRE_CUDA(cudaMalloc(&h->dev_d, sizeof(float) * on));
+    FIRE_CUDA(cudaMalloc(&h->dev_i, sizeof(long long) * on));
+    h->dev_o_cap = on;
+  }
+  memcpy(h->stage_q, host_queries, sizeof(float) * qn);
+  FIRE_CUDA(cudaMemcpyAsync(h->dev_q, h->stage_q, sizeof(float) * qn, cudaMemcpyHostToDevice, nullptr));
+  int rc = fire_knn_search(h, h->dev_q, Q, k, id_offset, h->dev_d, reinterpret_cast<int64_t*>(h->dev_i), nullptr);
+  if (rc != FIRE_OK) return rc;
+  FIRE_CUDA(cudaMemcpyAsync(h->stage_d, h->dev_d, sizeof(float) * on, cudaMemcpyDeviceToHost, nullptr));
+  FIRE_CUDA(cudaMemcpyAsync(h->stage_i, h->dev_i, sizeof(long long) * on, cudaMemcpyDeviceToHost, nullptr));
+  FIRE_CUDA(cudaStreamSynchronize(nullptr));
+  memcpy(host_out_dist, h->stage_d, sizeof(float) * on);
+  memcpy(host_out_ids, h->stage_i, sizeof(long long) * on);
+  return FIRE_OK;
+}
+
+int fire_knn_merge(const float* dists, const int64_t* ids, int Q, int k, int G, float* out_dist, int64_t* out_ids,
+                   fire_stream_t stream) {
+  if (!dists || !ids || !out_dist || !out_ids) return fail(FIRE_ERR_ARG, "fire_knn_merge: NULL argument");
+  if (Q <= 0 || k < 1 || G < 1 || G > 32 * KNN_MAX_LISTS_PER_LANE)
+    return fail(FIRE_ERR_ARG, "fire_knn_merge: Q=%d k=%d G=%d out of range", Q, k, G);
+  const int blocks = (Q + 7) / 8;
+  knn_merge_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(dists, reinterpret_cast<const long long*>(ids), Q, k, G,
+                                                                           out_dist, reinterpret_cast<long long*>(out_ids));
+  FIRE_LAUNCH_CHECK("knn_merge_kernel");
+  count_launch();
+  return FIRE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,124 @@
+/* fire_b200.h - C ABI of libfire_b200.so, the sm_100a identification hot path for FIRE.
+ *
+ * The reference (IvanYachUkr/FACE-Identification-in-Real-time-Environments-FIRE) is pure Python;
+ * it has no FFI of its own.  Its operator boundary for this path is three Python surfaces, and
+ * each entry point below replaces the third-party native call that surface makes today:
+ *
+ *   fire_preprocess        <- cv2.resize(INTER_AREA) + /255      modules/encoder.py:19-27
+ *                             crop slice                         modules/face_recognition.py:412-420
+ *   fire_ingest_f32        <- the NHWC float batch handed to     modules/encoder.py:16-17
+ *   fire_facenet_*         <- onnxruntime InferenceSession.run   facenet_gpu.py:72,127
+ *   fire_knn_create/add    <- hnswlib Index.init_index/add_items modules/hnsw_manager.py:29,127,137
+ *   fire_knn_search        <- hnswlib Index.knn_query            modules/hnsw_manager.py:147,237
+ *   fire_knn_merge         <- (new) multi-GPU partial top-k merge after the NCCL all-gather
+ *
+ * Conventions
+ *   - plain C, no exceptions; every function returns FIRE_OK (0) or a negative FIRE_ERR_* code and
+ *     leaves a message retrievable with fire_last_error() (thread-local).
+ *   - pointers are DEVICE pointers owned by the caller unless the parameter is named host_*.
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream)
+ *     and the functions do not synchronise, except the *_host convenience calls, which copy
+ *     host<->device and return when the result is in the host buffers.
+ *   - one handle lives on the device that was current at *_create; a handle is not re-entrant.
+ *   - there is no CPU fallback: without a usable sm_100 device every compute call fails.
+ */
+#ifndef FIRE_B200_H_
+#define FIRE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FIRE_OK 0
+#define FIRE_ERR_ARG (-1)         /* bad argument */
+#define FIRE_ERR_CUDA (-2)        /* a CUDA runtime / driver call failed */
+#define FIRE_ERR_STATE (-3)       /* handle in the wrong state (e.g. index full, k > count) */
+#define FIRE_ERR_UNSUPPORTED (-4) /* device is not sm_100, or a size outside the kernels' range */
+
+typedef void* fire_stream_t;
+typedef struct fire_net fire_net_t;
+typedef struct fire_knn fire_knn_t;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int fire_init(int device);                 /* cudaSetDevice + checks compute capability 10.x */
+const char* fire_last_error(void);
+const char* fire_version(void);
+uint64_t fire_launch_count(void);          /* number of kernels this library has launched so far */
+
+/* ---- K1: crop + resize + normalise  (modules/encoder.py:19-27, face_recognition.py:412-420) */
+#define FIRE_PRE_REFERENCE 0 /* cv2 INTER_AREA semantics on uint8, re-quantised to uint8, then /255 */
+#define FIRE_PRE_NORTHSTAR 1 /* float half-pixel bilinear + per-crop prewhiten (not in the reference) */
+#define FIRE_PRE_FLAG_SWAP_RB 16 /* OR into mode: reverse channel order (BGR<->RGB) while sampling */
+
+/* frames      : uint8 HWC3 images packed in one device allocation
+ * frame_desc  : int64 [n_frames][4] = {byte offset into frames, H, W, row stride in bytes}
+ * boxes_xywh  : int32 [n_boxes][4]  = x, y, w, h exactly as the detector/tracker emits them; the
+ *               reference's clamp rule is applied here: each of x,y,w,h = max(0, .) independently,
+ *               then the far edge is clipped to the frame (numpy slicing).  Empty crops produce an
+ *               all-zero output and status 1 in box_status.
+ * box_frame   : int32 [n_boxes] frame index of every box
+ * out_f16     : fp16 [n_boxes][160][160][8]  network input: pixel-scale (0..255 == 0..1 in the
+ *               reference), channels 3..7 zero.                       (may be NULL)
+ * out_f32     : float [n_boxes][160][160][3] exactly what preprocess_for_encoder returns (may be NULL)
+ * box_status  : int32 [n_boxes] 0 = ok, 1 = empty crop (may be NULL)
+ */
+int fire_preprocess(const uint8_t* frames, const int64_t* frame_desc, int n_frames, const int32_t* boxes_xywh,
+                    const int32_t* box_frame, int n_boxes, int mode, void* out_f16, float* out_f32,
+                    int32_t* box_status, fire_stream_t stream);
+
+/* float NHWC [B][160][160][3] in the reference's [0,1] scale -> fp16 [B][160][160][8] network input */
+int fire_ingest_f32(const float* in_nhwc3, int B, void* out_f16, fire_stream_t stream);
+
+/* ---- K2: FaceNet (Inception-ResNet-v1) forward  (facenet_gpu.py:116-129) -------------------- */
+/* host_blob: plan + folded fp16 weights as produced by fire_b200.weights.pack(). */
+int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out);
+int fire_facenet_destroy(fire_net_t* net);
+int fire_facenet_dim(const fire_net_t* net);                    /* 128 or 512 */
+size_t fire_facenet_workspace(const fire_net_t* net, int B);    /* bytes of scratch forward() needs */
+double fire_facenet_flops(const fire_net_t* net);               /* algorithmic FLOP per image */
+int fire_facenet_num_ops(const fire_net_t* net);
+/* in_f16: fp16 [B][160][160][8]; out_raw: float [B][D] un-normalised (what encode() returns);
+ * out_l2: float [B][D] rows divided by their L2 norm (face_recognition.py:225-229), may be NULL. */
+int fire_facenet_forward(fire_net_t* net, const void* in_f16, int B, float* out_raw, float* out_l2,
+                         void* workspace, size_t ws_bytes, fire_stream_t stream);
+/* Profiling aid: runs forward with a CUDA-event pair around every op; host_ms[n_ops] gets the
+ * per-op device time, host_flops[n_ops] the per-op algorithmic FLOP (0 for pools).  Synchronises. */
+int fire_facenet_profile(fire_net_t* net, const void* in_f16, int B, void* workspace, size_t ws_bytes,
+                         float* host_ms, double* host_flops, int n_ops, fire_stream_t stream);
+/* Debug aid: copy an internal activation buffer (index into the plan's buffer table) to the host as fp16. */
+int fire_facenet_read_buffer(fire_net_t* net, int buf, int B, const void* in_f16, const void* workspace,
+                             void* host_out, size_t bytes);
+
+/* ---- K3: exact cosine top-k over the enrolled gallery  (modules/hnsw_manager.py:135-149) ---- */
+int fire_knn_create(int D, size_t capacity, fire_knn_t** out);
+int fire_knn_destroy(fire_knn_t* h);
+int fire_knn_reset(fire_knn_t* h);                                  /* count = 0 */
+size_t fire_knn_count(const fire_knn_t* h);
+size_t fire_knn_capacity(const fire_knn_t* h);
+int fire_knn_dim(const fire_knn_t* h);
+/* Append n rows; each is normalised with 1/(||x||+1e-30) like hnswlib's cosine space. */
+int fire_knn_add(fire_knn_t* h, const float* rows, size_t n, fire_stream_t stream);
+int fire_knn_add_host(fire_knn_t* h, const float* host_rows, size_t n);
+/* Copy normalised rows [first, first+n) back to the host (persistence, tests). */
+int fire_knn_get_rows_host(fire_knn_t* h, size_t first, size_t n, float* host_out);
+/* Exact top-k by (distance asc, id asc), distance = 1 - <q^, g^>; ids = row index + id_offset.
+ * Requires 1 <= k <= min(count, 64).  out_dist [Q][k] float, out_ids [Q][k] int64. */
+int fire_knn_search(fire_knn_t* h, const float* queries, int Q, int k, int64_t id_offset, float* out_dist,
+                    int64_t* out_ids, fire_stream_t stream);
+int fire_knn_search_host(fire_knn_t* h, const float* host_queries, int Q, int k, int64_t id_offset,
+                         float* host_out_dist, int64_t* host_out_ids);
+/* Merge G partial results (dists/ids laid out [G][Q][k], each row ascending) into the global top-k. */
+int fire_knn_merge(const float* dists, const int64_t* ids, int Q, int k, int G, float* out_dist,
+                   int64_t* out_ids, fire_stream_t stream);
+/* Counters: queries answered so far / queries that needed the exact fp32 fallback scan. */
+int fire_knn_stats(fire_knn_t* h, uint64_t* host_queries_total, uint64_t* host_queries_fallback);
+/* Test hook: widen the fp16-filter safety margin (default 1.1e-3) to force the fallback path. */
+int fire_knn_set_margin(fire_knn_t* h, float eps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIRE_B200_H_ */

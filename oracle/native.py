@@ -1,0 +1,105 @@
+"""ctypes wrapper around oracle/_build/libfire_oracle.so (see fire_oracle.c for what it restates).
+
+ORACLE - test infrastructure only; the product never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libfire_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "fire_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-s", "-B"], check=True)
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = ctypes.CDLL(_SO)
+        L.fire_oracle_normalize.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+        L.fire_oracle_normalize.restype = None
+        L.fire_oracle_bf_knn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p,
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.fire_oracle_bf_knn.restype = ctypes.c_int
+        L.fire_oracle_resize_area_u8c3.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_long,
+                                                   ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.fire_oracle_resize_area_u8c3.restype = ctypes.c_int
+        L.fire_oracle_crop_preprocess.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_long] + \
+            [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p]
+        L.fire_oracle_crop_preprocess.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def normalize(x: np.ndarray) -> np.ndarray:
+    """hnswlib cosine-space normalisation of every row (bindings.cpp normalize_vector)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    x2 = x.reshape(-1, x.shape[-1])
+    out = np.empty_like(x2)
+    lib().fire_oracle_normalize(x2.ctypes.data, out.ctypes.data, x2.shape[0], x2.shape[1])
+    return out.reshape(x.shape)
+
+
+class BFIndexOracle:
+    """hnswlib.BFIndex(space='cosine') restated: add_items / knn_query / get_current_count."""
+
+    def __init__(self, dim: int):
+        self.dim = dim
+        self.rows = np.zeros((0, dim), dtype=np.float32)
+        self.labels = np.zeros((0,), dtype=np.uint64)
+
+    def add_items(self, data, ids=None):
+        data = np.asarray(data, dtype=np.float32).reshape(-1, self.dim)
+        if ids is None:
+            ids = np.arange(len(self.labels), len(self.labels) + len(data), dtype=np.uint64)
+        ids = np.asarray(ids, dtype=np.uint64).reshape(-1)
+        self.rows = np.concatenate([self.rows, normalize(data)], 0)
+        self.labels = np.concatenate([self.labels, ids], 0)
+
+    def get_current_count(self) -> int:
+        return len(self.labels)
+
+    def knn_query(self, data, k: int = 1, num_threads: int = 1):
+        q = normalize(np.asarray(data, dtype=np.float32).reshape(-1, self.dim))
+        if k > len(self.labels):
+            raise RuntimeError("Cannot return the results in a contiguous 2D array. Probably ef or M is too small")
+        labels = np.empty((q.shape[0], k), dtype=np.uint64)
+        dists = np.empty((q.shape[0], k), dtype=np.float32)
+        rows = np.ascontiguousarray(self.rows)
+        rc = lib().fire_oracle_bf_knn(rows.ctypes.data, self.labels.ctypes.data, rows.shape[0], self.dim, q.ctypes.data,
+                                      q.shape[0], k, labels.ctypes.data, dists.ctypes.data, num_threads)
+        assert rc == 0
+        return labels, dists
+
+
+def resize_area(img: np.ndarray, dh: int = 160, dw: int = 160) -> np.ndarray:
+    """cv2.resize(img, (dw, dh), interpolation=cv2.INTER_AREA) for uint8 HxWx3, restated."""
+    assert img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] == 3
+    out = np.empty((dh, dw, 3), dtype=np.uint8)
+    base = img.ctypes.data
+    rc = lib().fire_oracle_resize_area_u8c3(base, img.shape[0], img.shape[1], img.strides[0], out.ctypes.data, dh, dw)
+    assert rc == 0 and img.strides[1] == 3 and img.strides[2] == 1
+    return out
+
+
+def crop_preprocess(frame: np.ndarray, box) -> tuple:
+    """face_recognition.py:412-420 clamp + slice, then encoder.py:19-27.  Returns (status, u8[160,160,3], f32)."""
+    frame = np.ascontiguousarray(frame)
+    u8 = np.zeros((160, 160, 3), dtype=np.uint8)
+    f32 = np.zeros((160, 160, 3), dtype=np.float32)
+    x, y, w, h = (int(v) for v in box)
+    rc = lib().fire_oracle_crop_preprocess(frame.ctypes.data, frame.shape[0], frame.shape[1], frame.strides[0],
+                                           x, y, w, h, u8.ctypes.data, f32.ctypes.data)
+    return rc, u8, f32
