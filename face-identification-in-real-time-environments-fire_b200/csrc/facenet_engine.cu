@@ -1,0 +1,373 @@
+// facenet_engine.cu - executes the FaceNet plan (fire_b200/netplan.py) on one B200.
+//
+// Replaces onnxruntime's InferenceSession.run for weights/facenet{128,512}.onnx
+// (reference facenet_gpu.py:72,116-129).  The blob produced by fire_b200.weights.pack() carries
+// the op list, the buffer table (per-image offsets into one workspace arena, live ranges already
+// resolved) and the BN-folded fp16 weights; this file uploads the weights once, builds their TMA
+// descriptors once, and on every forward() enqueues one kernel per op on the caller's stream:
+//   conv_igemm_kernel (tcgen05)  x 105,  maxpool3x3s2_kernel x 3,  gap_kernel x 1,  l2norm_kernel x 1.
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "conv_igemm.cuh"
+#include "fire_internal.h"
+
+namespace fire {
+
+constexpr int OP_CONV = 1, OP_MAXPOOL = 2, OP_GAP = 3;
+constexpr uint32_t BLOB_VERSION = 3;
+
+#pragma pack(push, 1)
+struct BlobHeader {
+  char magic[8];
+  int32_t version, D, n_ops, n_bufs;
+  int64_t ws_bytes_per_image, weights_off, weights_bytes;
+  int32_t in_buf, out_buf;
+};
+struct BlobBuf {
+  int32_t H, W, C, elt;
+  int64_t offset;
+  int32_t external, pad;
+};
+struct BlobOp {
+  int32_t kind, src_buf, src_coff, dst_buf, dst_coff, res_buf, res_coff, H, W, Ho, Wo, kh, kw, stride, pad_h, pad_w, cin,
+      cout, k_pad, flags, bn_tile, pad;
+  int64_t w_off, b_off;
+};
+#pragma pack(pop)
+static_assert(sizeof(BlobHeader) == 56, "header layout must match weights.HEADER_DT");
+static_assert(sizeof(BlobBuf) == 32, "buffer layout must match weights.BUF_DT");
+static_assert(sizeof(BlobOp) == 104, "op layout must match weights.OP_DT");
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 stride-2 VALID max-pool, NHWC fp16, 8 channels (16 bytes) per thread, channel-offset store.
+__global__ void maxpool3x3s2_kernel(const __half* __restrict__ in, int in_ld, int in_coff, __half* __restrict__ out,
+                                    int out_ld, int out_coff, int B, int H, int W, int Ho, int Wo, int C) {
+  const int c8 = C >> 3;
+  const long long total = static_cast<long long>(B) * Ho * Wo * c8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cc = static_cast<int>(i % c8);
+    long long pix = i / c8;
+    const int wo = static_cast<int>(pix % Wo);
+    pix /= Wo;
+    const int ho = static_cast<int>(pix % Ho);
+    const int b = static_cast<int>(pix / Ho);
+    __half2 m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m[j] = __float2half2_rn(-65504.f);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const size_t off = (static_cast<size_t>(b * H + ho * 2 + r) * W + (wo * 2 + s)) * in_ld + in_coff + cc * 8;
+        uint4 q = __ldg(reinterpret_cast<const uint4*>(in + off));
+        const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], h[j]);
+      }
+    const size_t o = (static_cast<size_t>(b * Ho + ho) * Wo + wo) * out_ld + out_coff + cc * 8;
+    *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<uint4*>(m);
+  }
+}
+
+// global average pool over HW pixels (fp32 accumulation), NHWC fp16 -> [B, C] fp16
+__global__ void gap_kernel(const __half* __restrict__ in, int in_ld, int in_coff, __half* __restrict__ out, int out_ld,
+                           int B, int HW, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;    // one thread per (b, channel pair)
+  const int c2 = C >> 1;
+  if (i >= B * c2) return;
+  const int b = i / c2, c = (i - b * c2) * 2;
+  float s0 = 0.f, s1 = 0.f;
+  for (int p = 0; p < HW; ++p) {
+    float2 f = __half22float2(*reinterpret_cast<const __half2*>(in + (static_cast<size_t>(b) * HW + p) * in_ld + in_coff + c));
+    s0 += f.x; s1 += f.y;
+  }
+  const float inv = 1.0f / static_cast<float>(HW);
+  *reinterpret_cast<__half2*>(out + static_cast<size_t>(b) * out_ld + c) = __floats2half2_rn(s0 * inv, s1 * inv);
+}
+
+// rows / ||row||_2 (face_recognition.py:225-229); a zero row stays zero (the caller skips such faces)
+__global__ void l2norm_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int D) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= B) return;
+  float s = 0.f;
+  for (int c = lane; c < D; c += 32) { float v = in[static_cast<size_t>(row) * D + c]; s = fmaf(v, v, s); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float n = sqrtf(s);
+  const float inv = n > 0.f ? 1.0f / n : 0.f;
+  for (int c = lane; c < D; c += 32) {
+    float v = in[static_cast<size_t>(row) * D + c];
+    out[static_cast<size_t>(row) * D + c] = n > 0.f ? v * inv : v;
+  }
+}
+
+// float NHWC3 in [0,1] -> fp16 NHWC8 pixel scale (x*255; exact for x = k/255), channels 3..7 = 0
+__global__ void ingest_f32_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n_pix) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_pix;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float a = in[i * 3] * 255.0f, b = in[i * 3 + 1] * 255.0f, c = in[i * 3 + 2] * 255.0f;
+    uint4 q = make_uint4(pack_f16x2_sat(a, b), pack_f16x2_sat(c, 0.f), 0u, 0u);
+    *reinterpret_cast<uint4*>(out + i * 8) = q;
+  }
+}
+
+}  // namespace fire
+
+using namespace fire;
+
+struct OpRt {
+  BlobOp op;
+  CUtensorMap tmap_w;     // weights [cout][k_pad]
+  CUtensorMap tmap_a;     // activation matrix for TMA-mode convs (rebuilt when pointers / B change)
+  bool tma_a = false;
+  int stages = 0, tmem_cols = 0;
+  size_t smem = 0;
+  double flops_per_image = 0;
+};
+
+struct fire_net {
+  BlobHeader hdr;
+  std::vector<BlobBuf> bufs;
+  std::vector<OpRt> ops;
+  uint8_t* d_weights = nullptr;
+  // cache key of the activation tensor maps
+  const void* key_in = nullptr; const void* key_ws = nullptr; const void* key_out = nullptr; int key_B = 0;
+  double flops_per_image = 0;
+};
+
+static int pow2_cols(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+extern "C" {
+
+int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
+  if (!host_blob || !out) return fail(FIRE_ERR_ARG, "fire_facenet_create: NULL argument");
+  if (bytes < sizeof(BlobHeader)) return fail(FIRE_ERR_ARG, "fire_facenet_create: blob too small");
+  const uint8_t* p = static_cast<const uint8_t*>(host_blob);
+  BlobHeader h;
+  memcpy(&h, p, sizeof(h));
+  if (memcmp(h.magic, "FIREB200", 8) != 0 || h.version != (int32_t)BLOB_VERSION)
+    return fail(FIRE_ERR_ARG, "fire_facenet_create: bad magic/version (want FIREB200 v%u)", BLOB_VERSION);
+  const size_t meta = sizeof(BlobHeader) + sizeof(BlobBuf) * h.n_bufs + sizeof(BlobOp) * h.n_ops;
+  if (h.n_ops <= 0 || h.n_bufs <= 0 || meta > bytes || (size_t)(h.weights_off + h.weights_bytes) > bytes)
+    return fail(FIRE_ERR_ARG, "fire_facenet_create: truncated blob");
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(FIRE_ERR_CUDA, "no CUDA device (fire_b200 has no CPU fallback)");
+  fire_net* net = new (std::nothrow) fire_net();
+  if (!net) return fail(FIRE_ERR_STATE, "out of host memory");
+  net->hdr = h;
+  net->bufs.resize(h.n_bufs);
+  memcpy(net->bufs.data(), p + sizeof(BlobHeader), sizeof(BlobBuf) * h.n_bufs);
+  std::vector<BlobOp> ops(h.n_ops);
+  memcpy(ops.data(), p + sizeof(BlobHeader) + sizeof(BlobBuf) * h.n_bufs, sizeof(BlobOp) * h.n_ops);
+  cudaError_t e = cudaMalloc(&net->d_weights, h.weights_bytes);
+  if (e == cudaSuccess) e = cudaMemcpy(net->d_weights, p + h.weights_off, h.weights_bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(net->d_weights);
+    delete net;
+    return fail(FIRE_ERR_CUDA, "fire_facenet_create: weight upload failed: %s", cudaGetErrorString(e));
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      cudaFree(net->d_weights);
+      delete net;
+      return fail(FIRE_ERR_CUDA, "cudaFuncSetAttribute(conv_igemm_kernel): %s", cudaGetErrorString(e));
+    }
+    attr_done = true;
+  }
+  for (const BlobOp& o : ops) {
+    OpRt r;
+    r.op = o;
+    if (o.src_buf < 0 || o.src_buf >= h.n_bufs || o.dst_buf < 0 || o.dst_buf >= h.n_bufs || o.res_buf >= h.n_bufs) {
+      cudaFree(net->d_weights); delete net;
+      return fail(FIRE_ERR_ARG, "fire_facenet_create: op references a buffer out of range");
+    }
+    if (o.kind == OP_CONV) {
+      if (o.bn_tile < 16 || o.bn_tile > 256 || o.bn_tile % 16 || o.cout % o.bn_tile || o.k_pad % 64 || o.cin % 8) {
+        cudaFree(net->d_weights); delete net;
+        return fail(FIRE_ERR_ARG, "fire_facenet_create: conv op with unsupported tiling (cout=%d bn=%d k_pad=%d cin=%d)",
+                    o.cout, o.bn_tile, o.k_pad, o.cin);
+      }
+      int rc = make_tmap_f16_2d(&r.tmap_w, net->d_weights + o.w_off, (uint64_t)o.cout, (uint64_t)o.k_pad,
+                                (uint64_t)o.k_pad * 2, (uint32_t)o.bn_tile);
+      if (rc != FIRE_OK) { cudaFree(net->d_weights); delete net; return rc; }
+      r.tma_a = (o.kh == 1 && o.kw == 1 && o.stride == 1 && o.pad_h == 0 && o.pad_w == 0);
+      const size_t stage = CONV_A_STAGE_BYTES + (size_t)o.bn_tile * 128;
+      r.stages = 4;
+      while (r.stages > 3 && r.stages * stage + 2048 > 200 * 1024) r.stages--;
+      r.smem = 1024 + r.stages * stage + 256;
+      r.tmem_cols = pow2_cols(o.bn_tile);
+      r.flops_per_image = 2.0 * o.Ho * o.Wo * (double)o.cout * o.kh * o.kw * o.cin;
+      net->flops_per_image += r.flops_per_image;
+    }
+    net->ops.push_back(r);
+  }
+  *out = net;
+  return FIRE_OK;
+}
+
+int fire_facenet_destroy(fire_net_t* net) {
+  if (!net) return FIRE_OK;
+  cudaFree(net->d_weights);
+  delete net;
+  return FIRE_OK;
+}
+
+int fire_facenet_dim(const fire_net_t* net) { return net ? net->hdr.D : 0; }
+int fire_facenet_num_ops(const fire_net_t* net) { return net ? (int)net->ops.size() : 0; }
+double fire_facenet_flops(const fire_net_t* net) { return net ? net->flops_per_image : 0.0; }
+
+size_t fire_facenet_workspace(const fire_net_t* net, int B) {
+  if (!net || B <= 0) return 0;
+  return (size_t)net->hdr.ws_bytes_per_image * (size_t)B + 1024;
+}
+
+}  // extern "C"
+
+static void* buf_ptr(const fire_net* net, int buf, int B, const void* in, void* ws, void* out_raw) {
+  if (buf == net->hdr.in_buf) return const_cast<void*>(in);
+  if (buf == net->hdr.out_buf) return out_raw;
+  return static_cast<uint8_t*>(ws) + (size_t)net->bufs[buf].offset * (size_t)B;
+}
+
+static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float* out_raw, cudaStream_t st) {
+  const BlobOp& o = r.op;
+  const BlobBuf& sb = net->bufs[o.src_buf];
+  const BlobBuf& db = net->bufs[o.dst_buf];
+  const __half* src = static_cast<const __half*>(buf_ptr(net, o.src_buf, B, in, ws, out_raw));
+  void* dst = buf_ptr(net, o.dst_buf, B, in, ws, out_raw);
+  if (o.kind == OP_CONV) {
+    ConvParams p;
+    p.in = src; p.in_ld = sb.C; p.in_coff = o.src_coff;
+    p.out = dst; p.out_ld = db.C; p.out_coff = o.dst_coff;
+    p.res = nullptr; p.res_ld = 0; p.res_coff = 0;
+    if (o.res_buf >= 0) {
+      p.res = static_cast<const __half*>(buf_ptr(net, o.res_buf, B, in, ws, out_raw));
+      p.res_ld = net->bufs[o.res_buf].C; p.res_coff = o.res_coff;
+    }
+    p.bias = reinterpret_cast<const float*>(net->d_weights + o.b_off);
+    p.H = o.H; p.W = o.W; p.Ho = o.Ho; p.Wo = o.Wo; p.kh = o.kh; p.kw = o.kw; p.stride = o.stride;
+    p.pad_h = o.pad_h; p.pad_w = o.pad_w; p.cin = o.cin; p.cout = o.cout; p.k_real = o.kh * o.kw * o.cin;
+    p.nkb = o.k_pad / 64; p.flags = o.flags; p.bn_tile = o.bn_tile; p.M_total = B * o.Ho * o.Wo;
+    p.stages = r.stages; p.tma_a = r.tma_a ? 1 : 0; p.tmem_cols = r.tmem_cols;
+    dim3 grid((p.M_total + CONV_BM - 1) / CONV_BM, o.cout / o.bn_tile);
+    conv_igemm_kernel<<<grid, CONV_THREADS, r.smem, st>>>(r.tmap_w, r.tma_a ? r.tmap_a : r.tmap_w, p);
+    FIRE_LAUNCH_CHECK("conv_igemm_kernel");
+  } else if (o.kind == OP_MAXPOOL) {
+    const long long total = (long long)B * o.Ho * o.Wo * (o.cin / 8);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    maxpool3x3s2_kernel<<<blocks, 256, 0, st>>>(src, sb.C, o.src_coff, static_cast<__half*>(dst), db.C, o.dst_coff, B, o.H,
+                                                o.W, o.Ho, o.Wo, o.cin);
+    FIRE_LAUNCH_CHECK("maxpool3x3s2_kernel");
+  } else if (o.kind == OP_GAP) {
+    const int n = B * (o.cin / 2);
+    gap_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, sb.C, o.src_coff, static_cast<__half*>(dst), db.C, B, o.H * o.W, o.cin);
+    FIRE_LAUNCH_CHECK("gap_kernel");
+  } else {
+    return fail(FIRE_ERR_ARG, "unknown op kind %d", o.kind);
+  }
+  count_launch();
+  return FIRE_OK;
+}
+
+static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* ws, size_t ws_bytes) {
+  if (!net || !in || !out_raw || !ws) return fail(FIRE_ERR_ARG, "fire_facenet_forward: NULL argument");
+  if (B <= 0 || B > 4096) return fail(FIRE_ERR_UNSUPPORTED, "fire_facenet_forward: B=%d outside [1,4096]", B);
+  if (ws_bytes < fire_facenet_workspace(net, B))
+    return fail(FIRE_ERR_ARG, "fire_facenet_forward: workspace %zu < required %zu", ws_bytes, fire_facenet_workspace(net, B));
+  if ((reinterpret_cast<uintptr_t>(ws) & 255) || (reinterpret_cast<uintptr_t>(in) & 15))
+    return fail(FIRE_ERR_ARG, "fire_facenet_forward: workspace must be 256-byte and input 16-byte aligned");
+  if (net->key_in != in || net->key_ws != ws || net->key_out != out_raw || net->key_B != B) {
+    for (OpRt& r : net->ops) {
+      if (r.op.kind != OP_CONV || !r.tma_a) continue;
+      const BlobBuf& sb = net->bufs[r.op.src_buf];
+      const __half* src = static_cast<const __half*>(buf_ptr(net, r.op.src_buf, B, in, ws, out_raw)) + r.op.src_coff;
+      int rc = make_tmap_f16_2d(&r.tmap_a, src, (uint64_t)B * r.op.Ho * r.op.Wo, (uint64_t)r.op.cin, (uint64_t)sb.C * 2, CONV_BM);
+      if (rc != FIRE_OK) return rc;
+    }
+    net->key_in = in; net->key_ws = ws; net->key_out = out_raw; net->key_B = B;
+  }
+  return FIRE_OK;
+}
+
+extern "C" {
+
+int fire_facenet_forward(fire_net_t* net, const void* in_f16, int B, float* out_raw, float* out_l2, void* workspace,
+                         size_t ws_bytes, fire_stream_t stream) {
+  int rc = prepare(net, in_f16, B, out_raw, workspace, ws_bytes);
+  if (rc != FIRE_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (OpRt& r : net->ops) {
+    rc = run_op(net, r, B, in_f16, workspace, out_raw, st);
+    if (rc != FIRE_OK) return rc;
+  }
+  if (out_l2) {
+    l2norm_kernel<<<(B + 7) / 8, 256, 0, st>>>(out_raw, out_l2, B, net->hdr.D);
+    FIRE_LAUNCH_CHECK("l2norm_kernel");
+    count_launch();
+  }
+  return FIRE_OK;
+}
+
+int fire_facenet_profile(fire_net_t* net, const void* in_f16, int B, void* workspace, size_t ws_bytes, float* host_ms,
+                         double* host_flops, int n_ops, fire_stream_t stream) {
+  if (!net || !host_ms || n_ops < (int)net->ops.size()) return fail(FIRE_ERR_ARG, "fire_facenet_profile: bad arguments");
+  float* out_raw = nullptr;
+  FIRE_CUDA(cudaMalloc(&out_raw, sizeof(float) * (size_t)B * net->hdr.D));
+  int rc = prepare(net, in_f16, B, out_raw, workspace, ws_bytes);
+  if (rc != FIRE_OK) { cudaFree(out_raw); return rc; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<cudaEvent_t> ev(net->ops.size() + 1);
+  for (auto& e : ev) cudaEventCreate(&e);
+  cudaEventRecord(ev[0], st);
+  for (size_t i = 0; i < net->ops.size(); ++i) {
+    rc = run_op(net, net->ops[i], B, in_f16, workspace, out_raw, st);
+    if (rc != FIRE_OK) break;
+    cudaEventRecord(ev[i + 1], st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == FIRE_OK && e == cudaSuccess) {
+    for (size_t i = 0; i < net->ops.size(); ++i) {
+      cudaEventElapsedTime(&host_ms[i], ev[i], ev[i + 1]);
+      if (host_flops) host_flops[i] = net->ops[i].flops_per_image * B;
+    }
+  }
+  for (auto& x : ev) cudaEventDestroy(x);
+  cudaFree(out_raw);
+  net->key_in = nullptr;   // out_raw was temporary: force descriptor rebuild next time
+  if (rc != FIRE_OK) return rc;
+  if (e != cudaSuccess) return fail(FIRE_ERR_CUDA, "fire_facenet_profile: %s", cudaGetErrorString(e));
+  return FIRE_OK;
+}
+
+int fire_facenet_read_buffer(fire_net_t* net, int buf, int B, const void* in_f16, const void* workspace, void* host_out,
+                             size_t bytes) {
+  if (!net || buf < 0 || buf >= (int)net->bufs.size() || !host_out) return fail(FIRE_ERR_ARG, "fire_facenet_read_buffer: bad arguments");
+  const BlobBuf& b = net->bufs[buf];
+  const size_t need = (size_t)B * b.H * b.W * b.C * b.elt;
+  if (bytes < need) return fail(FIRE_ERR_ARG, "fire_facenet_read_buffer: need %zu bytes", need);
+  if (buf == net->hdr.out_buf) return fail(FIRE_ERR_ARG, "fire_facenet_read_buffer: the output buffer belongs to the caller");
+  const void* src = buf_ptr(net, buf, B, in_f16, const_cast<void*>(workspace), nullptr);
+  FIRE_CUDA(cudaMemcpy(host_out, src, need, cudaMemcpyDeviceToHost));
+  return FIRE_OK;
+}
+
+int fire_ingest_f32(const float* in_nhwc3, int B, void* out_f16, fire_stream_t stream) {
+  if (!in_nhwc3 || !out_f16 || B <= 0) return fail(FIRE_ERR_ARG, "fire_ingest_f32: bad arguments");
+  const long long n_pix = (long long)B * 160 * 160;
+  const int blocks = (int)std::min<long long>((n_pix + 255) / 256, 148 * 32);
+  ingest_f32_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(in_nhwc3, static_cast<__half*>(out_f16), n_pix);
+  FIRE_LAUNCH_CHECK("ingest_f32_kernel");
+  count_launch();
+  return FIRE_OK;
+}
+
+}  // extern "C"

@@ -219,6 +219,7 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       for (int c = 0; c < KNN_BN / 32; ++c) {
         if (c * 32 >= nvalid) break;
         uint32_t r[32];
+        __syncwarp();                                // tcgen05.ld is warp-collective: reconverge first
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * KNN_BN + c * 32), r);
         tmem_ld_wait();
         const int lim = nvalid - c * 32;          // >= 32 for full chunks
@@ -245,6 +246,7 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           }
         }
       }
+      __syncwarp();
       tc_fence_before();
       mbar_arrive(&tempty[buf]);
     }

@@ -1,0 +1,353 @@
+// preprocess.cu - fused crop + resize + normalise for batches of face boxes (K1 of DESIGN.md).
+//
+// Reference behaviour being replaced (per face, on the CPU):
+//   modules/face_recognition.py:412-420   x,y,w,h = max(0,.) each; face = image[y:y+h, x:x+w]
+//   modules/encoder.py:19-27              cv2.resize(face,(160,160),INTER_AREA) on uint8 -> /255.0
+//
+// FIRE_PRE_REFERENCE reproduces cv::resize(INTER_AREA) for 8UC3 bit for bit (every branch of
+// imgproc/resize.cpp that this call can take: copy, integer-scale box mean, fractional area
+// tables in float, fixed-point linear for up-scaled axes) and re-quantises to uint8 like the
+// reference does before dividing by 255.  FIRE_PRE_NORTHSTAR is the additive mode named by the
+// north star: float half-pixel bilinear + per-crop prewhiten (davidsandberg facenet.prewhiten).
+//
+// Layout: frames are uint8 HWC3 in HBM; the output is the network's input layout, fp16 NHWC with
+// the 3 channels padded to 8 (one 16-byte vector per pixel, pixel scale 0..255), so each thread
+// finishes with one coalesced 16-byte store.  The kernel is HBM/L2-bound integer/byte work; it
+// deliberately stays off the tensor cores.
+#include <cfloat>
+
+#include "fire_common.cuh"
+#include "fire_internal.h"
+
+namespace fire {
+
+constexpr int PRE_OUT = 160;
+constexpr int PRE_ROWS_PER_BLOCK = 16;
+constexpr int PRE_THREADS = 256;
+
+enum { PM_EMPTY = 0, PM_COPY = 1, PM_FAST = 2, PM_AREA = 3, PM_LINEAR = 4 };
+
+struct AreaEntry {        // source span of one output coordinate, cv::computeResizeAreaTab order
+  int s_left;             // index of the left partial cell (valid if has_left)
+  int s_mid0, n_mid;      // full cells [s_mid0, s_mid0 + n_mid)
+  int s_right;            // right partial cell (valid if has_right)
+  float a_left, a_mid, a_right;
+  int has_left, has_right;
+};
+struct LinEntry {
+  int ofs;                // source index
+  int a0, a1;             // 11-bit fixed-point weights
+  int edge;               // x only: dx >= xmax -> single tap * 2048
+};
+
+struct CropGeom {
+  const uint8_t* base;    // first byte of the crop (row y0, col x0)
+  long long stride;
+  int cw, ch, mode, iscale_x, iscale_y;
+  double scale_x, scale_y, inv_scale_x, inv_scale_y;
+};
+
+__device__ __forceinline__ int cv_floor_dev(double v) { int i = static_cast<int>(v); return i - (i > v); }
+__device__ __forceinline__ int cv_ceil_dev(double v) { int i = static_cast<int>(v); return i + (i < v); }
+
+// modules/face_recognition.py:412-420 + numpy slice clipping
+__device__ __forceinline__ void crop_geometry(const uint8_t* frames, const int64_t* fd, const int32_t* box, CropGeom& g) {
+  const long long off = fd[0];
+  const int H = static_cast<int>(fd[1]), W = static_cast<int>(fd[2]);
+  g.stride = fd[3];
+  int x = max(0, box[0]), y = max(0, box[1]), w = max(0, box[2]), h = max(0, box[3]);
+  const int x1 = min(W, x + w), y1 = min(H, y + h);
+  const int x0 = min(x, W), y0 = min(y, H);
+  g.cw = x1 - x0; g.ch = y1 - y0;
+  g.base = frames + off + static_cast<long long>(y0) * g.stride + static_cast<long long>(x0) * 3;
+  if (g.cw <= 0 || g.ch <= 0) { g.mode = PM_EMPTY; return; }
+  if (g.cw == PRE_OUT && g.ch == PRE_OUT) { g.mode = PM_COPY; return; }
+  g.inv_scale_x = static_cast<double>(PRE_OUT) / g.cw; g.inv_scale_y = static_cast<double>(PRE_OUT) / g.ch;
+  g.scale_x = 1. / g.inv_scale_x; g.scale_y = 1. / g.inv_scale_y;
+  g.iscale_x = __double2int_rn(g.scale_x); g.iscale_y = __double2int_rn(g.scale_y);
+  if (g.scale_x >= 1 && g.scale_y >= 1) {
+    const bool fast = fabs(g.scale_x - g.iscale_x) < DBL_EPSILON && fabs(g.scale_y - g.iscale_y) < DBL_EPSILON;
+    g.mode = fast ? PM_FAST : PM_AREA;
+  } else {
+    g.mode = PM_LINEAR;
+  }
+}
+
+__device__ __forceinline__ void area_entry(int d, int ssize, double scale, AreaEntry& e) {
+  const double fsx1 = d * scale, fsx2 = fsx1 + scale;
+  const double cell = fmin(scale, ssize - fsx1);
+  int sx1 = cv_ceil_dev(fsx1), sx2 = cv_floor_dev(fsx2);
+  sx2 = min(sx2, ssize - 1);
+  sx1 = min(sx1, sx2);
+  e.has_left = (sx1 - fsx1 > 1e-3);
+  e.s_left = sx1 - 1;
+  e.a_left = static_cast<float>((sx1 - fsx1) / cell);
+  e.s_mid0 = sx1; e.n_mid = max(0, sx2 - sx1);
+  e.a_mid = static_cast<float>(1.0 / cell);
+  e.has_right = (fsx2 - sx2 > 1e-3);
+  e.s_right = sx2;
+  e.a_right = static_cast<float>(fmin(fmin(fsx2 - sx2, 1.), cell) / cell);
+}
+
+__device__ __forceinline__ void linear_entry(int d, int ssize, double scale, double inv_scale, bool is_x, LinEntry& e) {
+  int s = cv_floor_dev(d * scale);
+  float f = static_cast<float>((d + 1) - (s + 1) * inv_scale);
+  f = f <= 0 ? 0.f : f - static_cast<float>(cv_floor_dev(f));
+  e.edge = 0;
+  if (is_x) {
+    if (s < 0) { f = 0; s = 0; }
+    if (s + 1 >= ssize) {
+      e.edge = 1;                        // contributes to xmax = min over such dx (monotone in dx)
+      if (s >= ssize - 1) { f = 0; s = ssize - 1; }
+    }
+  }
+  e.ofs = s;
+  const float c0 = 1.f - f;
+  e.a0 = min(32767, __float2int_rn(__fmul_rn(c0, 2048.f)));
+  e.a1 = min(32767, __float2int_rn(__fmul_rn(f, 2048.f)));
+}
+
+__device__ __forceinline__ void store_pixel(int v0, int v1, int v2, size_t pix, __half* out_f16, float* out_f32) {
+  if (out_f16) {
+    uint4 q = make_uint4(pack_f16x2_sat(static_cast<float>(v0), static_cast<float>(v1)),
+                         pack_f16x2_sat(static_cast<float>(v2), 0.f), 0u, 0u);
+    *reinterpret_cast<uint4*>(out_f16 + pix * 8) = q;
+  }
+  if (out_f32) {
+    out_f32[pix * 3 + 0] = __fdiv_rn(static_cast<float>(v0), 255.0f);
+    out_f32[pix * 3 + 1] = __fdiv_rn(static_cast<float>(v1), 255.0f);
+    out_f32[pix * 3 + 2] = __fdiv_rn(static_cast<float>(v2), 255.0f);
+  }
+}
+
+__global__ void __launch_bounds__(PRE_THREADS)
+preprocess_reference_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict__ frame_desc,
+                            const int32_t* __restrict__ boxes, const int32_t* __restrict__ box_frame, int swap_rb,
+                            __half* __restrict__ out_f16, float* __restrict__ out_f32, int32_t* __restrict__ status) {
+  __shared__ CropGeom g;
+  __shared__ AreaEntry ax[PRE_OUT];
+  __shared__ AreaEntry ay[PRE_ROWS_PER_BLOCK];
+  __shared__ LinEntry lx[PRE_OUT];
+  __shared__ LinEntry ly[PRE_ROWS_PER_BLOCK];
+  __shared__ int s_xmax;
+
+  const int box = blockIdx.x;
+  const int dy0 = blockIdx.y * PRE_ROWS_PER_BLOCK;
+  if (threadIdx.x == 0) {
+    crop_geometry(frames, frame_desc + 4 * static_cast<long long>(box_frame[box]), boxes + 4 * box, g);
+    s_xmax = PRE_OUT;
+    if (status && blockIdx.y == 0) status[box] = g.mode == PM_EMPTY ? 1 : 0;
+  }
+  __syncthreads();
+  const int mode = g.mode;
+  if (mode == PM_AREA) {
+    for (int i = threadIdx.x; i < PRE_OUT + PRE_ROWS_PER_BLOCK; i += PRE_THREADS) {
+      if (i < PRE_OUT) area_entry(i, g.cw, g.scale_x, ax[i]);
+      else area_entry(dy0 + i - PRE_OUT, g.ch, g.scale_y, ay[i - PRE_OUT]);
+    }
+  } else if (mode == PM_LINEAR) {
+    for (int i = threadIdx.x; i < PRE_OUT + PRE_ROWS_PER_BLOCK; i += PRE_THREADS) {
+      if (i < PRE_OUT) {
+        linear_entry(i, g.cw, g.scale_x, g.inv_scale_x, true, lx[i]);
+        if (lx[i].edge) atomicMin(&s_xmax, i);
+      } else {
+        linear_entry(dy0 + i - PRE_OUT, g.ch, g.scale_y, g.inv_scale_y, false, ly[i - PRE_OUT]);
+      }
+    }
+  }
+  __syncthreads();
+  const int xmax = s_xmax;
+  const uint8_t* __restrict__ src = g.base;
+  const long long st = g.stride;
+
+  for (int t = threadIdx.x; t < PRE_ROWS_PER_BLOCK * PRE_OUT; t += PRE_THREADS) {
+    const int ry = t / PRE_OUT, dx = t - ry * PRE_OUT, dy = dy0 + ry;
+    int v[3] = {0, 0, 0};
+    if (mode == PM_COPY) {
+      const uint8_t* s = src + dy * st + dx * 3;
+      v[0] = s[0]; v[1] = s[1]; v[2] = s[2];
+    } else if (mode == PM_FAST) {
+      const int ix = g.iscale_x, iy = g.iscale_y;
+      int sum[3] = {0, 0, 0};
+      for (int yy = 0; yy < iy; ++yy) {
+        const uint8_t* s = src + static_cast<long long>(dy * iy + yy) * st + static_cast<long long>(dx) * ix * 3;
+        for (int xx = 0; xx < ix; ++xx) { sum[0] += s[xx * 3]; sum[1] += s[xx * 3 + 1]; sum[2] += s[xx * 3 + 2]; }
+      }
+      if (ix == 2 && iy == 2) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = (sum[c] + 2) >> 2;
+      } else {
+        const float scale = 1.f / static_cast<float>(ix * iy);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = min(255, max(0, __float2int_rn(__fmul_rn(static_cast<float>(sum[c]), scale))));
+      }
+    } else if (mode == PM_AREA) {
+      const AreaEntry ex = ax[dx];
+      const AreaEntry ey = ay[ry];
+      float sum[3] = {0.f, 0.f, 0.f};
+      bool first = true;
+      const int ny = ey.has_left + ey.n_mid + ey.has_right;
+      for (int j = 0; j < ny; ++j) {
+        int sy; float beta;
+        if (ey.has_left && j == 0) { sy = ey.s_left; beta = ey.a_left; }
+        else if (j - ey.has_left < ey.n_mid) { sy = ey.s_mid0 + j - ey.has_left; beta = ey.a_mid; }
+        else { sy = ey.s_right; beta = ey.a_right; }
+        const uint8_t* s = src + static_cast<long long>(sy) * st;
+        float buf[3] = {0.f, 0.f, 0.f};
+        if (ex.has_left) {
+          const uint8_t* q = s + ex.s_left * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) buf[c] = __fadd_rn(buf[c], __fmul_rn(static_cast<float>(q[c]), ex.a_left));
+        }
+        for (int k = 0; k < ex.n_mid; ++k) {
+          const uint8_t* q = s + (ex.s_mid0 + k) * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) buf[c] = __fadd_rn(buf[c], __fmul_rn(static_cast<float>(q[c]), ex.a_mid));
+        }
+        if (ex.has_right) {
+          const uint8_t* q = s + ex.s_right * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) buf[c] = __fadd_rn(buf[c], __fmul_rn(static_cast<float>(q[c]), ex.a_right));
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          sum[c] = first ? __fmul_rn(beta, buf[c]) : __fadd_rn(sum[c], __fmul_rn(beta, buf[c]));
+        first = false;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = min(255, max(0, __float2int_rn(sum[c])));
+    } else if (mode == PM_LINEAR) {
+      const LinEntry ex = lx[dx];
+      const LinEntry ey = ly[ry];
+      const int r0 = min(max(ey.ofs, 0), g.ch - 1), r1 = min(max(ey.ofs + 1, 0), g.ch - 1);
+      const uint8_t* s0 = src + static_cast<long long>(r0) * st + ex.ofs * 3;
+      const uint8_t* s1 = src + static_cast<long long>(r1) * st + ex.ofs * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        int h0, h1;
+        if (dx < xmax) {
+          h0 = s0[c] * ex.a0 + s0[3 + c] * ex.a1;
+          h1 = s1[c] * ex.a0 + s1[3 + c] * ex.a1;
+        } else {
+          h0 = s0[c] * 2048; h1 = s1[c] * 2048;
+        }
+        v[c] = ((((ey.a0 * (h0 >> 4)) >> 16) + ((ey.a1 * (h1 >> 4)) >> 16) + 2) >> 2) & 0xFF;
+      }
+    }
+    if (swap_rb) { const int tmp = v[0]; v[0] = v[2]; v[2] = tmp; }
+    store_pixel(v[0], v[1], v[2], (static_cast<size_t>(box) * PRE_OUT + dy) * PRE_OUT + dx, out_f16, out_f32);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// NORTHSTAR mode: half-pixel bilinear in float + per-crop prewhiten.  One block per crop; pass 1
+// accumulates sum / sum-of-squares (double), pass 2 recomputes the taps (L1/L2 hits) and writes
+// y = (x - mean) / max(std, 1/sqrt(n)).  out_f16 carries 255*y (the engine folds 1/255 into conv 1).
+constexpr int NS_THREADS = 1024;
+
+__device__ __forceinline__ void bilinear_px(const uint8_t* __restrict__ src, long long st, int cw, int ch, float sxs,
+                                            float sys, int dx, int dy, float (&v)[3]) {
+  float fx = (dx + 0.5f) * sxs - 0.5f, fy = (dy + 0.5f) * sys - 0.5f;
+  fx = fminf(fmaxf(fx, 0.f), static_cast<float>(cw - 1));
+  fy = fminf(fmaxf(fy, 0.f), static_cast<float>(ch - 1));
+  const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+  const int x1 = min(x0 + 1, cw - 1), y1 = min(y0 + 1, ch - 1);
+  const float tx = fx - x0, ty = fy - y0;
+  const uint8_t* p00 = src + static_cast<long long>(y0) * st + x0 * 3;
+  const uint8_t* p01 = src + static_cast<long long>(y0) * st + x1 * 3;
+  const uint8_t* p10 = src + static_cast<long long>(y1) * st + x0 * 3;
+  const uint8_t* p11 = src + static_cast<long long>(y1) * st + x1 * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float top = __fadd_rn(__fmul_rn(1.f - tx, static_cast<float>(p00[c])), __fmul_rn(tx, static_cast<float>(p01[c])));
+    const float bot = __fadd_rn(__fmul_rn(1.f - tx, static_cast<float>(p10[c])), __fmul_rn(tx, static_cast<float>(p11[c])));
+    v[c] = __fadd_rn(__fmul_rn(1.f - ty, top), __fmul_rn(ty, bot));
+  }
+}
+
+__global__ void __launch_bounds__(NS_THREADS)
+preprocess_northstar_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict__ frame_desc,
+                            const int32_t* __restrict__ boxes, const int32_t* __restrict__ box_frame, int swap_rb,
+                            __half* __restrict__ out_f16, float* __restrict__ out_f32, int32_t* __restrict__ status) {
+  __shared__ CropGeom g;
+  __shared__ double red[2][NS_THREADS / 32];
+  __shared__ float s_mean, s_inv;
+  const int box = blockIdx.x;
+  if (threadIdx.x == 0) {
+    crop_geometry(frames, frame_desc + 4 * static_cast<long long>(box_frame[box]), boxes + 4 * box, g);
+    if (status) status[box] = g.mode == PM_EMPTY ? 1 : 0;
+  }
+  __syncthreads();
+  const size_t pix0 = static_cast<size_t>(box) * PRE_OUT * PRE_OUT;
+  if (g.mode == PM_EMPTY) {
+    for (int t = threadIdx.x; t < PRE_OUT * PRE_OUT; t += NS_THREADS) {
+      if (out_f16) *reinterpret_cast<uint4*>(out_f16 + (pix0 + t) * 8) = make_uint4(0, 0, 0, 0);
+      if (out_f32) { out_f32[(pix0 + t) * 3] = 0.f; out_f32[(pix0 + t) * 3 + 1] = 0.f; out_f32[(pix0 + t) * 3 + 2] = 0.f; }
+    }
+    return;
+  }
+  const float sxs = static_cast<float>(g.cw) / PRE_OUT, sys = static_cast<float>(g.ch) / PRE_OUT;
+  double s = 0., ss = 0.;
+  for (int t = threadIdx.x; t < PRE_OUT * PRE_OUT; t += NS_THREADS) {
+    float v[3];
+    bilinear_px(g.base, g.stride, g.cw, g.ch, sxs, sys, t % PRE_OUT, t / PRE_OUT, v);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { s += v[c]; ss += static_cast<double>(v[c]) * v[c]; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = ss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0., b = 0.;
+    for (int i = 0; i < NS_THREADS / 32; ++i) { a += red[0][i]; b += red[1][i]; }
+    const double n = 3.0 * PRE_OUT * PRE_OUT;
+    const double mean = a / n;
+    const double var = fmax(b / n - mean * mean, 0.);
+    const double sd = fmax(sqrt(var), 1.0 / sqrt(n));
+    s_mean = static_cast<float>(mean);
+    s_inv = static_cast<float>(1.0 / sd);
+  }
+  __syncthreads();
+  const float mean = s_mean, inv = s_inv;
+  for (int t = threadIdx.x; t < PRE_OUT * PRE_OUT; t += NS_THREADS) {
+    float v[3];
+    bilinear_px(g.base, g.stride, g.cw, g.ch, sxs, sys, t % PRE_OUT, t / PRE_OUT, v);
+    float y[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] = (v[c] - mean) * inv;
+    if (swap_rb) { const float tmp = y[0]; y[0] = y[2]; y[2] = tmp; }
+    if (out_f16)
+      *reinterpret_cast<uint4*>(out_f16 + (pix0 + t) * 8) =
+          make_uint4(pack_f16x2_sat(y[0] * 255.f, y[1] * 255.f), pack_f16x2_sat(y[2] * 255.f, 0.f), 0u, 0u);
+    if (out_f32) { out_f32[(pix0 + t) * 3] = y[0]; out_f32[(pix0 + t) * 3 + 1] = y[1]; out_f32[(pix0 + t) * 3 + 2] = y[2]; }
+  }
+}
+
+}  // namespace fire
+
+using namespace fire;
+
+extern "C" int fire_preprocess(const uint8_t* frames, const int64_t* frame_desc, int n_frames, const int32_t* boxes_xywh,
+                               const int32_t* box_frame, int n_boxes, int mode, void* out_f16, float* out_f32,
+                               int32_t* box_status, fire_stream_t stream) {
+  if (!frames || !frame_desc || !boxes_xywh || !box_frame) return fail(FIRE_ERR_ARG, "fire_preprocess: NULL argument");
+  if (!out_f16 && !out_f32) return fail(FIRE_ERR_ARG, "fire_preprocess: no output requested");
+  if (n_boxes <= 0 || n_frames <= 0) return fail(FIRE_ERR_ARG, "fire_preprocess: n_boxes=%d n_frames=%d", n_boxes, n_frames);
+  const int swap = (mode & FIRE_PRE_FLAG_SWAP_RB) ? 1 : 0;
+  const int m = mode & 15;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (m == FIRE_PRE_REFERENCE) {
+    dim3 grid(n_boxes, PRE_OUT / PRE_ROWS_PER_BLOCK);
+    preprocess_reference_kernel<<<grid, PRE_THREADS, 0, st>>>(frames, frame_desc, boxes_xywh, box_frame, swap,
+                                                              static_cast<__half*>(out_f16), out_f32, box_status);
+  } else if (m == FIRE_PRE_NORTHSTAR) {
+    preprocess_northstar_kernel<<<n_boxes, NS_THREADS, 0, st>>>(frames, frame_desc, boxes_xywh, box_frame, swap,
+                                                                static_cast<__half*>(out_f16), out_f32, box_status);
+  } else {
+    return fail(FIRE_ERR_ARG, "fire_preprocess: unknown mode %d", mode);
+  }
+  FIRE_LAUNCH_CHECK("preprocess kernel");
+  count_launch();
+  return FIRE_OK;
+}

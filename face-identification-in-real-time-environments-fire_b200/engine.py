@@ -1,0 +1,235 @@
+"""Device-level Python API over libfire_b200.so: torch tensors own the HBM, the kernels are ours.
+
+These classes are what the drop-in surfaces (encoder.py, hnsw_manager.py, preprocess.py) and
+bench.py are built from.  torch is used for device memory, streams and (in dist.py) NCCL only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import FireError, check
+from .netplan import IN_C_PAD, IN_HW, Plan
+from . import weights as W
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise FireError("fire_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch
+
+
+def _ptr(t) -> int:
+    return int(t.data_ptr())
+
+
+class FaceNetEngine:
+    """K2: the Inception-ResNet-v1 conv stack (replaces the onnxruntime session, facenet_gpu.py:72,127)."""
+
+    def __init__(self, D: int = 512, tensors: Optional[dict] = None, device: int = 0, fuse_siblings: bool = True,
+                 seed: int = 1234):
+        torch = _torch()
+        _lib.init(device)
+        self.device = torch.device("cuda", device)
+        self.D = D
+        self.plan = Plan(D, fuse_siblings=fuse_siblings)
+        if tensors is None:
+            tensors = W.synthetic_weights(D, seed)
+        self.blob = W.pack(self.plan, tensors)
+        h = C.c_void_p()
+        buf = C.create_string_buffer(self.blob, len(self.blob))
+        check(_lib.lib().fire_facenet_create(C.addressof(buf), len(self.blob), C.byref(h)))
+        self._h = h
+        self._ws = None
+        self._ws_B = 0
+        self.flops_per_image = float(_lib.lib().fire_facenet_flops(self._h))
+        self.num_ops = int(_lib.lib().fire_facenet_num_ops(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().fire_facenet_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _workspace(self, B: int):
+        torch = _torch()
+        need = int(_lib.lib().fire_facenet_workspace(self._h, B))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+        off = (-self._ws.data_ptr()) % 256
+        return self._ws.data_ptr() + off, self._ws.numel() - off
+
+    def forward(self, x_f16, want_l2: bool = True, out_raw=None, out_l2=None):
+        """x_f16: cuda fp16 [B,160,160,8] pixel-scale network input -> (raw [B,D] f32, l2 [B,D] f32 or None)."""
+        torch = _torch()
+        assert x_f16.is_cuda and x_f16.dtype == torch.float16 and x_f16.is_contiguous()
+        B = x_f16.shape[0]
+        assert tuple(x_f16.shape[1:]) == (IN_HW, IN_HW, IN_C_PAD), x_f16.shape
+        raw = out_raw if out_raw is not None else torch.empty(B, self.D, dtype=torch.float32, device=self.device)
+        l2 = (out_l2 if out_l2 is not None else torch.empty(B, self.D, dtype=torch.float32, device=self.device)) if want_l2 else None
+        ws_ptr, ws_bytes = self._workspace(B)
+        check(_lib.lib().fire_facenet_forward(self._h, _ptr(x_f16), B, _ptr(raw), _ptr(l2) if l2 is not None else None,
+                                              ws_ptr, ws_bytes, _lib.stream_ptr()))
+        return raw, l2
+
+    def ingest_unit_f32(self, x_f32):
+        """cuda float32 [B,160,160,3] in the reference's [0,1] scale -> fp16 [B,160,160,8] network input."""
+        torch = _torch()
+        assert x_f32.is_cuda and x_f32.dtype == torch.float32 and x_f32.is_contiguous()
+        B = x_f32.shape[0]
+        out = torch.empty(B, IN_HW, IN_HW, IN_C_PAD, dtype=torch.float16, device=self.device)
+        check(_lib.lib().fire_ingest_f32(_ptr(x_f32), B, _ptr(out), _lib.stream_ptr()))
+        return out
+
+    def encode_unit_f32(self, x_f32, want_l2: bool = True):
+        return self.forward(self.ingest_unit_f32(x_f32), want_l2=want_l2)
+
+    def profile(self, x_f16) -> Tuple[np.ndarray, np.ndarray]:
+        """Per-op device milliseconds and algorithmic FLOP for one forward of this batch."""
+        B = x_f16.shape[0]
+        ms = np.zeros(self.num_ops, dtype=np.float32)
+        fl = np.zeros(self.num_ops, dtype=np.float64)
+        ws_ptr, ws_bytes = self._workspace(B)
+        check(_lib.lib().fire_facenet_profile(self._h, _ptr(x_f16), B, ws_ptr, ws_bytes, ms.ctypes.data, fl.ctypes.data,
+                                              self.num_ops, _lib.stream_ptr()))
+        return ms, fl
+
+    def read_buffer(self, buf: int, x_f16) -> np.ndarray:
+        """Debug: activation buffer `buf` of the last forward on x_f16, as float32 [B,H,W,C]."""
+        B = x_f16.shape[0]
+        b = self.plan.bufs[buf]
+        out = np.empty((B, b.H, b.W, b.C), dtype=np.float16)
+        ws_ptr, _ = self._workspace(B)
+        _torch().cuda.synchronize()
+        check(_lib.lib().fire_facenet_read_buffer(self._h, buf, B, _ptr(x_f16), ws_ptr, out.ctypes.data, out.nbytes))
+        return out.astype(np.float32)
+
+
+class KnnIndex:
+    """K3: exact cosine top-k over a row-major gallery shard (replaces hnswlib, hnsw_manager.py:20-31,127-149)."""
+
+    def __init__(self, dim: int, capacity: int = 100000, device: int = 0):
+        torch = _torch()
+        _lib.init(device)
+        self.device = torch.device("cuda", device)
+        self.dim = dim
+        h = C.c_void_p()
+        check(_lib.lib().fire_knn_create(dim, capacity, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().fire_knn_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def count(self) -> int:
+        return int(_lib.lib().fire_knn_count(self._h))
+
+    @property
+    def capacity(self) -> int:
+        return int(_lib.lib().fire_knn_capacity(self._h))
+
+    def reset(self):
+        check(_lib.lib().fire_knn_reset(self._h))
+
+    def add(self, rows):
+        """rows: numpy [n,D] float32 (host path) or cuda float32 tensor (device path, async on the current stream)."""
+        if isinstance(rows, np.ndarray):
+            rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, self.dim)
+            check(_lib.lib().fire_knn_add_host(self._h, rows.ctypes.data, rows.shape[0]))
+        else:
+            torch = _torch()
+            assert rows.is_cuda and rows.dtype == torch.float32 and rows.is_contiguous() and rows.shape[-1] == self.dim
+            check(_lib.lib().fire_knn_add(self._h, _ptr(rows), rows.numel() // self.dim, _lib.stream_ptr()))
+
+    def rows(self, first: int = 0, n: Optional[int] = None) -> np.ndarray:
+        n = self.count - first if n is None else n
+        out = np.empty((n, self.dim), dtype=np.float32)
+        check(_lib.lib().fire_knn_get_rows_host(self._h, first, n, out.ctypes.data))
+        return out
+
+    def search(self, queries, k: int = 1, id_offset: int = 0, out_dist=None, out_ids=None):
+        """Exact top-k.  numpy in -> numpy (dist f32 [Q,k], ids int64 [Q,k]); cuda tensor in -> cuda tensors (async)."""
+        if isinstance(queries, np.ndarray):
+            q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
+            dist = np.empty((q.shape[0], k), dtype=np.float32)
+            ids = np.empty((q.shape[0], k), dtype=np.int64)
+            check(_lib.lib().fire_knn_search_host(self._h, q.ctypes.data, q.shape[0], k, id_offset, dist.ctypes.data,
+                                                  ids.ctypes.data))
+            return dist, ids
+        torch = _torch()
+        assert queries.is_cuda and queries.dtype == torch.float32 and queries.is_contiguous()
+        Q = queries.numel() // self.dim
+        dist = out_dist if out_dist is not None else torch.empty(Q, k, dtype=torch.float32, device=self.device)
+        ids = out_ids if out_ids is not None else torch.empty(Q, k, dtype=torch.int64, device=self.device)
+        check(_lib.lib().fire_knn_search(self._h, _ptr(queries), Q, k, id_offset, _ptr(dist), _ptr(ids), _lib.stream_ptr()))
+        return dist, ids
+
+    def stats(self) -> Tuple[int, int]:
+        a, b = C.c_uint64(), C.c_uint64()
+        check(_lib.lib().fire_knn_stats(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def set_margin(self, eps: float):
+        check(_lib.lib().fire_knn_set_margin(self._h, eps))
+
+
+def knn_merge(dists, ids):
+    """dists/ids: cuda [G,Q,k] per-shard results (rows ascending) -> global top-k (dist [Q,k], ids [Q,k])."""
+    torch = _torch()
+    G, Q, k = dists.shape
+    assert dists.is_contiguous() and ids.is_contiguous() and ids.dtype == torch.int64 and dists.dtype == torch.float32
+    od = torch.empty(Q, k, dtype=torch.float32, device=dists.device)
+    oi = torch.empty(Q, k, dtype=torch.int64, device=dists.device)
+    check(_lib.lib().fire_knn_merge(_ptr(dists), _ptr(ids), Q, k, G, _ptr(od), _ptr(oi), _lib.stream_ptr()))
+    return od, oi
+
+
+def preprocess_boxes(frames, frame_desc, boxes, box_frame, mode: int = _lib.PRE_REFERENCE, want_f16: bool = True,
+                     want_f32: bool = False):
+    """K1.  frames: cuda uint8 (flat or [F,H,W,3]); frame_desc: cuda int64 [F,4] (offset,H,W,stride);
+    boxes: cuda int32 [n,4] xywh; box_frame: cuda int32 [n].  Returns (f16 [n,160,160,8] | None,
+    f32 [n,160,160,3] | None, status int32 [n])."""
+    torch = _torch()
+    n = boxes.shape[0]
+    dev = frames.device
+    f16 = torch.empty(n, IN_HW, IN_HW, IN_C_PAD, dtype=torch.float16, device=dev) if want_f16 else None
+    f32 = torch.empty(n, IN_HW, IN_HW, 3, dtype=torch.float32, device=dev) if want_f32 else None
+    status = torch.empty(n, dtype=torch.int32, device=dev)
+    check(_lib.lib().fire_preprocess(_ptr(frames), _ptr(frame_desc), frame_desc.shape[0], _ptr(boxes), _ptr(box_frame), n,
+                                     mode, _ptr(f16) if f16 is not None else None, _ptr(f32) if f32 is not None else None,
+                                     _ptr(status), _lib.stream_ptr()))
+    return f16, f32, status
+
+
+def frames_to_device(frames_np):
+    """[F,H,W,3] uint8 numpy (or list of HxWx3 arrays of differing sizes) -> (cuda uint8 flat, cuda int64 desc [F,4])."""
+    torch = _torch()
+    if isinstance(frames_np, np.ndarray) and frames_np.ndim == 4:
+        frames_np = list(frames_np)
+    descs, chunks, off = [], [], 0
+    for f in frames_np:
+        f = np.ascontiguousarray(f, dtype=np.uint8)
+        assert f.ndim == 3 and f.shape[2] == 3
+        descs.append((off, f.shape[0], f.shape[1], f.shape[1] * 3))
+        chunks.append(f.reshape(-1))
+        off += f.size
+    flat = torch.from_numpy(np.concatenate(chunks)).cuda()
+    desc = torch.tensor(descs, dtype=torch.int64).cuda()
+    return flat, desc

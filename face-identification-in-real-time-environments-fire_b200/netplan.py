@@ -116,10 +116,11 @@ def _pick_bn_tile(cout: int) -> int:
 
 
 class Plan:
-    def __init__(self, D: int, fuse_siblings: bool = True):
+    def __init__(self, D: int, fuse_siblings: bool = True, reuse_buffers: bool = True):
         assert D in (128, 512)
         self.D = D
         self.fuse = fuse_siblings
+        self.reuse = reuse_buffers
         self.bufs: List[Buf] = []
         self.ops: List[Op] = []
         self.in_buf = self._buf(IN_HW, IN_HW, IN_C_PAD, external=True)
@@ -307,6 +308,10 @@ class Plan:
         for i in order:
             b = self.bufs[i]
             size = (b.bytes_per_image + align - 1) // align * align
+            if not self.reuse:          # debug layout: every buffer keeps its own memory
+                b.offset = top
+                top += size
+                continue
             busy = sorted((self.bufs[j].offset, self.bufs[j].offset + (self.bufs[j].bytes_per_image + align - 1) // align * align)
                           for j in placed if not (self.bufs[j].last < b.first or self.bufs[j].first > b.last))
             off = 0

@@ -22,7 +22,7 @@ def _f16(x: torch.Tensor) -> torch.Tensor:
 
 
 def run_plan(plan: Plan, blob: bytes, x_pix_nhwc8: np.ndarray, store_f16: bool = True,
-             honor_offsets: bool = True) -> np.ndarray:
+             honor_offsets: bool = True, return_buffers: bool = False):
     """x_pix_nhwc8: [B,160,160,8] float32 pixel-scale input (channels 3..7 zero).
     honor_offsets=True stores activations in one flat per-batch arena at the plan's offsets, so
     an allocator bug (overlapping live buffers) corrupts results here exactly as it would on GPU."""
@@ -70,7 +70,10 @@ def run_plan(plan: Plan, blob: bytes, x_pix_nhwc8: np.ndarray, store_f16: bool =
             else:
                 raise ValueError(op.kind)
             dstv[..., op.dst.c_off:op.dst.c_off + op.dst.c] = y
-    return view(plan.out_buf).reshape(B, plan.D).numpy().copy()
+    out = view(plan.out_buf).reshape(B, plan.D).numpy().copy()
+    if return_buffers:
+        return out, {i: view(i).numpy().copy() for i in range(len(plan.bufs)) if plan.bufs[i].first >= 0 or i == plan.in_buf}
+    return out
 
 
 def to_pixel_nhwc8(x_unit_nhwc3: np.ndarray) -> np.ndarray:
