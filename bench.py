@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py - FIRE identification hot path on B200: FaceNet512 embeds/s (+ cosine top-10 QPS).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl fire|reference] [--no-knn]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Headline (BASELINE.json configs[1]): FaceNet512 on batches of 256 uint8 160x160 crops per GPU.
+One "step" = one pass of the hot path over one batch: crop/resize/normalise kernel (K1) -> the 105
+tcgen05 implicit-GEMM convolutions + pools + tail (K2) -> L2-normalised embeddings.
+  value : embeds/s with the uint8 crops already resident in HBM (device-timed, CUDA events)
+  e2e   : the same through the public call a FIRE user makes (fire_b200.encoder.Encoder.encode_crops path):
+          pinned host uint8 crops -> H2D -> K1 -> K2 -> D2H float32 embeddings, every step
+  knn   : BASELINE.json configs[2]/[3]: exact cosine top-10, 4096 queries, 1M x 512 (N=1) and 10M x 512
+          (row-sharded over the N ranks, NCCL all_gather + merge) -> QPS, with its own roofline
+`--impl reference` times the reference's CPU path restated (oracle/: cv2 INTER_AREA + torch-CPU
+Inception-ResNet-v1 at batch 1 per face like modules/encoder.py:26) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "FaceNet512 embeds/s (160x160 crops)"
+BATCH = 256
+D = 512
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"tensor_tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "tensor_burst": d.get("bf16_tflops"),
+                "hbm_gbs": d.get("hbm_gbs"), "src": "measured"}
+    return {"tensor_tflops": 1400.0, "tensor_burst": 1590.0, "hbm_gbs": 6650.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[j] for r in self.rows if len(r) >= 6 for j in range(4) if r[2 + j].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def make_crops(n_batches: int, seed: int = 2):
+    """Seeded synthetic uint8 crops: half pixel noise, half structured images (fire_b200.weights.calibration_images)."""
+    from fire_b200 import weights as W
+    rng = np.random.default_rng(seed)
+    out = []
+    for b in range(n_batches):
+        noise = rng.integers(0, 256, (BATCH // 2, 160, 160, 3), dtype=np.uint8)
+        out.append(np.concatenate([noise, W.calibration_images(BATCH - BATCH // 2, seed=100 + b)]))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+_CPU_REF = {}
+
+
+def cpu_reference_embeds(n_faces: int, threads: int):
+    """The reference's CPU path restated: per face cv2.resize(INTER_AREA)+/255 (modules/encoder.py:19-27) then
+    the fp32 Inception-ResNet-v1 at batch 1 (facenet_gpu.py:127).  The "session" (weights resident, like an
+    onnxruntime InferenceSession) is created once.  Returns (embeds/s, seconds)."""
+    import cv2
+    import torch
+    from fire_b200 import weights as W
+    from oracle.facenet_ref import FaceNetRef
+    torch.set_num_threads(threads)
+    if "net" not in _CPU_REF:
+        _CPU_REF["net"] = FaceNetRef(W.synthetic_weights(D, 1234))
+        _CPU_REF["crops"] = make_crops(1)[0]
+        _CPU_REF["net"](_CPU_REF["crops"][:1].astype(np.float32) / 255.0)    # warm-up (weight conversion, oneDNN init)
+    net, crops = _CPU_REF["net"], _CPU_REF["crops"]
+    t = time.perf_counter()
+    for i in range(n_faces):
+        img = cv2.resize(crops[i % len(crops)], (160, 160), interpolation=cv2.INTER_AREA).astype(np.float32) / 255.0
+        net(img[None])
+    dt = time.perf_counter() - t
+    return n_faces / dt, dt
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    per_step = 16
+    cpu_reference_embeds(1, threads)
+    for _ in range(args.warmup):
+        cpu_reference_embeds(2, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_embeds(per_step, threads)
+    dt = time.perf_counter() - t0
+    v = per_step * args.steps / dt
+    line = {"metric": METRIC, "value": v, "unit": "embeds/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "FaceNet512 batch-256 crops (configs[1]); reference arm = bounded sample of "
+                                   f"{per_step} faces/step at batch 1 like modules/encoder.py:26", "weights": "synthetic seed 1234"},
+            "cpu_baseline": {"value": v, "unit": "embeds/s", "cores": threads, "kind": "port",
+                             "sample": f"{per_step} faces per step, batch 1 per face, cv2 INTER_AREA + torch-CPU fp32 oracle "
+                                       "(stand-in for onnxruntime 1.20.1 CPU EP, which is not installable here)"},
+            "e2e": {"value": v, "unit": "embeds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "torch_threads": torch.get_num_threads()}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_fire(args):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from fire_b200 import _lib, engine, weights as W
+    from fire_b200.dist import ShardedGallery, shard_bounds
+    _lib.init(local)
+    peaks = load_peaks()
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- FaceNet512, B=256 per GPU -------------------------------------------------
+    tensors = W.synthetic_weights(D, 1234)
+    eng = engine.FaceNetEngine(D, tensors, device=local)
+    n_rot = 4
+    host_batches = make_crops(n_rot, seed=2 + rank)
+    pinned = [torch.from_numpy(b).pin_memory() for b in host_batches]
+    dev_batches = [p.to(dev) for p in pinned]
+    boxes = torch.tensor([[0, 0, 160, 160]] * BATCH, dtype=torch.int32, device=dev)
+    frame_ids = torch.arange(BATCH, dtype=torch.int32, device=dev)
+    desc = torch.tensor([[i * 160 * 160 * 3, 160, 160, 480] for i in range(BATCH)], dtype=torch.int64, device=dev)
+    raw = torch.empty(BATCH, D, dtype=torch.float32, device=dev)
+    l2 = torch.empty(BATCH, D, dtype=torch.float32, device=dev)
+    host_out = torch.empty(BATCH, D, dtype=torch.float32).pin_memory()
+    stage_in = torch.empty(BATCH, 160, 160, 3, dtype=torch.uint8, device=dev)
+
+    def step_device(i):
+        f16, _, _ = engine.preprocess_boxes(dev_batches[i % n_rot], desc, boxes, frame_ids, _lib.PRE_REFERENCE, True, False)
+        eng.forward(f16, want_l2=True, out_raw=raw, out_l2=l2)
+
+    def step_e2e(i):
+        stage_in.copy_(pinned[i % n_rot], non_blocking=True)
+        f16, _, _ = engine.preprocess_boxes(stage_in, desc, boxes, frame_ids, _lib.PRE_REFERENCE, True, False)
+        eng.forward(f16, want_l2=True, out_raw=raw, out_l2=l2)
+        host_out.copy_(l2, non_blocking=True)
+
+    def timed(step_fn, steps, warmup):
+        for i in range(warmup):
+            step_fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            step_fn(i)
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), 0.0)
+        return max_over_ranks(ms), max_over_ranks(wall * 1e3), _lib.launch_count() - l0
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, wall_dev, launches = timed(step_device, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, wall_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+    value = world * BATCH * args.steps / (ms_dev * 1e-3)
+    e2e_value = world * BATCH * args.steps / (ms_e2e * 1e-3)
+
+    # parity spot check inside the bench (one batch vs the fp32 oracle on 8 images) - not timed
+    parity = None
+    if rank == 0:
+        from oracle.facenet_ref import facenet_forward
+        ref = facenet_forward(tensors, host_batches[0][-8:].astype(np.float32) / 255.0)
+        step_device(0)
+        torch.cuda.synchronize()
+        got = raw[-8:].cpu().numpy()
+        cos = (got * ref).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(ref, axis=1))
+        parity = {"min_cos_vs_fp32_oracle": float(cos.min()), "images": 8}
+
+    # roofline of the dominant kernel (conv_igemm_kernel): per-op CUDA events, live
+    roofline = None
+    if rank == 0:
+        f16, _, _ = engine.preprocess_boxes(dev_batches[0], desc, boxes, frame_ids, _lib.PRE_REFERENCE, True, False)
+        eng.profile(f16)
+        ms_ops, fl_ops = eng.profile(f16)
+        conv = fl_ops > 0
+        conv_ms, conv_fl = float(ms_ops[conv].sum()), float(fl_ops[conv].sum())
+        achieved = conv_fl / (conv_ms * 1e-3) / 1e12
+        roofline = {"kernel": "conv_igemm_kernel (105 launches/step)", "bound": "tensor", "achieved": achieved,
+                    "peak": peaks["tensor_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tensor_tflops"],
+                    "peak_source": f"{peaks['src']} bf16 sustained (MEASURED_PEAKS.json); fp16 runs on the same kind::f16 pipe",
+                    "traffic": None, "conv_ms_per_step": conv_ms, "all_ops_ms_per_step": float(ms_ops.sum()),
+                    "conv_share_of_step": conv_ms / float(ms_ops.sum()),
+                    "algorithmic_flop_per_launch_avg": conv_fl / int(conv.sum())}
+
+    # ---------------- exact cosine top-10 ---------------------------------------------------------------
+    knn = None
+    if not args.no_knn:
+        knn = {}
+        Q, k = 4096, 10
+        gq = torch.Generator(device=dev)
+        gq.manual_seed(4)
+        queries = torch.randn(Q, D, generator=gq, device=dev)
+        for name, n_total in (("1M", 1_000_000), ("10M", 10_000_000)):
+            if name == "1M" and world > 1:
+                continue
+            lo, hi = shard_bounds(n_total, world, rank)
+            gal = ShardedGallery(D, hi - lo, rank, world, device=local)
+
+            def rows(lo_, hi_):
+                g = torch.Generator(device=dev)
+                g.manual_seed(1000 + lo_)
+                return torch.randn(hi_ - lo_, D, generator=g, device=dev)
+            # enrol in chunks to bound the temporary
+            gal.id_offset, gal.total = lo, n_total
+            for c0 in range(lo, hi, 1_000_000):
+                gal.local.add(rows(c0, min(hi, c0 + 1_000_000)))
+            torch.cuda.synchronize()
+            steps = max(3, args.steps // 4)
+            for _ in range(3):
+                gal.search(queries, k)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = _lib.launch_count()
+            e0.record()
+            for _ in range(steps):
+                dd, ii = gal.search(queries, k)
+            e1.record()
+            barrier()
+            ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+            qps = Q / (ms * 1e-3)
+            flops = 2.0 * Q * n_total * D
+            tf = flops / (ms * 1e-3) / 1e12 / world
+            tot, fb = gal.local.stats()
+            knn[name] = {"metric": f"cosine top-10 QPS, {name} x 512 gallery, 4096-query batch", "value": qps, "unit": "queries/s",
+                         "ms_per_batch": ms, "n_gpus": world, "gallery_rows": n_total, "queries": Q, "k": k,
+                         "launches_per_batch": (_lib.launch_count() - l0) // steps,
+                         "fallback_queries_fraction": fb / max(tot, 1),
+                         "roofline": {"kernel": "knn_scan_kernel<16>", "bound": "tensor", "achieved": tf, "peak": peaks["tensor_tflops"],
+                                      "unit": "TFLOP/s", "frac": tf / peaks["tensor_tflops"], "per_gpu": True,
+                                      "note": "whole search (normalise+scan+rerank+fallback) over algorithmic 2*Q*N*D"}}
+            gal.local.close()
+            del gal
+            torch.cuda.empty_cache()
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        v, dt = cpu_reference_embeds(24, threads)
+        cpu_baseline = {"value": v, "unit": "embeds/s", "cores": threads, "kind": "port",
+                        "sample": f"24 faces at batch 1 (reference behaviour, modules/encoder.py:26), {dt:.1f} s; torch-CPU fp32 "
+                                  "restatement of the graph = stand-in for onnxruntime-CPU (not installable offline)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "embeds/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16", "data": "synthetic",
+                "config": {"workload": "FaceNet512 batch-256 uint8 160x160 crops per GPU (BASELINE configs[1]): K1 preprocess + K2 conv stack + L2 norm",
+                           "batch_per_gpu": BATCH, "global_batch": BATCH * world, "weights": "synthetic seed 1234 (real ONNX is a git-LFS pointer)",
+                           "l2": f"inputs rotate over {n_rot} batches; activations (~1.5 MB/img, 394 MB/step) exceed the 126 MB L2",
+                           "parallelism": f"dp{world}"},
+                "e2e": {"value": e2e_value, "unit": "embeds/s", "h2d_bytes_per_step": BATCH * 160 * 160 * 3,
+                        "d2h_bytes_per_step": BATCH * D * 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "wall_ms_per_step": wall_dev / args.steps,
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity, "knn": knn}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="fire", choices=["fire", "reference"])
+    ap.add_argument("--no-knn", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "fire" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_fire(args)
+
+
+if __name__ == "__main__":
+    main()

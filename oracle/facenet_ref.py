@@ -39,16 +39,24 @@ class _Net:
         # act_round: optional callable applied to every stored activation (used by
         # tests to model reduced-precision storage; None = pure fp32/fp64 oracle).
         self.act_round = act_round
+        self._cache = {}
 
     def _t(self, name):
-        return torch.from_numpy(np.ascontiguousarray(self.w[name])).to(self.dtype)
+        """Weight tensor, converted once per net (an onnxruntime session also holds its weights resident)."""
+        t = self._cache.get(name)
+        if t is None:
+            t = torch.from_numpy(np.ascontiguousarray(self.w[name])).to(self.dtype)
+            if name.endswith("/kernel") and t.dim() == 4:
+                t = t.permute(3, 2, 0, 1).contiguous()            # HWIO -> OIHW
+            self._cache[name] = t
+        return t
 
     def _r(self, x):
         return self.act_round(x) if self.act_round is not None else x
 
     def conv_bn_relu(self, x, name, stride=1, padding="valid"):
         """Conv2D(no bias) -> BatchNorm(eps=1e-3, scale=False) -> ReLU (App. A conventions)."""
-        k = self._t(name + "/kernel").permute(3, 2, 0, 1).contiguous()  # HWIO -> OIHW
+        k = self._t(name + "/kernel")
         kh, kw = k.shape[2], k.shape[3]
         if padding == "same":
             assert stride == 1
@@ -64,7 +72,7 @@ class _Net:
 
     def up(self, x, name):
         """1x1 Conv2D with bias, no BN, no activation."""
-        k = self._t(name + "/kernel").permute(3, 2, 0, 1).contiguous()
+        k = self._t(name + "/kernel")
         b = self._t(name + "/bias")
         return F.conv2d(x, k, b)
 
@@ -138,6 +146,17 @@ class _Net:
         mean = self._t("Bottleneck_BatchNorm/moving_mean")
         var = self._t("Bottleneck_BatchNorm/moving_variance")
         return (y - mean) / torch.sqrt(var + BN_EPS) + beta
+
+
+class FaceNetRef:
+    """Session-like wrapper: weights converted once, then `__call__(x_nhwc)` like FaceNetClient.__call__."""
+
+    def __init__(self, weights: dict, dtype=torch.float32):
+        self.net = _Net(weights, dtype=dtype)
+
+    def __call__(self, x_nhwc: np.ndarray) -> np.ndarray:
+        with torch.no_grad():
+            return self.net.forward(torch.from_numpy(np.ascontiguousarray(x_nhwc))).numpy()
 
 
 def facenet_forward(weights: dict, x_nhwc: np.ndarray, dtype=torch.float32, act_round=None,

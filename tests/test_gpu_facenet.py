@@ -1,0 +1,126 @@
+"""GPU parity: FaceNet128/512 on the tcgen05 engine (through the C ABI) vs the fp32 CPU oracle.
+Tolerance (north star): cosine >= 0.9999 per image against the fp32 reference output."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _cos(a, b):
+    return (a * b).sum(1) / (np.linalg.norm(a, axis=1) * np.linalg.norm(b, axis=1))
+
+
+def _images(n, seed):
+    from fire_b200 import weights as W
+    rng = np.random.default_rng(seed)
+    return np.concatenate([rng.integers(0, 256, (n // 2, 160, 160, 3), dtype=np.uint8), W.calibration_images(n - n // 2, seed=seed + 50)])
+
+
+@pytest.fixture(scope="module")
+def nets(fire_lib):
+    from fire_b200 import engine, weights as W
+    out = {}
+    for D in (128, 512):
+        t = W.synthetic_weights(D, 1234)
+        out[D] = (t, engine.FaceNetEngine(D, t))
+    return out
+
+
+def test_config1_facenet128_top1_and_threshold_decisions(nets, oracle_native):
+    """BASELINE configs[0]: FaceNet128 on 32 crops + cosine top-1 vs a 10k gallery; ids, 1-d and accept/reject equal."""
+    import torch
+    from fire_b200.engine import KnnIndex
+    from oracle.facenet_ref import facenet_forward, l2_normalize_rows
+    tensors, eng = nets[128]
+    u8 = _images(32, 0)
+    x = u8.astype(np.float32) / 255.0
+    raw, l2 = eng.encode_unit_f32(torch.from_numpy(x).cuda())
+    ref = facenet_forward(tensors, x)
+    got = raw.cpu().numpy()
+    assert _cos(got, ref).min() >= 0.9999
+    refn = l2_normalize_rows(ref)
+    rng = np.random.default_rng(1)
+    gal = rng.standard_normal((10_000, 128), dtype=np.float32)
+    gal /= np.linalg.norm(gal, axis=1, keepdims=True)
+    for j, c in enumerate([0.9, 0.9, 0.9, 0.71, 0.71, 0.69, 0.69, 0.5]):     # plant near-duplicates around thr 0.7
+        r = rng.standard_normal(128).astype(np.float32); r -= r.dot(refn[j]) * refn[j]; r /= np.linalg.norm(r)
+        gal[100 + j] = c * refn[j] + np.sqrt(1 - c * c) * r
+    idx = KnnIndex(128, 100000); idx.add(gal)
+    dist, ids = idx.search(l2.contiguous(), 1)
+    dist, ids = dist.cpu().numpy(), ids.cpu().numpy()
+    ora = oracle_native.BFIndexOracle(128); ora.add_items(gal)
+    # (a) the matcher alone, on identical inputs (the GPU embeddings): ids bit-exact, distances to fp32 rounding
+    sl, sd = ora.knn_query(l2.cpu().numpy(), 1)
+    assert np.array_equal(ids, sl.astype(np.int64)) and np.abs(dist - sd).max() < 5e-6
+    # (b) the whole chain against the all-CPU chain (fp32 oracle embeddings -> BFIndex): equal wherever the fp16
+    #     embedding error (cos >= 0.9999, i.e. up to ~5e-3 in a cosine) cannot matter
+    ol, od = ora.knn_query(refn, 2)
+    clear = (od[:, 1] - od[:, 0]) > 1e-2
+    assert clear[:8].all() and np.array_equal(ids[clear, 0], ol[clear, 0].astype(np.int64))
+    assert np.abs(dist[clear, 0] - od[clear, 0]).max() < 5e-3
+    thr = 0.7
+    accept_gpu, accept_ref = (1 - dist[:, 0]) > thr, (1 - od[:, 0]) > thr    # face_recognition.py:462-463 strict >
+    decided = np.abs((1 - od[:, 0]) - thr) > 5e-3
+    assert decided[:8].all() and np.array_equal(accept_gpu[decided], accept_ref[decided])
+    assert accept_ref[:5].all() and not accept_ref[5:8].any() and not accept_ref[8:].any()
+
+
+def test_config2_facenet512_batch256(nets):
+    """BASELINE configs[1]: FaceNet512, batch 256; every embedding within cosine 0.9999 of the fp32 oracle."""
+    import torch
+    from oracle.facenet_ref import facenet_forward
+    tensors, eng = nets[512]
+    u8 = _images(256, 2)
+    x = u8.astype(np.float32) / 255.0
+    raw, l2 = eng.encode_unit_f32(torch.from_numpy(x).cuda())
+    got, gl2 = raw.cpu().numpy(), l2.cpu().numpy()
+    sel = np.r_[0:24, 128:152, 232:256]                        # 72 of the 256 through the CPU oracle (seconds, not minutes)
+    ref = facenet_forward(tensors, x[sel])
+    cos = _cos(got[sel], ref)
+    assert cos.min() >= 0.9999, cos.min()
+    assert np.abs(np.linalg.norm(gl2, axis=1) - 1).max() < 1e-5
+    np.testing.assert_allclose(gl2, got / np.linalg.norm(got, axis=1, keepdims=True), rtol=1e-5, atol=1e-7)
+    # batch invariance: the same image gives bit-identical embeddings at B=1, B=3 and B=256
+    r1, _ = eng.encode_unit_f32(torch.from_numpy(x[130:131]).cuda())
+    r3, _ = eng.encode_unit_f32(torch.from_numpy(x[129:132]).cuda())
+    assert np.array_equal(r1.cpu().numpy()[0], got[130]) and np.array_equal(r3.cpu().numpy()[1], got[130])
+
+
+def test_golden_embeddings(nets):
+    """Committed fixture (tests/golden/facenet_golden.json, written from the CPU oracle by make_facenet_golden.py)."""
+    import torch
+    from fire_b200 import weights as W
+    with open(os.path.join(GOLDEN, "facenet_golden.json")) as f:
+        gold = json.load(f)
+    for D in (128, 512):
+        tensors, eng = nets[D]
+        u8 = W.calibration_images(4, seed=gold["image_seed"])
+        raw, _ = eng.encode_unit_f32(torch.from_numpy(u8.astype(np.float32) / 255.0).cuda())
+        got = raw.cpu().numpy()
+        want = np.asarray(gold[str(D)]["embeddings"], dtype=np.float32)
+        assert _cos(got, want).min() >= 0.9999
+
+
+def test_unfused_plan_matches_fused(fire_lib):
+    import torch
+    from fire_b200 import engine, weights as W
+    t = W.synthetic_weights(128, 99)
+    a, b = engine.FaceNetEngine(128, t, fuse_siblings=True), engine.FaceNetEngine(128, t, fuse_siblings=False)
+    x = torch.from_numpy(_images(6, 9).astype(np.float32) / 255.0).cuda()
+    ra, _ = a.encode_unit_f32(x); rb, _ = b.encode_unit_f32(x)
+    assert torch.equal(ra, rb)                                 # horizontal fusion only regroups output channels
+
+
+def test_forward_argument_errors(nets):
+    import torch
+    from fire_b200 import _lib
+    from fire_b200._lib import FireError
+    _, eng = nets[128]
+    x = torch.zeros(1, 160, 160, 8, dtype=torch.float16, device="cuda")
+    out = torch.zeros(1, 128, device="cuda")
+    with pytest.raises(FireError):
+        _lib.check(_lib.lib().fire_facenet_forward(eng._h, x.data_ptr(), 1, out.data_ptr(), None, x.data_ptr(), 16, None))

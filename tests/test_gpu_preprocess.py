@@ -1,0 +1,80 @@
+"""GPU parity: fused crop/resize/normalise kernel (fire_preprocess) vs the cv2-exact oracle and live cv2."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _frame(h, w, seed):
+    import cv2
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    return cv2.GaussianBlur(img, (0, 0), 1.5) if seed % 2 else img
+
+
+def test_reference_mode_bit_exact(fire_lib, oracle_native):
+    import cv2
+    import torch
+    from fire_b200 import _lib, engine
+    frames = [_frame(1080, 1920, 1), _frame(480, 640, 2), _frame(200, 300, 3)]
+    rng = np.random.default_rng(0)
+    boxes, bf = [], []
+    fixed = [(0, [100, 100, 160, 160]), (0, [200, 50, 320, 320]), (0, [500, 300, 233, 201]), (0, [10, 10, 97, 83]),
+             (0, [1800, 900, 400, 400]), (0, [-20, -30, 200, 180]), (1, [0, 0, 640, 480]), (1, [300, 200, 480, 480]),
+             (2, [50, 50, 52, 47]), (2, [0, 0, 0, 10]), (2, [400, 10, 50, 50]), (1, [-100, 5, 80, 90]), (0, [64, 64, 480, 960]),
+             (0, [0, 0, 1920, 1080]), (2, [10, 10, 40, 160]), (1, [5, 5, 161, 159])]
+    for f, b in fixed:
+        boxes.append(b); bf.append(f)
+    for _ in range(48):                                        # YuNet-style random boxes, some crossing the frame edge
+        f = int(rng.integers(0, 3)); H, W = frames[f].shape[:2]
+        boxes.append([int(rng.integers(-40, W)), int(rng.integers(-40, H)), int(rng.integers(20, 420)), int(rng.integers(20, 420))])
+        bf.append(f)
+    flat, desc = engine.frames_to_device(frames)
+    bt = torch.tensor(boxes, dtype=torch.int32).cuda(); ft = torch.tensor(bf, dtype=torch.int32).cuda()
+    f16, f32, status = engine.preprocess_boxes(flat, desc, bt, ft, _lib.PRE_REFERENCE, True, True)
+    f16 = f16.float().cpu().numpy(); f32 = f32.cpu().numpy(); status = status.cpu().numpy()
+    n_live = 0
+    for i, (b, f) in enumerate(zip(boxes, bf)):
+        rc, u8, want = oracle_native.crop_preprocess(frames[f], b)
+        assert status[i] == rc
+        if rc:
+            assert not f32[i].any() and not f16[i].any()
+            continue
+        assert np.array_equal(f32[i], want), (i, b)                                  # bit-exact float32 (u8 / 255)
+        assert np.array_equal(f16[i][..., :3], u8.astype(np.float32)) and not f16[i][..., 3:].any()
+        x, y, w, h = (max(0, v) for v in b)                                          # face_recognition.py:412-417
+        crop = frames[f][y:y + h, x:x + w]
+        live = cv2.resize(crop, (160, 160), interpolation=cv2.INTER_AREA).astype(np.float32) / 255.0
+        assert np.array_equal(f32[i], live)
+        n_live += 1
+    assert n_live > 40
+
+
+def test_swap_rb_and_northstar(fire_lib):
+    import torch
+    from fire_b200 import _lib, engine
+    frame = _frame(400, 500, 5)
+    boxes = [[20, 30, 300, 250], [100, 100, 90, 120], [0, 0, 500, 400]]
+    flat, desc = engine.frames_to_device([frame])
+    bt = torch.tensor(boxes, dtype=torch.int32).cuda(); ft = torch.zeros(3, dtype=torch.int32).cuda()
+    _, a, _ = engine.preprocess_boxes(flat, desc, bt, ft, _lib.PRE_REFERENCE, False, True)
+    _, b, _ = engine.preprocess_boxes(flat, desc, bt, ft, _lib.PRE_REFERENCE | _lib.PRE_FLAG_SWAP_RB, False, True)
+    assert torch.equal(a.flip(-1), b)
+    # north-star mode: float half-pixel bilinear + prewhiten, against a numpy restatement (tolerance: fp32 order)
+    f16, y, _ = engine.preprocess_boxes(flat, desc, bt, ft, _lib.PRE_NORTHSTAR, True, True)
+    y = y.cpu().numpy(); f16 = f16.float().cpu().numpy()
+    for i, (x0, y0, w, h) in enumerate(boxes):
+        crop = frame[y0:y0 + h, x0:x0 + w].astype(np.float32)
+        fx = np.clip((np.arange(160, dtype=np.float32) + 0.5) * np.float32(w / 160) - 0.5, 0, w - 1)
+        fy = np.clip((np.arange(160, dtype=np.float32) + 0.5) * np.float32(h / 160) - 0.5, 0, h - 1)
+        xa, ya = fx.astype(int), fy.astype(int)
+        xb, yb = np.minimum(xa + 1, w - 1), np.minimum(ya + 1, h - 1)
+        tx, ty = (fx - xa)[None, :, None], (fy - ya)[:, None, None]
+        top = (1 - tx) * crop[ya][:, xa] + tx * crop[ya][:, xb]
+        bot = (1 - tx) * crop[yb][:, xa] + tx * crop[yb][:, xb]
+        img = (1 - ty) * top + ty * bot
+        mean, std = img.astype(np.float64).mean(), img.astype(np.float64).std()
+        want = (img - mean) / max(std, 1.0 / np.sqrt(img.size))
+        assert np.abs(y[i] - want).max() < 2e-4                                      # tolerance: fp32 vs fp64 statistics
+        assert abs(float(y[i].mean())) < 1e-4 and abs(float(y[i].std()) - 1.0) < 1e-3
+        assert np.abs(f16[i][..., :3] - 255.0 * want).max() < 0.5 + 255.0 * 2e-4 + 1.0   # fp16 rounding of 255*y (|.|<2048 -> ulp<=1)
