@@ -57,7 +57,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -226,7 +226,10 @@ def run_fire(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.5)                      # let nvidia-smi start streaming before the timed region
     ms_dev, wall_dev, launches = timed(step_device, args.steps, args.warmup)
+    if rank == 0:
+        time.sleep(0.15)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, wall_e2e, _ = timed(step_e2e, args.steps, args.warmup)
     value = world * BATCH * args.steps / (ms_dev * 1e-3)
@@ -282,7 +285,7 @@ def run_fire(args):
             for c0 in range(lo, hi, 1_000_000):
                 gal.local.add(rows(c0, min(hi, c0 + 1_000_000)))
             torch.cuda.synchronize()
-            steps = max(3, args.steps // 4)
+            steps = max(3, min(20, args.steps // 4))
             for _ in range(3):
                 gal.search(queries, k)
             barrier()
@@ -338,8 +341,8 @@ def run_fire(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="fire", choices=["fire", "reference"])
     ap.add_argument("--no-knn", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

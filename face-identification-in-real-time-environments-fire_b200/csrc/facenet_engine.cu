@@ -6,6 +6,8 @@
 // resolved) and the BN-folded fp16 weights; this file uploads the weights once, builds their TMA
 // descriptors once, and on every forward() enqueues one kernel per op on the caller's stream:
 //   conv_igemm_kernel (tcgen05)  x 105,  maxpool3x3s2_kernel x 3,  gap_kernel x 1,  l2norm_kernel x 1.
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -120,13 +122,32 @@ using namespace fire;
 
 struct OpRt {
   BlobOp op;
-  CUtensorMap tmap_w;     // weights [cout][k_pad]
+  CUtensorMap tmap_w;     // weights [cout][k_pad], box rows = bn_tile (rebuilt when the tiling changes with B)
   CUtensorMap tmap_a;     // activation matrix for TMA-mode convs (rebuilt when pointers / B change)
   bool tma_a = false;
-  int stages = 0, tmem_cols = 0;
+  int bn_tile = 0, stages = 0, tmem_cols = 0, m_tiles = 0, n_tiles = 0;
   size_t smem = 0;
   double flops_per_image = 0;
 };
+
+// N tile for one layer at one batch size.  Large layers take the widest tile (fewest re-reads of the activation
+// K-blocks); layers with few M tiles are cut along N until the persistent grid covers the SMs.  Cost model in
+// SM cycles per tile: main loop = nkb * max(MMA, L2->smem fill at ~32 B/cycle/SM), epilogue ~120 cycles per
+// 16-column chunk, ~1200 cycles fixed; total = waves * tile.
+static int pick_bn_tile(int cout, int m_tiles, int nkb, int sms) {
+  int best = 16;
+  double best_cost = 1e30;
+  for (int d = 16; d <= 256 && d <= cout; d += 16) {
+    if (cout % d) continue;
+    const long long tiles = (long long)m_tiles * (cout / d);
+    const long long waves = (tiles + sms - 1) / sms;
+    const double fill = (16384.0 + 128.0 * d) / 32.0;
+    const double tile = nkb * std::max(2.0 * d, fill) + 1200.0 + (d / 16) * 120.0;
+    const double cost = waves * tile;
+    if (cost < best_cost * 0.999 || (cost <= best_cost * 1.001 && d > best)) { best_cost = cost; best = d; }
+  }
+  return best;
+}
 
 struct fire_net {
   BlobHeader hdr;
@@ -136,6 +157,7 @@ struct fire_net {
   // cache key of the activation tensor maps
   const void* key_in = nullptr; const void* key_ws = nullptr; const void* key_out = nullptr; int key_B = 0;
   double flops_per_image = 0;
+  bool pdl = true;        // programmatic dependent launch between conv layers (FIRE_B200_PDL=0 disables)
 };
 
 static int pow2_cols(int n) {
@@ -191,25 +213,19 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
       return fail(FIRE_ERR_ARG, "fire_facenet_create: op references a buffer out of range");
     }
     if (o.kind == OP_CONV) {
-      if (o.bn_tile < 16 || o.bn_tile > 256 || o.bn_tile % 16 || o.cout % o.bn_tile || o.k_pad % 64 || o.cin % 8) {
+      if (o.cout % 16 || o.cout > CONV_MAX_COUT || o.k_pad % 64 || o.cin % 8) {
         cudaFree(net->d_weights); delete net;
-        return fail(FIRE_ERR_ARG, "fire_facenet_create: conv op with unsupported tiling (cout=%d bn=%d k_pad=%d cin=%d)",
-                    o.cout, o.bn_tile, o.k_pad, o.cin);
+        return fail(FIRE_ERR_ARG, "fire_facenet_create: conv op with unsupported shape (cout=%d k_pad=%d cin=%d)",
+                    o.cout, o.k_pad, o.cin);
       }
-      int rc = make_tmap_f16_2d(&r.tmap_w, net->d_weights + o.w_off, (uint64_t)o.cout, (uint64_t)o.k_pad,
-                                (uint64_t)o.k_pad * 2, (uint32_t)o.bn_tile);
-      if (rc != FIRE_OK) { cudaFree(net->d_weights); delete net; return rc; }
       r.tma_a = (o.kh == 1 && o.kw == 1 && o.stride == 1 && o.pad_h == 0 && o.pad_w == 0);
-      const size_t stage = CONV_A_STAGE_BYTES + (size_t)o.bn_tile * 128;
-      r.stages = 4;
-      while (r.stages > 3 && r.stages * stage + 2048 > 200 * 1024) r.stages--;
-      r.smem = 1024 + r.stages * stage + 256;
-      r.tmem_cols = pow2_cols(o.bn_tile);
       r.flops_per_image = 2.0 * o.Ho * o.Wo * (double)o.cout * o.kh * o.kw * o.cin;
       net->flops_per_image += r.flops_per_image;
     }
     net->ops.push_back(r);
   }
+  const char* pdl_env = getenv("FIRE_B200_PDL");
+  net->pdl = !(pdl_env && pdl_env[0] == '0');
   *out = net;
   return FIRE_OK;
 }
@@ -238,7 +254,7 @@ static void* buf_ptr(const fire_net* net, int buf, int B, const void* in, void* 
   return static_cast<uint8_t*>(ws) + (size_t)net->bufs[buf].offset * (size_t)B;
 }
 
-static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float* out_raw, cudaStream_t st) {
+static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float* out_raw, cudaStream_t st, bool pdl) {
   const BlobOp& o = r.op;
   const BlobBuf& sb = net->bufs[o.src_buf];
   const BlobBuf& db = net->bufs[o.dst_buf];
@@ -256,11 +272,20 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
     p.bias = reinterpret_cast<const float*>(net->d_weights + o.b_off);
     p.H = o.H; p.W = o.W; p.Ho = o.Ho; p.Wo = o.Wo; p.kh = o.kh; p.kw = o.kw; p.stride = o.stride;
     p.pad_h = o.pad_h; p.pad_w = o.pad_w; p.cin = o.cin; p.cout = o.cout; p.k_real = o.kh * o.kw * o.cin;
-    p.nkb = o.k_pad / 64; p.flags = o.flags; p.bn_tile = o.bn_tile; p.M_total = B * o.Ho * o.Wo;
+    p.nkb = o.k_pad / 64; p.flags = o.flags; p.bn_tile = r.bn_tile; p.M_total = B * o.Ho * o.Wo;
     p.stages = r.stages; p.tma_a = r.tma_a ? 1 : 0; p.tmem_cols = r.tmem_cols;
-    dim3 grid((p.M_total + CONV_BM - 1) / CONV_BM, o.cout / o.bn_tile);
-    conv_igemm_kernel<<<grid, CONV_THREADS, r.smem, st>>>(r.tmap_w, r.tma_a ? r.tmap_a : r.tmap_w, p);
-    FIRE_LAUNCH_CHECK("conv_igemm_kernel");
+    p.m_tiles = r.m_tiles; p.n_tiles = r.n_tiles; p.pdl = pdl ? 1 : 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)std::min<long long>((long long)r.m_tiles * r.n_tiles, device_sm_count()));
+    cfg.blockDim = dim3(CONV_THREADS);
+    cfg.dynamicSmemBytes = r.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    FIRE_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, r.tmap_w, r.tma_a ? r.tmap_a : r.tmap_w, p));
   } else if (o.kind == OP_MAXPOOL) {
     const long long total = (long long)B * o.Ho * o.Wo * (o.cin / 8);
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
@@ -286,8 +311,25 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
   if ((reinterpret_cast<uintptr_t>(ws) & 255) || (reinterpret_cast<uintptr_t>(in) & 15))
     return fail(FIRE_ERR_ARG, "fire_facenet_forward: workspace must be 256-byte and input 16-byte aligned");
   if (net->key_in != in || net->key_ws != ws || net->key_out != out_raw || net->key_B != B) {
+    const int sms = device_sm_count();
     for (OpRt& r : net->ops) {
-      if (r.op.kind != OP_CONV || !r.tma_a) continue;
+      if (r.op.kind != OP_CONV) continue;
+      const BlobOp& o = r.op;
+      r.m_tiles = (B * o.Ho * o.Wo + CONV_BM - 1) / CONV_BM;
+      const int bn = pick_bn_tile(o.cout, r.m_tiles, o.k_pad / 64, sms);
+      if (bn != r.bn_tile) {
+        int rc = make_tmap_f16_2d(&r.tmap_w, net->d_weights + o.w_off, (uint64_t)o.cout, (uint64_t)o.k_pad,
+                                  (uint64_t)o.k_pad * 2, (uint32_t)bn);
+        if (rc != FIRE_OK) return rc;
+        r.bn_tile = bn;
+      }
+      r.n_tiles = o.cout / bn;
+      const size_t stage = CONV_A_STAGE_BYTES + (size_t)bn * 128;
+      r.stages = (int)std::min<size_t>(6, (200 * 1024) / stage);
+      r.stages = std::max(3, r.stages);
+      r.smem = 1024 + r.stages * stage + CONV_MAX_COUT * sizeof(float) + 256;
+      r.tmem_cols = pow2_cols(2 * bn);
+      if (!r.tma_a) continue;
       const BlobBuf& sb = net->bufs[r.op.src_buf];
       const __half* src = static_cast<const __half*>(buf_ptr(net, r.op.src_buf, B, in, ws, out_raw)) + r.op.src_coff;
       int rc = make_tmap_f16_2d(&r.tmap_a, src, (uint64_t)B * r.op.Ho * r.op.Wo, (uint64_t)r.op.cin, (uint64_t)sb.C * 2, CONV_BM);
@@ -306,7 +348,7 @@ int fire_facenet_forward(fire_net_t* net, const void* in_f16, int B, float* out_
   if (rc != FIRE_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (OpRt& r : net->ops) {
-    rc = run_op(net, r, B, in_f16, workspace, out_raw, st);
+    rc = run_op(net, r, B, in_f16, workspace, out_raw, st, net->pdl);
     if (rc != FIRE_OK) return rc;
   }
   if (out_l2) {
@@ -329,7 +371,7 @@ int fire_facenet_profile(fire_net_t* net, const void* in_f16, int B, void* works
   for (auto& e : ev) cudaEventCreate(&e);
   cudaEventRecord(ev[0], st);
   for (size_t i = 0; i < net->ops.size(); ++i) {
-    rc = run_op(net, net->ops[i], B, in_f16, workspace, out_raw, st);
+    rc = run_op(net, net->ops[i], B, in_f16, workspace, out_raw, st, false);   // no overlap: clean per-op times
     if (rc != FIRE_OK) break;
     cudaEventRecord(ev[i + 1], st);
   }

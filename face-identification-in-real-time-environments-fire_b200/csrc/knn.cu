@@ -30,7 +30,7 @@ constexpr int KNN_THREADS = 192;             // warp0 TMA, warp1 MMA, warps 2..5
 constexpr int KNN_A_KB_BYTES = KNN_BM * 128; // one 64-wide K block of the query tile
 constexpr int KNN_B_STAGE_BYTES = KNN_BN * 128;
 constexpr int KNN_MAX_LISTS_PER_LANE = 10;   // merge routines handle up to 320 sorted lists
-constexpr float KNN_DEFAULT_EPS = 1.1e-3f;   // >= 2^-10 (two fp16 roundings, Cauchy-Schwarz) + accumulation slack
+constexpr float KNN_DEFAULT_EPS = 3e-5f;     // slack on top of the measured fp16 rounding-error bound (fp32 accumulation order)
 constexpr size_t KNN_SMEM_BUDGET = 232448 - 2048;
 
 struct KnnScanParams {
@@ -47,8 +47,11 @@ struct KnnScanParams {
 // ------------------------------------------------------------------------------------------------
 // normalise rows like hnswlib's cosine space: x * (1 / (sqrt(sum x^2) + 1e-30))
 // one warp per row; writes the fp32 normalised row and its fp16 rounding.
+// Also measures ||x^ - fp16(x^)||_2 of every row: per query into row_err[], max over gallery rows into *max_err
+// (positive floats order like their bit patterns, so atomicMax on the bits is a float max).
 __global__ void knn_normalize_kernel(const float* __restrict__ in, size_t n, int D, float* __restrict__ out32,
-                                     __half* __restrict__ out16, size_t n_pad16) {
+                                     __half* __restrict__ out16, size_t n_pad16, float* __restrict__ row_err,
+                                     int* __restrict__ max_err) {
   size_t row = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (row >= n_pad16) return;
@@ -65,6 +68,7 @@ __global__ void knn_normalize_kernel(const float* __restrict__ in, size_t n, int
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   float inv = 1.0f / (sqrtf(s) + 1e-30f);
+  float e2 = 0.f;
   for (int c = lane * 4; c < D; c += 128) {
     float4 v = *reinterpret_cast<const float4*>(x + c);
     v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
@@ -72,6 +76,16 @@ __global__ void knn_normalize_kernel(const float* __restrict__ in, size_t n, int
     __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
     uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
     *reinterpret_cast<uint2*>(out16 + row * D + c) = pk;
+    const float2 fa = __half22float2(a), fb = __half22float2(b);
+    const float d0 = v.x - fa.x, d1 = v.y - fa.y, d2 = v.z - fb.x, d3 = v.w - fb.y;
+    e2 = fmaf(d0, d0, e2); e2 = fmaf(d1, d1, e2); e2 = fmaf(d2, d2, e2); e2 = fmaf(d3, d3, e2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+  if (lane == 0) {
+    const float e = sqrtf(e2) * 1.0001f;              // round the norm itself upwards
+    if (row_err) row_err[row] = e;
+    if (max_err) atomicMax(max_err, __float_as_int(e));
   }
 }
 
@@ -221,7 +235,7 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         uint32_t r[32];
         __syncwarp();                                // tcgen05.ld is warp-collective: reconverge first
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * KNN_BN + c * 32), r);
-        tmem_ld_wait();
+        tmem_ld_wait(r);
         const int lim = nvalid - c * 32;          // >= 32 for full chunks
         if (lim < 32) {
 #pragma unroll
@@ -330,7 +344,8 @@ __device__ __forceinline__ void warp_merge_lists(int G, int len, int n_out, Get 
 template <int KP>
 __global__ void knn_rerank_kernel(const float* __restrict__ qn, const float* __restrict__ g32,
                                   const float* __restrict__ cand_score, const uint32_t* __restrict__ cand_idx, int S,
-                                  int D, int Q, int k, int64_t id_offset, float eps, float* __restrict__ out_dist,
+                                  int D, int Q, int k, int64_t id_offset, float slack, const float* __restrict__ q_err,
+                                  const int* __restrict__ g_max_err, float* __restrict__ out_dist,
                                   long long* __restrict__ out_ids, uint32_t* __restrict__ flagged,
                                   uint32_t* __restrict__ flagged_count) {
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -416,8 +431,12 @@ __global__ void knn_rerank_kernel(const float* __restrict__ qn, const float* __r
   float cmin = __shfl_sync(0xffffffffu, sel_score[EPL - 1], (KP - 1) & 31);
   uint32_t last_idx = __shfl_sync(0xffffffffu, sel_idx[EPL - 1], (KP - 1) & 31);
   const bool list_full = last_idx != 0xFFFFFFFFu;
-  // rows outside the list have fp16 score <= cmin, hence exact cosine <= cmin + eps.  They cannot
-  // enter the top-k iff cmin + eps < (1 - kth_dist).
+  // |<q,g> - <q16,g16>| <= ||dq||*||g16|| + ||q16||*||dg|| + ||dq||*||dg||  with the MEASURED rounding-error norms
+  // (dq = q^ - fp16(q^), dg likewise, max over the shard) plus slack for the fp32 accumulation order.
+  // Rows outside the list have fp16 score <= cmin, hence exact cosine <= cmin + eps: they cannot enter the
+  // top-k iff cmin + eps < (1 - kth_dist).
+  const float eq = q_err[q], eg = __int_as_float(*g_max_err);
+  const float eps = (eq + eg) * 1.0005f + eq * eg + slack;
   if (lane == 0 && list_full && (cmin + eps >= 1.0f - kth_dist)) {
     uint32_t slot = atomicAdd(flagged_count, 1u);
     flagged[slot] = static_cast<uint32_t>(q);
@@ -584,6 +603,8 @@ struct fire_knn {
   int q_cap = 0;              // queries the scratch can hold (multiple of 128)
   int s_cap = 0, kp_cap = 0;
   float* qn32 = nullptr;
+  float* q_err = nullptr;       // [q_cap] ||q^ - fp16(q^)||
+  int* g_max_err = nullptr;     // [1] max over gallery rows of ||g^ - fp16(g^)|| (float bits)
   __half* q16 = nullptr;
   float* cand_score = nullptr;
   uint32_t* cand_idx = nullptr;
@@ -607,9 +628,10 @@ static int knn_ensure_scratch(fire_knn* h, int Q, int S, int KP, int k) {
   if (q_pad > h->q_cap || S > h->s_cap || KP > h->kp_cap) {
     const int nq = std::max(q_pad, h->q_cap), ns = std::max(S, h->s_cap), nkp = std::max(KP, h->kp_cap);
     FIRE_CUDA(cudaDeviceSynchronize());
-    cudaFree(h->qn32); cudaFree(h->q16); cudaFree(h->cand_score); cudaFree(h->cand_idx); cudaFree(h->flagged);
-    h->qn32 = nullptr; h->q16 = nullptr; h->cand_score = nullptr; h->cand_idx = nullptr; h->flagged = nullptr;
+    cudaFree(h->qn32); cudaFree(h->q16); cudaFree(h->cand_score); cudaFree(h->cand_idx); cudaFree(h->flagged); cudaFree(h->q_err);
+    h->q_err = nullptr; h->qn32 = nullptr; h->q16 = nullptr; h->cand_score = nullptr; h->cand_idx = nullptr; h->flagged = nullptr;
     FIRE_CUDA(cudaMalloc(&h->qn32, sizeof(float) * nq * h->D));
+    FIRE_CUDA(cudaMalloc(&h->q_err, sizeof(float) * nq));
     FIRE_CUDA(cudaMalloc(&h->q16, sizeof(__half) * nq * h->D));
     FIRE_CUDA(cudaMalloc(&h->cand_score, sizeof(float) * static_cast<size_t>(nq) * ns * nkp));
     FIRE_CUDA(cudaMalloc(&h->cand_idx, sizeof(uint32_t) * static_cast<size_t>(nq) * ns * nkp));
@@ -665,13 +687,18 @@ int fire_knn_create(int D, size_t capacity, fire_knn_t** out) {
     return fail(FIRE_ERR_CUDA, "fire_knn_create: cudaMalloc of %zu x %d gallery failed: %s", capacity, D,
                 cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
   }
+  if (cudaMalloc(&h->g_max_err, sizeof(int)) != cudaSuccess || cudaMemset(h->g_max_err, 0, sizeof(int)) != cudaSuccess) {
+    cudaFree(h->g32); cudaFree(h->g16); cudaFree(h->g_max_err);
+    delete h;
+    return fail(FIRE_ERR_CUDA, "fire_knn_create: cudaMalloc failed");
+  }
   *out = h;
   return FIRE_OK;
 }
 
 int fire_knn_destroy(fire_knn_t* h) {
   if (!h) return FIRE_OK;
-  cudaFree(h->g32); cudaFree(h->g16); cudaFree(h->qn32); cudaFree(h->q16); cudaFree(h->cand_score);
+  cudaFree(h->g32); cudaFree(h->g16); cudaFree(h->g_max_err); cudaFree(h->q_err); cudaFree(h->qn32); cudaFree(h->q16); cudaFree(h->cand_score);
   cudaFree(h->cand_idx); cudaFree(h->flagged); cudaFree(h->flagged_count); cudaFree(h->stats);
   cudaFree(h->part_dist); cudaFree(h->part_idx);
   if (h->stage_q) cudaFreeHost(h->stage_q);
@@ -686,6 +713,7 @@ int fire_knn_destroy(fire_knn_t* h) {
 int fire_knn_reset(fire_knn_t* h) {
   if (!h) return fail(FIRE_ERR_ARG, "NULL handle");
   h->count = 0;
+  FIRE_CUDA(cudaMemset(h->g_max_err, 0, sizeof(int)));
   return FIRE_OK;
 }
 size_t fire_knn_count(const fire_knn_t* h) { return h ? h->count : 0; }
@@ -701,7 +729,7 @@ int fire_knn_add(fire_knn_t* h, const float* rows, size_t n, fire_stream_t strea
   const size_t warps_per_block = 8;
   const size_t blocks = (n + warps_per_block - 1) / warps_per_block;
   knn_normalize_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(rows, n, h->D, h->g32 + h->count * h->D,
-                                                                       h->g16 + h->count * h->D, n);
+                                                                       h->g16 + h->count * h->D, n, nullptr, h->g_max_err);
   FIRE_LAUNCH_CHECK("knn_normalize_kernel(add)");
   count_launch();
   h->count += n;
@@ -784,7 +812,7 @@ int fire_knn_search(fire_knn_t* h, const float* queries, int Q, int k, int64_t i
     const size_t q_pad = static_cast<size_t>(QB) * KNN_BM;
     const size_t blocks = (q_pad + 7) / 8;
     knn_normalize_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(queries, static_cast<size_t>(Q), D, h->qn32,
-                                                                         h->q16, q_pad);
+                                                                         h->q16, q_pad, h->q_err, nullptr);
     FIRE_LAUNCH_CHECK("knn_normalize_kernel(query)");
     count_launch();
   }
@@ -812,10 +840,10 @@ int fire_knn_search(fire_knn_t* h, const float* queries, int Q, int k, int64_t i
     const int blocks = (Q + 7) / 8;
     if (KP == 16)
       knn_rerank_kernel<16><<<blocks, 256, 0, st>>>(h->qn32, h->g32, h->cand_score, h->cand_idx, S, D, Q, k, id_offset, h->eps,
-                                                    out_dist, reinterpret_cast<long long*>(out_ids), h->flagged, h->flagged_count);
+                                                    h->q_err, h->g_max_err, out_dist, reinterpret_cast<long long*>(out_ids), h->flagged, h->flagged_count);
     else
       knn_rerank_kernel<64><<<blocks, 256, 0, st>>>(h->qn32, h->g32, h->cand_score, h->cand_idx, S, D, Q, k, id_offset, h->eps,
-                                                    out_dist, reinterpret_cast<long long*>(out_ids), h->flagged, h->flagged_count);
+                                                    h->q_err, h->g_max_err, out_dist, reinterpret_cast<long long*>(out_ids), h->flagged, h->flagged_count);
     FIRE_LAUNCH_CHECK("knn_rerank_kernel");
     count_launch();
   }

@@ -115,7 +115,7 @@ int fire_knn_merge(const float* dists, const int64_t* ids, int Q, int k, int G, 
                    int64_t* out_ids, fire_stream_t stream);
 /* Counters: queries answered so far / queries that needed the exact fp32 fallback scan. */
 int fire_knn_stats(fire_knn_t* h, uint64_t* host_queries_total, uint64_t* host_queries_fallback);
-/* Test hook: widen the fp16-filter safety margin (default 1.1e-3) to force the fallback path. */
+/* Test hook: widen the fp16-filter safety margin (default: 3e-5 on top of the measured fp16 rounding bound) to force the fallback path. */
 int fire_knn_set_margin(fire_knn_t* h, float eps);
 
 #ifdef __cplusplus
