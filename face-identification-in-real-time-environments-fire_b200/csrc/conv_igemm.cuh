@@ -16,7 +16,8 @@
 //               residual loads of chunk c+1 are in flight while chunk c is finished;
 //   warps 6-9   A-gather producers for k x k / strided / padded layers: 16-byte cp.async copies
 //               (zero-fill for padding and the K tail) straight into the 128-byte-swizzled layout
-//               the UMMA descriptor expects, signalled two K-blocks late so copies stay in flight.
+//               the UMMA descriptor expects; each thread's cp.async.mbarrier.arrive.noinc signals the stage
+//               when its copies land, so the producers run a full ring ahead without ever waiting on data.
 // The smem ring runs across tile boundaries, so a CTA never drains its pipeline between tiles.
 // With programmatic dependent launch the prologue (barriers, TMEM, bias, descriptor prefetch) of
 // layer i+1 overlaps the tail of layer i; griddepcontrol.wait guards the first activation access.
@@ -29,10 +30,10 @@ namespace fire {
 constexpr int CONV_BM = 128;
 constexpr int CONV_THREADS = 320;
 constexpr int CONV_A_STAGE_BYTES = CONV_BM * 128;
-constexpr int CONV_LAG = 2;                // cp.async groups in flight before a stage is signalled
+constexpr int CONV_RES_DEPTH = 4;          // residual chunks prefetched ahead of the chunk being finished
 constexpr int CONV_MAX_COUT = 1792;
 
-constexpr int CF_RELU = 1, CF_RESIDUAL = 2, CF_OUT_F32 = 4;
+constexpr int CF_RELU = 1, CF_RESIDUAL = 2, CF_OUT_F32 = 4, CF_GATHER_L1 = 256;
 
 struct ConvParams {
   const __half* in;  int in_ld, in_coff;
@@ -190,33 +191,38 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       const bool mvalid = m < p.M_total;
       const __half* resp = has_res && mvalid ? p.res + static_cast<size_t>(m) * p.res_ld + p.res_coff + n0 : nullptr;
       uint32_t ra[16], rb[16];
-      uint4 qa[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}, qb[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-      if (resp) { qa[0] = __ldg(reinterpret_cast<const uint4*>(resp)); qa[1] = __ldg(reinterpret_cast<const uint4*>(resp) + 1); }
+      uint4 q[CONV_RES_DEPTH][2];
+#pragma unroll
+      for (int j = 0; j < CONV_RES_DEPTH; ++j) {       // residual of the first chunks: in flight while the MMAs still run
+        q[j][0] = make_uint4(0, 0, 0, 0); q[j][1] = make_uint4(0, 0, 0, 0);
+        if (resp && j < n_chunks) {
+          q[j][0] = __ldg(reinterpret_cast<const uint4*>(resp + j * 16));
+          q[j][1] = __ldg(reinterpret_cast<const uint4*>(resp + j * 16) + 1);
+        }
+      }
       mbar_wait(&acc_full[buf], (lt >> 1) & 1, 14);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * p.bn_tile);
       __syncwarp();
       tmem_ld_32x16(taddr, ra);
-      for (int c = 0; c < n_chunks; c += 2) {
-        // ---- chunk c lives in (ra, qa); prefetch chunk c+1 into (rb, qb)
-        tmem_ld_wait(ra);
-        const bool has_b = c + 1 < n_chunks;
-        __syncwarp();
-        if (has_b) {
-          tmem_ld_32x16(taddr + static_cast<uint32_t>((c + 1) * 16), rb);
-          if (resp) { qb[0] = __ldg(reinterpret_cast<const uint4*>(resp + (c + 1) * 16)); qb[1] = __ldg(reinterpret_cast<const uint4*>(resp + (c + 1) * 16) + 1); }
+      for (int c0 = 0; c0 < n_chunks; c0 += CONV_RES_DEPTH) {
+#pragma unroll
+        for (int j = 0; j < CONV_RES_DEPTH; ++j) {
+          const int c = c0 + j;
+          if (c >= n_chunks) break;                    // warp-uniform
+          // chunk c sits in ra (j even) / rb (j odd); start the TMEM load of chunk c+1 into the other set
+          if (j & 1) tmem_ld_wait(rb); else tmem_ld_wait(ra);
+          __syncwarp();
+          if (c + 1 < n_chunks) {
+            if (j & 1) tmem_ld_32x16(taddr + static_cast<uint32_t>((c + 1) * 16), ra);
+            else tmem_ld_32x16(taddr + static_cast<uint32_t>((c + 1) * 16), rb);
+          }
+          if (mvalid) conv_finish_chunk(p, (j & 1) ? rb : ra, q[j], s_bias, m, n0 + c * 16, relu, has_res, out_f32);
+          if (resp && c + CONV_RES_DEPTH < n_chunks) {  // refill this slot with the residual of chunk c + depth
+            q[j][0] = __ldg(reinterpret_cast<const uint4*>(resp + (c + CONV_RES_DEPTH) * 16));
+            q[j][1] = __ldg(reinterpret_cast<const uint4*>(resp + (c + CONV_RES_DEPTH) * 16) + 1);
+          }
         }
-        if (mvalid) conv_finish_chunk(p, ra, qa, s_bias, m, n0 + c * 16, relu, has_res, out_f32);
-        if (!has_b) break;
-        // ---- chunk c+1 lives in (rb, qb); prefetch chunk c+2 into (ra, qa)
-        tmem_ld_wait(rb);
-        const bool has_a = c + 2 < n_chunks;
-        __syncwarp();
-        if (has_a) {
-          tmem_ld_32x16(taddr + static_cast<uint32_t>((c + 2) * 16), ra);
-          if (resp) { qa[0] = __ldg(reinterpret_cast<const uint4*>(resp + (c + 2) * 16)); qa[1] = __ldg(reinterpret_cast<const uint4*>(resp + (c + 2) * 16) + 1); }
-        }
-        if (mvalid) conv_finish_chunk(p, rb, qb, s_bias, m, n0 + (c + 1) * 16, relu, has_res, out_f32);
       }
       __syncwarp();
       tc_fence_before();
@@ -227,6 +233,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const int g = threadIdx.x - 192;                // 0..127
     const int chunk = g & 7, rbase = g >> 3;        // 8 lanes cover one 128-byte row
     const int HoWo = p.Ho * p.Wo;
+    const bool use_l1 = p.flags & CF_GATHER_L1;
     if (p.pdl) pdl_wait();
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -261,19 +268,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           const int ih = ih0[i] + r, iw = iw0[i] + sx;
           const bool ok = kvalid && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
           const __half* src = ok ? p.in + (base_off[i] + tap_off) : p.in;
-          cp_async_16(a_s + sw128_offset(rbase + 16 * i, chunk), src, ok);
+          if (use_l1) cp_async_16_ca(a_s + sw128_offset(rbase + 16 * i, chunk), src, ok);
+          else cp_async_16(a_s + sw128_offset(rbase + 16 * i, chunk), src, ok);
         }
-        cp_async_commit();
-        if (it >= CONV_LAG) {
-          cp_async_wait<CONV_LAG>();
-          fence_proxy_async_smem();
-          mbar_arrive(&full[(it - CONV_LAG) % p.stages]);
-        }
+        cp_async_mbar_arrive_noinc(&full[s]);         // counted arrival fires when this thread's copies have landed
       }
     }
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    for (int j = max(0, it - CONV_LAG); j < it; ++j) mbar_arrive(&full[j % p.stages]);
+    cp_async_wait_all();                              // do not exit with copies in flight
   }
 
   tc_fence_before();

@@ -158,6 +158,8 @@ struct fire_net {
   const void* key_in = nullptr; const void* key_ws = nullptr; const void* key_out = nullptr; int key_B = 0;
   double flops_per_image = 0;
   bool pdl = true;        // programmatic dependent launch between conv layers (FIRE_B200_PDL=0 disables)
+  bool gather_l1 = false; // cp.async.ca instead of .cg for the A gather (FIRE_B200_GATHER_L1=1)
+  int max_stages = 8;
 };
 
 static int pow2_cols(int n) {
@@ -226,6 +228,10 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
   }
   const char* pdl_env = getenv("FIRE_B200_PDL");
   net->pdl = !(pdl_env && pdl_env[0] == '0');
+  const char* l1_env = getenv("FIRE_B200_GATHER_L1");
+  net->gather_l1 = l1_env && l1_env[0] == '1';
+  const char* st_env = getenv("FIRE_B200_MAX_STAGES");
+  if (st_env) net->max_stages = std::max(3, std::min(12, atoi(st_env)));
   *out = net;
   return FIRE_OK;
 }
@@ -275,6 +281,7 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
     p.nkb = o.k_pad / 64; p.flags = o.flags; p.bn_tile = r.bn_tile; p.M_total = B * o.Ho * o.Wo;
     p.stages = r.stages; p.tma_a = r.tma_a ? 1 : 0; p.tmem_cols = r.tmem_cols;
     p.m_tiles = r.m_tiles; p.n_tiles = r.n_tiles; p.pdl = pdl ? 1 : 0;
+    if (net->gather_l1) p.flags |= CF_GATHER_L1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)std::min<long long>((long long)r.m_tiles * r.n_tiles, device_sm_count()));
     cfg.blockDim = dim3(CONV_THREADS);
@@ -325,7 +332,7 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
       }
       r.n_tiles = o.cout / bn;
       const size_t stage = CONV_A_STAGE_BYTES + (size_t)bn * 128;
-      r.stages = (int)std::min<size_t>(6, (200 * 1024) / stage);
+      r.stages = (int)std::min<size_t>(net->max_stages, (200 * 1024) / stage);
       r.stages = std::max(3, r.stages);
       r.smem = 1024 + r.stages * stage + CONV_MAX_COUT * sizeof(float) + 256;
       r.tmem_cols = pow2_cols(2 * bn);

@@ -108,10 +108,34 @@ __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc,
   uint32_t n = valid ? 16u : 0u;   // src-size 0 => 16 bytes of zeros are written
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(n) : "memory");
 }
+// .ca variant: allocate in L1 as well (the 3x3 taps of neighbouring output pixels re-read the same input bytes)
+__device__ __forceinline__ void cp_async_16_ca(uint32_t smem_dst, const void* gsrc, bool valid) {
+  uint32_t n = valid ? 16u : 0u;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(n) : "memory");
+}
+// Arrive on `bar` (counted, .noinc) once every cp.async this thread has issued so far has landed in smem.
+// This is how CUTLASS' sm100 cp.async main loop hands generic-proxy-filled stages to tcgen05.mma.
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {   // wait until at most n groups are pending (n in 0..7)
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    case 6: cp_async_wait<6>(); break;
+    default: cp_async_wait<7>(); break;
+  }
 }
 
 // ---------------------------------------------------------------- TMEM

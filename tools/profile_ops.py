@@ -28,20 +28,20 @@ for _ in range(reps):
 ms /= reps
 print(f"# FaceNet{D} B={B}: {ms.sum():.3f} ms/forward (sum of per-op events) = {B / ms.sum() * 1e3:.0f} embeds/s; "
       f"{fl.sum() / ms.sum() / 1e9:.1f} TFLOP/s")
-print(f"{'op':>3} {'label':38} {'M':>8} {'N':>5} {'K':>5} {'tile':>4} {'mode':>6} {'grid':>7} {'ms':>8} {'TFLOP/s':>8} {'GB/s(min)':>9} {'%':>5}")
+print(f"{'op':>3} {'label':38} {'M':>8} {'N':>5} {'K':>5} {'mode':>6} {'Mtiles':>7} {'ms':>8} {'TFLOP/s':>8} {'GB/s(min)':>9} {'%':>5}")
 groups = {}
 for i, op in enumerate(eng.plan.ops):
     M = B * op.Ho * op.Wo
     if op.kind == OP_CONV:
         mode = "tma" if (op.kh == 1 and op.kw == 1 and op.stride == 1) else "gather"
-        grid = ((M + 127) // 128) * (op.cout // op.bn_tile)
+        grid = (M + 127) // 128
         tf = fl[i] / ms[i] / 1e9
         byts = 2 * (B * op.H * op.W * op.cin + M * op.cout + op.cout * op.k_pad)
         K = op.k_real
     else:
         mode, grid, tf, K = "pool", 0, 0.0, 0
         byts = 2 * (B * op.H * op.W * op.cin + M * op.cout)
-    print(f"{i:3d} {op.label:38} {M:8d} {op.cout:5d} {K:5d} {op.bn_tile:4d} {mode:>6} {grid:7d} {ms[i]:8.4f} {tf:8.1f} "
+    print(f"{i:3d} {op.label:38} {M:8d} {op.cout:5d} {K:5d} {mode:>6} {grid:7d} {ms[i]:8.4f} {tf:8.1f} "
           f"{byts / ms[i] / 1e6:9.0f} {100 * ms[i] / ms.sum():5.1f}")
     key = op.label.split("_")[0] if not op.label.startswith("Conv2d") else "Stem"
     groups[key] = groups.get(key, 0.0) + ms[i]
