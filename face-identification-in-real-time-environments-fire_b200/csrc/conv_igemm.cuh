@@ -6,18 +6,21 @@
 //   D[m, n] = sum_k A[m, k] * W[n, k]      m = output pixel (b, ho, wo), n = output channel,
 //                                          k = (tap r,s ; input channel c), tap-major
 //
-// Persistent CTAs (one per SM) walk the (m-tile, n-tile) list; five warp roles run concurrently:
+// Persistent CTAs (one per SM) walk the (m-tile, n-tile) list; the warp roles run concurrently:
 //   warp 0      TMA producer: weight K-blocks (always) and, for 1x1/stride-1 layers, the activation
 //               K-blocks too (the activation matrix [M, C] is then a plain 2-D tensor);
 //   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=bn_tile, K=16) into one of TWO
 //               TMEM accumulators, so the epilogue of tile t overlaps the main loop of tile t+1;
-//   warps 2-5   epilogue: tcgen05.ld -> +bias (staged in smem) -> +residual -> ReLU -> fp16/fp32
-//               store at a channel offset of the destination buffer (concat for free); the TMEM and
-//               residual loads of chunk c+1 are in flight while chunk c is finished;
-//   warps 6-9   A-gather producers for k x k / strided / padded layers: 16-byte cp.async copies
-//               (zero-fill for padding and the K tail) straight into the 128-byte-swizzled layout
-//               the UMMA descriptor expects; each thread's cp.async.mbarrier.arrive.noinc signals the stage
-//               when its copies land, so the producers run a full ring ahead without ever waiting on data.
+//   warps 2-5   epilogue: tcgen05.ld -> +bias (smem) -> +residual (smem) -> ReLU -> fp16 -> per-warp
+//               smem staging -> row-contiguous 16-byte global stores at a channel offset of the
+//               destination buffer (concat for free).  Thread = accumulator row only while talking
+//               to TMEM; every global access is coalesced along the channel dimension;
+//   warps 6-13  helpers.  k x k / strided / padded layers: A-gather producers - 16-byte cp.async
+//               (zero-fill for padding and the K tail) straight into the 128-byte-swizzled layout the
+//               UMMA descriptor expects, each thread's cp.async.mbarrier.arrive.noinc signalling the
+//               stage when its copies land; index math uses precomputed magic-number division and
+//               per-row tap-validity masks.  1x1 layers with a residual: the same warps prefetch the
+//               residual tile of the NEXT tile into a double-buffered smem stage with coalesced cp.async.
 // The smem ring runs across tile boundaries, so a CTA never drains its pipeline between tiles.
 // With programmatic dependent launch the prologue (barriers, TMEM, bias, descriptor prefetch) of
 // layer i+1 overlaps the tail of layer i; griddepcontrol.wait guards the first activation access.
@@ -28,12 +31,22 @@
 namespace fire {
 
 constexpr int CONV_BM = 128;
-constexpr int CONV_THREADS = 320;
+constexpr int CONV_HELPER_WARPS = 8;
+constexpr int CONV_HELPER_THREADS = CONV_HELPER_WARPS * 32;            // 256
+constexpr int CONV_THREADS = 64 + 128 + CONV_HELPER_THREADS;           // 448
+constexpr int CONV_ROWS_PER_GATHER_THREAD = CONV_BM / (CONV_HELPER_THREADS / 8);   // 4
 constexpr int CONV_A_STAGE_BYTES = CONV_BM * 128;
-constexpr int CONV_RES_DEPTH = 4;          // residual chunks prefetched ahead of the chunk being finished
 constexpr int CONV_MAX_COUT = 1792;
+constexpr int CONV_STAGE_COLS = 128;       // columns staged per epilogue pass (sOut width)
 
 constexpr int CF_RELU = 1, CF_RESIDUAL = 2, CF_OUT_F32 = 4, CF_GATHER_L1 = 256;
+
+struct FastDiv {            // q = x / d for 0 <= x < 2^31  (mul = ceil(2^sh / d), sh = 31 + ceil(log2 d))
+  uint32_t mul, sh;
+};
+__device__ __forceinline__ int fdiv(int x, FastDiv f) {
+  return static_cast<int>((static_cast<unsigned long long>(static_cast<uint32_t>(x)) * f.mul) >> f.sh);
+}
 
 struct ConvParams {
   const __half* in;  int in_ld, in_coff;
@@ -43,6 +56,8 @@ struct ConvParams {
   int H, W, Ho, Wo, kh, kw, stride, pad_h, pad_w;
   int cin, cout, k_real, nkb, flags, bn_tile, M_total, stages, tma_a, tmem_cols;
   int m_tiles, n_tiles, pdl;
+  int res_smem;                 // residual tile prefetched into smem by the helper warps (tma_a && residual)
+  FastDiv d_howo, d_wo, d_cin, d_kw, d_unit_res, d_unit_out;
 };
 
 __device__ __forceinline__ void tmem_alloc_rt(uint32_t* smem_slot, uint32_t cols) {
@@ -55,12 +70,19 @@ __device__ __forceinline__ void tmem_dealloc_rt(uint32_t taddr, uint32_t cols) {
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-// finish one 16-column chunk of one output row: bias, residual, ReLU, convert, store
-__device__ __forceinline__ void conv_finish_chunk(const ConvParams& p, const uint32_t (&r)[16], const uint4 (&q)[2],
-                                                  const float* s_bias, int m, int n, bool relu, bool has_res, bool out_f32) {
-  float v[16];
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// one 16-column chunk of one accumulator row: bias, residual, ReLU -> 16 floats in v[]
+__device__ __forceinline__ void conv_chunk_math(const uint32_t (&r)[16], const uint4 (&q)[2], const float* s_bias, int n,
+                                                bool relu, bool has_res, float (&v)[16]) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + s_bias[n + j];
   if (has_res) {
@@ -77,15 +99,6 @@ __device__ __forceinline__ void conv_finish_chunk(const ConvParams& p, const uin
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
   }
-  if (out_f32) {
-    float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + p.out_coff + n);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  } else {
-    uint4* op = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + static_cast<size_t>(m) * p.out_ld + p.out_coff + n);
-    op[0] = make_uint4(pack_f16x2_sat(v[0], v[1]), pack_f16x2_sat(v[2], v[3]), pack_f16x2_sat(v[4], v[5]), pack_f16x2_sat(v[6], v[7]));
-    op[1] = make_uint4(pack_f16x2_sat(v[8], v[9]), pack_f16x2_sat(v[10], v[11]), pack_f16x2_sat(v[12], v[13]), pack_f16x2_sat(v[14], v[15]));
-  }
 }
 
 __global__ void __launch_bounds__(CONV_THREADS, 1)
@@ -94,15 +107,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_stage_bytes = p.bn_tile * 128;
+  const int sw_cols = min(p.bn_tile, CONV_STAGE_COLS);             // columns per staging pass
+  const int out_pitch = sw_cols * 2 + 16;                          // bytes; (pitch/16) odd -> conflict-free row-per-lane access
+  const int res_pitch = p.bn_tile * 2 + 16;
   uint8_t* sA = smem;
   uint8_t* sB = smem + static_cast<size_t>(p.stages) * CONV_A_STAGE_BYTES;
   float* s_bias = reinterpret_cast<float*>(sB + static_cast<size_t>(p.stages) * b_stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + CONV_MAX_COUT);
+  uint8_t* sOut = reinterpret_cast<uint8_t*>(s_bias + CONV_MAX_COUT);                  // [4 warps][32 rows][out_pitch]
+  uint8_t* sRes = sOut + 4 * 32 * out_pitch;                                            // [2][128 rows][res_pitch] (res_smem only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRes + (p.res_smem ? 2 * CONV_BM * res_pitch : 0));
   uint64_t* full = bars;
   uint64_t* empty = bars + p.stages;
   uint64_t* acc_full = empty + p.stages;      // [2]
   uint64_t* acc_empty = acc_full + 2;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* res_full = acc_empty + 2;         // [2]
+  uint64_t* res_empty = res_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -113,9 +133,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   }
   if (warp == 1) {
     if (lane == 0) {
-      const uint32_t full_count = p.tma_a ? 1u : 1u + 128u;
+      const uint32_t full_count = p.tma_a ? 1u : 1u + CONV_HELPER_THREADS;
       for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], full_count); mbar_init(&empty[s], 1); }
-      for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128);
+        mbar_init(&res_full[b], CONV_HELPER_THREADS); mbar_init(&res_empty[b], 128);
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -181,7 +204,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const bool relu = p.flags & CF_RELU, has_res = p.flags & CF_RESIDUAL, out_f32 = p.flags & CF_OUT_F32;
-    const int n_chunks = p.bn_tile >> 4;
+    const bool res_smem = p.res_smem != 0;
+    const uint32_t my_out = smem_u32(sOut) + static_cast<uint32_t>((warp - 2) * 32 * out_pitch);
+    // coalesced copy-out geometry: 16-byte units, U per row; lane starts at unit `lane` and advances 32 units per step
+    const int U = sw_cols >> 3;
+    const int u_row0 = fdiv(lane, p.d_unit_out), u_col0 = lane - u_row0 * U;
+    const int u_drow = fdiv(32, p.d_unit_out), u_dcol = 32 - u_drow * U;
     if (p.pdl) pdl_wait();                            // residual reads / output writes depend on earlier layers
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
@@ -189,92 +217,144 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       const int n0 = (tile % p.n_tiles) * p.bn_tile, m0 = (tile / p.n_tiles) * CONV_BM;
       const int m = m0 + row;
       const bool mvalid = m < p.M_total;
-      const __half* resp = has_res && mvalid ? p.res + static_cast<size_t>(m) * p.res_ld + p.res_coff + n0 : nullptr;
-      uint32_t ra[16], rb[16];
-      uint4 q[CONV_RES_DEPTH][2];
-#pragma unroll
-      for (int j = 0; j < CONV_RES_DEPTH; ++j) {       // residual of the first chunks: in flight while the MMAs still run
-        q[j][0] = make_uint4(0, 0, 0, 0); q[j][1] = make_uint4(0, 0, 0, 0);
-        if (resp && j < n_chunks) {
-          q[j][0] = __ldg(reinterpret_cast<const uint4*>(resp + j * 16));
-          q[j][1] = __ldg(reinterpret_cast<const uint4*>(resp + j * 16) + 1);
-        }
-      }
+      const __half* resp = has_res && !res_smem && mvalid ? p.res + static_cast<size_t>(m) * p.res_ld + p.res_coff + n0 : nullptr;
+      const uint32_t my_res = smem_u32(sRes) + static_cast<uint32_t>(buf * CONV_BM * res_pitch + row * res_pitch);
+      if (res_smem) mbar_wait(&res_full[buf], (lt >> 1) & 1, 16);
       mbar_wait(&acc_full[buf], (lt >> 1) & 1, 14);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * p.bn_tile);
-      __syncwarp();
-      tmem_ld_32x16(taddr, ra);
-      for (int c0 = 0; c0 < n_chunks; c0 += CONV_RES_DEPTH) {
+      for (int cg = 0; cg < p.bn_tile; cg += sw_cols) {
+        const int n_chunks = sw_cols >> 4;
+        uint32_t ra[16], rb[16];
+        __syncwarp();
+        tmem_ld_32x16(taddr + static_cast<uint32_t>(cg), ra);
+        for (int c = 0; c < n_chunks; c += 2) {
 #pragma unroll
-        for (int j = 0; j < CONV_RES_DEPTH; ++j) {
-          const int c = c0 + j;
-          if (c >= n_chunks) break;                    // warp-uniform
-          // chunk c sits in ra (j even) / rb (j odd); start the TMEM load of chunk c+1 into the other set
-          if (j & 1) tmem_ld_wait(rb); else tmem_ld_wait(ra);
-          __syncwarp();
-          if (c + 1 < n_chunks) {
-            if (j & 1) tmem_ld_32x16(taddr + static_cast<uint32_t>((c + 1) * 16), ra);
-            else tmem_ld_32x16(taddr + static_cast<uint32_t>((c + 1) * 16), rb);
-          }
-          if (mvalid) conv_finish_chunk(p, (j & 1) ? rb : ra, q[j], s_bias, m, n0 + c * 16, relu, has_res, out_f32);
-          if (resp && c + CONV_RES_DEPTH < n_chunks) {  // refill this slot with the residual of chunk c + depth
-            q[j][0] = __ldg(reinterpret_cast<const uint4*>(resp + (c + CONV_RES_DEPTH) * 16));
-            q[j][1] = __ldg(reinterpret_cast<const uint4*>(resp + (c + CONV_RES_DEPTH) * 16) + 1);
+          for (int j = 0; j < 2; ++j) {
+            const int cc = c + j;
+            if (cc >= n_chunks) break;               // warp-uniform
+            if (j) tmem_ld_wait(rb); else tmem_ld_wait(ra);
+            __syncwarp();
+            if (cc + 1 < n_chunks) {
+              if (j) tmem_ld_32x16(taddr + static_cast<uint32_t>(cg + (cc + 1) * 16), ra);
+              else tmem_ld_32x16(taddr + static_cast<uint32_t>(cg + (cc + 1) * 16), rb);
+            }
+            const int col = cg + cc * 16;            // column inside the tile
+            uint4 q[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+            if (res_smem) { q[0] = lds128(my_res + col * 2); q[1] = lds128(my_res + col * 2 + 16); }
+            else if (resp) { q[0] = __ldg(reinterpret_cast<const uint4*>(resp + col)); q[1] = __ldg(reinterpret_cast<const uint4*>(resp + col) + 1); }
+            float v[16];
+            conv_chunk_math(j ? rb : ra, q, s_bias, n0 + col, relu, has_res, v);
+            if (out_f32) {
+              if (mvalid) {
+                float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + p.out_coff + n0 + col);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) op[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+              }
+            } else {
+              const uint32_t dst = my_out + static_cast<uint32_t>(lane * out_pitch + cc * 32);
+              sts128(dst, make_uint4(pack_f16x2_sat(v[0], v[1]), pack_f16x2_sat(v[2], v[3]), pack_f16x2_sat(v[4], v[5]), pack_f16x2_sat(v[6], v[7])));
+              sts128(dst + 16, make_uint4(pack_f16x2_sat(v[8], v[9]), pack_f16x2_sat(v[10], v[11]), pack_f16x2_sat(v[12], v[13]), pack_f16x2_sat(v[14], v[15])));
+            }
           }
         }
+        if (cg + sw_cols >= p.bn_tile) {             // accumulator and residual stage fully consumed: hand them back early
+          __syncwarp();
+          tc_fence_before();
+          mbar_arrive(&acc_empty[buf]);
+          if (res_smem) mbar_arrive(&res_empty[buf]);
+        }
+        if (!out_f32) {
+          __syncwarp();
+          // staged sub-tile (32 rows x sw_cols) -> global, 16 bytes per lane, lanes contiguous along the row
+          __half* obase = static_cast<__half*>(p.out) + static_cast<size_t>(m0 + quarter * 32) * p.out_ld + p.out_coff + n0 + cg;
+          int ur = u_row0, uc = u_col0;
+          const int rows_left = p.M_total - (m0 + quarter * 32);
+          for (int it2 = 0; it2 < U; ++it2) {
+            if (ur < rows_left) {
+              const uint4 val = lds128(my_out + static_cast<uint32_t>(ur * out_pitch + uc * 16));
+              *reinterpret_cast<uint4*>(obase + static_cast<size_t>(ur) * p.out_ld + uc * 8) = val;
+            }
+            ur += u_drow; uc += u_dcol;
+            if (uc >= U) { uc -= U; ++ur; }
+          }
+          __syncwarp();
+        }
       }
-      __syncwarp();
-      tc_fence_before();
-      mbar_arrive(&acc_empty[buf]);
     }
   } else if (!p.tma_a) {
-    // ---------------------------------------------------------------- A gather producers (4 warps)
-    const int g = threadIdx.x - 192;                // 0..127
-    const int chunk = g & 7, rbase = g >> 3;        // 8 lanes cover one 128-byte row
-    const int HoWo = p.Ho * p.Wo;
+    // ---------------------------------------------------------------- A gather producers (8 warps)
+    const int g = threadIdx.x - 192;                // 0..255
+    const int chunk = g & 7, rbase = g >> 3;        // 8 lanes cover one 128-byte row; rows rbase + 32*i
     const bool use_l1 = p.flags & CF_GATHER_L1;
+    const uint32_t sw_const = static_cast<uint32_t>(rbase * 128 + ((chunk ^ (rbase & 7)) << 4));   // (row & 7) == (rbase & 7)
+    const int HoWo = p.Ho * p.Wo;
     if (p.pdl) pdl_wait();
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.n_tiles) * CONV_BM;
-      int base_off[8];
-      short ih0[8], iw0[8];
+      int base_off[CONV_ROWS_PER_GATHER_THREAD];
+      uint32_t vmask[CONV_ROWS_PER_GATHER_THREAD];  // bits 0..6: tap rows r with ih in range; bits 8..14: tap cols s with iw in range
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = m0 + rbase + 16 * i;
+      for (int i = 0; i < CONV_ROWS_PER_GATHER_THREAD; ++i) {
+        const int m = m0 + rbase + 32 * i;
+        vmask[i] = 0; base_off[i] = 0;
         if (m < p.M_total) {
-          const int n = m / HoWo, rem = m - n * HoWo;
-          const int ho = rem / p.Wo, wo = rem - ho * p.Wo;
-          ih0[i] = static_cast<short>(ho * p.stride - p.pad_h);
-          iw0[i] = static_cast<short>(wo * p.stride - p.pad_w);
-          base_off[i] = ((n * p.H + ih0[i]) * p.W + iw0[i]) * p.in_ld + p.in_coff;
-        } else {
-          ih0[i] = -30000; iw0[i] = -30000; base_off[i] = 0;      // always out of bounds -> zero fill
+          const int n = fdiv(m, p.d_howo), rem = m - n * HoWo;
+          const int ho = fdiv(rem, p.d_wo), wo = rem - ho * p.Wo;
+          const int ih0 = ho * p.stride - p.pad_h, iw0 = wo * p.stride - p.pad_w;
+          base_off[i] = ((n * p.H + ih0) * p.W + iw0) * p.in_ld + p.in_coff;
+          uint32_t mk = 0;
+#pragma unroll
+          for (int t = 0; t < 7; ++t) {
+            if (t < p.kh && static_cast<unsigned>(ih0 + t) < static_cast<unsigned>(p.H)) mk |= 1u << t;
+            if (t < p.kw && static_cast<unsigned>(iw0 + t) < static_cast<unsigned>(p.W)) mk |= 1u << (8 + t);
+          }
+          vmask[i] = mk;
         }
       }
       for (int kb = 0; kb < p.nkb; ++kb, ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(&empty[s], ph ^ 1, 13);
         const int k = kb * 64 + chunk * 8;
-        const int tap = k / p.cin, c = k - tap * p.cin;
-        const int r = tap / p.kw, sx = tap - r * p.kw;
-        const bool kvalid = k < p.k_real;
+        const int tap = fdiv(k, p.d_cin), c = k - tap * p.cin;
+        const int r = fdiv(tap, p.d_kw), sx = tap - r * p.kw;
+        const uint32_t need = k < p.k_real ? ((1u << r) | (1u << (8 + sx))) : 0xFFFFFFFFu;   // K tail: never valid
         const int tap_off = (r * p.W + sx) * p.in_ld + c;
-        const uint32_t a_s = smem_u32(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES);
+        const uint32_t a_s = smem_u32(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES) + sw_const;
+        mbar_wait(&empty[s], ph ^ 1, 13);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int ih = ih0[i] + r, iw = iw0[i] + sx;
-          const bool ok = kvalid && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+        for (int i = 0; i < CONV_ROWS_PER_GATHER_THREAD; ++i) {
+          const bool ok = (vmask[i] & need) == need;
           const __half* src = ok ? p.in + (base_off[i] + tap_off) : p.in;
-          if (use_l1) cp_async_16_ca(a_s + sw128_offset(rbase + 16 * i, chunk), src, ok);
-          else cp_async_16(a_s + sw128_offset(rbase + 16 * i, chunk), src, ok);
+          if (use_l1) cp_async_16_ca(a_s + i * 32 * 128, src, ok);
+          else cp_async_16(a_s + i * 32 * 128, src, ok);
         }
         cp_async_mbar_arrive_noinc(&full[s]);         // counted arrival fires when this thread's copies have landed
       }
     }
     cp_async_wait_all();                              // do not exit with copies in flight
+  } else if (p.res_smem) {
+    // ---------------------------------------------------------------- residual prefetchers (8 warps, 1x1 layers)
+    const int g = threadIdx.x - 192;
+    const int U = p.bn_tile >> 3;                     // 16-byte units per residual row
+    const int total_units = CONV_BM * U;
+    if (p.pdl) pdl_wait();
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const int n0 = (tile % p.n_tiles) * p.bn_tile, m0 = (tile / p.n_tiles) * CONV_BM;
+      mbar_wait(&res_empty[buf], ((lt >> 1) & 1) ^ 1, 17);
+      const uint32_t dst0 = smem_u32(sRes) + static_cast<uint32_t>(buf * CONV_BM * res_pitch);
+      for (int u = g; u < total_units; u += CONV_HELPER_THREADS) {
+        const int rr = fdiv(u, p.d_unit_res), cc = u - rr * U;
+        const bool ok = m0 + rr < p.M_total;
+        const __half* src = ok ? p.res + static_cast<size_t>(m0 + rr) * p.res_ld + p.res_coff + n0 + cc * 8 : p.res;
+        cp_async_16(dst0 + static_cast<uint32_t>(rr * res_pitch + cc * 16), src, ok);
+      }
+      cp_async_mbar_arrive_noinc(&res_full[buf]);
+    }
+    cp_async_wait_all();
   }
 
   tc_fence_before();

@@ -126,6 +126,7 @@ struct OpRt {
   CUtensorMap tmap_a;     // activation matrix for TMA-mode convs (rebuilt when pointers / B change)
   bool tma_a = false;
   int bn_tile = 0, stages = 0, tmem_cols = 0, m_tiles = 0, n_tiles = 0;
+  bool res_smem = false;
   size_t smem = 0;
   double flops_per_image = 0;
 };
@@ -134,11 +135,13 @@ struct OpRt {
 // K-blocks); layers with few M tiles are cut along N until the persistent grid covers the SMs.  Cost model in
 // SM cycles per tile: main loop = nkb * max(MMA, L2->smem fill at ~32 B/cycle/SM), epilogue ~120 cycles per
 // 16-column chunk, ~1200 cycles fixed; total = waves * tile.
-static int pick_bn_tile(int cout, int m_tiles, int nkb, int sms) {
+static int pick_bn_tile(int cout, int m_tiles, int nkb, int sms, bool residual_in_smem) {
   int best = 16;
   double best_cost = 1e30;
   for (int d = 16; d <= 256 && d <= cout; d += 16) {
     if (cout % d) continue;
+    if (d > CONV_STAGE_COLS && d != 2 * CONV_STAGE_COLS) continue;   // epilogue stages 128 columns per pass
+    if (residual_in_smem && d > CONV_STAGE_COLS) continue;            // double-buffered residual stage must fit
     const long long tiles = (long long)m_tiles * (cout / d);
     const long long waves = (tiles + sms - 1) / sms;
     const double fill = (16384.0 + 128.0 * d) / 32.0;
@@ -147,6 +150,15 @@ static int pick_bn_tile(int cout, int m_tiles, int nkb, int sms) {
     if (cost < best_cost * 0.999 || (cost <= best_cost * 1.001 && d > best)) { best_cost = cost; best = d; }
   }
   return best;
+}
+
+static FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  int s = 0;
+  while ((1ll << s) < d) ++s;
+  f.sh = 31 + s;
+  f.mul = static_cast<uint32_t>(((1ull << f.sh) + d - 1) / static_cast<unsigned long long>(d));
+  return f;
 }
 
 struct fire_net {
@@ -282,6 +294,9 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
     p.stages = r.stages; p.tma_a = r.tma_a ? 1 : 0; p.tmem_cols = r.tmem_cols;
     p.m_tiles = r.m_tiles; p.n_tiles = r.n_tiles; p.pdl = pdl ? 1 : 0;
     if (net->gather_l1) p.flags |= CF_GATHER_L1;
+    p.res_smem = r.res_smem ? 1 : 0;
+    p.d_howo = make_fastdiv(o.Ho * o.Wo); p.d_wo = make_fastdiv(o.Wo); p.d_cin = make_fastdiv(o.cin); p.d_kw = make_fastdiv(o.kw);
+    p.d_unit_res = make_fastdiv(r.bn_tile / 8); p.d_unit_out = make_fastdiv(std::min(r.bn_tile, CONV_STAGE_COLS) / 8);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)std::min<long long>((long long)r.m_tiles * r.n_tiles, device_sm_count()));
     cfg.blockDim = dim3(CONV_THREADS);
@@ -323,7 +338,8 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
       if (r.op.kind != OP_CONV) continue;
       const BlobOp& o = r.op;
       r.m_tiles = (B * o.Ho * o.Wo + CONV_BM - 1) / CONV_BM;
-      const int bn = pick_bn_tile(o.cout, r.m_tiles, o.k_pad / 64, sms);
+      const bool res_smem = r.tma_a && (o.flags & CF_RESIDUAL);
+      const int bn = pick_bn_tile(o.cout, r.m_tiles, o.k_pad / 64, sms, res_smem);
       if (bn != r.bn_tile) {
         int rc = make_tmap_f16_2d(&r.tmap_w, net->d_weights + o.w_off, (uint64_t)o.cout, (uint64_t)o.k_pad,
                                   (uint64_t)o.k_pad * 2, (uint32_t)bn);
@@ -332,9 +348,13 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
       }
       r.n_tiles = o.cout / bn;
       const size_t stage = CONV_A_STAGE_BYTES + (size_t)bn * 128;
-      r.stages = (int)std::min<size_t>(net->max_stages, (200 * 1024) / stage);
-      r.stages = std::max(3, r.stages);
-      r.smem = 1024 + r.stages * stage + CONV_MAX_COUT * sizeof(float) + 256;
+      const size_t out_stage = 4 * 32 * (size_t)(std::min(bn, CONV_STAGE_COLS) * 2 + 16);
+      const size_t res_stage = res_smem ? 2 * (size_t)CONV_BM * (bn * 2 + 16) : 0;
+      const size_t fixed = 1024 + CONV_MAX_COUT * sizeof(float) + out_stage + res_stage + 256;
+      r.stages = (int)std::min<size_t>(net->max_stages, (232448 - fixed) / stage);
+      if (r.stages < 2) return fail(FIRE_ERR_UNSUPPORTED, "conv tile %d does not fit shared memory", bn);
+      r.smem = fixed + r.stages * stage;
+      r.res_smem = res_smem;
       r.tmem_cols = pow2_cols(2 * bn);
       if (!r.tma_a) continue;
       const BlobBuf& sb = net->bufs[r.op.src_buf];
