@@ -39,7 +39,8 @@ constexpr int CONV_A_STAGE_BYTES = CONV_BM * 128;
 constexpr int CONV_MAX_COUT = 1792;
 constexpr int CONV_STAGE_COLS = 128;       // columns staged per epilogue pass (sOut width)
 
-constexpr int CF_RELU = 1, CF_RESIDUAL = 2, CF_OUT_F32 = 4, CF_GATHER_L1 = 256;
+constexpr int CF_RELU = 1, CF_RESIDUAL = 2, CF_OUT_F32 = 4;
+constexpr int CF_DBG_NOGATHER = 1 << 16, CF_DBG_NOSTORE = 1 << 17, CF_DBG_NOMMA = 1 << 18;   // timing experiments only (wrong results)
 
 struct FastDiv {            // q = x / d for 0 <= x < 2^31  (mul = ceil(2^sh / d), sh = 31 + ceil(log2 d))
   uint32_t mul, sh;
@@ -57,7 +58,7 @@ struct ConvParams {
   int cin, cout, k_real, nkb, flags, bn_tile, M_total, stages, tma_a, tmem_cols;
   int m_tiles, n_tiles, pdl;
   int res_smem;                 // residual tile prefetched into smem by the helper warps (tma_a && residual)
-  FastDiv d_howo, d_wo, d_cin, d_kw, d_unit_res, d_unit_out;
+  FastDiv d_howo, d_wo, d_cin, d_kw, d_unit_res, d_unit_out, d_ntiles;
 };
 
 __device__ __forceinline__ void tmem_alloc_rt(uint32_t* smem_slot, uint32_t cols) {
@@ -80,11 +81,17 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// one 16-column chunk of one accumulator row: bias, residual, ReLU -> 16 floats in v[]
-__device__ __forceinline__ void conv_chunk_math(const uint32_t (&r)[16], const uint4 (&q)[2], const float* s_bias, int n,
-                                                bool relu, bool has_res, float (&v)[16]) {
+// one 16-column chunk of one accumulator row: + bias (4 x LDS.128), + residual -> 16 floats in v[]
+__device__ __forceinline__ void conv_chunk_math(const uint32_t (&r)[16], const uint4 (&q)[2], uint32_t s_bias_addr, bool has_res,
+                                                float (&v)[16]) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + s_bias[n + j];
+  for (int j = 0; j < 4; ++j) {
+    const uint4 b = lds128(s_bias_addr + j * 16);
+    v[4 * j] = __uint_as_float(r[4 * j]) + __uint_as_float(b.x);
+    v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + __uint_as_float(b.y);
+    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + __uint_as_float(b.z);
+    v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + __uint_as_float(b.w);
+  }
   if (has_res) {
     const __half2* h0 = reinterpret_cast<const __half2*>(&q[0]);
     const __half2* h1 = reinterpret_cast<const __half2*>(&q[1]);
@@ -95,10 +102,11 @@ __device__ __forceinline__ void conv_chunk_math(const uint32_t (&r)[16], const u
       v[8 + 2 * j] += f1.x; v[8 + 2 * j + 1] += f1.y;
     }
   }
-  if (relu) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-  }
+}
+// fp32 pair -> packed fp16 with ReLU (lo = 0) or without (lo = -65504) and saturation at +65504, done on the packed pair
+__device__ __forceinline__ uint32_t pack_f16x2_clamp(float a, float b, __half2 lo, __half2 hi) {
+  __half2 h = __hmin2(__hmax2(__floats2half2_rn(a, b), lo), hi);
+  return *reinterpret_cast<uint32_t*>(&h);
 }
 
 __global__ void __launch_bounds__(CONV_THREADS, 1)
@@ -158,12 +166,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     if (lane == 0) {
       const uint32_t tx = static_cast<uint32_t>(b_stage_bytes) + (p.tma_a ? CONV_A_STAGE_BYTES : 0);
       bool waited = !p.pdl || !p.tma_a;
-      int it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n0 = (tile % p.n_tiles) * p.bn_tile, m0 = (tile / p.n_tiles) * CONV_BM;
-        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+        const int mt = fdiv(tile, p.d_ntiles);
+        const int n0 = (tile - mt * p.n_tiles) * p.bn_tile, m0 = mt * CONV_BM;
+        for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(&empty[s], ph ^ 1, 11);
           mbar_arrive_expect_tx(&full[s], tx);
           tma_load_2d_hint(sB + static_cast<size_t>(s) * b_stage_bytes, &tmap_w, &full[s], kb * 64, n0, kEvictLast);
@@ -171,6 +179,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             if (!waited) { pdl_wait(); waited = true; }     // activations come from the previous layer
             tma_load_2d(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES, &tmap_a, &full[s], kb * 64, m0);
           }
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -178,23 +187,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(CONV_BM, p.bn_tile);
-      int it = 0, lt = 0;
+      int lt = 0, s = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
         const int buf = lt & 1;
         mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1, 15);
         tc_fence_after();
         const uint32_t d = tmem_base + static_cast<uint32_t>(buf * p.bn_tile);
-        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+        for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(&full[s], ph, 12);
           tc_fence_after();
           const uint32_t a0 = smem_u32(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES);
           const uint32_t b0 = smem_u32(sB + static_cast<size_t>(s) * b_stage_bytes);
+          if (!(p.flags & CF_DBG_NOMMA))
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_f16(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty[s]);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         umma_commit(&acc_full[buf]);
       }
@@ -205,6 +215,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const int row = quarter * 32 + lane;
     const bool relu = p.flags & CF_RELU, has_res = p.flags & CF_RESIDUAL, out_f32 = p.flags & CF_OUT_F32;
     const bool res_smem = p.res_smem != 0;
+    const uint32_t s_bias_u32 = smem_u32(s_bias);
+    const __half2 h_lo = __float2half2_rn(relu ? 0.f : -65504.f), h_hi = __float2half2_rn(65504.f);
     const uint32_t my_out = smem_u32(sOut) + static_cast<uint32_t>((warp - 2) * 32 * out_pitch);
     // coalesced copy-out geometry: 16-byte units, U per row; lane starts at unit `lane` and advances 32 units per step
     const int U = sw_cols >> 3;
@@ -214,7 +226,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
-      const int n0 = (tile % p.n_tiles) * p.bn_tile, m0 = (tile / p.n_tiles) * CONV_BM;
+      const int mt = fdiv(tile, p.d_ntiles);
+      const int n0 = (tile - mt * p.n_tiles) * p.bn_tile, m0 = mt * CONV_BM;
       const int m = m0 + row;
       const bool mvalid = m < p.M_total;
       const __half* resp = has_res && !res_smem && mvalid ? p.res + static_cast<size_t>(m) * p.res_ld + p.res_coff + n0 : nullptr;
@@ -244,8 +257,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             if (res_smem) { q[0] = lds128(my_res + col * 2); q[1] = lds128(my_res + col * 2 + 16); }
             else if (resp) { q[0] = __ldg(reinterpret_cast<const uint4*>(resp + col)); q[1] = __ldg(reinterpret_cast<const uint4*>(resp + col) + 1); }
             float v[16];
-            conv_chunk_math(j ? rb : ra, q, s_bias, n0 + col, relu, has_res, v);
+            conv_chunk_math(j ? rb : ra, q, s_bias_u32 + static_cast<uint32_t>((n0 + col) * 4), has_res, v);
             if (out_f32) {
+              if (relu) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+              }
               if (mvalid) {
                 float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + p.out_coff + n0 + col);
 #pragma unroll
@@ -253,8 +270,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
               }
             } else {
               const uint32_t dst = my_out + static_cast<uint32_t>(lane * out_pitch + cc * 32);
-              sts128(dst, make_uint4(pack_f16x2_sat(v[0], v[1]), pack_f16x2_sat(v[2], v[3]), pack_f16x2_sat(v[4], v[5]), pack_f16x2_sat(v[6], v[7])));
-              sts128(dst + 16, make_uint4(pack_f16x2_sat(v[8], v[9]), pack_f16x2_sat(v[10], v[11]), pack_f16x2_sat(v[12], v[13]), pack_f16x2_sat(v[14], v[15])));
+              sts128(dst, make_uint4(pack_f16x2_clamp(v[0], v[1], h_lo, h_hi), pack_f16x2_clamp(v[2], v[3], h_lo, h_hi),
+                                     pack_f16x2_clamp(v[4], v[5], h_lo, h_hi), pack_f16x2_clamp(v[6], v[7], h_lo, h_hi)));
+              sts128(dst + 16, make_uint4(pack_f16x2_clamp(v[8], v[9], h_lo, h_hi), pack_f16x2_clamp(v[10], v[11], h_lo, h_hi),
+                                          pack_f16x2_clamp(v[12], v[13], h_lo, h_hi), pack_f16x2_clamp(v[14], v[15], h_lo, h_hi)));
             }
           }
         }
@@ -267,16 +286,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         if (!out_f32) {
           __syncwarp();
           // staged sub-tile (32 rows x sw_cols) -> global, 16 bytes per lane, lanes contiguous along the row
-          __half* obase = static_cast<__half*>(p.out) + static_cast<size_t>(m0 + quarter * 32) * p.out_ld + p.out_coff + n0 + cg;
-          int ur = u_row0, uc = u_col0;
           const int rows_left = p.M_total - (m0 + quarter * 32);
+          int ur = u_row0, uc = u_col0;
+          uint32_t sp = my_out + static_cast<uint32_t>(u_row0 * out_pitch + u_col0 * 16);
+          uint8_t* gp = reinterpret_cast<uint8_t*>(static_cast<__half*>(p.out) + static_cast<size_t>(m0 + quarter * 32 + u_row0) * p.out_ld +
+                                                   p.out_coff + n0 + cg + u_col0 * 8);
+          const uint32_t s_step = static_cast<uint32_t>(u_drow * out_pitch + u_dcol * 16), s_wrap = static_cast<uint32_t>(out_pitch - U * 16);
+          const long long g_step = static_cast<long long>(u_drow) * p.out_ld * 2 + u_dcol * 16, g_wrap = static_cast<long long>(p.out_ld) * 2 - U * 16;
+          const bool do_store = !(p.flags & CF_DBG_NOSTORE);
           for (int it2 = 0; it2 < U; ++it2) {
-            if (ur < rows_left) {
-              const uint4 val = lds128(my_out + static_cast<uint32_t>(ur * out_pitch + uc * 16));
-              *reinterpret_cast<uint4*>(obase + static_cast<size_t>(ur) * p.out_ld + uc * 8) = val;
-            }
-            ur += u_drow; uc += u_dcol;
-            if (uc >= U) { uc -= U; ++ur; }
+            if (ur < rows_left && do_store) *reinterpret_cast<uint4*>(gp) = lds128(sp);
+            ur += u_drow; uc += u_dcol; sp += s_step; gp += g_step;
+            if (uc >= U) { uc -= U; ++ur; sp += s_wrap; gp += g_wrap; }
           }
           __syncwarp();
         }
@@ -286,51 +307,47 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     // ---------------------------------------------------------------- A gather producers (8 warps)
     const int g = threadIdx.x - 192;                // 0..255
     const int chunk = g & 7, rbase = g >> 3;        // 8 lanes cover one 128-byte row; rows rbase + 32*i
-    const bool use_l1 = p.flags & CF_GATHER_L1;
-    const uint32_t sw_const = static_cast<uint32_t>(rbase * 128 + ((chunk ^ (rbase & 7)) << 4));   // (row & 7) == (rbase & 7)
+    const uint32_t sw_const = smem_u32(sA) + static_cast<uint32_t>(rbase * 128 + ((chunk ^ (rbase & 7)) << 4));   // (row & 7) == (rbase & 7)
     const int HoWo = p.Ho * p.Wo;
+    const bool do_copy = !(p.flags & CF_DBG_NOGATHER);
+    const __half* __restrict__ inp = p.in;
     if (p.pdl) pdl_wait();
-    int it = 0;
+    int s = 0;
+    uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.n_tiles) * CONV_BM;
+      const int m0 = fdiv(tile, p.d_ntiles) * CONV_BM;
       int base_off[CONV_ROWS_PER_GATHER_THREAD];
-      uint32_t vmask[CONV_ROWS_PER_GATHER_THREAD];  // bits 0..6: tap rows r with ih in range; bits 8..14: tap cols s with iw in range
+      uint32_t vmask[CONV_ROWS_PER_GATHER_THREAD];  // bits 0..7: tap rows r with ih in range; bits 8..15: tap cols s with iw in range
 #pragma unroll
       for (int i = 0; i < CONV_ROWS_PER_GATHER_THREAD; ++i) {
         const int m = m0 + rbase + 32 * i;
-        vmask[i] = 0; base_off[i] = 0;
-        if (m < p.M_total) {
-          const int n = fdiv(m, p.d_howo), rem = m - n * HoWo;
-          const int ho = fdiv(rem, p.d_wo), wo = rem - ho * p.Wo;
-          const int ih0 = ho * p.stride - p.pad_h, iw0 = wo * p.stride - p.pad_w;
-          base_off[i] = ((n * p.H + ih0) * p.W + iw0) * p.in_ld + p.in_coff;
-          uint32_t mk = 0;
-#pragma unroll
-          for (int t = 0; t < 7; ++t) {
-            if (t < p.kh && static_cast<unsigned>(ih0 + t) < static_cast<unsigned>(p.H)) mk |= 1u << t;
-            if (t < p.kw && static_cast<unsigned>(iw0 + t) < static_cast<unsigned>(p.W)) mk |= 1u << (8 + t);
-          }
-          vmask[i] = mk;
-        }
+        const int n = fdiv(m, p.d_howo), rem = m - n * HoWo;
+        const int ho = fdiv(rem, p.d_wo), wo = rem - ho * p.Wo;
+        const int ih0 = ho * p.stride - p.pad_h, iw0 = wo * p.stride - p.pad_w;
+        base_off[i] = ((n * p.H + ih0) * p.W + iw0) * p.in_ld + p.in_coff;
+        // taps r in [max(0,-ih0), min(kh, H-ih0)) and s in [max(0,-iw0), min(kw, W-iw0)) read inside the image
+        const int r_lo = max(0, -ih0), r_hi = min(p.kh, p.H - ih0), c_lo = max(0, -iw0), c_hi = min(p.kw, p.W - iw0);
+        const uint32_t rm = r_hi > r_lo ? ((1u << r_hi) - (1u << r_lo)) : 0u;
+        const uint32_t cm = c_hi > c_lo ? ((1u << c_hi) - (1u << c_lo)) : 0u;
+        vmask[i] = m < p.M_total ? (rm | (cm << 8)) : 0u;
       }
-      for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        const int k = kb * 64 + chunk * 8;
+      int k = chunk * 8;
+      for (int kb = 0; kb < p.nkb; ++kb, k += 64) {
         const int tap = fdiv(k, p.d_cin), c = k - tap * p.cin;
         const int r = fdiv(tap, p.d_kw), sx = tap - r * p.kw;
-        const uint32_t need = k < p.k_real ? ((1u << r) | (1u << (8 + sx))) : 0xFFFFFFFFu;   // K tail: never valid
+        const uint32_t need = k < p.k_real ? ((1u << r) | (256u << sx)) : 0xFFFFFFFFu;   // K tail: never valid
         const int tap_off = (r * p.W + sx) * p.in_ld + c;
-        const uint32_t a_s = smem_u32(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES) + sw_const;
+        const uint32_t a_s = sw_const + static_cast<uint32_t>(s * CONV_A_STAGE_BYTES);
         mbar_wait(&empty[s], ph ^ 1, 13);
+        if (do_copy) {
 #pragma unroll
-        for (int i = 0; i < CONV_ROWS_PER_GATHER_THREAD; ++i) {
-          const bool ok = (vmask[i] & need) == need;
-          const __half* src = ok ? p.in + (base_off[i] + tap_off) : p.in;
-          if (use_l1) cp_async_16_ca(a_s + i * 32 * 128, src, ok);
-          else cp_async_16(a_s + i * 32 * 128, src, ok);
+          for (int i = 0; i < CONV_ROWS_PER_GATHER_THREAD; ++i) {
+            const bool ok = (vmask[i] & need) == need;
+            cp_async_16(a_s + i * 32 * 128, inp + (ok ? base_off[i] + tap_off : 0), ok);
+          }
         }
         cp_async_mbar_arrive_noinc(&full[s]);         // counted arrival fires when this thread's copies have landed
+        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
     cp_async_wait_all();                              // do not exit with copies in flight
@@ -343,7 +360,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
-      const int n0 = (tile % p.n_tiles) * p.bn_tile, m0 = (tile / p.n_tiles) * CONV_BM;
+      const int mt = fdiv(tile, p.d_ntiles);
+      const int n0 = (tile - mt * p.n_tiles) * p.bn_tile, m0 = mt * CONV_BM;
       mbar_wait(&res_empty[buf], ((lt >> 1) & 1) ^ 1, 17);
       const uint32_t dst0 = smem_u32(sRes) + static_cast<uint32_t>(buf * CONV_BM * res_pitch);
       for (int u = g; u < total_units; u += CONV_HELPER_THREADS) {

@@ -172,6 +172,7 @@ struct fire_net {
   bool pdl = true;        // programmatic dependent launch between conv layers (FIRE_B200_PDL=0 disables)
   bool gather_l1 = false; // cp.async.ca instead of .cg for the A gather (FIRE_B200_GATHER_L1=1)
   int max_stages = 8;
+  int dbg_flags = 0;      // FIRE_B200_DBG: timing experiments (1 = no gather copies, 2 = no epilogue stores, 4 = no MMA)
 };
 
 static int pow2_cols(int n) {
@@ -242,6 +243,8 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
   net->pdl = !(pdl_env && pdl_env[0] == '0');
   const char* l1_env = getenv("FIRE_B200_GATHER_L1");
   net->gather_l1 = l1_env && l1_env[0] == '1';
+  const char* dbg_env = getenv("FIRE_B200_DBG");
+  if (dbg_env) net->dbg_flags = (atoi(dbg_env) & 7) << 16;
   const char* st_env = getenv("FIRE_B200_MAX_STAGES");
   if (st_env) net->max_stages = std::max(3, std::min(12, atoi(st_env)));
   *out = net;
@@ -293,9 +296,10 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
     p.nkb = o.k_pad / 64; p.flags = o.flags; p.bn_tile = r.bn_tile; p.M_total = B * o.Ho * o.Wo;
     p.stages = r.stages; p.tma_a = r.tma_a ? 1 : 0; p.tmem_cols = r.tmem_cols;
     p.m_tiles = r.m_tiles; p.n_tiles = r.n_tiles; p.pdl = pdl ? 1 : 0;
-    if (net->gather_l1) p.flags |= CF_GATHER_L1;
+    p.flags |= net->dbg_flags;
     p.res_smem = r.res_smem ? 1 : 0;
     p.d_howo = make_fastdiv(o.Ho * o.Wo); p.d_wo = make_fastdiv(o.Wo); p.d_cin = make_fastdiv(o.cin); p.d_kw = make_fastdiv(o.kw);
+    p.d_ntiles = make_fastdiv(r.n_tiles);
     p.d_unit_res = make_fastdiv(r.bn_tile / 8); p.d_unit_out = make_fastdiv(std::min(r.bn_tile, CONV_STAGE_COLS) / 8);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)std::min<long long>((long long)r.m_tiles * r.n_tiles, device_sm_count()));

@@ -44,21 +44,24 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the warp SLEEPS in hardware until the phase completes (or ~10 ms pass)
+// instead of spinning, so waiting roles do not steal issue slots from the warps doing the work.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680)
       : "memory");
   return ok != 0;
 }
 static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag) {
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > FIRE_WATCHDOG_CYCLES) {
+  const long long t0 = clock64();
+  for (int spin = 0;; ++spin) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((spin & 15) == 15 && clock64() - t0 > FIRE_WATCHDOG_CYCLES) {
       printf("fire_b200: mbarrier watchdog (tag %d, block %d,%d, thread %d, parity %u)\n", tag, blockIdx.x,
              blockIdx.y, threadIdx.x, parity);
       __trap();
