@@ -60,11 +60,13 @@ class ShardedGallery:
             return d, i
         d = d if torch.is_tensor(d) else torch.from_numpy(np.ascontiguousarray(d))
         i = i if torch.is_tensor(i) else torch.from_numpy(np.ascontiguousarray(i))
-        gd = torch.empty((self.world,) + tuple(d.shape), dtype=d.dtype, device=d.device)
-        gi = torch.empty((self.world,) + tuple(i.shape), dtype=i.dtype, device=i.device)
+        Q, k = d.shape
+        # rank-major concatenation == [G][Q][k] in memory (the layout fire_knn_merge reads); gloo accepts only this form
+        gd = torch.empty((self.world * Q, k), dtype=d.dtype, device=d.device)
+        gi = torch.empty((self.world * Q, k), dtype=i.dtype, device=i.device)
         dist.all_gather_into_tensor(gd, d.contiguous(), group=self.group)
         dist.all_gather_into_tensor(gi, i.contiguous(), group=self.group)
-        return self.merge_fn(gd, gi)
+        return self.merge_fn(gd.view(self.world, Q, k), gi.view(self.world, Q, k))
 
 
 def gather_embeddings(local_emb, world: int, group=None):
