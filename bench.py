@@ -158,6 +158,8 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------------
 def run_fire(args):
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line (NCCL prints its version there)
     import torch
     import torch.distributed as dist
     rank, world, local = dist_env()
