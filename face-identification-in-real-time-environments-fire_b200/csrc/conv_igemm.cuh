@@ -9,6 +9,12 @@
 // Persistent CTAs (one per SM) walk the (m-tile, n-tile) list; the warp roles run concurrently:
 //   warp 0      TMA producer: weight K-blocks (always) and, for 1x1/stride-1 layers, the activation
 //               K-blocks too (the activation matrix [M, C] is then a plain 2-D tensor);
+//   warps 14-16 extra TMA producers.  Measured on B200 (tools/umma_probe.cu part 3/4): the chain
+//               try_wait -> arrive.expect_tx -> cp.async.bulk.tensor costs one thread ~600-800 cycles per
+//               stage whatever the box size, i.e. ONE issuing thread tops out near 20 B/clk/SM, while
+//               issuers in different warps scale linearly (4 x 16 KB boxes reach the 17 TB/s L2 limit).
+//               Stages are therefore dealt round-robin to n_issuers threads in different warps; n_issuers
+//               divides the ring depth, so a slot always belongs to the same thread (parity waits cannot alias);
 //   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=bn_tile, K=16) into one of TWO
 //               TMEM accumulators, so the epilogue of tile t overlaps the main loop of tile t+1;
 //   warps 2-5   epilogue: tcgen05.ld -> +bias (smem) -> +residual (smem) -> ReLU -> fp16 -> per-warp
@@ -33,7 +39,8 @@ namespace fire {
 constexpr int CONV_BM = 128;
 constexpr int CONV_HELPER_WARPS = 8;
 constexpr int CONV_HELPER_THREADS = CONV_HELPER_WARPS * 32;            // 256
-constexpr int CONV_THREADS = 64 + 128 + CONV_HELPER_THREADS;           // 448
+constexpr int CONV_EXTRA_ISSUERS = 3;                                   // warps 14..16: additional TMA issuing threads
+constexpr int CONV_THREADS = 64 + 128 + CONV_HELPER_THREADS + 32 * CONV_EXTRA_ISSUERS;   // 544
 constexpr int CONV_ROWS_PER_GATHER_THREAD = CONV_BM / (CONV_HELPER_THREADS / 8);   // 4
 constexpr int CONV_A_STAGE_BYTES = CONV_BM * 128;
 constexpr int CONV_MAX_COUT = 1792;
@@ -58,6 +65,8 @@ struct ConvParams {
   int cin, cout, k_real, nkb, flags, bn_tile, M_total, stages, tma_a, tmem_cols;
   int m_tiles, n_tiles, pdl;
   int res_smem;                 // residual tile prefetched into smem by the helper warps (tma_a && residual)
+  long long* trace;             // debug timeline: [gridDim.x][8] globaltimer stamps (nullptr = off)
+  int n_issuers;                // TMA issuing threads (1, 2 or 4; divides `stages`), stage g is issued by thread g % n_issuers
   FastDiv d_howo, d_wo, d_cin, d_kw, d_unit_res, d_unit_out, d_ntiles;
 };
 
@@ -69,6 +78,12 @@ __device__ __forceinline__ void tmem_alloc_rt(uint32_t* smem_slot, uint32_t cols
 __device__ __forceinline__ void tmem_dealloc_rt(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define CONV_TRACE(slot) do { if (p.trace) p.trace[blockIdx.x * 8 + (slot)] = globaltimer_ns(); } while (0)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -134,6 +149,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
+  if (threadIdx.x == 0) CONV_TRACE(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_w);
@@ -159,26 +175,32 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) CONV_TRACE(1);
   if (p.pdl) pdl_launch_dependents();               // let the next layer start its own prologue
 
-  if (warp == 0) {
-    // ---------------------------------------------------------------- TMA producer
-    if (lane == 0) {
+  const int issuer = warp == 0 ? 0 : (warp >= 14 ? warp - 13 : -1);
+  if (issuer >= 0) {
+    // ---------------------------------------------------------------- TMA producers (stage g belongs to issuer g % n_issuers)
+    if (lane == 0 && issuer < p.n_issuers) {
       const uint32_t tx = static_cast<uint32_t>(b_stage_bytes) + (p.tma_a ? CONV_A_STAGE_BYTES : 0);
       bool waited = !p.pdl || !p.tma_a;
-      int s = 0;
+      int s = 0, turn = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = fdiv(tile, p.d_ntiles);
         const int n0 = (tile - mt * p.n_tiles) * p.bn_tile, m0 = mt * CONV_BM;
         for (int kb = 0; kb < p.nkb; ++kb) {
-          mbar_wait(&empty[s], ph ^ 1, 11);
-          mbar_arrive_expect_tx(&full[s], tx);
-          tma_load_2d_hint(sB + static_cast<size_t>(s) * b_stage_bytes, &tmap_w, &full[s], kb * 64, n0, kEvictLast);
-          if (p.tma_a) {
-            if (!waited) { pdl_wait(); waited = true; }     // activations come from the previous layer
-            tma_load_2d(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES, &tmap_a, &full[s], kb * 64, m0);
+          if (turn == issuer) {
+            mbar_wait(&empty[s], ph ^ 1, 11);
+            mbar_arrive_expect_tx(&full[s], tx);
+            tma_load_2d_hint(sB + static_cast<size_t>(s) * b_stage_bytes, &tmap_w, &full[s], kb * 64, n0, kEvictLast);
+            if (p.tma_a) {
+              if (!waited) { pdl_wait(); waited = true; }     // activations come from the previous layer
+              tma_load_2d(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES, &tmap_a, &full[s], kb * 64, m0);
+            }
+            if (issuer == 0 && tile == blockIdx.x && kb == 0) CONV_TRACE(2);
           }
+          if (++turn == p.n_issuers) turn = 0;
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -197,6 +219,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(&full[s], ph, 12);
           tc_fence_after();
+          if (lt == 0 && kb == 0) CONV_TRACE(3);
           const uint32_t a0 = smem_u32(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES);
           const uint32_t b0 = smem_u32(sB + static_cast<size_t>(s) * b_stage_bytes);
           if (!(p.flags & CF_DBG_NOMMA))
@@ -208,6 +231,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         }
         umma_commit(&acc_full[buf]);
       }
+      CONV_TRACE(4);
     }
   } else if (warp < 6) {
     // ---------------------------------------------------------------- epilogue (4 warps)
@@ -235,6 +259,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       if (res_smem) mbar_wait(&res_full[buf], (lt >> 1) & 1, 16);
       mbar_wait(&acc_full[buf], (lt >> 1) & 1, 14);
       tc_fence_after();
+      if (lt == 0 && threadIdx.x == 64) CONV_TRACE(5);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * p.bn_tile);
       for (int cg = 0; cg < p.bn_tile; cg += sw_cols) {
         const int n_chunks = sw_cols >> 4;
@@ -303,6 +328,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         }
       }
     }
+    if (threadIdx.x == 64) CONV_TRACE(6);
   } else if (!p.tma_a) {
     // ---------------------------------------------------------------- A gather producers (8 warps)
     const int g = threadIdx.x - 192;                // 0..255
@@ -381,6 +407,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     tc_fence_after();
     tmem_dealloc_rt(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
+  if (threadIdx.x == 0) CONV_TRACE(7);
 }
 
 }  // namespace fire

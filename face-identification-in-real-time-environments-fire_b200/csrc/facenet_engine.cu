@@ -7,6 +7,7 @@
 // descriptors once, and on every forward() enqueues one kernel per op on the caller's stream:
 //   conv_igemm_kernel (tcgen05)  x 105,  maxpool3x3s2_kernel x 3,  gap_kernel x 1,  l2norm_kernel x 1.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -125,7 +126,7 @@ struct OpRt {
   CUtensorMap tmap_w;     // weights [cout][k_pad], box rows = bn_tile (rebuilt when the tiling changes with B)
   CUtensorMap tmap_a;     // activation matrix for TMA-mode convs (rebuilt when pointers / B change)
   bool tma_a = false;
-  int bn_tile = 0, stages = 0, tmem_cols = 0, m_tiles = 0, n_tiles = 0;
+  int bn_tile = 0, stages = 0, n_issuers = 1, tmem_cols = 0, m_tiles = 0, n_tiles = 0;
   bool res_smem = false;
   size_t smem = 0;
   double flops_per_image = 0;
@@ -172,6 +173,8 @@ struct fire_net {
   bool pdl = true;        // programmatic dependent launch between conv layers (FIRE_B200_PDL=0 disables)
   bool gather_l1 = false; // cp.async.ca instead of .cg for the A gather (FIRE_B200_GATHER_L1=1)
   int max_stages = 8;
+  int n_issuers = 1 + CONV_EXTRA_ISSUERS;   // TMA issuing threads per CTA (FIRE_B200_ISSUERS=1..3)
+  long long* d_trace = nullptr; int trace_op = -1;   // FIRE_B200_TRACE_OP=<op index>: in-kernel timeline of that op (profile only)
   int dbg_flags = 0;      // FIRE_B200_DBG: timing experiments (1 = no gather copies, 2 = no epilogue stores, 4 = no MMA)
 };
 
@@ -245,6 +248,13 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
   net->gather_l1 = l1_env && l1_env[0] == '1';
   const char* dbg_env = getenv("FIRE_B200_DBG");
   if (dbg_env) net->dbg_flags = (atoi(dbg_env) & 7) << 16;
+  const char* tr_env = getenv("FIRE_B200_TRACE_OP");
+  if (tr_env && atoi(tr_env) >= 0 && atoi(tr_env) < (int)net->ops.size()) {
+    net->trace_op = atoi(tr_env);
+    cudaMalloc(&net->d_trace, 8 * 8 * 256);
+  }
+  const char* is_env = getenv("FIRE_B200_ISSUERS");
+  if (is_env) net->n_issuers = std::max(1, std::min(1 + CONV_EXTRA_ISSUERS, atoi(is_env)));   // 1, 2 or 4 are used
   const char* st_env = getenv("FIRE_B200_MAX_STAGES");
   if (st_env) net->max_stages = std::max(3, std::min(12, atoi(st_env)));
   *out = net;
@@ -254,6 +264,7 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
 int fire_facenet_destroy(fire_net_t* net) {
   if (!net) return FIRE_OK;
   cudaFree(net->d_weights);
+  cudaFree(net->d_trace);
   delete net;
   return FIRE_OK;
 }
@@ -298,6 +309,8 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
     p.m_tiles = r.m_tiles; p.n_tiles = r.n_tiles; p.pdl = pdl ? 1 : 0;
     p.flags |= net->dbg_flags;
     p.res_smem = r.res_smem ? 1 : 0;
+    p.n_issuers = r.n_issuers;
+    p.trace = (net->d_trace && &r == &net->ops[net->trace_op]) ? net->d_trace : nullptr;
     p.d_howo = make_fastdiv(o.Ho * o.Wo); p.d_wo = make_fastdiv(o.Wo); p.d_cin = make_fastdiv(o.cin); p.d_kw = make_fastdiv(o.kw);
     p.d_ntiles = make_fastdiv(r.n_tiles);
     p.d_unit_res = make_fastdiv(r.bn_tile / 8); p.d_unit_out = make_fastdiv(std::min(r.bn_tile, CONV_STAGE_COLS) / 8);
@@ -357,6 +370,10 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
       const size_t fixed = 1024 + CONV_MAX_COUT * sizeof(float) + out_stage + res_stage + 256;
       r.stages = (int)std::min<size_t>(net->max_stages, (232448 - fixed) / stage);
       if (r.stages < 2) return fail(FIRE_ERR_UNSUPPORTED, "conv tile %d does not fit shared memory", bn);
+      // TMA issuing threads: the ring depth is rounded down to a multiple of their number (see conv_igemm.cuh)
+      r.n_issuers = 1;
+      for (int j = 4; j >= 2; j >>= 1)
+        if (j <= net->n_issuers && r.stages >= j) { r.n_issuers = j; r.stages = r.stages / j * j; break; }
       r.smem = fixed + r.stages * stage;
       r.res_smem = res_smem;
       r.tmem_cols = pow2_cols(2 * bn);
@@ -411,6 +428,22 @@ int fire_facenet_profile(fire_net_t* net, const void* in_f16, int B, void* works
     for (size_t i = 0; i < net->ops.size(); ++i) {
       cudaEventElapsedTime(&host_ms[i], ev[i], ev[i + 1]);
       if (host_flops) host_flops[i] = net->ops[i].flops_per_image * B;
+    }
+  }
+  if (net->d_trace && rc == FIRE_OK && e == cudaSuccess) {
+    std::vector<long long> t(8 * 256);
+    cudaMemcpy(t.data(), net->d_trace, t.size() * 8, cudaMemcpyDeviceToHost);
+    const OpRt& r = net->ops[net->trace_op];
+    const int grid = (int)std::min<long long>((long long)r.m_tiles * r.n_tiles, device_sm_count());
+    long long t0 = t[0];
+    for (int c = 0; c < grid; ++c) t0 = std::min(t0, t[c * 8]);
+    const char* names[8] = {"entry", "setup done", "first TMA issued", "first full", "last MMA commit", "first acc_full", "epilogue done", "exit"};
+    fprintf(stderr, "trace op %d: grid %d, tiles %d x %d, bn %d, nkb %d, stages %d, issuers %d, event ms %.4f\n", net->trace_op, grid,
+            r.m_tiles, r.n_tiles, r.bn_tile, r.op.k_pad / 64, r.stages, r.n_issuers, host_ms[net->trace_op]);
+    for (int k = 0; k < 8; ++k) {
+      long long mn = 1ll << 62, mx = 0; double avg = 0;
+      for (int c = 0; c < grid; ++c) { long long v = t[c * 8 + k] - t0; mn = std::min(mn, v); mx = std::max(mx, v); avg += (double)v; }
+      fprintf(stderr, "  %-18s min %7lld  avg %9.0f  max %7lld ns after the first CTA entered\n", names[k], mn, avg / grid, mx);
     }
   }
   for (auto& x : ev) cudaEventDestroy(x);

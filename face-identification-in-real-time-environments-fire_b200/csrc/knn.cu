@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 
 #include "fire_common.cuh"
@@ -26,7 +27,8 @@ namespace fire {
 
 constexpr int KNN_BM = 128;                  // queries per CTA  (UMMA M)
 constexpr int KNN_BN = 256;                  // gallery rows per accumulator tile (UMMA N)
-constexpr int KNN_THREADS = 192;             // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int KNN_ISSUERS = 3;               // max TMA issuing threads: one thread sustains only ~1 box per 600-800 cycles (tools/umma_probe.cu)
+constexpr int KNN_THREADS = 192 + 32 * (KNN_ISSUERS - 1);   // warp0 TMA, warp1 MMA, warps 2..5 epilogue, warps 6.. extra TMA issuers
 constexpr int KNN_A_KB_BYTES = KNN_BM * 128; // one 64-wide K block of the query tile
 constexpr int KNN_B_STAGE_BYTES = KNN_BN * 128;
 constexpr int KNN_MAX_LISTS_PER_LANE = 10;   // merge routines handle up to 320 sorted lists
@@ -40,6 +42,7 @@ struct KnnScanParams {
   int rows_per_split;   // multiple of KNN_BN
   int QB;               // query blocks of 128
   int stages;
+  int n_issuers;        // divides `stages`, so a ring slot always belongs to the same issuing thread (no parity aliasing)
   float* cand_score;    // [QB*128][S][KP]
   uint32_t* cand_idx;
 };
@@ -172,20 +175,26 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      mbar_arrive_expect_tx(a_full, static_cast<uint32_t>(p.nkb) * KNN_A_KB_BYTES);
-      for (int kb = 0; kb < p.nkb; ++kb)
-        tma_load_2d_hint(sA + static_cast<size_t>(kb) * KNN_A_KB_BYTES, &tmap_q, a_full, kb * 64, qb * KNN_BM, kEvictLast);
-      int it = 0;
+  const int issuer = warp == 0 ? 0 : (warp >= 6 ? warp - 5 : -1);
+  if (issuer >= 0) {
+    // ------------------------------------------------------------------ TMA producers (stage `it` belongs to issuer it % n_issuers)
+    if (lane == 0 && issuer < p.n_issuers) {
+      if (issuer == 0) {
+        mbar_arrive_expect_tx(a_full, static_cast<uint32_t>(p.nkb) * KNN_A_KB_BYTES);
+        for (int kb = 0; kb < p.nkb; ++kb)
+          tma_load_2d_hint(sA + static_cast<size_t>(kb) * KNN_A_KB_BYTES, &tmap_q, a_full, kb * 64, qb * KNN_BM, kEvictLast);
+      }
+      int it = 0, s = 0, turn = 0;
+      uint32_t ph = 0;
       for (int t = 0; t < n_tiles; ++t) {
         for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(&empty[s], ph ^ 1, 1);
-          mbar_arrive_expect_tx(&full[s], KNN_B_STAGE_BYTES);
-          tma_load_2d(sB + static_cast<size_t>(s) * KNN_B_STAGE_BYTES, &tmap_g, &full[s], kb * 64, row0 + t * KNN_BN);
+          if (turn == issuer) {
+            mbar_wait(&empty[s], ph ^ 1, 1);
+            mbar_arrive_expect_tx(&full[s], KNN_B_STAGE_BYTES);
+            tma_load_2d(sB + static_cast<size_t>(s) * KNN_B_STAGE_BYTES, &tmap_g, &full[s], kb * 64, row0 + t * KNN_BN);
+          }
+          if (++turn == p.n_issuers) turn = 0;
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -829,6 +838,11 @@ int fire_knn_search(fire_knn_t* h, const float* queries, int Q, int k, int64_t i
   int stages = static_cast<int>((KNN_SMEM_BUDGET - a_bytes - bar_bytes) / KNN_B_STAGE_BYTES);
   stages = std::max(2, std::min(stages, 6));
   p.stages = stages;
+  p.n_issuers = stages % 3 == 0 ? 3 : (stages % 2 == 0 ? 2 : 1);
+  if (const char* e = getenv("FIRE_B200_KNN_ISSUERS")) {            // A/B experiments only
+    const int j = atoi(e);
+    if (j >= 1 && j <= KNN_ISSUERS && stages % j == 0) p.n_issuers = j;
+  }
   p.cand_score = h->cand_score; p.cand_idx = h->cand_idx;
   const size_t smem_bytes = 1024 + a_bytes + static_cast<size_t>(stages) * KNN_B_STAGE_BYTES + bar_bytes;
 
