@@ -3,32 +3,33 @@
 // One launch = one Conv(+folded BN)(+bias)(+residual)(+ReLU) layer of the FaceNet plan
 // (reference: the onnxruntime session at facenet_gpu.py:127; graph in SURVEY App. A).
 //
-//   D[m, n] = sum_k A[m, k] * W[n, k]      m = output pixel (b, ho, wo), n = output channel,
-//                                          k = (tap r,s ; input channel c), tap-major
+//   D[m, n] = bias[n] + sum_k A[m, k] * W[n, k] (+ R[m, n])      m = output pixel (b, ho, wo), n = output channel,
+//                                                                 k = (tap r,s ; input channel c), tap-major
 //
-// Persistent CTAs (one per SM) walk the (m-tile, n-tile) list; the warp roles run concurrently:
-//   warp 0      TMA producer: weight K-blocks (always) and, for 1x1/stride-1 layers, the activation
-//               K-blocks too (the activation matrix [M, C] is then a plain 2-D tensor);
-//   warps 14-16 extra TMA producers.  Measured on B200 (tools/umma_probe.cu part 3/4): the chain
-//               try_wait -> arrive.expect_tx -> cp.async.bulk.tensor costs one thread ~600-800 cycles per
-//               stage whatever the box size, i.e. ONE issuing thread tops out near 20 B/clk/SM, while
-//               issuers in different warps scale linearly (4 x 16 KB boxes reach the 17 TB/s L2 limit).
-//               Stages are therefore dealt round-robin to n_issuers threads in different warps; n_issuers
-//               divides the ring depth, so a slot always belongs to the same thread (parity waits cannot alias);
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=bn_tile, K=16) into one of TWO
-//               TMEM accumulators, so the epilogue of tile t overlaps the main loop of tile t+1;
-//   warps 2-5   epilogue: tcgen05.ld -> +bias (smem) -> +residual (smem) -> ReLU -> fp16 -> per-warp
-//               smem staging -> row-contiguous 16-byte global stores at a channel offset of the
-//               destination buffer (concat for free).  Thread = accumulator row only while talking
-//               to TMEM; every global access is coalesced along the channel dimension;
-//   warps 6-13  helpers.  k x k / strided / padded layers: A-gather producers - 16-byte cp.async
-//               (zero-fill for padding and the K tail) straight into the 128-byte-swizzled layout the
-//               UMMA descriptor expects, each thread's cp.async.mbarrier.arrive.noinc signalling the
-//               stage when its copies land; index math uses precomputed magic-number division and
-//               per-row tap-validity masks.  1x1 layers with a residual: the same warps prefetch the
-//               residual tile of the NEXT tile into a double-buffered smem stage with coalesced cp.async.
+// EVERYTHING additive runs on the tensor core, so the epilogue is only "convert and store":
+//   * bias      : the first MMA of a tile is ones[128 x 16] * biasT[bn x 16]^T with accumulate = 0, where the bias
+//                 row holds fp16 hi and lo parts of the fp32 bias (hi + lo carries ~22 bits) - it initialises TMEM;
+//   * residual  : x + up(cat) is "one more K block": the residual tile [128 x 64] is TMA-loaded like an activation
+//                 K-block and multiplied by a constant 64 x 64 identity (exact: fp16 * 1.0 accumulated in fp32).
+//
+// Persistent CTAs (one per SM) walk the (m-tile, n-tile) list; warp roles:
+//   warp 0      TMA producer: weight K-blocks (always); for 1x1/stride-1 layers also the activation K-blocks (the
+//               activation matrix [M, C] is a plain 2-D tensor) and the residual K-blocks;
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=bn_tile, K=16) into one of TWO TMEM accumulators,
+//               so the epilogue of tile t overlaps the main loop of tile t+1;
+//   warps 2-9   epilogue, two warps per TMEM lane quarter, 16-column chunks interleaved between them:
+//               tcgen05.ld -> cvt.rn[.relu].satfinite.f16x2 -> swizzled smem staging -> TMA store (one lane per quarter)
+//               at a channel offset of the destination buffer (concat for free); rows past M are clipped by the TMA;
+//   warps 10-17 k x k / strided / padded layers: A-gather producers - 16-byte cp.async (zero-fill for padding and
+//               the K tail) straight into the 128-byte-swizzled layout the UMMA descriptor expects, each thread's
+//               cp.async.mbarrier.arrive.noinc signalling the stage when its copies land.
+//               1x1 layers: warps 10-12 are extra TMA issuers.  Measured on B200 (tools/umma_probe.cu part 3/4): the
+//               chain try_wait -> arrive.expect_tx -> cp.async.bulk.tensor costs one thread ~600-800 cycles per
+//               stage whatever the box size, while issuers in different warps scale linearly; stages are dealt
+//               round-robin to n_issuers threads, n_issuers divides the ring depth so a slot always belongs to the
+//               same thread (parity waits cannot alias).
 // The smem ring runs across tile boundaries, so a CTA never drains its pipeline between tiles.
-// With programmatic dependent launch the prologue (barriers, TMEM, bias, descriptor prefetch) of
+// With programmatic dependent launch the prologue (barriers, TMEM, constants, descriptor prefetch) of
 // layer i+1 overlaps the tail of layer i; griddepcontrol.wait guards the first activation access.
 #pragma once
 
@@ -37,14 +38,17 @@
 namespace fire {
 
 constexpr int CONV_BM = 128;
+constexpr int CONV_EPI_WARPS = 8;
+constexpr int CONV_FIRST_EPI_WARP = 2;
+constexpr int CONV_FIRST_HELPER_WARP = CONV_FIRST_EPI_WARP + CONV_EPI_WARPS;      // 10
 constexpr int CONV_HELPER_WARPS = 8;
-constexpr int CONV_HELPER_THREADS = CONV_HELPER_WARPS * 32;            // 256
-constexpr int CONV_EXTRA_ISSUERS = 3;                                   // warps 14..16: additional TMA issuing threads
-constexpr int CONV_THREADS = 64 + 128 + CONV_HELPER_THREADS + 32 * CONV_EXTRA_ISSUERS;   // 544
-constexpr int CONV_ROWS_PER_GATHER_THREAD = CONV_BM / (CONV_HELPER_THREADS / 8);   // 4
+constexpr int CONV_HELPER_THREADS = CONV_HELPER_WARPS * 32;                       // 256
+constexpr int CONV_THREADS = 32 * (CONV_FIRST_HELPER_WARP + CONV_HELPER_WARPS);   // 576
+constexpr int CONV_MAX_ISSUERS = 4;                                               // warp 0 + helper warps 10..12
+constexpr int CONV_ROWS_PER_GATHER_THREAD = CONV_BM / (CONV_HELPER_THREADS / 8);  // 4
 constexpr int CONV_A_STAGE_BYTES = CONV_BM * 128;
 constexpr int CONV_MAX_COUT = 1792;
-constexpr int CONV_STAGE_COLS = 128;       // columns staged per epilogue pass (sOut width)
+constexpr int CONV_PASS_COLS = 128;        // columns staged per epilogue pass
 
 constexpr int CF_RELU = 1, CF_RESIDUAL = 2, CF_OUT_F32 = 4;
 constexpr int CF_DBG_NOGATHER = 1 << 16, CF_DBG_NOSTORE = 1 << 17, CF_DBG_NOMMA = 1 << 18;   // timing experiments only (wrong results)
@@ -56,18 +60,38 @@ __device__ __forceinline__ int fdiv(int x, FastDiv f) {
   return static_cast<int>((static_cast<unsigned long long>(static_cast<uint32_t>(x)) * f.mul) >> f.sh);
 }
 
+// Shared-memory carve-up, computed identically on the host (sizing) and the device.
+struct ConvSmem {
+  uint32_t a, b, bias, ones, zero, ident, out, bars, total;
+};
+__host__ __device__ inline ConvSmem conv_smem_layout(int stages, int bn, int cout, int n_res) {
+  ConvSmem L;
+  uint32_t o = 0;
+  L.a = o;     o += static_cast<uint32_t>(stages) * CONV_A_STAGE_BYTES;
+  L.b = o;     o += static_cast<uint32_t>(stages) * bn * 128;
+  L.bias = o;  o += static_cast<uint32_t>(cout) * 16;       // [cout] x {hi, lo, 0 x 6} fp16: K-chunk 0 of the bias operand
+  L.ones = o;  o += CONV_BM * 16;                           // [128] x {1, 1, 0 x 6}: K-chunk 0 of the ones operand
+  L.zero = o;  o += 256 * 16;                               // K-chunk 1 of both (all zero)
+  o = (o + 1023) & ~1023u;
+  L.ident = o; o += n_res ? 64 * 128 : 0;                   // 64 x 64 identity, 128-byte swizzle
+  L.out = o;   o += 4 * 32 * (bn < CONV_PASS_COLS ? bn : CONV_PASS_COLS) * 2;   // per-quarter staging for the TMA store
+  L.bars = o;  o += 256;
+  L.total = o;
+  return L;
+}
+
 struct ConvParams {
-  const __half* in;  int in_ld, in_coff;
-  void* out;         int out_ld, out_coff;
-  const __half* res; int res_ld, res_coff;
-  const float* bias;
+  const __half* in;  int in_ld, in_coff;      // gather mode input
+  void* out;         int out_ld, out_coff;    // CF_OUT_F32 only (fp16 outputs go through tmap_out)
+  const uint4* bias16;                        // [cout] x {hi, lo, 0...} fp16
   int H, W, Ho, Wo, kh, kw, stride, pad_h, pad_w;
   int cin, cout, k_real, nkb, flags, bn_tile, M_total, stages, tma_a, tmem_cols;
   int m_tiles, n_tiles, pdl;
-  int res_smem;                 // residual tile prefetched into smem by the helper warps (tma_a && residual)
+  int n_res;                    // residual K-blocks per tile (bn_tile / 64 when CF_RESIDUAL, else 0)
+  int box_cols;                 // columns per TMA-store box: 64 / 32 / 16 (128B / 64B / 32B swizzle)
   long long* trace;             // debug timeline: [gridDim.x][8] globaltimer stamps (nullptr = off)
   int n_issuers;                // TMA issuing threads (1, 2 or 4; divides `stages`), stage g is issued by thread g % n_issuers
-  FastDiv d_howo, d_wo, d_cin, d_kw, d_unit_res, d_unit_out, d_ntiles;
+  FastDiv d_howo, d_wo, d_cin, d_kw, d_ntiles;
 };
 
 __device__ __forceinline__ void tmem_alloc_rt(uint32_t* smem_slot, uint32_t cols) {
@@ -87,89 +111,90 @@ __device__ __forceinline__ long long globaltimer_ns() {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-
-// one 16-column chunk of one accumulator row: + bias (4 x LDS.128), + residual -> 16 floats in v[]
-__device__ __forceinline__ void conv_chunk_math(const uint32_t (&r)[16], const uint4 (&q)[2], uint32_t s_bias_addr, bool has_res,
-                                                float (&v)[16]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint4 b = lds128(s_bias_addr + j * 16);
-    v[4 * j] = __uint_as_float(r[4 * j]) + __uint_as_float(b.x);
-    v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + __uint_as_float(b.y);
-    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + __uint_as_float(b.z);
-    v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + __uint_as_float(b.w);
-  }
-  if (has_res) {
-    const __half2* h0 = reinterpret_cast<const __half2*>(&q[0]);
-    const __half2* h1 = reinterpret_cast<const __half2*>(&q[1]);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f0 = __half22float2(h0[j]), f1 = __half22float2(h1[j]);
-      v[2 * j] += f0.x; v[2 * j + 1] += f0.y;
-      v[8 + 2 * j] += f1.x; v[8 + 2 * j + 1] += f1.y;
-    }
-  }
+// two fp32 accumulators -> packed fp16 pair (lo = a, hi = b), saturating at +-65504, optional ReLU: ONE F2FP each
+__device__ __forceinline__ uint32_t cvt_pack_relu(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(b)), "f"(__uint_as_float(a)));
+  return r;
 }
-// fp32 pair -> packed fp16 with ReLU (lo = 0) or without (lo = -65504) and saturation at +65504, done on the packed pair
-__device__ __forceinline__ uint32_t pack_f16x2_clamp(float a, float b, __half2 lo, __half2 hi) {
-  __half2 h = __hmin2(__hmax2(__floats2half2_rn(a, b), lo), hi);
-  return *reinterpret_cast<uint32_t*>(&h);
+__device__ __forceinline__ uint32_t cvt_pack(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(b)), "f"(__uint_as_float(a)));
+  return r;
+}
+
+// one 16-column chunk (16 fp32 accumulators of this lane's row) -> 32 bytes of fp16 in the swizzled staging box
+__device__ __forceinline__ void conv_stage_chunk(const uint32_t (&r)[16], bool relu, uint32_t row_addr, uint32_t u0, uint32_t swz) {
+  uint4 lo, hi;
+  if (relu) {
+    lo = make_uint4(cvt_pack_relu(r[0], r[1]), cvt_pack_relu(r[2], r[3]), cvt_pack_relu(r[4], r[5]), cvt_pack_relu(r[6], r[7]));
+    hi = make_uint4(cvt_pack_relu(r[8], r[9]), cvt_pack_relu(r[10], r[11]), cvt_pack_relu(r[12], r[13]), cvt_pack_relu(r[14], r[15]));
+  } else {
+    lo = make_uint4(cvt_pack(r[0], r[1]), cvt_pack(r[2], r[3]), cvt_pack(r[4], r[5]), cvt_pack(r[6], r[7]));
+    hi = make_uint4(cvt_pack(r[8], r[9]), cvt_pack(r[10], r[11]), cvt_pack(r[12], r[13]), cvt_pack(r[14], r[15]));
+  }
+  sts128(row_addr + ((u0 ^ swz) << 4), lo);
+  sts128(row_addr + (((u0 + 1) ^ swz) << 4), hi);
 }
 
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
+                  const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out,
                   const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const ConvSmem L = conv_smem_layout(p.stages, p.bn_tile, p.cout, p.n_res);
   const int b_stage_bytes = p.bn_tile * 128;
-  const int sw_cols = min(p.bn_tile, CONV_STAGE_COLS);             // columns per staging pass
-  const int out_pitch = sw_cols * 2 + 16;                          // bytes; (pitch/16) odd -> conflict-free row-per-lane access
-  const int res_pitch = p.bn_tile * 2 + 16;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + static_cast<size_t>(p.stages) * CONV_A_STAGE_BYTES;
-  float* s_bias = reinterpret_cast<float*>(sB + static_cast<size_t>(p.stages) * b_stage_bytes);
-  uint8_t* sOut = reinterpret_cast<uint8_t*>(s_bias + CONV_MAX_COUT);                  // [4 warps][32 rows][out_pitch]
-  uint8_t* sRes = sOut + 4 * 32 * out_pitch;                                            // [2][128 rows][res_pitch] (res_smem only)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRes + (p.res_smem ? 2 * CONV_BM * res_pitch : 0));
+  uint8_t* sA = smem + L.a;
+  uint8_t* sB = smem + L.b;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* full = bars;
   uint64_t* empty = bars + p.stages;
   uint64_t* acc_full = empty + p.stages;      // [2]
   uint64_t* acc_empty = acc_full + 2;         // [2]
-  uint64_t* res_full = acc_empty + 2;         // [2]
-  uint64_t* res_empty = res_full + 2;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
+  const int nk_total = p.nkb + p.n_res;
+  const bool out_f32 = p.flags & CF_OUT_F32;
   if (threadIdx.x == 0) CONV_TRACE(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_w);
     if (p.tma_a) tma_prefetch_desc(&tmap_a);
+    if (p.n_res) tma_prefetch_desc(&tmap_res);
+    if (!out_f32) tma_prefetch_desc(&tmap_out);
   }
   if (warp == 1) {
     if (lane == 0) {
       const uint32_t full_count = p.tma_a ? 1u : 1u + CONV_HELPER_THREADS;
       for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], full_count); mbar_init(&empty[s], 1); }
-      for (int b = 0; b < 2; ++b) {
-        mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128);
-        mbar_init(&res_full[b], CONV_HELPER_THREADS); mbar_init(&res_empty[b], 128);
-      }
+      for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], CONV_EPI_WARPS * 32); }
       fence_barrier_init();
     }
     __syncwarp();
     tmem_alloc_rt(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
   }
-  if (warp >= 2 && warp < 6) {                      // bias is a weight: safe to read before the dependency wait
-    for (int i = threadIdx.x - 64; i < p.cout; i += 128) s_bias[i] = __ldg(p.bias + i);
+  if (warp >= CONV_FIRST_EPI_WARP) {
+    // constant MMA operands (weights-side data: safe to read before the dependency wait)
+    const int t = threadIdx.x - CONV_FIRST_EPI_WARP * 32;                 // 0..511
+    uint4* s_bias = reinterpret_cast<uint4*>(smem + L.bias);
+    for (int i = t; i < p.cout; i += (CONV_THREADS - CONV_FIRST_EPI_WARP * 32)) s_bias[i] = __ldg(p.bias16 + i);
+    if (t < CONV_BM) reinterpret_cast<uint4*>(smem + L.ones)[t] = make_uint4(0x3C003C00u, 0u, 0u, 0u);   // {1.0h, 1.0h, 0...}
+    if (t < 256) reinterpret_cast<uint4*>(smem + L.zero)[t] = make_uint4(0u, 0u, 0u, 0u);
+    if (p.n_res) {                                                       // 64 x 64 identity, rows of 128 bytes, SW128
+      const int row = t >> 3, u = t & 7;                                 // 512 threads = 64 rows x 8 units
+      const int e = row - u * 8;                                         // element index of the 1.0 inside this unit
+      const uint32_t one = (e & 1) ? 0x3C000000u : 0x00003C00u;
+      const int wi = (e >= 0 && e < 8) ? (e >> 1) : -1;
+      *reinterpret_cast<uint4*>(smem + L.ident + sw128_offset(row, u)) =
+          make_uint4(wi == 0 ? one : 0u, wi == 1 ? one : 0u, wi == 2 ? one : 0u, wi == 3 ? one : 0u);
+    }
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -178,7 +203,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   if (threadIdx.x == 0) CONV_TRACE(1);
   if (p.pdl) pdl_launch_dependents();               // let the next layer start its own prologue
 
-  const int issuer = warp == 0 ? 0 : (warp >= 14 ? warp - 13 : -1);
+  const int issuer = warp == 0 ? 0
+                   : (p.tma_a && warp >= CONV_FIRST_HELPER_WARP && warp < CONV_FIRST_HELPER_WARP + CONV_MAX_ISSUERS - 1)
+                       ? warp - CONV_FIRST_HELPER_WARP + 1 : -1;
   if (issuer >= 0) {
     // ---------------------------------------------------------------- TMA producers (stage g belongs to issuer g % n_issuers)
     if (lane == 0 && issuer < p.n_issuers) {
@@ -189,16 +216,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = fdiv(tile, p.d_ntiles);
         const int n0 = (tile - mt * p.n_tiles) * p.bn_tile, m0 = mt * CONV_BM;
-        for (int kb = 0; kb < p.nkb; ++kb) {
+        for (int kb = 0; kb < nk_total; ++kb) {
           if (turn == issuer) {
             mbar_wait(&empty[s], ph ^ 1, 11);
-            mbar_arrive_expect_tx(&full[s], tx);
-            tma_load_2d_hint(sB + static_cast<size_t>(s) * b_stage_bytes, &tmap_w, &full[s], kb * 64, n0, kEvictLast);
-            if (p.tma_a) {
-              if (!waited) { pdl_wait(); waited = true; }     // activations come from the previous layer
-              tma_load_2d(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES, &tmap_a, &full[s], kb * 64, m0);
+            if (kb < p.nkb) {
+              mbar_arrive_expect_tx(&full[s], tx);
+              tma_load_2d_hint(sB + static_cast<size_t>(s) * b_stage_bytes, &tmap_w, &full[s], kb * 64, n0, kEvictLast);
+              if (p.tma_a) {
+                if (!waited) { pdl_wait(); waited = true; }     // activations come from the previous layer
+                tma_load_2d(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES, &tmap_a, &full[s], kb * 64, m0);
+              }
+            } else {                                            // residual K-block: [128 rows x 64 channels] of x
+              if (!waited) { pdl_wait(); waited = true; }
+              mbar_arrive_expect_tx(&full[s], CONV_A_STAGE_BYTES);
+              tma_load_2d(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES, &tmap_res, &full[s], n0 + (kb - p.nkb) * 64, m0);
             }
-            if (issuer == 0 && tile == blockIdx.x && kb == 0) CONV_TRACE(2);
+            if (issuer == 0 && tile == static_cast<int>(blockIdx.x) && kb == 0) CONV_TRACE(2);
           }
           if (++turn == p.n_issuers) turn = 0;
           if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -209,23 +242,46 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(CONV_BM, p.bn_tile);
+      const uint32_t idesc64 = umma_idesc_f16(CONV_BM, 64);
+      const uint32_t ones_addr = smem_u32(smem + L.ones), zero_addr = smem_u32(smem + L.zero);
+      const uint32_t bias_addr = smem_u32(smem + L.bias), ident_addr = smem_u32(smem + L.ident);
+      const uint64_t ones_desc = umma_desc_nosw(ones_addr, zero_addr - ones_addr, 128);
+      const bool do_mma = !(p.flags & CF_DBG_NOMMA);
       int lt = 0, s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
         const int buf = lt & 1;
+        const int mt = fdiv(tile, p.d_ntiles);
+        const int n0 = (tile - mt * p.n_tiles) * p.bn_tile;
         mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1, 15);
         tc_fence_after();
         const uint32_t d = tmem_base + static_cast<uint32_t>(buf * p.bn_tile);
+        {                                                       // D = ones * bias^T : initialises the accumulator
+          const uint32_t b_addr = bias_addr + static_cast<uint32_t>(n0) * 16;
+          umma_f16(d, ones_desc, umma_desc_nosw(b_addr, zero_addr - b_addr, 128), idesc, 0u);
+        }
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(&full[s], ph, 12);
           tc_fence_after();
           if (lt == 0 && kb == 0) CONV_TRACE(3);
           const uint32_t a0 = smem_u32(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES);
           const uint32_t b0 = smem_u32(sB + static_cast<size_t>(s) * b_stage_bytes);
-          if (!(p.flags & CF_DBG_NOMMA))
+          if (do_mma) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_f16(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, 1u);
+          }
+          umma_commit(&empty[s]);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        for (int j = 0; j < p.n_res; ++j) {                     // D[:, 64j .. 64j+63] += R_j * I
+          mbar_wait(&full[s], ph, 18);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES);
+          if (do_mma) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(d + static_cast<uint32_t>(j * 64), umma_desc_sw128(a0 + k * 32), umma_desc_sw128(ident_addr + k * 32), idesc64, 1u);
+          }
           umma_commit(&empty[s]);
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
@@ -233,106 +289,99 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       }
       CONV_TRACE(4);
     }
-  } else if (warp < 6) {
-    // ---------------------------------------------------------------- epilogue (4 warps)
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const bool relu = p.flags & CF_RELU, has_res = p.flags & CF_RESIDUAL, out_f32 = p.flags & CF_OUT_F32;
-    const bool res_smem = p.res_smem != 0;
-    const uint32_t s_bias_u32 = smem_u32(s_bias);
-    const __half2 h_lo = __float2half2_rn(relu ? 0.f : -65504.f), h_hi = __float2half2_rn(65504.f);
-    const uint32_t my_out = smem_u32(sOut) + static_cast<uint32_t>((warp - 2) * 32 * out_pitch);
-    // coalesced copy-out geometry: 16-byte units, U per row; lane starts at unit `lane` and advances 32 units per step
-    const int U = sw_cols >> 3;
-    const int u_row0 = fdiv(lane, p.d_unit_out), u_col0 = lane - u_row0 * U;
-    const int u_drow = fdiv(32, p.d_unit_out), u_dcol = 32 - u_drow * U;
-    if (p.pdl) pdl_wait();                            // residual reads / output writes depend on earlier layers
+  } else if (warp < CONV_FIRST_HELPER_WARP) {
+    // ---------------------------------------------------------------- epilogue (8 warps, 2 per TMEM lane quarter)
+    const int quarter = warp & 3, half = (warp - CONV_FIRST_EPI_WARP) >> 2;
+    const bool relu = p.flags & CF_RELU;
+    const bool leader = half == 0 && lane == 0;                 // issues this quarter's TMA stores
+    const int pass_cols = min(p.bn_tile, CONV_PASS_COLS);
+    const int rowbytes = p.box_cols * 2, box_bytes = 32 * rowbytes, chunks_per_box = p.box_cols >> 4;
+    const uint32_t swz = p.box_cols == 64 ? (lane & 7) : p.box_cols == 32 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
+    const uint32_t my_stage = smem_u32(smem + L.out) + static_cast<uint32_t>(quarter * 32 * pass_cols * 2);
+    const uint32_t my_row = my_stage + static_cast<uint32_t>(lane * rowbytes);
+    const bool do_store = !(p.flags & CF_DBG_NOSTORE);
+    if (p.pdl && (leader || out_f32)) pdl_wait();               // output writes must not overtake readers of the previous layers
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
       const int mt = fdiv(tile, p.d_ntiles);
       const int n0 = (tile - mt * p.n_tiles) * p.bn_tile, m0 = mt * CONV_BM;
-      const int m = m0 + row;
-      const bool mvalid = m < p.M_total;
-      const __half* resp = has_res && !res_smem && mvalid ? p.res + static_cast<size_t>(m) * p.res_ld + p.res_coff + n0 : nullptr;
-      const uint32_t my_res = smem_u32(sRes) + static_cast<uint32_t>(buf * CONV_BM * res_pitch + row * res_pitch);
-      if (res_smem) mbar_wait(&res_full[buf], (lt >> 1) & 1, 16);
       mbar_wait(&acc_full[buf], (lt >> 1) & 1, 14);
       tc_fence_after();
-      if (lt == 0 && threadIdx.x == 64) CONV_TRACE(5);
+      if (lt == 0 && threadIdx.x == CONV_FIRST_EPI_WARP * 32) CONV_TRACE(5);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * p.bn_tile);
-      for (int cg = 0; cg < p.bn_tile; cg += sw_cols) {
-        const int n_chunks = sw_cols >> 4;
-        uint32_t ra[16], rb[16];
-        __syncwarp();
-        tmem_ld_32x16(taddr + static_cast<uint32_t>(cg), ra);
-        for (int c = 0; c < n_chunks; c += 2) {
+      if (out_f32) {
+        // fp32 output (the bottleneck GEMM only): thread = row, direct 16-byte stores
+        const int m = m0 + quarter * 32 + lane;
+        const int n_chunks = p.bn_tile >> 4;
+        for (int c = half; c < n_chunks; c += 2) {
+          uint32_t r[16];
+          __syncwarp();
+          tmem_ld_32x16(taddr + static_cast<uint32_t>(c * 16), r);
+          tmem_ld_wait(r);
+          if (m < p.M_total && do_store) {
+            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + p.out_coff + n0 + c * 16);
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int cc = c + j;
-            if (cc >= n_chunks) break;               // warp-uniform
-            if (j) tmem_ld_wait(rb); else tmem_ld_wait(ra);
-            __syncwarp();
-            if (cc + 1 < n_chunks) {
-              if (j) tmem_ld_32x16(taddr + static_cast<uint32_t>(cg + (cc + 1) * 16), ra);
-              else tmem_ld_32x16(taddr + static_cast<uint32_t>(cg + (cc + 1) * 16), rb);
-            }
-            const int col = cg + cc * 16;            // column inside the tile
-            uint4 q[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-            if (res_smem) { q[0] = lds128(my_res + col * 2); q[1] = lds128(my_res + col * 2 + 16); }
-            else if (resp) { q[0] = __ldg(reinterpret_cast<const uint4*>(resp + col)); q[1] = __ldg(reinterpret_cast<const uint4*>(resp + col) + 1); }
-            float v[16];
-            conv_chunk_math(j ? rb : ra, q, s_bias_u32 + static_cast<uint32_t>((n0 + col) * 4), has_res, v);
-            if (out_f32) {
-              if (relu) {
-#pragma unroll
-                for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
-              }
-              if (mvalid) {
-                float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + p.out_coff + n0 + col);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) op[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
-              }
-            } else {
-              const uint32_t dst = my_out + static_cast<uint32_t>(lane * out_pitch + cc * 32);
-              sts128(dst, make_uint4(pack_f16x2_clamp(v[0], v[1], h_lo, h_hi), pack_f16x2_clamp(v[2], v[3], h_lo, h_hi),
-                                     pack_f16x2_clamp(v[4], v[5], h_lo, h_hi), pack_f16x2_clamp(v[6], v[7], h_lo, h_hi)));
-              sts128(dst + 16, make_uint4(pack_f16x2_clamp(v[8], v[9], h_lo, h_hi), pack_f16x2_clamp(v[10], v[11], h_lo, h_hi),
-                                          pack_f16x2_clamp(v[12], v[13], h_lo, h_hi), pack_f16x2_clamp(v[14], v[15], h_lo, h_hi)));
+            for (int e = 0; e < 4; ++e) {
+              float4 v = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]), __uint_as_float(r[4 * e + 2]), __uint_as_float(r[4 * e + 3]));
+              if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+              op[e] = v;
             }
           }
         }
-        if (cg + sw_cols >= p.bn_tile) {             // accumulator and residual stage fully consumed: hand them back early
+        __syncwarp();
+        tc_fence_before();
+        mbar_arrive(&acc_empty[buf]);
+        continue;
+      }
+      for (int cg = 0; cg < p.bn_tile; cg += CONV_PASS_COLS) {
+        const int cols = min(CONV_PASS_COLS, p.bn_tile - cg);
+        const int n_chunks = cols >> 4;
+        if (leader) bulk_wait_read_all();                       // the previous pass' stores have left the staging buffer
+        named_bar_sync(1 + quarter, 64);
+        uint32_t ra[16], rb[16];
+        int c = half;
+        __syncwarp();
+        if (c < n_chunks) tmem_ld_32x16(taddr + static_cast<uint32_t>(cg + c * 16), ra);
+        for (; c < n_chunks; c += 4) {
+          // chunk c (in ra), prefetch c + 2 (into rb)
+          tmem_ld_wait(ra);
+          __syncwarp();
+          if (c + 2 < n_chunks) tmem_ld_32x16(taddr + static_cast<uint32_t>(cg + (c + 2) * 16), rb);
+          {
+            const int box = c / chunks_per_box, cb = c - box * chunks_per_box;
+            conv_stage_chunk(ra, relu, my_row + static_cast<uint32_t>(box * box_bytes), static_cast<uint32_t>(2 * cb), swz);
+          }
+          if (c + 2 < n_chunks) {
+            tmem_ld_wait(rb);
+            __syncwarp();
+            if (c + 4 < n_chunks) tmem_ld_32x16(taddr + static_cast<uint32_t>(cg + (c + 4) * 16), ra);
+            const int c2 = c + 2;
+            const int box = c2 / chunks_per_box, cb = c2 - box * chunks_per_box;
+            conv_stage_chunk(rb, relu, my_row + static_cast<uint32_t>(box * box_bytes), static_cast<uint32_t>(2 * cb), swz);
+          }
+        }
+        if (cg + CONV_PASS_COLS >= p.bn_tile) {                 // accumulator fully read: hand it back before storing
           __syncwarp();
           tc_fence_before();
           mbar_arrive(&acc_empty[buf]);
-          if (res_smem) mbar_arrive(&res_empty[buf]);
         }
-        if (!out_f32) {
-          __syncwarp();
-          // staged sub-tile (32 rows x sw_cols) -> global, 16 bytes per lane, lanes contiguous along the row
-          const int rows_left = p.M_total - (m0 + quarter * 32);
-          int ur = u_row0, uc = u_col0;
-          uint32_t sp = my_out + static_cast<uint32_t>(u_row0 * out_pitch + u_col0 * 16);
-          uint8_t* gp = reinterpret_cast<uint8_t*>(static_cast<__half*>(p.out) + static_cast<size_t>(m0 + quarter * 32 + u_row0) * p.out_ld +
-                                                   p.out_coff + n0 + cg + u_col0 * 8);
-          const uint32_t s_step = static_cast<uint32_t>(u_drow * out_pitch + u_dcol * 16), s_wrap = static_cast<uint32_t>(out_pitch - U * 16);
-          const long long g_step = static_cast<long long>(u_drow) * p.out_ld * 2 + u_dcol * 16, g_wrap = static_cast<long long>(p.out_ld) * 2 - U * 16;
-          const bool do_store = !(p.flags & CF_DBG_NOSTORE);
-          for (int it2 = 0; it2 < U; ++it2) {
-            if (ur < rows_left && do_store) *reinterpret_cast<uint4*>(gp) = lds128(sp);
-            ur += u_drow; uc += u_dcol; sp += s_step; gp += g_step;
-            if (uc >= U) { uc -= U; ++ur; sp += s_wrap; gp += g_wrap; }
-          }
-          __syncwarp();
+        fence_proxy_async_smem();                               // staging writes -> visible to the TMA (async proxy)
+        named_bar_sync(1 + quarter, 64);
+        if (leader && do_store && m0 + quarter * 32 < p.M_total) {
+          const int n_boxes = cols / p.box_cols;
+          for (int b = 0; b < n_boxes; ++b)
+            tma_store_2d(&tmap_out, my_stage + static_cast<uint32_t>(b * box_bytes), n0 + cg + b * p.box_cols, m0 + quarter * 32);
+          bulk_commit_group();
         }
       }
     }
-    if (threadIdx.x == 64) CONV_TRACE(6);
+    if (leader) bulk_wait_all();                                // stores complete before the CTA exits
+    if (threadIdx.x == CONV_FIRST_EPI_WARP * 32) CONV_TRACE(6);
   } else if (!p.tma_a) {
     // ---------------------------------------------------------------- A gather producers (8 warps)
-    const int g = threadIdx.x - 192;                // 0..255
-    const int chunk = g & 7, rbase = g >> 3;        // 8 lanes cover one 128-byte row; rows rbase + 32*i
+    const int g = threadIdx.x - CONV_FIRST_HELPER_WARP * 32;   // 0..255
+    const int chunk = g & 7, rbase = g >> 3;                    // 8 lanes cover one 128-byte row; rows rbase + 32*i
     const uint32_t sw_const = smem_u32(sA) + static_cast<uint32_t>(rbase * 128 + ((chunk ^ (rbase & 7)) << 4));   // (row & 7) == (rbase & 7)
     const int HoWo = p.Ho * p.Wo;
     const bool do_copy = !(p.flags & CF_DBG_NOGATHER);
@@ -377,28 +426,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       }
     }
     cp_async_wait_all();                              // do not exit with copies in flight
-  } else if (p.res_smem) {
-    // ---------------------------------------------------------------- residual prefetchers (8 warps, 1x1 layers)
-    const int g = threadIdx.x - 192;
-    const int U = p.bn_tile >> 3;                     // 16-byte units per residual row
-    const int total_units = CONV_BM * U;
-    if (p.pdl) pdl_wait();
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-      const int buf = lt & 1;
-      const int mt = fdiv(tile, p.d_ntiles);
-      const int n0 = (tile - mt * p.n_tiles) * p.bn_tile, m0 = mt * CONV_BM;
-      mbar_wait(&res_empty[buf], ((lt >> 1) & 1) ^ 1, 17);
-      const uint32_t dst0 = smem_u32(sRes) + static_cast<uint32_t>(buf * CONV_BM * res_pitch);
-      for (int u = g; u < total_units; u += CONV_HELPER_THREADS) {
-        const int rr = fdiv(u, p.d_unit_res), cc = u - rr * U;
-        const bool ok = m0 + rr < p.M_total;
-        const __half* src = ok ? p.res + static_cast<size_t>(m0 + rr) * p.res_ld + p.res_coff + n0 + cc * 8 : p.res;
-        cp_async_16(dst0 + static_cast<uint32_t>(rr * res_pitch + cc * 16), src, ok);
-      }
-      cp_async_mbar_arrive_noinc(&res_full[buf]);
-    }
-    cp_async_wait_all();
   }
 
   tc_fence_before();

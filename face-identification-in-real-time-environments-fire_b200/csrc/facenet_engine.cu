@@ -125,9 +125,12 @@ struct OpRt {
   BlobOp op;
   CUtensorMap tmap_w;     // weights [cout][k_pad], box rows = bn_tile (rebuilt when the tiling changes with B)
   CUtensorMap tmap_a;     // activation matrix for TMA-mode convs (rebuilt when pointers / B change)
+  CUtensorMap tmap_res;   // residual matrix (up convs): box 64 columns x 128 rows
+  CUtensorMap tmap_out;   // output slice, box = box_cols x 32 rows (TMA store)
   bool tma_a = false;
   int bn_tile = 0, stages = 0, n_issuers = 1, tmem_cols = 0, m_tiles = 0, n_tiles = 0;
-  bool res_smem = false;
+  int n_res = 0, box_cols = 64;
+  size_t bias16_off = 0;  // byte offset of this op's [cout] x {hi, lo, 0 x 6} fp16 bias rows in d_bias16
   size_t smem = 0;
   double flops_per_image = 0;
 };
@@ -136,17 +139,17 @@ struct OpRt {
 // K-blocks); layers with few M tiles are cut along N until the persistent grid covers the SMs.  Cost model in
 // SM cycles per tile: main loop = nkb * max(MMA, L2->smem fill at ~32 B/cycle/SM), epilogue ~120 cycles per
 // 16-column chunk, ~1200 cycles fixed; total = waves * tile.
-static int pick_bn_tile(int cout, int m_tiles, int nkb, int sms, bool residual_in_smem) {
+static int pick_bn_tile(int cout, int m_tiles, int nkb, int sms, bool residual) {
   int best = 16;
   double best_cost = 1e30;
   for (int d = 16; d <= 256 && d <= cout; d += 16) {
     if (cout % d) continue;
-    if (d > CONV_STAGE_COLS && d != 2 * CONV_STAGE_COLS) continue;   // epilogue stages 128 columns per pass
-    if (residual_in_smem && d > CONV_STAGE_COLS) continue;            // double-buffered residual stage must fit
+    if (residual && d % 64) continue;                                 // residual K-blocks are 64 columns wide
     const long long tiles = (long long)m_tiles * (cout / d);
     const long long waves = (tiles + sms - 1) / sms;
     const double fill = (16384.0 + 128.0 * d) / 32.0;
-    const double tile = nkb * std::max(2.0 * d, fill) + 1200.0 + (d / 16) * 120.0;
+    const int nk = nkb + (residual ? d / 64 : 0);
+    const double tile = nk * std::max(2.0 * d, fill) + 1200.0 + (d / 16) * 60.0;
     const double cost = waves * tile;
     if (cost < best_cost * 0.999 || (cost <= best_cost * 1.001 && d > best)) { best_cost = cost; best = d; }
   }
@@ -167,13 +170,14 @@ struct fire_net {
   std::vector<BlobBuf> bufs;
   std::vector<OpRt> ops;
   uint8_t* d_weights = nullptr;
+  uint8_t* d_bias16 = nullptr;   // per conv op: [cout] x {fp16 hi, fp16 lo, 0 x 6} of the fp32 bias (the bias MMA operand)
   // cache key of the activation tensor maps
   const void* key_in = nullptr; const void* key_ws = nullptr; const void* key_out = nullptr; int key_B = 0;
   double flops_per_image = 0;
   bool pdl = true;        // programmatic dependent launch between conv layers (FIRE_B200_PDL=0 disables)
   bool gather_l1 = false; // cp.async.ca instead of .cg for the A gather (FIRE_B200_GATHER_L1=1)
   int max_stages = 8;
-  int n_issuers = 1 + CONV_EXTRA_ISSUERS;   // TMA issuing threads per CTA (FIRE_B200_ISSUERS=1..3)
+  int n_issuers = CONV_MAX_ISSUERS;   // TMA issuing threads per CTA in 1x1 layers (FIRE_B200_ISSUERS=1|2|4)
   long long* d_trace = nullptr; int trace_op = -1;   // FIRE_B200_TRACE_OP=<op index>: in-kernel timeline of that op (profile only)
   int dbg_flags = 0;      // FIRE_B200_DBG: timing experiments (1 = no gather copies, 2 = no epilogue stores, 4 = no MMA)
 };
@@ -213,6 +217,33 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
     delete net;
     return fail(FIRE_ERR_CUDA, "fire_facenet_create: weight upload failed: %s", cudaGetErrorString(e));
   }
+  {
+    // bias operand of the bias MMA: per output channel {fp16 hi, fp16 lo, 0 x 6}, hi + lo ~ the fp32 bias to 2^-22
+    size_t total = 0;
+    for (const BlobOp& o : ops) if (o.kind == OP_CONV) total += (size_t)o.cout * 16;
+    std::vector<uint16_t> tab(total / 2, 0);
+    size_t off = 0;
+    for (const BlobOp& o : ops) {
+      if (o.kind != OP_CONV) continue;
+      if ((size_t)(h.weights_off + o.b_off) + (size_t)o.cout * 4 > bytes) { cudaFree(net->d_weights); delete net; return fail(FIRE_ERR_ARG, "fire_facenet_create: bias out of range"); }
+      const float* b = reinterpret_cast<const float*>(p + h.weights_off + o.b_off);
+      for (int c = 0; c < o.cout; ++c) {
+        float v = std::min(std::max(b[c], -60000.f), 60000.f);
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        memcpy(&tab[off / 2 + (size_t)c * 8], &hi, 2);
+        memcpy(&tab[off / 2 + (size_t)c * 8 + 1], &lo, 2);
+      }
+      off += (size_t)o.cout * 16;
+    }
+    e = cudaMalloc(&net->d_bias16, std::max<size_t>(total, 16));
+    if (e == cudaSuccess) e = cudaMemcpy(net->d_bias16, tab.data(), total, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(net->d_weights); cudaFree(net->d_bias16);
+      delete net;
+      return fail(FIRE_ERR_CUDA, "fire_facenet_create: bias upload failed: %s", cudaGetErrorString(e));
+    }
+  }
   static bool attr_done = false;
   if (!attr_done) {
     e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -223,6 +254,7 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
     }
     attr_done = true;
   }
+  size_t bias16_off = 0;
   for (const BlobOp& o : ops) {
     OpRt r;
     r.op = o;
@@ -237,6 +269,12 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
                     o.cout, o.k_pad, o.cin);
       }
       r.tma_a = (o.kh == 1 && o.kw == 1 && o.stride == 1 && o.pad_h == 0 && o.pad_w == 0);
+      if ((o.flags & CF_RESIDUAL) && (!r.tma_a || o.cout % 64)) {
+        cudaFree(net->d_weights); cudaFree(net->d_bias16); delete net;
+        return fail(FIRE_ERR_ARG, "fire_facenet_create: residual is supported on 1x1/stride-1 convs with cout %% 64 == 0");
+      }
+      r.bias16_off = bias16_off;
+      bias16_off += (size_t)o.cout * 16;
       r.flops_per_image = 2.0 * o.Ho * o.Wo * (double)o.cout * o.kh * o.kw * o.cin;
       net->flops_per_image += r.flops_per_image;
     }
@@ -254,7 +292,7 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
     cudaMalloc(&net->d_trace, 8 * 8 * 256);
   }
   const char* is_env = getenv("FIRE_B200_ISSUERS");
-  if (is_env) net->n_issuers = std::max(1, std::min(1 + CONV_EXTRA_ISSUERS, atoi(is_env)));   // 1, 2 or 4 are used
+  if (is_env) net->n_issuers = std::max(1, std::min(CONV_MAX_ISSUERS, atoi(is_env)));   // 1, 2 or 4 are used
   const char* st_env = getenv("FIRE_B200_MAX_STAGES");
   if (st_env) net->max_stages = std::max(3, std::min(12, atoi(st_env)));
   *out = net;
@@ -264,6 +302,7 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
 int fire_facenet_destroy(fire_net_t* net) {
   if (!net) return FIRE_OK;
   cudaFree(net->d_weights);
+  cudaFree(net->d_bias16);
   cudaFree(net->d_trace);
   delete net;
   return FIRE_OK;
@@ -296,24 +335,18 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
     ConvParams p;
     p.in = src; p.in_ld = sb.C; p.in_coff = o.src_coff;
     p.out = dst; p.out_ld = db.C; p.out_coff = o.dst_coff;
-    p.res = nullptr; p.res_ld = 0; p.res_coff = 0;
-    if (o.res_buf >= 0) {
-      p.res = static_cast<const __half*>(buf_ptr(net, o.res_buf, B, in, ws, out_raw));
-      p.res_ld = net->bufs[o.res_buf].C; p.res_coff = o.res_coff;
-    }
-    p.bias = reinterpret_cast<const float*>(net->d_weights + o.b_off);
+    p.bias16 = reinterpret_cast<const uint4*>(net->d_bias16 + r.bias16_off);
     p.H = o.H; p.W = o.W; p.Ho = o.Ho; p.Wo = o.Wo; p.kh = o.kh; p.kw = o.kw; p.stride = o.stride;
     p.pad_h = o.pad_h; p.pad_w = o.pad_w; p.cin = o.cin; p.cout = o.cout; p.k_real = o.kh * o.kw * o.cin;
     p.nkb = o.k_pad / 64; p.flags = o.flags; p.bn_tile = r.bn_tile; p.M_total = B * o.Ho * o.Wo;
     p.stages = r.stages; p.tma_a = r.tma_a ? 1 : 0; p.tmem_cols = r.tmem_cols;
     p.m_tiles = r.m_tiles; p.n_tiles = r.n_tiles; p.pdl = pdl ? 1 : 0;
     p.flags |= net->dbg_flags;
-    p.res_smem = r.res_smem ? 1 : 0;
+    p.n_res = r.n_res; p.box_cols = r.box_cols;
     p.n_issuers = r.n_issuers;
     p.trace = (net->d_trace && &r == &net->ops[net->trace_op]) ? net->d_trace : nullptr;
     p.d_howo = make_fastdiv(o.Ho * o.Wo); p.d_wo = make_fastdiv(o.Wo); p.d_cin = make_fastdiv(o.cin); p.d_kw = make_fastdiv(o.kw);
     p.d_ntiles = make_fastdiv(r.n_tiles);
-    p.d_unit_res = make_fastdiv(r.bn_tile / 8); p.d_unit_out = make_fastdiv(std::min(r.bn_tile, CONV_STAGE_COLS) / 8);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)std::min<long long>((long long)r.m_tiles * r.n_tiles, device_sm_count()));
     cfg.blockDim = dim3(CONV_THREADS);
@@ -324,7 +357,8 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    FIRE_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, r.tmap_w, r.tma_a ? r.tmap_a : r.tmap_w, p));
+    FIRE_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, r.tmap_w, r.tma_a ? r.tmap_a : r.tmap_w, r.n_res ? r.tmap_res : r.tmap_w,
+                                 (o.flags & CF_OUT_F32) ? r.tmap_w : r.tmap_out, p));
   } else if (o.kind == OP_MAXPOOL) {
     const long long total = (long long)B * o.Ho * o.Wo * (o.cin / 8);
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
@@ -355,8 +389,8 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
       if (r.op.kind != OP_CONV) continue;
       const BlobOp& o = r.op;
       r.m_tiles = (B * o.Ho * o.Wo + CONV_BM - 1) / CONV_BM;
-      const bool res_smem = r.tma_a && (o.flags & CF_RESIDUAL);
-      const int bn = pick_bn_tile(o.cout, r.m_tiles, o.k_pad / 64, sms, res_smem);
+      const bool residual = (o.flags & CF_RESIDUAL) != 0;
+      const int bn = pick_bn_tile(o.cout, r.m_tiles, o.k_pad / 64, sms, residual);
       if (bn != r.bn_tile) {
         int rc = make_tmap_f16_2d(&r.tmap_w, net->d_weights + o.w_off, (uint64_t)o.cout, (uint64_t)o.k_pad,
                                   (uint64_t)o.k_pad * 2, (uint32_t)bn);
@@ -364,24 +398,38 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
         r.bn_tile = bn;
       }
       r.n_tiles = o.cout / bn;
+      r.n_res = residual ? bn / 64 : 0;
+      r.box_cols = bn % 64 == 0 ? 64 : (bn % 32 == 0 ? 32 : 16);
       const size_t stage = CONV_A_STAGE_BYTES + (size_t)bn * 128;
-      const size_t out_stage = 4 * 32 * (size_t)(std::min(bn, CONV_STAGE_COLS) * 2 + 16);
-      const size_t res_stage = res_smem ? 2 * (size_t)CONV_BM * (bn * 2 + 16) : 0;
-      const size_t fixed = 1024 + CONV_MAX_COUT * sizeof(float) + out_stage + res_stage + 256;
+      const size_t fixed = conv_smem_layout(0, bn, o.cout, r.n_res).total + 1024;     // + alignment slack
       r.stages = (int)std::min<size_t>(net->max_stages, (232448 - fixed) / stage);
       if (r.stages < 2) return fail(FIRE_ERR_UNSUPPORTED, "conv tile %d does not fit shared memory", bn);
-      // TMA issuing threads: the ring depth is rounded down to a multiple of their number (see conv_igemm.cuh)
+      // TMA issuing threads (1x1 layers): the ring depth is rounded down to a multiple of their number (see conv_igemm.cuh)
       r.n_issuers = 1;
-      for (int j = 4; j >= 2; j >>= 1)
-        if (j <= net->n_issuers && r.stages >= j) { r.n_issuers = j; r.stages = r.stages / j * j; break; }
-      r.smem = fixed + r.stages * stage;
-      r.res_smem = res_smem;
+      if (r.tma_a)
+        for (int j = 4; j >= 2; j >>= 1)
+          if (j <= net->n_issuers && r.stages >= j && r.stages % j == 0) { r.n_issuers = j; break; }
+      r.smem = conv_smem_layout(r.stages, bn, o.cout, r.n_res).total + 1024;
       r.tmem_cols = pow2_cols(2 * bn);
-      if (!r.tma_a) continue;
-      const BlobBuf& sb = net->bufs[r.op.src_buf];
-      const __half* src = static_cast<const __half*>(buf_ptr(net, r.op.src_buf, B, in, ws, out_raw)) + r.op.src_coff;
-      int rc = make_tmap_f16_2d(&r.tmap_a, src, (uint64_t)B * r.op.Ho * r.op.Wo, (uint64_t)r.op.cin, (uint64_t)sb.C * 2, CONV_BM);
-      if (rc != FIRE_OK) return rc;
+      const BlobBuf& sb = net->bufs[o.src_buf];
+      const BlobBuf& db = net->bufs[o.dst_buf];
+      const uint64_t M = (uint64_t)B * o.Ho * o.Wo;
+      if (r.tma_a) {
+        const __half* src = static_cast<const __half*>(buf_ptr(net, o.src_buf, B, in, ws, out_raw)) + o.src_coff;
+        int rc = make_tmap_f16_2d(&r.tmap_a, src, M, (uint64_t)o.cin, (uint64_t)sb.C * 2, CONV_BM);
+        if (rc != FIRE_OK) return rc;
+      }
+      if (r.n_res) {
+        const BlobBuf& rb = net->bufs[o.res_buf];
+        const __half* res = static_cast<const __half*>(buf_ptr(net, o.res_buf, B, in, ws, out_raw)) + o.res_coff;
+        int rc = make_tmap_f16_2d(&r.tmap_res, res, M, (uint64_t)o.cout, (uint64_t)rb.C * 2, CONV_BM);
+        if (rc != FIRE_OK) return rc;
+      }
+      if (!(o.flags & CF_OUT_F32)) {
+        const __half* dst = static_cast<const __half*>(buf_ptr(net, o.dst_buf, B, in, ws, out_raw)) + o.dst_coff;
+        int rc = make_tmap_f16_2d_ex(&r.tmap_out, dst, M, (uint64_t)o.cout, (uint64_t)db.C * 2, (uint32_t)r.box_cols, 32);
+        if (rc != FIRE_OK) return rc;
+      }
     }
     net->key_in = in; net->key_ws = ws; net->key_out = out_raw; net->key_B = B;
   }

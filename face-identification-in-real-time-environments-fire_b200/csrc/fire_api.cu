@@ -45,21 +45,32 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
-                     uint32_t box_rows) {
+int make_tmap_f16_2d_ex(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                        uint32_t box_cols, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(FIRE_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (row_stride_bytes & 15) || box_rows == 0 || box_rows > 256)
     return fail(FIRE_ERR_ARG, "tensor map: base/stride must be 16-byte aligned, box rows in [1,256]");
+  CUtensorMapSwizzle sw;
+  switch (box_cols) {
+    case 64: sw = CU_TENSOR_MAP_SWIZZLE_128B; break;
+    case 32: sw = CU_TENSOR_MAP_SWIZZLE_64B; break;
+    case 16: sw = CU_TENSOR_MAP_SWIZZLE_32B; break;
+    default: return fail(FIRE_ERR_ARG, "tensor map: box of %u fp16 columns is not a swizzle width (16/32/64)", box_cols);
+  }
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {row_stride_bytes};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(FIRE_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return FIRE_OK;
+}
+
+int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                     uint32_t box_rows) {
+  return make_tmap_f16_2d_ex(out, base, rows, cols, row_stride_bytes, 64, box_rows);
 }
 
 int device_sm_count() {

@@ -34,6 +34,10 @@ int fail(int code, const char* fmt, ...);
 int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
                      uint32_t box_rows);
 
+// Same with a box of `box_cols` fp16 columns (64 / 32 / 16 -> 128B / 64B / 32B swizzle); used for loads and stores.
+int make_tmap_f16_2d_ex(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                        uint32_t box_cols, uint32_t box_rows);
+
 int device_sm_count();
 
 // Launch counter (every kernel launch of this library bumps it; bench.py reports it as gpu_launches).
