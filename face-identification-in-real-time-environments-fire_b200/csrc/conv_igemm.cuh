@@ -74,7 +74,7 @@ __host__ __device__ inline ConvSmem conv_smem_layout(int stages, int bn, int cou
   L.zero = o;  o += 256 * 16;                               // K-chunk 1 of both (all zero)
   o = (o + 1023) & ~1023u;
   L.ident = o; o += n_res ? 64 * 128 : 0;                   // 64 x 64 identity, 128-byte swizzle
-  L.out = o;   o += 4 * 32 * (bn < CONV_PASS_COLS ? bn : CONV_PASS_COLS) * 2;   // per-quarter staging for the TMA store
+  L.out = o;   o += 2 * 4 * 32 * (bn < CONV_PASS_COLS ? bn : CONV_PASS_COLS) * 2;   // [2 buffers][4 quarters] staging for the TMA store
   L.bars = o;  o += 256;
   L.total = o;
   return L;
@@ -297,8 +297,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const int pass_cols = min(p.bn_tile, CONV_PASS_COLS);
     const int rowbytes = p.box_cols * 2, box_bytes = 32 * rowbytes, chunks_per_box = p.box_cols >> 4;
     const uint32_t swz = p.box_cols == 64 ? (lane & 7) : p.box_cols == 32 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
-    const uint32_t my_stage = smem_u32(smem + L.out) + static_cast<uint32_t>(quarter * 32 * pass_cols * 2);
-    const uint32_t my_row = my_stage + static_cast<uint32_t>(lane * rowbytes);
+    const uint32_t stage_buf_bytes = static_cast<uint32_t>(4 * 32 * pass_cols * 2);                 // one staging buffer (4 quarters)
+    const uint32_t my_stage0 = smem_u32(smem + L.out) + static_cast<uint32_t>(quarter * 32 * pass_cols * 2);
+    uint32_t sbuf = 0;                                          // staging buffer of the next pass (alternates)
     const bool do_store = !(p.flags & CF_DBG_NOSTORE);
     if (p.pdl && (leader || out_f32)) pdl_wait();               // output writes must not overtake readers of the previous layers
     int lt = 0;
@@ -337,7 +338,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       for (int cg = 0; cg < p.bn_tile; cg += CONV_PASS_COLS) {
         const int cols = min(CONV_PASS_COLS, p.bn_tile - cg);
         const int n_chunks = cols >> 4;
-        if (leader) bulk_wait_read_all();                       // the previous pass' stores have left the staging buffer
+        const uint32_t my_stage = my_stage0 + sbuf * stage_buf_bytes;
+        const uint32_t my_row = my_stage + static_cast<uint32_t>(lane * rowbytes);
+        sbuf ^= 1;
+        if (leader) bulk_wait_read_1();                         // the stores issued two passes ago have left this staging buffer
         named_bar_sync(1 + quarter, 64);
         uint32_t ra[16], rb[16];
         int c = half;

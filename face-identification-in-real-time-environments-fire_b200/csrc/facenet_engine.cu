@@ -178,6 +178,7 @@ struct fire_net {
   bool gather_l1 = false; // cp.async.ca instead of .cg for the A gather (FIRE_B200_GATHER_L1=1)
   int max_stages = 8;
   int n_issuers = CONV_MAX_ISSUERS;   // TMA issuing threads per CTA in 1x1 layers (FIRE_B200_ISSUERS=1|2|4)
+  bool trace_all = false;   // FIRE_B200_TRACE_ALL=1: forward() records every conv's timeline, synchronises and prints it
   long long* d_trace = nullptr; int trace_op = -1;   // FIRE_B200_TRACE_OP=<op index>: in-kernel timeline of that op (profile only)
   int dbg_flags = 0;      // FIRE_B200_DBG: timing experiments (1 = no gather copies, 2 = no epilogue stores, 4 = no MMA)
 };
@@ -291,6 +292,13 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
     net->trace_op = atoi(tr_env);
     cudaMalloc(&net->d_trace, 8 * 8 * 256);
   }
+  const char* ta_env = getenv("FIRE_B200_TRACE_ALL");
+  if (ta_env && ta_env[0] == '1') {
+    net->trace_all = true; net->trace_op = 0;
+    cudaFree(net->d_trace);
+    cudaMalloc(&net->d_trace, net->ops.size() * 8 * 8 * 256);
+    cudaMemset(net->d_trace, 0, net->ops.size() * 8 * 8 * 256);
+  }
   const char* is_env = getenv("FIRE_B200_ISSUERS");
   if (is_env) net->n_issuers = std::max(1, std::min(CONV_MAX_ISSUERS, atoi(is_env)));   // 1, 2 or 4 are used
   const char* st_env = getenv("FIRE_B200_MAX_STAGES");
@@ -344,7 +352,8 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
     p.flags |= net->dbg_flags;
     p.n_res = r.n_res; p.box_cols = r.box_cols;
     p.n_issuers = r.n_issuers;
-    p.trace = (net->d_trace && &r == &net->ops[net->trace_op]) ? net->d_trace : nullptr;
+    p.trace = !net->d_trace ? nullptr : net->trace_all ? net->d_trace + (size_t)(&r - net->ops.data()) * 8 * 256
+              : (&r == &net->ops[net->trace_op] ? net->d_trace : nullptr);
     p.d_howo = make_fastdiv(o.Ho * o.Wo); p.d_wo = make_fastdiv(o.Wo); p.d_cin = make_fastdiv(o.cin); p.d_kw = make_fastdiv(o.kw);
     p.d_ntiles = make_fastdiv(r.n_tiles);
     cudaLaunchConfig_t cfg = {};
@@ -406,9 +415,11 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
       if (r.stages < 2) return fail(FIRE_ERR_UNSUPPORTED, "conv tile %d does not fit shared memory", bn);
       // TMA issuing threads (1x1 layers): the ring depth is rounded down to a multiple of their number (see conv_igemm.cuh)
       r.n_issuers = 1;
-      if (r.tma_a)
-        for (int j = 4; j >= 2; j >>= 1)
-          if (j <= net->n_issuers && r.stages >= j && r.stages % j == 0) { r.n_issuers = j; break; }
+      if (r.tma_a && net->n_issuers > 1) {
+        if (r.stages > 4 && r.stages % 4 && r.stages % 3) --r.stages;        // 5 -> 4, 7 -> 6: a ring the issuers can share
+        for (int j = std::min(net->n_issuers, CONV_MAX_ISSUERS); j >= 2; --j)
+          if (r.stages % j == 0) { r.n_issuers = j; break; }
+      }
       r.smem = conv_smem_layout(r.stages, bn, o.cout, r.n_res).total + 1024;
       r.tmem_cols = pow2_cols(2 * bn);
       const BlobBuf& sb = net->bufs[o.src_buf];
@@ -451,6 +462,28 @@ int fire_facenet_forward(fire_net_t* net, const void* in_f16, int B, float* out_
     l2norm_kernel<<<(B + 7) / 8, 256, 0, st>>>(out_raw, out_l2, B, net->hdr.D);
     FIRE_LAUNCH_CHECK("l2norm_kernel");
     count_launch();
+  }
+  if (net->trace_all) {
+    FIRE_CUDA(cudaStreamSynchronize(st));
+    std::vector<long long> t(net->ops.size() * 8 * 256);
+    cudaMemcpy(t.data(), net->d_trace, t.size() * 8, cudaMemcpyDeviceToHost);
+    long long t0 = 0, prev_exit = 0;
+    fprintf(stderr, "# op grid | first entry, setup, first full(max), last MMA commit(max), epilogue done(max), last exit [ns since op 0 entered] | span | gap to previous exit\n");
+    for (size_t i = 0; i < net->ops.size(); ++i) {
+      const OpRt& r = net->ops[i];
+      if (r.op.kind != OP_CONV) continue;
+      const int grid = (int)std::min<long long>((long long)r.m_tiles * r.n_tiles, device_sm_count());
+      const long long* q = &t[i * 8 * 256];
+      long long e0 = 1ll << 62, su = 0, ff = 0, mc = 0, ed = 0, ex = 0;
+      for (int c = 0; c < grid; ++c) {
+        e0 = std::min(e0, q[c * 8]); su = std::max(su, q[c * 8 + 1]); ff = std::max(ff, q[c * 8 + 3]);
+        mc = std::max(mc, q[c * 8 + 4]); ed = std::max(ed, q[c * 8 + 6]); ex = std::max(ex, q[c * 8 + 7]);
+      }
+      if (t0 == 0) { t0 = e0; prev_exit = e0; }
+      fprintf(stderr, "%3zu %3d | %8lld %8lld %8lld %8lld %8lld %8lld | %6lld | %6lld\n", i, grid, e0 - t0, su - t0, ff - t0, mc - t0,
+              ed - t0, ex - t0, ex - e0, e0 - prev_exit);
+      prev_exit = ex;
+    }
   }
   return FIRE_OK;
 }

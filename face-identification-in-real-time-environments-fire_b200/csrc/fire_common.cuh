@@ -111,6 +111,8 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk stores of this thread have finished READING shared memory (the staging buffer may be reused)
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the most recent committed group of bulk stores have finished reading shared memory (double-buffered staging)
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 // all committed bulk stores of this thread are complete (writes performed)
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // named barrier among `count` threads (count a multiple of 32); id 0 is __syncthreads
