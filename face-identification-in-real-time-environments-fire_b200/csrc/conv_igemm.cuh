@@ -208,7 +208,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                        ? warp - CONV_FIRST_HELPER_WARP + 1 : -1;
   if (issuer >= 0) {
     // ---------------------------------------------------------------- TMA producers (stage g belongs to issuer g % n_issuers)
-    if (lane == 0 && issuer < p.n_issuers) {
+    // Whole-warp loops with one ELECTED lane issuing keep addresses and descriptors in uniform registers; a
+    // divergent `if (lane == 0)` body makes ptxas wrap every UTMALDG / UTCHMMA in an ELECT + R2UR + BRA.U.ANY loop.
+    if (issuer < p.n_issuers) {
       const uint32_t tx = static_cast<uint32_t>(b_stage_bytes) + (p.tma_a ? CONV_A_STAGE_BYTES : 0);
       bool waited = !p.pdl || !p.tma_a;
       int s = 0, turn = 0;
@@ -219,19 +221,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         for (int kb = 0; kb < nk_total; ++kb) {
           if (turn == issuer) {
             mbar_wait(&empty[s], ph ^ 1, 11);
-            if (kb < p.nkb) {
-              mbar_arrive_expect_tx(&full[s], tx);
-              tma_load_2d_hint(sB + static_cast<size_t>(s) * b_stage_bytes, &tmap_w, &full[s], kb * 64, n0, kEvictLast);
-              if (p.tma_a) {
-                if (!waited) { pdl_wait(); waited = true; }     // activations come from the previous layer
-                tma_load_2d(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES, &tmap_a, &full[s], kb * 64, m0);
+            if (!waited && (p.tma_a || kb >= p.nkb)) { pdl_wait(); waited = true; }     // activations come from the previous layer
+            if (elect_one()) {
+              if (kb < p.nkb) {
+                mbar_arrive_expect_tx(&full[s], tx);
+                tma_load_2d_hint(sB + static_cast<size_t>(s) * b_stage_bytes, &tmap_w, &full[s], kb * 64, n0, kEvictLast);
+                if (p.tma_a) tma_load_2d(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES, &tmap_a, &full[s], kb * 64, m0);
+              } else {                                          // residual K-block: [128 rows x 64 channels] of x
+                mbar_arrive_expect_tx(&full[s], CONV_A_STAGE_BYTES);
+                tma_load_2d(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES, &tmap_res, &full[s], n0 + (kb - p.nkb) * 64, m0);
               }
-            } else {                                            // residual K-block: [128 rows x 64 channels] of x
-              if (!waited) { pdl_wait(); waited = true; }
-              mbar_arrive_expect_tx(&full[s], CONV_A_STAGE_BYTES);
-              tma_load_2d(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES, &tmap_res, &full[s], n0 + (kb - p.nkb) * 64, m0);
             }
-            if (issuer == 0 && tile == static_cast<int>(blockIdx.x) && kb == 0) CONV_TRACE(2);
+            __syncwarp();
+            if (issuer == 0 && lane == 0 && tile == static_cast<int>(blockIdx.x) && kb == 0) CONV_TRACE(2);
           }
           if (++turn == p.n_issuers) turn = 0;
           if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -239,14 +241,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // ---------------------------------------------------------------- MMA issuer (whole warp loops, one elected lane issues)
+    {
       const uint32_t idesc = umma_idesc_f16(CONV_BM, p.bn_tile);
       const uint32_t idesc64 = umma_idesc_f16(CONV_BM, 64);
       const uint32_t ones_addr = smem_u32(smem + L.ones), zero_addr = smem_u32(smem + L.zero);
       const uint32_t bias_addr = smem_u32(smem + L.bias), ident_addr = smem_u32(smem + L.ident);
       const uint64_t ones_desc = umma_desc_nosw(ones_addr, zero_addr - ones_addr, 128);
       const bool do_mma = !(p.flags & CF_DBG_NOMMA);
+      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
       int lt = 0, s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
@@ -256,38 +259,45 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1, 15);
         tc_fence_after();
         const uint32_t d = tmem_base + static_cast<uint32_t>(buf * p.bn_tile);
-        {                                                       // D = ones * bias^T : initialises the accumulator
+        if (elect_one()) {                                      // D = ones * bias^T : initialises the accumulator
           const uint32_t b_addr = bias_addr + static_cast<uint32_t>(n0) * 16;
           umma_f16(d, ones_desc, umma_desc_nosw(b_addr, zero_addr - b_addr, 128), idesc, 0u);
         }
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(&full[s], ph, 12);
           tc_fence_after();
-          if (lt == 0 && kb == 0) CONV_TRACE(3);
-          const uint32_t a0 = smem_u32(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES);
-          const uint32_t b0 = smem_u32(sB + static_cast<size_t>(s) * b_stage_bytes);
-          if (do_mma) {
+          if (lt == 0 && kb == 0 && lane == 0) CONV_TRACE(3);
+          if (elect_one()) {
+            const uint32_t a0 = a_base + static_cast<uint32_t>(s * CONV_A_STAGE_BYTES);
+            const uint32_t b0 = b_base + static_cast<uint32_t>(s * b_stage_bytes);
+            if (do_mma) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, 1u);
+              for (int k = 0; k < 4; ++k) umma_f16(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, 1u);
+            }
+            umma_commit(&empty[s]);
           }
-          umma_commit(&empty[s]);
+          __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         for (int j = 0; j < p.n_res; ++j) {                     // D[:, 64j .. 64j+63] += R_j * I
           mbar_wait(&full[s], ph, 18);
           tc_fence_after();
-          const uint32_t a0 = smem_u32(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES);
-          if (do_mma) {
+          if (elect_one()) {
+            const uint32_t a0 = a_base + static_cast<uint32_t>(s * CONV_A_STAGE_BYTES);
+            if (do_mma) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16(d + static_cast<uint32_t>(j * 64), umma_desc_sw128(a0 + k * 32), umma_desc_sw128(ident_addr + k * 32), idesc64, 1u);
+              for (int k = 0; k < 4; ++k)
+                umma_f16(d + static_cast<uint32_t>(j * 64), umma_desc_sw128(a0 + k * 32), umma_desc_sw128(ident_addr + k * 32), idesc64, 1u);
+            }
+            umma_commit(&empty[s]);
           }
-          umma_commit(&empty[s]);
+          __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(&acc_full[buf]);
+        if (elect_one()) umma_commit(&acc_full[buf]);
+        __syncwarp();
       }
-      CONV_TRACE(4);
+      if (lane == 0) CONV_TRACE(4);
     }
   } else if (warp < CONV_FIRST_HELPER_WARP) {
     // ---------------------------------------------------------------- epilogue (8 warps, 2 per TMEM lane quarter)

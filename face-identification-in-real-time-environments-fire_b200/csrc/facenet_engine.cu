@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "conv_igemm.cuh"
+#include "conv_strip.cuh"
 #include "fire_internal.h"
 
 namespace fire {
@@ -130,6 +131,8 @@ struct OpRt {
   bool tma_a = false;
   int bn_tile = 0, stages = 0, n_issuers = 1, tmem_cols = 0, m_tiles = 0, n_tiles = 0;
   int n_res = 0, box_cols = 64;
+  bool strip = false;     // stride-1 k x k layer run by conv_strip_kernel (halo patch + shifted descriptors)
+  int Wbox = 0, R = 0, Hbox = 0, row_blocks = 0, a_stage_bytes = 0;
   size_t bias16_off = 0;  // byte offset of this op's [cout] x {hi, lo, 0 x 6} fp16 bias rows in d_bias16
   size_t smem = 0;
   double flops_per_image = 0;
@@ -178,6 +181,7 @@ struct fire_net {
   bool gather_l1 = false; // cp.async.ca instead of .cg for the A gather (FIRE_B200_GATHER_L1=1)
   int max_stages = 8;
   int n_issuers = CONV_MAX_ISSUERS;   // TMA issuing threads per CTA in 1x1 layers (FIRE_B200_ISSUERS=1|2|4)
+  bool use_strip = true;    // FIRE_B200_STRIP=0 forces the gather path for every k x k layer (A/B experiments)
   bool trace_all = false;   // FIRE_B200_TRACE_ALL=1: forward() records every conv's timeline, synchronises and prints it
   long long* d_trace = nullptr; int trace_op = -1;   // FIRE_B200_TRACE_OP=<op index>: in-kernel timeline of that op (profile only)
   int dbg_flags = 0;      // FIRE_B200_DBG: timing experiments (1 = no gather copies, 2 = no epilogue stores, 4 = no MMA)
@@ -248,6 +252,7 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
   static bool attr_done = false;
   if (!attr_done) {
     e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       cudaFree(net->d_weights);
       delete net;
@@ -290,14 +295,17 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
   const char* tr_env = getenv("FIRE_B200_TRACE_OP");
   if (tr_env && atoi(tr_env) >= 0 && atoi(tr_env) < (int)net->ops.size()) {
     net->trace_op = atoi(tr_env);
-    cudaMalloc(&net->d_trace, 8 * 8 * 256);
+    cudaMalloc(&net->d_trace, 8 * 8 * 512);
+    cudaMemset(net->d_trace, 0, 8 * 8 * 512);
   }
+  const char* sp_env = getenv("FIRE_B200_STRIP");
+  net->use_strip = !(sp_env && sp_env[0] == '0');
   const char* ta_env = getenv("FIRE_B200_TRACE_ALL");
   if (ta_env && ta_env[0] == '1') {
     net->trace_all = true; net->trace_op = 0;
     cudaFree(net->d_trace);
-    cudaMalloc(&net->d_trace, net->ops.size() * 8 * 8 * 256);
-    cudaMemset(net->d_trace, 0, net->ops.size() * 8 * 8 * 256);
+    cudaMalloc(&net->d_trace, net->ops.size() * 4096 * 8);
+    cudaMemset(net->d_trace, 0, net->ops.size() * 4096 * 8);
   }
   const char* is_env = getenv("FIRE_B200_ISSUERS");
   if (is_env) net->n_issuers = std::max(1, std::min(CONV_MAX_ISSUERS, atoi(is_env)));   // 1, 2 or 4 are used
@@ -340,6 +348,31 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
   const __half* src = static_cast<const __half*>(buf_ptr(net, o.src_buf, B, in, ws, out_raw));
   void* dst = buf_ptr(net, o.dst_buf, B, in, ws, out_raw);
   if (o.kind == OP_CONV) {
+    if (r.strip) {
+      StripParams q;
+      q.bias16 = reinterpret_cast<const uint4*>(net->d_bias16 + r.bias16_off);
+      q.cin = o.cin; q.cout = o.cout; q.kh = o.kh; q.kw = o.kw; q.pad_h = o.pad_h; q.pad_w = o.pad_w;
+      q.k16_steps = o.kh * o.kw * o.cin / 16; q.nkb = o.k_pad / 64;
+      q.Wbox = r.Wbox; q.R = r.R; q.Hbox = r.Hbox; q.row_blocks = r.row_blocks; q.total_tiles = B * r.row_blocks;
+      q.a_stage_bytes = r.a_stage_bytes; q.stages = r.stages; q.tmem_cols = r.tmem_cols; q.flags = o.flags | net->dbg_flags;
+      q.pdl = pdl ? 1 : 0; q.box_cols = r.box_cols;
+      q.trace = !net->d_trace ? nullptr : net->trace_all ? net->d_trace + (size_t)(&r - net->ops.data()) * 4096
+                : (&r == &net->ops[net->trace_op] ? net->d_trace : nullptr);
+      q.d_rowblocks = make_fastdiv(r.row_blocks);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)std::min<long long>((long long)B * r.row_blocks, device_sm_count()));
+      cfg.blockDim = dim3(STRIP_THREADS);
+      cfg.dynamicSmemBytes = r.smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = pdl ? 1 : 0;
+      FIRE_CUDA(cudaLaunchKernelEx(&cfg, conv_strip_kernel, r.tmap_w, r.tmap_a, r.tmap_out, q));
+      count_launch();
+      return FIRE_OK;
+    }
     ConvParams p;
     p.in = src; p.in_ld = sb.C; p.in_coff = o.src_coff;
     p.out = dst; p.out_ld = db.C; p.out_coff = o.dst_coff;
@@ -352,7 +385,7 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
     p.flags |= net->dbg_flags;
     p.n_res = r.n_res; p.box_cols = r.box_cols;
     p.n_issuers = r.n_issuers;
-    p.trace = !net->d_trace ? nullptr : net->trace_all ? net->d_trace + (size_t)(&r - net->ops.data()) * 8 * 256
+    p.trace = !net->d_trace ? nullptr : net->trace_all ? net->d_trace + (size_t)(&r - net->ops.data()) * 4096
               : (&r == &net->ops[net->trace_op] ? net->d_trace : nullptr);
     p.d_howo = make_fastdiv(o.Ho * o.Wo); p.d_wo = make_fastdiv(o.Wo); p.d_cin = make_fastdiv(o.cin); p.d_kw = make_fastdiv(o.kw);
     p.d_ntiles = make_fastdiv(r.n_tiles);
@@ -398,6 +431,47 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
       if (r.op.kind != OP_CONV) continue;
       const BlobOp& o = r.op;
       r.m_tiles = (B * o.Ho * o.Wo + CONV_BM - 1) / CONV_BM;
+      r.strip = false;
+      {
+        // strip mode: stride-1 k x k, one swizzle-wide channel panel, weights resident in shared memory
+        const int wbox = o.Wo + o.kw - 1;
+        const bool shape_ok = net->use_strip && o.stride == 1 && o.kh * o.kw > 1 && (o.cin == 16 || o.cin == 32 || o.cin == 64) &&
+                              o.cout <= 256 && !(o.flags & (CF_RESIDUAL | CF_OUT_F32)) && wbox <= CONV_BM &&
+                              (size_t)(o.k_pad / 64) * o.cout * 128 <= 96 * 1024 && (o.kh * o.kw * o.cin) % 16 == 0;
+        if (shape_ok) {
+          r.strip = true;
+          r.Wbox = wbox;
+          r.R = std::min(o.Ho, CONV_BM / wbox);
+          r.Hbox = r.R + o.kh - 1;
+          r.row_blocks = (o.Ho + r.R - 1) / r.R;
+          const int rows_alloc = std::max(r.Hbox * wbox, CONV_BM + (o.kh - 1) * wbox + o.kw - 1);
+          r.a_stage_bytes = (rows_alloc * o.cin * 2 + 1023) / 1024 * 1024;
+          r.bn_tile = 0;                       // force a fresh weight map below
+          int rc = make_tmap_f16_2d(&r.tmap_w, net->d_weights + o.w_off, (uint64_t)o.cout, (uint64_t)o.k_pad, (uint64_t)o.k_pad * 2,
+                                    (uint32_t)o.cout);
+          if (rc != FIRE_OK) return rc;
+          r.box_cols = o.cout % 64 == 0 ? 64 : (o.cout % 32 == 0 ? 32 : 16);
+          const size_t fixed = strip_smem_layout(0, r.a_stage_bytes, o.k_pad / 64, o.cout).total + 1024;
+          r.stages = (int)std::min<size_t>(6, (232448 - fixed) / r.a_stage_bytes);
+          if (r.stages < 2) r.strip = false;
+          else {
+            r.smem = strip_smem_layout(r.stages, r.a_stage_bytes, o.k_pad / 64, o.cout).total + 1024;
+            r.tmem_cols = pow2_cols(2 * o.cout);
+            const BlobBuf& sb = net->bufs[o.src_buf];
+            const BlobBuf& db = net->bufs[o.dst_buf];
+            const __half* src = static_cast<const __half*>(buf_ptr(net, o.src_buf, B, in, ws, out_raw)) + o.src_coff;
+            const __half* dst = static_cast<const __half*>(buf_ptr(net, o.dst_buf, B, in, ws, out_raw)) + o.dst_coff;
+            rc = make_tmap_f16_nhwc(&r.tmap_a, src, (uint64_t)o.cin, (uint64_t)o.W, (uint64_t)o.H, (uint64_t)B, (uint64_t)sb.C,
+                                    (uint32_t)o.cin, (uint32_t)r.Wbox, (uint32_t)r.Hbox);
+            if (rc != FIRE_OK) return rc;
+            rc = make_tmap_f16_nhwc(&r.tmap_out, dst, (uint64_t)o.cout, (uint64_t)o.Wo, (uint64_t)o.Ho, (uint64_t)B, (uint64_t)db.C,
+                                    (uint32_t)r.box_cols, (uint32_t)r.Wbox, (uint32_t)r.R);
+            if (rc != FIRE_OK) return rc;
+            r.n_tiles = 1; r.n_res = 0; r.n_issuers = 1;
+            continue;
+          }
+        }
+      }
       const bool residual = (o.flags & CF_RESIDUAL) != 0;
       const int bn = pick_bn_tile(o.cout, r.m_tiles, o.k_pad / 64, sms, residual);
       if (bn != r.bn_tile) {
@@ -465,15 +539,15 @@ int fire_facenet_forward(fire_net_t* net, const void* in_f16, int B, float* out_
   }
   if (net->trace_all) {
     FIRE_CUDA(cudaStreamSynchronize(st));
-    std::vector<long long> t(net->ops.size() * 8 * 256);
+    std::vector<long long> t(net->ops.size() * 4096);
     cudaMemcpy(t.data(), net->d_trace, t.size() * 8, cudaMemcpyDeviceToHost);
     long long t0 = 0, prev_exit = 0;
     fprintf(stderr, "# op grid | first entry, setup, first full(max), last MMA commit(max), epilogue done(max), last exit [ns since op 0 entered] | span | gap to previous exit\n");
     for (size_t i = 0; i < net->ops.size(); ++i) {
       const OpRt& r = net->ops[i];
       if (r.op.kind != OP_CONV) continue;
-      const int grid = (int)std::min<long long>((long long)r.m_tiles * r.n_tiles, device_sm_count());
-      const long long* q = &t[i * 8 * 256];
+      const int grid = (int)std::min<long long>(r.strip ? (long long)B * r.row_blocks : (long long)r.m_tiles * r.n_tiles, device_sm_count());
+      const long long* q = &t[i * 4096];
       long long e0 = 1ll << 62, su = 0, ff = 0, mc = 0, ed = 0, ex = 0;
       for (int c = 0; c < grid; ++c) {
         e0 = std::min(e0, q[c * 8]); su = std::max(su, q[c * 8 + 1]); ff = std::max(ff, q[c * 8 + 3]);
@@ -512,15 +586,25 @@ int fire_facenet_profile(fire_net_t* net, const void* in_f16, int B, void* works
     }
   }
   if (net->d_trace && rc == FIRE_OK && e == cudaSuccess) {
-    std::vector<long long> t(8 * 256);
+    std::vector<long long> t(8 * 512);
     cudaMemcpy(t.data(), net->d_trace, t.size() * 8, cudaMemcpyDeviceToHost);
     const OpRt& r = net->ops[net->trace_op];
-    const int grid = (int)std::min<long long>((long long)r.m_tiles * r.n_tiles, device_sm_count());
+    const int grid = (int)std::min<long long>(r.strip ? (long long)B * r.row_blocks : (long long)r.m_tiles * r.n_tiles, device_sm_count());
     long long t0 = t[0];
     for (int c = 0; c < grid; ++c) t0 = std::min(t0, t[c * 8]);
     const char* names[8] = {"entry", "setup done", "first TMA issued", "first full", "last MMA commit", "first acc_full", "epilogue done", "exit"};
     fprintf(stderr, "trace op %d: grid %d, tiles %d x %d, bn %d, nkb %d, stages %d, issuers %d, event ms %.4f\n", net->trace_op, grid,
             r.m_tiles, r.n_tiles, r.bn_tile, r.op.k_pad / 64, r.stages, r.n_issuers, host_ms[net->trace_op]);
+    if (r.strip) {
+      const char* ph[7] = {"wait_group.read", "barrier 1", "acc_full wait", "tmem ld + cvt + sts + arrive", "fence.proxy.async", "barrier 2", "TMA store issue"};
+      const long long* q = &t[8 * 148];
+      fprintf(stderr, "  epilogue leader, cycles per tile (CTA 0 .. avg over CTAs), tiles per CTA %lld:\n", q[7]);
+      for (int k = 0; k < 7; ++k) {
+        double avg = 0;
+        for (int c = 0; c < grid; ++c) avg += (double)q[c * 8 + k] / (double)std::max<long long>(q[c * 8 + 7], 1);
+        fprintf(stderr, "    %-30s %8.0f .. %8.0f\n", ph[k], (double)q[k] / (double)std::max<long long>(q[7], 1), avg / grid);
+      }
+    }
     for (int k = 0; k < 8; ++k) {
       long long mn = 1ll << 62, mx = 0; double avg = 0;
       for (int c = 0; c < grid; ++c) { long long v = t[c * 8 + k] - t0; mn = std::min(mn, v); mx = std::max(mx, v); avg += (double)v; }

@@ -117,6 +117,33 @@ __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // named barrier among `count` threads (count a multiple of 32); id 0 is __syncthreads
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// 4D tiled load / store (coordinates inner -> outer: c, w, h, n); out-of-range elements load as zero / are not stored.
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// Shared-memory matrix descriptor, K-major, swizzled rows of `row_bytes` in {32, 64, 128}: 8-row groups are
+// 8 * row_bytes apart.  The start address may be advanced by whole rows (tap shifts) - the swizzle is a function of
+// absolute address bits, base_offset stays 0 (measured: tools/umma_probe.cu part 2).
+__device__ __forceinline__ uint64_t umma_desc_swz(uint32_t smem_addr, uint32_t row_bytes) {
+  const uint64_t code = row_bytes == 128 ? 2ull : row_bytes == 64 ? 4ull : 6ull;
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((8 * row_bytes) >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= code << 61;
+  return d;
+}
 // L2 eviction-priority policies (createpolicy encodings used by CUTLASS' TMA::CacheHintSm90).
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;

@@ -38,6 +38,12 @@ int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 int make_tmap_f16_2d_ex(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
                         uint32_t box_cols, uint32_t box_rows);
 
+// 4-D view {C, W, H, N} of an NHWC fp16 buffer whose pixels are `ld_elems` channels apart (C <= ld_elems: a channel
+// slice); box = (box_c channels, box_w, box_h, 1 image), swizzle = box_c * 2 bytes.  Out-of-range coordinates
+// (negative included) read as zero and are not written: this is how 'same' padding and ragged edges are handled.
+int make_tmap_f16_nhwc(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint64_t ld_elems,
+                       uint32_t box_c, uint32_t box_w, uint32_t box_h);
+
 int device_sm_count();
 
 // Launch counter (every kernel launch of this library bumps it; bench.py reports it as gpu_launches).

@@ -476,6 +476,144 @@ static void part4() {
   cudaFree(dout);
 }
 
+// ------------------------------------------------------------------------------------------------ part 5
+// Cost of a chain of tcgen05.mma (M=128, N, K=16) into ONE accumulator as a function of the A layout and of the
+// row shift of the A descriptor: cycles from the first issue until the commit barrier fires.
+__global__ void __launch_bounds__(128, 1) umma_time_kernel(int layout, int N, int n_mma, int shift_rows, int wbox, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                 // 64 KB of zeros
+  uint8_t* sB = smem + 64 * 1024;     // 64 KB of zeros
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  for (int i = threadIdx.x; i < 128 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_alloc<256>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_f16(128, N);
+    const uint32_t rowbytes = layout == 3 ? 128u : layout == 2 ? 64u : 32u;
+    const uint32_t code = layout == 3 ? 2u : layout == 2 ? 4u : 6u;
+    long long best = 1ll << 60;
+    for (int rep = 0; rep < 5; ++rep) {
+      const long long t0 = clock64();
+      for (int j = 0; j < n_mma; ++j) {
+        // tap-like walk: shift = shift_rows * ((j / 2) % 3) + wbox * ((j / 2) / 3), k half = j & 1
+        const int tap = j >> 1;
+        const uint32_t rows = static_cast<uint32_t>(shift_rows * (tap % 3) + wbox * (tap / 3));
+        const uint32_t a_addr = smem_u32(sA) + rows * rowbytes + (j & 1) * 32;
+        const uint64_t ad = layout == 0 ? umma_desc_nosw(smem_u32(sA) + rows * 16, 8192, 128) : make_desc(a_addr, 16, 8 * rowbytes, code, 0);
+        umma_f16(tmem, ad, umma_desc_sw128(smem_u32(sB) + (j & 3) * 32), idesc, j ? 1u : 0u);
+      }
+      umma_commit(&bar);
+      mbar_wait(&bar, rep & 1, 7);
+      const long long t1 = clock64();
+      if (rep >= 1 && t1 - t0 < best) best = t1 - t0;
+    }
+    out[0] = best;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc<256>(tmem); }
+}
+
+static void part5() {
+  printf("== part 5: cycles for a chain of n tcgen05.mma (M=128, K=16) + commit, by A layout / row shift ==\n");
+  CK(cudaFuncSetAttribute(umma_time_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 130 * 1024));
+  long long* dout;
+  CK(cudaMalloc(&dout, 8));
+  const char* lname[] = {"none/planar-8", "SW32", "SW64", "SW128"};
+  for (int N : {32, 64, 256}) {
+    for (int layout : {3, 2, 0}) {
+      for (int shift : {0, 1, 8}) {
+        printf("  N=%-3d A layout %-14s tap shift %d row(s), patch width %2d:", N, lname[layout], shift, shift ? 79 : 0);
+        for (int n : {1, 2, 18, 36}) {
+          umma_time_kernel<<<1, 128, 130 * 1024>>>(layout, N, n, shift, shift ? 79 : 0, dout);
+          CK(cudaDeviceSynchronize());
+          long long h;
+          CK(cudaMemcpy(&h, dout, 8, cudaMemcpyDeviceToHost));
+          printf("  n=%-2d %5lld", n, h);
+        }
+        printf("\n");
+      }
+    }
+  }
+  cudaFree(dout);
+}
+
+// ------------------------------------------------------------------------------------------------ part 6
+// Is the ~100-cycle cost of a small-N tcgen05.mma an accumulator-dependency latency or an issue limit?
+// n_acc independent accumulators are fed round-robin by n_thr issuing threads (one per warp).
+__global__ void __launch_bounds__(128, 1) umma_ilp_kernel(int N, int n_mma, int n_acc, int n_thr, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 64 * 1024;
+  __shared__ uint64_t bar[4];
+  __shared__ uint32_t tmem_slot;
+  for (int i = threadIdx.x; i < 128 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1); fence_barrier_init(); }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_alloc<512>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0 && warp < n_thr) {
+    const uint32_t idesc = umma_idesc_f16(128, N);
+    long long best = 1ll << 60;
+    for (int rep = 0; rep < 5; ++rep) {
+      const long long t0 = clock64();
+      // this thread owns accumulators a = warp, warp + n_thr, ...; n_mma MMAs per accumulator, interleaved
+      for (int j = 0; j < n_mma; ++j)
+        for (int a = warp; a < n_acc; a += n_thr)
+          umma_f16(tmem + a * N, umma_desc_sw128(smem_u32(sA) + (j & 3) * 32 + a * 16384), umma_desc_sw128(smem_u32(sB) + (j & 3) * 32), idesc,
+                   j ? 1u : 0u);
+      umma_commit(&bar[warp]);
+      mbar_wait(&bar[warp], rep & 1, 8);
+      const long long t1 = clock64();
+      if (rep >= 1 && t1 - t0 < best) best = t1 - t0;
+    }
+    out[warp] = best;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc<512>(tmem); }
+}
+
+static void part6() {
+  printf("== part 6: n tcgen05.mma (M=128, K=16) per accumulator, n_acc accumulators, n_thr issuing threads: cycles (max over threads) ==\n");
+  CK(cudaFuncSetAttribute(umma_ilp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 130 * 1024));
+  long long* dout;
+  CK(cudaMalloc(&dout, 32));
+  for (int N : {32, 64, 128}) {
+    for (int n_acc : {1, 2, 4}) {
+      for (int n_thr : {1, 2, 4}) {
+        if (n_thr > n_acc || n_acc * N > 512) continue;
+        printf("  N=%-3d accumulators %d issuing threads %d:", N, n_acc, n_thr);
+        for (int n : {18, 36}) {
+          umma_ilp_kernel<<<1, 128, 130 * 1024>>>(N, n, n_acc, n_thr, dout);
+          CK(cudaDeviceSynchronize());
+          long long h[4];
+          CK(cudaMemcpy(h, dout, 32, cudaMemcpyDeviceToHost));
+          long long mx = 0;
+          for (int i = 0; i < n_thr; ++i) mx = h[i] > mx ? h[i] : mx;
+          printf("  n=%-2d %5lld (%.0f clk per MMA)", n, mx, (double)mx / (n * n_acc));
+        }
+        printf("\n");
+      }
+    }
+  }
+  cudaFree(dout);
+}
+
 int main(int argc, char** argv) {
   const int which = argc > 1 ? atoi(argv[1]) : 3;
   CK(cudaSetDevice(0));
@@ -483,5 +621,7 @@ int main(int argc, char** argv) {
   if (which & 1) part1();
   if (which & 4) part3();
   if (which & 8) part4();
+  if (which & 16) part5();
+  if (which & 32) part6();
   return 0;
 }
