@@ -8,8 +8,8 @@ Headline (BASELINE.json configs[1]): FaceNet512 on batches of 256 uint8 160x160 
 One "step" = one pass of the hot path over one batch: crop/resize/normalise kernel (K1) -> the 105
 tcgen05 implicit-GEMM convolutions + pools + tail (K2) -> L2-normalised embeddings.
   value : embeds/s with the uint8 crops already resident in HBM (device-timed, CUDA events)
-  e2e   : the same through the public call a FIRE user makes (fire_b200.encoder.Encoder.encode_crops path):
-          pinned host uint8 crops -> H2D -> K1 -> K2 -> D2H float32 embeddings, every step
+  e2e   : the same through the public streaming call (fire_b200.engine.CropEncodePipeline.submit):
+          pinned host uint8 crops -> H2D -> K1 -> K2 -> D2H float32 embeddings, every step (H2D double-buffered)
   knn   : BASELINE.json configs[2]/[3]: exact cosine top-10, 4096 queries, 1M x 512 (N=1) and 10M x 512
           (row-sharded over the N ranks, NCCL all_gather + merge) -> QPS, with its own roofline
 `--impl reference` times the reference's CPU path restated (oracle/: cv2 INTER_AREA + torch-CPU
@@ -196,18 +196,18 @@ def run_fire(args):
     desc = torch.tensor([[i * 160 * 160 * 3, 160, 160, 480] for i in range(BATCH)], dtype=torch.int64, device=dev)
     raw = torch.empty(BATCH, D, dtype=torch.float32, device=dev)
     l2 = torch.empty(BATCH, D, dtype=torch.float32, device=dev)
-    host_out = torch.empty(BATCH, D, dtype=torch.float32).pin_memory()
-    stage_in = torch.empty(BATCH, 160, 160, 3, dtype=torch.uint8, device=dev)
 
     def step_device(i):
         f16, _, _ = engine.preprocess_boxes(dev_batches[i % n_rot], desc, boxes, frame_ids, _lib.PRE_REFERENCE, True, False)
         eng.forward(f16, want_l2=True, out_raw=raw, out_l2=l2)
 
+    pipe = engine.CropEncodePipeline(eng, BATCH, depth=2, normalize=True)
+
     def step_e2e(i):
-        stage_in.copy_(pinned[i % n_rot], non_blocking=True)
-        f16, _, _ = engine.preprocess_boxes(stage_in, desc, boxes, frame_ids, _lib.PRE_REFERENCE, True, False)
-        eng.forward(f16, want_l2=True, out_raw=raw, out_l2=l2)
-        host_out.copy_(l2, non_blocking=True)
+        # the public streaming call: pinned host crops -> H2D (copy stream) -> K1 -> K2 -> D2H of the embeddings; the
+        # H2D of step i+1 overlaps the kernels of step i.  Every step's result lands in pinned host memory before the
+        # closing synchronize of the timed region.
+        pipe.submit(pinned[i % n_rot])
 
     def timed(step_fn, steps, warmup):
         for i in range(warmup):

@@ -7,8 +7,8 @@
 //                                                                 k = (tap r,s ; input channel c), tap-major
 //
 // EVERYTHING additive runs on the tensor core, so the epilogue is only "convert and store":
-//   * bias      : the first MMA of a tile is ones[128 x 16] * biasT[bn x 16]^T with accumulate = 0, where the bias
-//                 row holds fp16 hi and lo parts of the fp32 bias (hi + lo carries ~22 bits) - it initialises TMEM;
+//   * bias      : the last MMA of a tile is ones[128 x 16] * biasT[bn x 16]^T, where the bias row holds fp16 hi and lo
+//                 parts of the fp32 bias (hi + lo carries ~22 bits);
 //   * residual  : x + up(cat) is "one more K block": the residual tile [128 x 64] is TMA-loaded like an activation
 //                 K-block and multiplied by a constant 64 x 64 identity (exact: fp16 * 1.0 accumulated in fp32).
 //
@@ -51,6 +51,7 @@ constexpr int CONV_MAX_COUT = 1792;
 constexpr int CONV_PASS_COLS = 128;        // columns staged per epilogue pass
 
 constexpr int CF_RELU = 1, CF_RESIDUAL = 2, CF_OUT_F32 = 4;
+constexpr int CF_DBG_PHASES = 1 << 19;     // with a trace buffer: per-role cycle accounting (strip kernel)
 constexpr int CF_DBG_NOGATHER = 1 << 16, CF_DBG_NOSTORE = 1 << 17, CF_DBG_NOMMA = 1 << 18;   // timing experiments only (wrong results)
 
 struct FastDiv {            // q = x / d for 0 <= x < 2^31  (mul = ceil(2^sh / d), sh = 31 + ceil(log2 d))
@@ -155,7 +156,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   uint64_t* empty = bars + p.stages;
   uint64_t* acc_full = empty + p.stages;      // [2]
   uint64_t* acc_empty = acc_full + 2;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* bias_ready = acc_empty + 2;       // the bias operand has landed in shared memory (filled after the setup barrier)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_ready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -174,6 +176,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       const uint32_t full_count = p.tma_a ? 1u : 1u + CONV_HELPER_THREADS;
       for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], full_count); mbar_init(&empty[s], 1); }
       for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], CONV_EPI_WARPS * 32); }
+      mbar_init(bias_ready, CONV_EPI_WARPS * 32);
       fence_barrier_init();
     }
     __syncwarp();
@@ -182,8 +185,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   if (warp >= CONV_FIRST_EPI_WARP) {
     // constant MMA operands (weights-side data: safe to read before the dependency wait)
     const int t = threadIdx.x - CONV_FIRST_EPI_WARP * 32;                 // 0..511
-    uint4* s_bias = reinterpret_cast<uint4*>(smem + L.bias);
-    for (int i = t; i < p.cout; i += (CONV_THREADS - CONV_FIRST_EPI_WARP * 32)) s_bias[i] = __ldg(p.bias16 + i);
     if (t < CONV_BM) reinterpret_cast<uint4*>(smem + L.ones)[t] = make_uint4(0x3C003C00u, 0u, 0u, 0u);   // {1.0h, 1.0h, 0...}
     if (t < 256) reinterpret_cast<uint4*>(smem + L.zero)[t] = make_uint4(0u, 0u, 0u, 0u);
     if (p.n_res) {                                                       // 64 x 64 identity, rows of 128 bytes, SW128
@@ -212,31 +213,40 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     // divergent `if (lane == 0)` body makes ptxas wrap every UTMALDG / UTCHMMA in an ELECT + R2UR + BRA.U.ANY loop.
     if (issuer < p.n_issuers) {
       const uint32_t tx = static_cast<uint32_t>(b_stage_bytes) + (p.tma_a ? CONV_A_STAGE_BYTES : 0);
-      bool waited = !p.pdl || !p.tma_a;
-      int s = 0, turn = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = fdiv(tile, p.d_ntiles);
-        const int n0 = (tile - mt * p.n_tiles) * p.bn_tile, m0 = mt * CONV_BM;
-        for (int kb = 0; kb < nk_total; ++kb) {
-          if (turn == issuer) {
-            mbar_wait(&empty[s], ph ^ 1, 11);
-            if (!waited && (p.tma_a || kb >= p.nkb)) { pdl_wait(); waited = true; }     // activations come from the previous layer
-            if (elect_one()) {
-              if (kb < p.nkb) {
-                mbar_arrive_expect_tx(&full[s], tx);
-                tma_load_2d_hint(sB + static_cast<size_t>(s) * b_stage_bytes, &tmap_w, &full[s], kb * 64, n0, kEvictLast);
-                if (p.tma_a) tma_load_2d(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES, &tmap_a, &full[s], kb * 64, m0);
-              } else {                                          // residual K-block: [128 rows x 64 channels] of x
-                mbar_arrive_expect_tx(&full[s], CONV_A_STAGE_BYTES);
-                tma_load_2d(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES, &tmap_res, &full[s], n0 + (kb - p.nkb) * 64, m0);
+      // Pass 0 (1x1 layers under PDL only): the WEIGHT halves of the first ring fill do not depend on the previous
+      // layer, so they are in flight before griddepcontrol.wait; pass 1 issues everything else.
+      const int prefill = (p.pdl && p.tma_a) ? p.stages : 0;
+      for (int pass = prefill ? 0 : 1; pass < 2; ++pass) {
+        if (pass == 1 && p.pdl && p.tma_a) pdl_wait();          // activations / residual come from the previous layer
+        int s = 0, turn = 0, g = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          const int mt = fdiv(tile, p.d_ntiles);
+          const int n0 = (tile - mt * p.n_tiles) * p.bn_tile, m0 = mt * CONV_BM;
+          for (int kb = 0; kb < nk_total; ++kb, ++g) {
+            if (pass == 0 && g >= prefill) break;
+            if (turn == issuer) {
+              const bool pre = g < prefill;                      // this slot's expect_tx (and weight load) happened in pass 0
+              if (!pre || pass == 0) mbar_wait(&empty[s], ph ^ 1, 11);
+              if (elect_one()) {
+                if (kb < p.nkb) {
+                  if (!pre || pass == 0) {
+                    mbar_arrive_expect_tx(&full[s], tx);
+                    tma_load_2d_hint(sB + static_cast<size_t>(s) * b_stage_bytes, &tmap_w, &full[s], kb * 64, n0, kEvictLast);
+                  }
+                  if (p.tma_a && pass == 1) tma_load_2d(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES, &tmap_a, &full[s], kb * 64, m0);
+                } else if (pass == 1) {                           // residual K-block: [128 rows x 64 channels] of x
+                  mbar_arrive_expect_tx(&full[s], CONV_A_STAGE_BYTES);
+                  tma_load_2d(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES, &tmap_res, &full[s], n0 + (kb - p.nkb) * 64, m0);
+                }
               }
+              __syncwarp();
+              if (pass == 1 && issuer == 0 && lane == 0 && g == 0) CONV_TRACE(2);
             }
-            __syncwarp();
-            if (issuer == 0 && lane == 0 && tile == static_cast<int>(blockIdx.x) && kb == 0) CONV_TRACE(2);
+            if (++turn == p.n_issuers) turn = 0;
+            if (++s == p.stages) { s = 0; ph ^= 1; }
           }
-          if (++turn == p.n_issuers) turn = 0;
-          if (++s == p.stages) { s = 0; ph ^= 1; }
+          if (pass == 0 && g >= prefill) break;
         }
       }
     }
@@ -259,10 +269,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1, 15);
         tc_fence_after();
         const uint32_t d = tmem_base + static_cast<uint32_t>(buf * p.bn_tile);
-        if (elect_one()) {                                      // D = ones * bias^T : initialises the accumulator
-          const uint32_t b_addr = bias_addr + static_cast<uint32_t>(n0) * 16;
-          umma_f16(d, ones_desc, umma_desc_nosw(b_addr, zero_addr - b_addr, 128), idesc, 0u);
-        }
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(&full[s], ph, 12);
           tc_fence_after();
@@ -272,7 +278,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             const uint32_t b0 = b_base + static_cast<uint32_t>(s * b_stage_bytes);
             if (do_mma) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, 1u);
+              for (int k = 0; k < 4; ++k) umma_f16(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
             }
             umma_commit(&empty[s]);
           }
@@ -294,7 +300,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        if (elect_one()) umma_commit(&acc_full[buf]);
+        if (lt == 0) mbar_wait(bias_ready, 0, 19);
+        if (elect_one()) {                                      // D += ones * bias^T, then publish the accumulator
+          const uint32_t b_addr = bias_addr + static_cast<uint32_t>(n0) * 16;
+          umma_f16(d, ones_desc, umma_desc_nosw(b_addr, zero_addr - b_addr, 128), idesc, 1u);
+          umma_commit(&acc_full[buf]);
+        }
         __syncwarp();
       }
       if (lane == 0) CONV_TRACE(4);
@@ -311,6 +322,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const uint32_t my_stage0 = smem_u32(smem + L.out) + static_cast<uint32_t>(quarter * 32 * pass_cols * 2);
     uint32_t sbuf = 0;                                          // staging buffer of the next pass (alternates)
     const bool do_store = !(p.flags & CF_DBG_NOSTORE);
+    {
+      // bias operand (a weight: no dependency wait needed); only needed by the LAST MMA of the first tile, so it is
+      // fetched here, off the critical path of the prologue
+      uint4* s_bias = reinterpret_cast<uint4*>(smem + L.bias);
+      for (int i = threadIdx.x - CONV_FIRST_EPI_WARP * 32; i < p.cout; i += CONV_EPI_WARPS * 32) s_bias[i] = __ldg(p.bias16 + i);
+      fence_proxy_async_smem();
+      mbar_arrive(bias_ready);
+    }
     if (p.pdl && (leader || out_f32)) pdl_wait();               // output writes must not overtake readers of the previous layers
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {

@@ -14,13 +14,18 @@
 // per tile the producer issues one TMA, the MMA thread issues kh*kw*Cin/16 tcgen05.mma, the epilogue converts.
 // The Wbox - Wo garbage columns of each row (and rows past Ho) are computed but never stored: the 4-D TMA store
 // clips them against the output tensor's extents.  Weights stay resident for the whole launch.
+// Flat mode (wide images, where R whole rows would fill little of the 128-row MMA): the OUTPUT buffer is allocated
+// with row pitch Wbox, a tile is 128 consecutive positions of that pitched space (any start, mid-row included - the
+// A descriptor just starts (f0 mod Wbox) rows into the patch) and the garbage columns land in the padding, which no
+// consumer reads (their tensor maps end at Wo).
 #pragma once
 
 #include "conv_igemm.cuh"
 
 namespace fire {
 
-constexpr int STRIP_THREADS = 32 * (2 + CONV_EPI_WARPS);     // warp 0 producer, warp 1 MMA, warps 2-9 epilogue
+constexpr int STRIP_THREADS = 32 * (3 + CONV_EPI_WARPS);     // warp 0 producer, warp 1 MMA, warps 2-9 epilogue, warp 10 TMA stores
+constexpr int STRIP_MAX_ACC = 8;                             // TMEM accumulators (tiles in flight between MMA and epilogue)
 
 struct StripSmem {
   uint32_t a, b, bias, ones, zero, out, bars, total;
@@ -35,7 +40,7 @@ __host__ __device__ inline StripSmem strip_smem_layout(int stages, int a_stage_b
   L.zero = o; o += 256 * 16;
   o = (o + 1023) & ~1023u;
   L.out = o;  o += 2u * CONV_BM * cout * 2;                  // [2 buffers][cout / box_cols boxes][128 rows][box_cols * 2 bytes]
-  L.bars = o; o += 256;
+  L.bars = o; o += 512;
   L.total = o;
   return L;
 }
@@ -46,11 +51,15 @@ struct StripParams {
   int k16_steps;          // kh * kw * cin / 16
   int nkb;                // resident weight K-blocks (k_pad / 64)
   int Wbox, R, Hbox;      // patch: Wbox = Wo + kw - 1 pixels wide, R output rows per tile, Hbox = R + kh - 1
-  int row_blocks;         // ceil(Ho / R)
+  int row_blocks;         // tiles per image: ceil(Ho / R), or ceil(Ho * Wbox / 128) in flat mode
   int total_tiles;        // images * row_blocks
+  int flat;               // 1: a tile is 128 consecutive positions of the image's [Ho][Wbox] pitched position space (the output
+                          //    buffer has row pitch Wbox, so the garbage columns land in its padding); 0: R whole rows
+  int Ho;
   int a_stage_bytes, stages, tmem_cols, flags, pdl, box_cols;
+  int n_acc;              // TMEM accumulators (power of two, <= STRIP_MAX_ACC); the MMA warp interleaves n_acc / 2 tiles
   long long* trace;
-  FastDiv d_rowblocks;
+  FastDiv d_rowblocks, d_wbox;
 };
 
 __global__ void __launch_bounds__(STRIP_THREADS, 1)
@@ -64,9 +73,11 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + p.stages;
-  uint64_t* acc_full = a_empty + p.stages;    // [2]
-  uint64_t* acc_empty = acc_full + 2;         // [2]
-  uint64_t* w_full = acc_empty + 2;
+  uint64_t* acc_full = a_empty + p.stages;            // [STRIP_MAX_ACC]
+  uint64_t* acc_empty = acc_full + STRIP_MAX_ACC;     // [STRIP_MAX_ACC]
+  uint64_t* out_full = acc_empty + STRIP_MAX_ACC;     // [2] staging buffer written by the epilogue warps
+  uint64_t* out_empty = out_full + 2;                 // [2] staging buffer read by the TMA store
+  uint64_t* w_full = out_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -82,14 +93,15 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-      for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], CONV_EPI_WARPS * 32); }
+      for (int b = 0; b < STRIP_MAX_ACC; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], CONV_EPI_WARPS * 32); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&out_full[b], CONV_EPI_WARPS * 32); mbar_init(&out_empty[b], 1); }
       mbar_init(w_full, 1);
       fence_barrier_init();
     }
     __syncwarp();
     tmem_alloc_rt(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
   }
-  if (warp >= CONV_FIRST_EPI_WARP) {
+  if (warp >= CONV_FIRST_EPI_WARP && warp < CONV_FIRST_EPI_WARP + CONV_EPI_WARPS) {
     const int t = threadIdx.x - CONV_FIRST_EPI_WARP * 32;                 // 0..255
     uint4* s_bias = reinterpret_cast<uint4*>(smem + L.bias);
     for (int i = t; i < p.cout; i += CONV_EPI_WARPS * 32) s_bias[i] = __ldg(p.bias16 + i);
@@ -118,7 +130,8 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n = fdiv(tile, p.d_rowblocks), y0 = (tile - n * p.row_blocks) * p.R;
+        const int n = fdiv(tile, p.d_rowblocks), tin = tile - n * p.row_blocks;
+        const int y0 = p.flat ? fdiv(tin * CONV_BM, p.d_wbox) : tin * p.R;      // first output row of the tile
         mbar_wait(&a_empty[s], ph ^ 1, 21);
         if (elect_one()) {
           mbar_arrive_expect_tx(&a_full[s], box_bytes);
@@ -144,72 +157,118 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       const uint64_t b_desc_hi = umma_desc_sw128(0u);
       mbar_wait(w_full, 0, 22);
       tc_fence_after();
-      int lt = 0, s = 0;
+      // A small-N tcgen05.mma costs ~100 cycles when it depends on the previous one through the accumulator
+      // (tools/umma_probe.cu part 5/6), so G = n_acc / 2 tiles are accumulated side by side: the K loop is the outer
+      // loop and the G independent accumulators the inner one.
+      const int G = p.n_acc >> 1;
+      const int my_tiles = static_cast<int>(blockIdx.x) < p.total_tiles ? (p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
+      int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-        const int buf = lt & 1;
-        mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1, 23);
+      long long tm[3] = {0, 0, 0};
+      const bool prof = p.trace != nullptr && (p.flags & CF_DBG_PHASES);
+      for (int lt0 = 0; lt0 < my_tiles; lt0 += G) {
+        const int cnt = min(G, my_tiles - lt0);
+        long long c0 = prof ? clock64() : 0, c1;
+        for (int i = 0; i < cnt; ++i) {
+          const int l = lt0 + i;
+          mbar_wait(&acc_empty[l & (p.n_acc - 1)], (static_cast<uint32_t>(l / p.n_acc) & 1u) ^ 1u, 23);
+        }
         tc_fence_after();
-        const uint32_t d = tmem_base + static_cast<uint32_t>(buf * p.cout);
-        if (elect_one()) umma_f16(d, ones_desc, bias_desc, idesc, 0u);           // D = ones * bias^T
-        mbar_wait(&a_full[s], ph, 24);
-        tc_fence_after();
-        if (lt == 0 && lane == 0) CONV_TRACE(3);
-        const uint32_t a_base = smem_u32(sA + static_cast<size_t>(s) * p.a_stage_bytes);
+        if (prof) { c1 = clock64(); tm[0] += c1 - c0; c0 = c1; }
         if (elect_one()) {
-          uint32_t a_row = a_base, a_tap = a_base, b_addr = b_base;           // start of tap row r / of tap (r, sx)
+          for (int i = 0; i < cnt; ++i)
+            umma_f16(tmem_base + static_cast<uint32_t>(((lt0 + i) & (p.n_acc - 1)) * p.cout), ones_desc, bias_desc, idesc, 0u);   // D = ones * bias^T
+        }
+        {
+          int si = s;
+          uint32_t phi = ph;
+          for (int i = 0; i < cnt; ++i) {
+            mbar_wait(&a_full[si], phi, 24);
+            if (++si == p.stages) { si = 0; phi ^= 1; }
+          }
+        }
+        tc_fence_after();
+        if (prof) { c1 = clock64(); tm[1] += c1 - c0; c0 = c1; }
+        if (lt0 == 0 && lane == 0) CONV_TRACE(3);
+        if (elect_one()) {
+          const uint32_t a_ring = smem_u32(sA);
+          uint32_t tile_base[STRIP_MAX_ACC / 2], tile_acc[STRIP_MAX_ACC / 2];   // per tile of the group: A start address, accumulator
+          {
+            int si = s;
+#pragma unroll
+            for (int i = 0; i < STRIP_MAX_ACC / 2; ++i) {
+              const int tile_i = static_cast<int>(blockIdx.x) + (lt0 + i) * static_cast<int>(gridDim.x);
+              const int tin = tile_i - fdiv(tile_i, p.d_rowblocks) * p.row_blocks;
+              const int f0 = tin * CONV_BM;
+              // flat mode: the tile starts (f0 mod Wbox) rows into its patch
+              const uint32_t start = p.flat ? static_cast<uint32_t>((f0 - fdiv(f0, p.d_wbox) * p.Wbox) * in_row_bytes) : 0u;
+              tile_base[i] = a_ring + static_cast<uint32_t>(si * p.a_stage_bytes) + start;
+              tile_acc[i] = tmem_base + static_cast<uint32_t>(((lt0 + i) & (p.n_acc - 1)) * p.cout);
+              if (++si == p.stages) si = 0;
+            }
+          }
+          uint32_t row_off = 0, tap_off = 0, b_addr = b_base;     // byte offset of tap row r / of tap (r, sx) inside a patch
           int sx = 0, c0 = 0;
           for (int j = 0; j < p.k16_steps; ++j) {
-            umma_f16(d, a_desc_hi | static_cast<uint64_t>(((a_tap + c0 * 2) & 0x3FFFF) >> 4),
-                     b_desc_hi | static_cast<uint64_t>((b_addr & 0x3FFFF) >> 4), idesc, 1u);
+            const uint64_t bdesc = b_desc_hi | static_cast<uint64_t>((b_addr & 0x3FFFF) >> 4);
+#pragma unroll
+            for (int i = 0; i < STRIP_MAX_ACC / 2; ++i) {
+              if (i < cnt) {
+                const uint32_t a_addr = tile_base[i] + tap_off + static_cast<uint32_t>(c0 * 2);
+                umma_f16(tile_acc[i], a_desc_hi | static_cast<uint64_t>((a_addr & 0x3FFFF) >> 4), bdesc, idesc, 1u);
+              }
+            }
             c0 += 16;
             b_addr += ((j & 3) == 3) ? static_cast<uint32_t>(b_kb_bytes - 96) : 32u;
             if (c0 == p.cin) {
               c0 = 0;
-              a_tap += in_row_bytes;
-              if (++sx == p.kw) { sx = 0; a_row += p.Wbox * in_row_bytes; a_tap = a_row; }
+              tap_off += in_row_bytes;
+              if (++sx == p.kw) { sx = 0; row_off += p.Wbox * in_row_bytes; tap_off = row_off; }
             }
           }
-          umma_commit(&a_empty[s]);
-          umma_commit(&acc_full[buf]);
+          int si = s;
+          for (int i = 0; i < cnt; ++i) {
+            umma_commit(&a_empty[si]);
+            umma_commit(&acc_full[(lt0 + i) & (p.n_acc - 1)]);
+            if (++si == p.stages) si = 0;
+          }
         }
         __syncwarp();
-        if (++s == p.stages) { s = 0; ph ^= 1; }
+        if (prof) { c1 = clock64(); tm[2] += c1 - c0; }
+        for (int i = 0; i < cnt; ++i)
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+      if (prof && lane == 0) {
+        long long* q = p.trace + 8 * 148 + blockIdx.x * 8;
+        q[0] = tm[0]; q[1] = tm[1]; q[2] = tm[2]; q[7] = my_tiles;
       }
       if (lane == 0) CONV_TRACE(4);
     }
-  } else {
+  } else if (warp < CONV_FIRST_EPI_WARP + CONV_EPI_WARPS) {
     // ---------------------------------------------------------------- epilogue (8 warps, 2 per TMEM lane quarter)
     const int quarter = warp & 3, half = (warp - CONV_FIRST_EPI_WARP) >> 2;
     const bool relu = p.flags & CF_RELU;
-    const bool leader = threadIdx.x == CONV_FIRST_EPI_WARP * 32;
     const int rowbytes = p.box_cols * 2, chunks_per_box = p.box_cols >> 4;
     const int box_bytes = CONV_BM * rowbytes;                   // one column box of the whole 128-row tile
-    const int n_boxes = p.cout / p.box_cols, n_chunks = p.cout >> 4;
+    const int n_chunks = p.cout >> 4;
     const int m = quarter * 32 + lane;
     const uint32_t swz = p.box_cols == 64 ? (m & 7) : p.box_cols == 32 ? ((m >> 1) & 3) : ((m >> 2) & 1);
-    const bool active = quarter * 32 < p.R * p.Wbox;            // this quarter holds at least one real patch position
+    const bool active = p.flat || quarter * 32 < p.R * p.Wbox;  // this quarter holds at least one real patch position
     const uint32_t stage_buf_bytes = static_cast<uint32_t>(CONV_BM * p.cout * 2);
     const uint32_t stage0 = smem_u32(smem + L.out);
-    uint32_t sbuf = 0;
-    if (p.pdl && leader) pdl_wait();
-    long long acc_t[7] = {0, 0, 0, 0, 0, 0, 0};
-    const bool prof = leader && p.trace != nullptr;
+    long long te[3] = {0, 0, 0};
+    const bool prof = p.trace != nullptr && (p.flags & CF_DBG_PHASES) && threadIdx.x == CONV_FIRST_EPI_WARP * 32;
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-      const int buf = lt & 1;
+      const int buf = lt & (p.n_acc - 1), ob = lt & 1;
+      const uint32_t stage = stage0 + static_cast<uint32_t>(ob) * stage_buf_bytes;
       long long c0 = prof ? clock64() : 0, c1;
-      const int n = fdiv(tile, p.d_rowblocks), y0 = (tile - n * p.row_blocks) * p.R;
-      const uint32_t stage = stage0 + sbuf * stage_buf_bytes;
-      sbuf ^= 1;
-      if (leader) bulk_wait_read_1();                           // the store issued two tiles ago has left this staging buffer
-      if (prof) { c1 = clock64(); acc_t[0] += c1 - c0; c0 = c1; }
-      named_bar_sync(5, CONV_EPI_WARPS * 32);
-      if (prof) { c1 = clock64(); acc_t[1] += c1 - c0; c0 = c1; }
-      mbar_wait(&acc_full[buf], (lt >> 1) & 1, 25);
+      mbar_wait(&out_empty[ob], ((lt >> 1) & 1) ^ 1, 26);       // the store of two tiles ago has left this staging buffer
+      if (prof) { c1 = clock64(); te[0] += c1 - c0; c0 = c1; }
+      mbar_wait(&acc_full[buf], static_cast<uint32_t>(lt / p.n_acc) & 1u, 25);
       tc_fence_after();
-      if (prof) { c1 = clock64(); acc_t[2] += c1 - c0; c0 = c1; }
-      if (lt == 0 && leader) CONV_TRACE(5);
+      if (prof) { c1 = clock64(); te[1] += c1 - c0; c0 = c1; }
+      if (lt == 0 && threadIdx.x == CONV_FIRST_EPI_WARP * 32) CONV_TRACE(5);
       if (active) {
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * p.cout);
         const uint32_t my_row = stage + static_cast<uint32_t>(m * rowbytes);
@@ -225,23 +284,42 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       __syncwarp();
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);
-      if (prof) { c1 = clock64(); acc_t[3] += c1 - c0; c0 = c1; }
-      fence_proxy_async_smem();
-      if (prof) { c1 = clock64(); acc_t[4] += c1 - c0; c0 = c1; }
-      named_bar_sync(5, CONV_EPI_WARPS * 32);
-      if (prof) { c1 = clock64(); acc_t[5] += c1 - c0; c0 = c1; }
-      if (leader && !(p.flags & CF_DBG_NOSTORE)) {
-        for (int b = 0; b < n_boxes; ++b)
-          tma_store_4d(&tmap_out, stage + static_cast<uint32_t>(b * box_bytes), b * p.box_cols, 0, y0, n);
-        bulk_commit_group();
-      }
-      if (prof) { c1 = clock64(); acc_t[6] += c1 - c0; }
+      fence_proxy_async_smem();                                 // staging writes -> visible to the TMA (async proxy)
+      mbar_arrive(&out_full[ob]);
+      if (prof) { c1 = clock64(); te[2] += c1 - c0; }
     }
-    if (leader) { bulk_wait_all(); CONV_TRACE(6); }
     if (prof) {
-      for (int i = 0; i < 7; ++i) p.trace[8 * 256 * 0 + 8 * 148 + blockIdx.x * 8 + i] = acc_t[i];
-      p.trace[8 * 148 + blockIdx.x * 8 + 7] = lt;
+      long long* q = p.trace + 8 * 148 + blockIdx.x * 8;
+      q[3] = te[0]; q[4] = te[1]; q[5] = te[2];
     }
+    if (threadIdx.x == CONV_FIRST_EPI_WARP * 32) CONV_TRACE(6);
+  } else {
+    // ---------------------------------------------------------------- TMA store warp: one 4-D store per column box of a tile
+    const int rowbytes = p.box_cols * 2, box_bytes = CONV_BM * rowbytes, n_boxes = p.cout / p.box_cols;
+    const uint32_t stage_buf_bytes = static_cast<uint32_t>(CONV_BM * p.cout * 2);
+    const uint32_t stage0 = smem_u32(smem + L.out);
+    if (p.pdl) pdl_wait();                                      // output writes must not overtake readers of the previous layers
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const int ob = lt & 1;
+      const int n = fdiv(tile, p.d_rowblocks), tin = tile - n * p.row_blocks;
+      mbar_wait(&out_full[ob], (lt >> 1) & 1, 27);
+      if (elect_one()) {
+        if (!(p.flags & CF_DBG_NOSTORE)) {
+          for (int b = 0; b < n_boxes; ++b) {
+            const uint32_t src = stage0 + static_cast<uint32_t>(ob) * stage_buf_bytes + static_cast<uint32_t>(b * box_bytes);
+            if (p.flat) tma_store_3d(&tmap_out, src, b * p.box_cols, tin * CONV_BM, n);      // {channel, position, image}
+            else tma_store_4d(&tmap_out, src, b * p.box_cols, 0, tin * p.R, n);               // {channel, x, y, image}
+          }
+        }
+        bulk_commit_group();
+        bulk_wait_read_all();                                   // staging buffer read: hand it back
+        mbar_arrive(&out_empty[ob]);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) bulk_wait_all();                           // stores complete before the CTA exits
+    __syncwarp();
   }
 
   tc_fence_before();

@@ -20,7 +20,7 @@
 namespace fire {
 
 constexpr int OP_CONV = 1, OP_MAXPOOL = 2, OP_GAP = 3;
-constexpr uint32_t BLOB_VERSION = 3;
+constexpr uint32_t BLOB_VERSION = 4;
 
 #pragma pack(push, 1)
 struct BlobHeader {
@@ -32,7 +32,7 @@ struct BlobHeader {
 struct BlobBuf {
   int32_t H, W, C, elt;
   int64_t offset;
-  int32_t external, pad;
+  int32_t external, Wp;     // Wp: row pitch in pixels (0 = W); > W for the outputs of flat-mode strip convs
 };
 struct BlobOp {
   int32_t kind, src_buf, src_coff, dst_buf, dst_coff, res_buf, res_coff, H, W, Ho, Wo, kh, kw, stride, pad_h, pad_w, cin,
@@ -47,7 +47,7 @@ static_assert(sizeof(BlobOp) == 104, "op layout must match weights.OP_DT");
 // ---------------------------------------------------------------------------------------------
 // 3x3 stride-2 VALID max-pool, NHWC fp16, 8 channels (16 bytes) per thread, channel-offset store.
 __global__ void maxpool3x3s2_kernel(const __half* __restrict__ in, int in_ld, int in_coff, __half* __restrict__ out,
-                                    int out_ld, int out_coff, int B, int H, int W, int Ho, int Wo, int C) {
+                                    int out_ld, int out_coff, int B, int H, int W, int Ho, int Wo, int C) {   // W = input row pitch
   const int c8 = C >> 3;
   const long long total = static_cast<long long>(B) * Ho * Wo * c8;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -132,7 +132,8 @@ struct OpRt {
   int bn_tile = 0, stages = 0, n_issuers = 1, tmem_cols = 0, m_tiles = 0, n_tiles = 0;
   int n_res = 0, box_cols = 64;
   bool strip = false;     // stride-1 k x k layer run by conv_strip_kernel (halo patch + shifted descriptors)
-  int Wbox = 0, R = 0, Hbox = 0, row_blocks = 0, a_stage_bytes = 0;
+  int Wbox = 0, R = 0, Hbox = 0, row_blocks = 0, a_stage_bytes = 0, n_acc = 2;
+  bool flat = false;      // strip conv with flat 128-position tiles (the destination buffer is pitched to Wbox)
   size_t bias16_off = 0;  // byte offset of this op's [cout] x {hi, lo, 0 x 6} fp16 bias rows in d_bias16
   size_t smem = 0;
   double flops_per_image = 0;
@@ -186,6 +187,8 @@ struct fire_net {
   long long* d_trace = nullptr; int trace_op = -1;   // FIRE_B200_TRACE_OP=<op index>: in-kernel timeline of that op (profile only)
   int dbg_flags = 0;      // FIRE_B200_DBG: timing experiments (1 = no gather copies, 2 = no epilogue stores, 4 = no MMA)
 };
+
+static inline int buf_wp(const BlobBuf& b) { return b.Wp > 0 ? b.Wp : b.W; }
 
 static int pow2_cols(int n) {
   int c = 32;
@@ -354,8 +357,10 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
       q.cin = o.cin; q.cout = o.cout; q.kh = o.kh; q.kw = o.kw; q.pad_h = o.pad_h; q.pad_w = o.pad_w;
       q.k16_steps = o.kh * o.kw * o.cin / 16; q.nkb = o.k_pad / 64;
       q.Wbox = r.Wbox; q.R = r.R; q.Hbox = r.Hbox; q.row_blocks = r.row_blocks; q.total_tiles = B * r.row_blocks;
+      q.flat = r.flat ? 1 : 0; q.Ho = o.Ho; q.d_wbox = make_fastdiv(r.Wbox);
       q.a_stage_bytes = r.a_stage_bytes; q.stages = r.stages; q.tmem_cols = r.tmem_cols; q.flags = o.flags | net->dbg_flags;
-      q.pdl = pdl ? 1 : 0; q.box_cols = r.box_cols;
+      if (net->d_trace && !net->trace_all) q.flags |= CF_DBG_PHASES;
+      q.pdl = pdl ? 1 : 0; q.box_cols = r.box_cols; q.n_acc = r.n_acc;
       q.trace = !net->d_trace ? nullptr : net->trace_all ? net->d_trace + (size_t)(&r - net->ops.data()) * 4096
                 : (&r == &net->ops[net->trace_op] ? net->d_trace : nullptr);
       q.d_rowblocks = make_fastdiv(r.row_blocks);
@@ -405,7 +410,7 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
     const long long total = (long long)B * o.Ho * o.Wo * (o.cin / 8);
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
     maxpool3x3s2_kernel<<<blocks, 256, 0, st>>>(src, sb.C, o.src_coff, static_cast<__half*>(dst), db.C, o.dst_coff, B, o.H,
-                                                o.W, o.Ho, o.Wo, o.cin);
+                                                buf_wp(sb), o.Ho, o.Wo, o.cin);      // reads a pitched input through its pitch
     FIRE_LAUNCH_CHECK("maxpool3x3s2_kernel");
   } else if (o.kind == OP_GAP) {
     const int n = B * (o.cin / 2);
@@ -438,13 +443,30 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
         const bool shape_ok = net->use_strip && o.stride == 1 && o.kh * o.kw > 1 && (o.cin == 16 || o.cin == 32 || o.cin == 64) &&
                               o.cout <= 256 && !(o.flags & (CF_RESIDUAL | CF_OUT_F32)) && wbox <= CONV_BM &&
                               (size_t)(o.k_pad / 64) * o.cout * 128 <= 96 * 1024 && (o.kh * o.kw * o.cin) % 16 == 0;
+        const BlobBuf& sbuf = net->bufs[o.src_buf];
+        const BlobBuf& dbuf = net->bufs[o.dst_buf];
+        if (!shape_ok && (buf_wp(dbuf) != dbuf.W || buf_wp(sbuf) != sbuf.W))
+          return fail(FIRE_ERR_UNSUPPORTED, "op %d touches a pitched buffer but cannot run in strip mode (FIRE_B200_STRIP=0 needs Plan(pitched=False))",
+                      (int)(&r - net->ops.data()));
         if (shape_ok) {
           r.strip = true;
           r.Wbox = wbox;
-          r.R = std::min(o.Ho, CONV_BM / wbox);
-          r.Hbox = r.R + o.kh - 1;
-          r.row_blocks = (o.Ho + r.R - 1) / r.R;
-          const int rows_alloc = std::max(r.Hbox * wbox, CONV_BM + (o.kh - 1) * wbox + o.kw - 1);
+          r.flat = buf_wp(dbuf) != dbuf.W;
+          if (r.flat && buf_wp(dbuf) != wbox)
+            return fail(FIRE_ERR_ARG, "pitched destination of op %d must have pitch Wo + kw - 1 = %d", (int)(&r - net->ops.data()), wbox);
+          int rows_alloc;
+          if (r.flat) {
+            const int rows_out = (wbox - 1 + CONV_BM - 1) / wbox + 1;          // output rows a 128-position tile can touch
+            r.R = 0;
+            r.Hbox = rows_out + o.kh - 1;
+            r.row_blocks = (o.Ho * wbox + CONV_BM - 1) / CONV_BM;
+            rows_alloc = std::max(r.Hbox * wbox, wbox - 1 + CONV_BM + (o.kh - 1) * wbox + o.kw - 1);
+          } else {
+            r.R = std::min(o.Ho, CONV_BM / wbox);
+            r.Hbox = r.R + o.kh - 1;
+            r.row_blocks = (o.Ho + r.R - 1) / r.R;
+            rows_alloc = std::max(r.Hbox * wbox, CONV_BM + (o.kh - 1) * wbox + o.kw - 1);
+          }
           r.a_stage_bytes = (rows_alloc * o.cin * 2 + 1023) / 1024 * 1024;
           r.bn_tile = 0;                       // force a fresh weight map below
           int rc = make_tmap_f16_2d(&r.tmap_w, net->d_weights + o.w_off, (uint64_t)o.cout, (uint64_t)o.k_pad, (uint64_t)o.k_pad * 2,
@@ -452,20 +474,27 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
           if (rc != FIRE_OK) return rc;
           r.box_cols = o.cout % 64 == 0 ? 64 : (o.cout % 32 == 0 ? 32 : 16);
           const size_t fixed = strip_smem_layout(0, r.a_stage_bytes, o.k_pad / 64, o.cout).total + 1024;
-          r.stages = (int)std::min<size_t>(6, (232448 - fixed) / r.a_stage_bytes);
+          r.stages = (int)std::min<size_t>(8, (232448 - fixed) / r.a_stage_bytes);
+          r.n_acc = std::min(STRIP_MAX_ACC, 512 / pow2_cols(o.cout));          // accumulators side by side in TMEM
+          if (const char* e = getenv("FIRE_B200_STRIP_ACC")) r.n_acc = std::max(2, std::min(r.n_acc, atoi(e)));   // A/B experiments (power of two)
+          while (r.n_acc > 2 && r.n_acc / 2 > r.stages) r.n_acc >>= 1;
           if (r.stages < 2) r.strip = false;
           else {
             r.smem = strip_smem_layout(r.stages, r.a_stage_bytes, o.k_pad / 64, o.cout).total + 1024;
-            r.tmem_cols = pow2_cols(2 * o.cout);
+            r.tmem_cols = pow2_cols(r.n_acc * o.cout);
             const BlobBuf& sb = net->bufs[o.src_buf];
             const BlobBuf& db = net->bufs[o.dst_buf];
             const __half* src = static_cast<const __half*>(buf_ptr(net, o.src_buf, B, in, ws, out_raw)) + o.src_coff;
             const __half* dst = static_cast<const __half*>(buf_ptr(net, o.dst_buf, B, in, ws, out_raw)) + o.dst_coff;
             rc = make_tmap_f16_nhwc(&r.tmap_a, src, (uint64_t)o.cin, (uint64_t)o.W, (uint64_t)o.H, (uint64_t)B, (uint64_t)sb.C,
-                                    (uint32_t)o.cin, (uint32_t)r.Wbox, (uint32_t)r.Hbox);
+                                    (uint64_t)buf_wp(sb), (uint32_t)o.cin, (uint32_t)r.Wbox, (uint32_t)r.Hbox);
             if (rc != FIRE_OK) return rc;
-            rc = make_tmap_f16_nhwc(&r.tmap_out, dst, (uint64_t)o.cout, (uint64_t)o.Wo, (uint64_t)o.Ho, (uint64_t)B, (uint64_t)db.C,
-                                    (uint32_t)r.box_cols, (uint32_t)r.Wbox, (uint32_t)r.R);
+            if (r.flat)
+              rc = make_tmap_f16_pos3d(&r.tmap_out, dst, (uint64_t)o.cout, (uint64_t)o.Ho * r.Wbox, (uint64_t)B, (uint64_t)db.C,
+                                       (uint32_t)r.box_cols, CONV_BM);
+            else
+              rc = make_tmap_f16_nhwc(&r.tmap_out, dst, (uint64_t)o.cout, (uint64_t)o.Wo, (uint64_t)o.Ho, (uint64_t)B, (uint64_t)db.C,
+                                      (uint64_t)o.Wo, (uint32_t)r.box_cols, (uint32_t)r.Wbox, (uint32_t)r.R);
             if (rc != FIRE_OK) return rc;
             r.n_tiles = 1; r.n_res = 0; r.n_issuers = 1;
             continue;
@@ -596,13 +625,14 @@ int fire_facenet_profile(fire_net_t* net, const void* in_f16, int B, void* works
     fprintf(stderr, "trace op %d: grid %d, tiles %d x %d, bn %d, nkb %d, stages %d, issuers %d, event ms %.4f\n", net->trace_op, grid,
             r.m_tiles, r.n_tiles, r.bn_tile, r.op.k_pad / 64, r.stages, r.n_issuers, host_ms[net->trace_op]);
     if (r.strip) {
-      const char* ph[7] = {"wait_group.read", "barrier 1", "acc_full wait", "tmem ld + cvt + sts + arrive", "fence.proxy.async", "barrier 2", "TMA store issue"};
+      const char* ph[6] = {"MMA warp: wait acc_empty", "MMA warp: wait a_full", "MMA warp: issue + commit", "epilogue: wait out_empty", "epilogue: wait acc_full",
+                           "epilogue: ld + cvt + sts + arrive"};
       const long long* q = &t[8 * 148];
-      fprintf(stderr, "  epilogue leader, cycles per tile (CTA 0 .. avg over CTAs), tiles per CTA %lld:\n", q[7]);
-      for (int k = 0; k < 7; ++k) {
+      fprintf(stderr, "  cycles per tile (avg over CTAs), tiles per CTA %lld, accumulators %d, stages %d:\n", q[7], r.n_acc, r.stages);
+      for (int k = 0; k < 6; ++k) {
         double avg = 0;
         for (int c = 0; c < grid; ++c) avg += (double)q[c * 8 + k] / (double)std::max<long long>(q[c * 8 + 7], 1);
-        fprintf(stderr, "    %-30s %8.0f .. %8.0f\n", ph[k], (double)q[k] / (double)std::max<long long>(q[7], 1), avg / grid);
+        fprintf(stderr, "    %-36s %8.0f\n", ph[k], avg / grid);
       }
     }
     for (int k = 0; k < 8; ++k) {
@@ -623,7 +653,7 @@ int fire_facenet_read_buffer(fire_net_t* net, int buf, int B, const void* in_f16
                              size_t bytes) {
   if (!net || buf < 0 || buf >= (int)net->bufs.size() || !host_out) return fail(FIRE_ERR_ARG, "fire_facenet_read_buffer: bad arguments");
   const BlobBuf& b = net->bufs[buf];
-  const size_t need = (size_t)B * b.H * b.W * b.C * b.elt;
+  const size_t need = (size_t)B * b.H * buf_wp(b) * b.C * b.elt;
   if (bytes < need) return fail(FIRE_ERR_ARG, "fire_facenet_read_buffer: need %zu bytes", need);
   if (buf == net->hdr.out_buf) return fail(FIRE_ERR_ARG, "fire_facenet_read_buffer: the output buffer belongs to the caller");
   const void* src = buf_ptr(net, buf, B, in_f16, const_cast<void*>(workspace), nullptr);

@@ -75,7 +75,7 @@ int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 
 
 int make_tmap_f16_nhwc(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint64_t ld_elems,
-                       uint32_t box_c, uint32_t box_w, uint32_t box_h) {
+                       uint64_t w_pitch, uint32_t box_c, uint32_t box_w, uint32_t box_h) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(FIRE_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld_elems & 7) || box_w == 0 || box_w > 256 || box_h == 0 || box_h > 256)
@@ -88,12 +88,36 @@ int make_tmap_f16_nhwc(CUtensorMap* out, const void* base, uint64_t C, uint64_t 
     default: return fail(FIRE_ERR_ARG, "NHWC tensor map: box of %u channels is not a swizzle width (16/32/64)", box_c);
   }
   cuuint64_t gdim[4] = {C, W, H, N};
-  cuuint64_t gstride[3] = {ld_elems * 2, W * ld_elems * 2, H * W * ld_elems * 2};
+  cuuint64_t gstride[3] = {ld_elems * 2, w_pitch * ld_elems * 2, H * w_pitch * ld_elems * 2};
   cuuint32_t box[4] = {box_c, box_w, box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(FIRE_ERR_CUDA, "cuTensorMapEncodeTiled (4-D) failed with CUresult %d", (int)r);
+  return FIRE_OK;
+}
+
+
+int make_tmap_f16_pos3d(CUtensorMap* out, const void* base, uint64_t C, uint64_t positions, uint64_t N, uint64_t ld_elems,
+                        uint32_t box_c, uint32_t box_pos) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(FIRE_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld_elems & 7) || box_pos == 0 || box_pos > 256)
+    return fail(FIRE_ERR_ARG, "position tensor map: base/stride must be 16-byte aligned, box rows in [1,256]");
+  CUtensorMapSwizzle sw;
+  switch (box_c) {
+    case 64: sw = CU_TENSOR_MAP_SWIZZLE_128B; break;
+    case 32: sw = CU_TENSOR_MAP_SWIZZLE_64B; break;
+    case 16: sw = CU_TENSOR_MAP_SWIZZLE_32B; break;
+    default: return fail(FIRE_ERR_ARG, "position tensor map: box of %u channels is not a swizzle width (16/32/64)", box_c);
+  }
+  cuuint64_t gdim[3] = {C, positions, N};
+  cuuint64_t gstride[2] = {ld_elems * 2, positions * ld_elems * 2};
+  cuuint32_t box[3] = {box_c, box_pos, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FIRE_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
   return FIRE_OK;
 }
 

@@ -131,6 +131,12 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t smem
                "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 // Shared-memory matrix descriptor, K-major, swizzled rows of `row_bytes` in {32, 64, 128}: 8-row groups are
 // 8 * row_bytes apart.  The start address may be advanced by whole rows (tap shifts) - the swizzle is a function of
 // absolute address bits, base_offset stays 0 (measured: tools/umma_probe.cu part 2).

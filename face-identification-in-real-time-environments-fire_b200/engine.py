@@ -107,11 +107,72 @@ class FaceNetEngine:
         """Debug: activation buffer `buf` of the last forward on x_f16, as float32 [B,H,W,C]."""
         B = x_f16.shape[0]
         b = self.plan.bufs[buf]
-        out = np.empty((B, b.H, b.W, b.C), dtype=np.float16)
+        out = np.empty((B, b.H, b.Wp or b.W, b.C), dtype=np.float16)
         ws_ptr, _ = self._workspace(B)
         _torch().cuda.synchronize()
         check(_lib.lib().fire_facenet_read_buffer(self._h, buf, B, _ptr(x_f16), ws_ptr, out.ctypes.data, out.nbytes))
-        return out.astype(np.float32)
+        return out[:, :, :b.W, :].astype(np.float32)          # drop the row-pitch padding of pitched buffers
+
+
+
+class CropEncodePipeline:
+    """Streaming encode of fixed-size batches of 160x160 uint8 crops held in PINNED host memory.
+
+    The reference encodes one face per ``session.run`` (modules/face_recognition.py:404-486); this is the batched
+    counterpart a caller that collects crops would use.  ``submit()`` enqueues, without synchronising,
+      host -> device copy (its own stream)  ->  K1 crop/resize/normalise  ->  K2 FaceNet  ->  device -> host copy
+    with ``depth`` staging buffers, so the copy of batch i+1 overlaps the kernels of batch i.
+    ``result(ticket)`` waits for that batch only and returns the pinned float32 [B, D] embeddings (L2-normalised
+    like modules/face_recognition.py:225-229 when ``normalize``)."""
+
+    def __init__(self, engine: "FaceNetEngine", batch: int, depth: int = 2, normalize: bool = True,
+                 mode: int = _lib.PRE_REFERENCE):
+        torch = _torch()
+        self.eng, self.batch, self.depth, self.normalize, self.mode = engine, batch, max(2, depth), normalize, mode
+        dev = engine.device
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.stage = [torch.empty(batch, IN_HW, IN_HW, 3, dtype=torch.uint8, device=dev) for _ in range(self.depth)]
+        self.raw = [torch.empty(batch, engine.D, dtype=torch.float32, device=dev) for _ in range(self.depth)]
+        self.l2 = [torch.empty(batch, engine.D, dtype=torch.float32, device=dev) for _ in range(self.depth)]
+        self.host = [torch.empty(batch, engine.D, dtype=torch.float32).pin_memory() for _ in range(self.depth)]
+        self.ev_in = [torch.cuda.Event() for _ in range(self.depth)]      # H2D of slot landed
+        self.ev_free = [torch.cuda.Event() for _ in range(self.depth)]    # kernels reading the slot's staging buffer are done
+        self.ev_out = [torch.cuda.Event() for _ in range(self.depth)]     # D2H of slot landed
+        self.boxes = torch.tensor([[0, 0, IN_HW, IN_HW]] * batch, dtype=torch.int32, device=dev)
+        self.box_frame = torch.arange(batch, dtype=torch.int32, device=dev)
+        self.desc = torch.tensor([[i * IN_HW * IN_HW * 3, IN_HW, IN_HW, IN_HW * 3] for i in range(batch)], dtype=torch.int64, device=dev)
+        self.n = 0
+        self.h2d_bytes = batch * IN_HW * IN_HW * 3
+        self.d2h_bytes = batch * engine.D * 4
+
+    def submit(self, crops_pinned_u8) -> int:
+        torch = _torch()
+        assert crops_pinned_u8.dtype == torch.uint8 and tuple(crops_pinned_u8.shape) == (self.batch, IN_HW, IN_HW, 3)
+        slot = self.n % self.depth
+        main = torch.cuda.current_stream()
+        if self.n >= self.depth:
+            self.copy_stream.wait_event(self.ev_free[slot])            # do not overwrite a staging buffer still being read
+            self.ev_out[slot].synchronize()                            # the caller may still be reading host[slot]? it was handed out `depth` submits ago
+        with torch.cuda.stream(self.copy_stream):
+            self.stage[slot].copy_(crops_pinned_u8, non_blocking=True)
+            self.ev_in[slot].record(self.copy_stream)
+        main.wait_event(self.ev_in[slot])
+        f16, _, _ = preprocess_boxes(self.stage[slot], self.desc, self.boxes, self.box_frame, self.mode, True, False)
+        self.ev_free[slot].record(main)
+        self.eng.forward(f16, want_l2=self.normalize, out_raw=self.raw[slot], out_l2=self.l2[slot] if self.normalize else None)
+        self.host[slot].copy_(self.l2[slot] if self.normalize else self.raw[slot], non_blocking=True)
+        self.ev_out[slot].record(main)
+        self.n += 1
+        return self.n - 1
+
+    def result(self, ticket: int):
+        assert self.n - self.depth <= ticket < self.n, "result() must be read before `depth` later submits reuse the slot"
+        slot = ticket % self.depth
+        self.ev_out[slot].synchronize()
+        return self.host[slot]
+
+    def drain(self):
+        _torch().cuda.current_stream().synchronize()
 
 
 class KnnIndex:

@@ -42,10 +42,12 @@ class Buf:
     last: int = -1               # last op index that touches it
     offset: int = -1             # per-image byte offset in the workspace (assigned by allocate())
     external: bool = False       # network input / outputs are bound by the caller, not the workspace
+    Wp: int = 0                  # row pitch in pixels (0 = W).  The outputs of the wide stem convs are stored with pitch
+                                 # W + kw - 1 so the strip kernel can use flat 128-position tiles (csrc/conv_strip.cuh)
 
     @property
     def bytes_per_image(self) -> int:
-        return self.H * self.W * self.C * self.elt
+        return self.H * (self.Wp or self.W) * self.C * self.elt
 
 
 @dataclass
@@ -116,9 +118,10 @@ def _pick_bn_tile(cout: int) -> int:
 
 
 class Plan:
-    def __init__(self, D: int, fuse_siblings: bool = True, reuse_buffers: bool = True):
+    def __init__(self, D: int, fuse_siblings: bool = True, reuse_buffers: bool = True, pitched: bool = True):
         assert D in (128, 512)
         self.D = D
+        self.pitched = pitched
         self.fuse = fuse_siblings
         self.reuse = reuse_buffers
         self.bufs: List[Buf] = []
@@ -128,8 +131,8 @@ class Plan:
         self.allocate()
 
     # ---- construction helpers -------------------------------------------------------------
-    def _buf(self, H, W, C, elt=2, external=False) -> int:
-        self.bufs.append(Buf(H, W, C, elt, external=external))
+    def _buf(self, H, W, C, elt=2, external=False, Wp=0) -> int:
+        self.bufs.append(Buf(H, W, C, elt, external=external, Wp=Wp if self.pitched else 0))
         return len(self.bufs) - 1
 
     def _touch(self, s: Optional[Slice], idx: int):
@@ -183,8 +186,8 @@ class Plan:
         B = self._buf
         x = self.whole(self.in_buf)
         t = B(79, 79, 32); self.conv("Conv2d_1a_3x3", x, self.whole(t), 3, 3, 2, cin_real=3, in_scale=1.0 / 255.0); x = self.whole(t)
-        t = B(77, 77, 32); self.conv("Conv2d_2a_3x3", x, self.whole(t), 3, 3); x = self.whole(t)
-        t = B(77, 77, 64); self.conv("Conv2d_2b_3x3", x, self.whole(t), 3, 3, same=True); x = self.whole(t)
+        t = B(77, 77, 32, Wp=79); self.conv("Conv2d_2a_3x3", x, self.whole(t), 3, 3); x = self.whole(t)
+        t = B(77, 77, 64, Wp=79); self.conv("Conv2d_2b_3x3", x, self.whole(t), 3, 3, same=True); x = self.whole(t)
         t = B(38, 38, 64); self.maxpool(x, self.whole(t), "MaxPool_3a_3x3"); x = self.whole(t)
         t = B(38, 38, 80); self.conv("Conv2d_3b_1x1", x, self.whole(t)); x = self.whole(t)
         t = B(36, 36, 192); self.conv("Conv2d_4a_3x3", x, self.whole(t), 3, 3); x = self.whole(t)

@@ -19,13 +19,13 @@ import numpy as np
 from .netplan import BN_EPS, OP_CONV, Plan
 
 MAGIC = b"FIREB200"
-BLOB_VERSION = 3
+BLOB_VERSION = 4
 
 HEADER_DT = np.dtype([("magic", "S8"), ("version", "<i4"), ("D", "<i4"), ("n_ops", "<i4"), ("n_bufs", "<i4"),
                       ("ws_bytes_per_image", "<i8"), ("weights_off", "<i8"), ("weights_bytes", "<i8"),
                       ("in_buf", "<i4"), ("out_buf", "<i4")])
 BUF_DT = np.dtype([("H", "<i4"), ("W", "<i4"), ("C", "<i4"), ("elt", "<i4"), ("offset", "<i8"),
-                   ("external", "<i4"), ("pad", "<i4")])
+                   ("external", "<i4"), ("Wp", "<i4")])
 OP_DT = np.dtype([("kind", "<i4"), ("src_buf", "<i4"), ("src_coff", "<i4"), ("dst_buf", "<i4"), ("dst_coff", "<i4"),
                   ("res_buf", "<i4"), ("res_coff", "<i4"), ("H", "<i4"), ("W", "<i4"), ("Ho", "<i4"), ("Wo", "<i4"),
                   ("kh", "<i4"), ("kw", "<i4"), ("stride", "<i4"), ("pad_h", "<i4"), ("pad_w", "<i4"),
@@ -195,7 +195,7 @@ def pack(plan: Plan, tensors: dict) -> bytes:
 
     bufs = np.zeros(len(plan.bufs), dtype=BUF_DT)
     for i, b in enumerate(plan.bufs):
-        bufs[i] = (b.H, b.W, b.C, b.elt, max(b.offset, 0), int(b.external), 0)
+        bufs[i] = (b.H, b.W, b.C, b.elt, max(b.offset, 0), int(b.external), b.Wp)
     ops = np.zeros(len(plan.ops), dtype=OP_DT)
     for i, o in enumerate(plan.ops):
         res_buf, res_coff = (o.res.buf, o.res.c_off) if o.res is not None else (-1, 0)
