@@ -31,12 +31,12 @@ class FaceNetEngine:
     """K2: the Inception-ResNet-v1 conv stack (replaces the onnxruntime session, facenet_gpu.py:72,127)."""
 
     def __init__(self, D: int = 512, tensors: Optional[dict] = None, device: int = 0, fuse_siblings: bool = True,
-                 seed: int = 1234):
+                 seed: int = 1234, pitched: bool = True):
         torch = _torch()
         _lib.init(device)
         self.device = torch.device("cuda", device)
         self.D = D
-        self.plan = Plan(D, fuse_siblings=fuse_siblings)
+        self.plan = Plan(D, fuse_siblings=fuse_siblings, pitched=pitched)
         if tensors is None:
             tensors = W.synthetic_weights(D, seed)
         self.blob = W.pack(self.plan, tensors)

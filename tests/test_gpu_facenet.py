@@ -118,6 +118,55 @@ def test_unfused_plan_matches_fused(fire_lib):
     assert torch.equal(ra, rb)                                 # horizontal fusion only regroups output channels
 
 
+def test_strip_kernel_matches_gather_kernel(fire_lib, monkeypatch):
+    """conv_strip_kernel (halo patch + shifted descriptors, flat tiles over pitched buffers) against the im2col-gather
+    path of conv_igemm_kernel on the same weights: same products, same fp32 accumulation, only the order in which the
+    bias joins the sum differs."""
+    import torch
+    from fire_b200 import engine, weights as W
+    t = W.synthetic_weights(128, 7)
+    x = torch.from_numpy(_images(5, 11).astype(np.float32) / 255.0).cuda()
+    a = engine.FaceNetEngine(128, t)                                   # strip kernels on (default)
+    ra, _ = a.encode_unit_f32(x)
+    monkeypatch.setenv("FIRE_B200_STRIP", "0")
+    b = engine.FaceNetEngine(128, t, pitched=False)                    # every k x k layer through the gather path
+    rb, _ = b.encode_unit_f32(x)
+    ra, rb = ra.cpu().numpy(), rb.cpu().numpy()
+    assert _cos(ra, rb).min() >= 0.99999          # one-ulp fp16 flips (bias joins the fp32 sum first vs last) through ~100 layers
+    assert np.abs(ra - rb).max() <= 1e-2 * np.abs(rb).max()
+    # per-layer: the first strip layer's output buffer (Conv2d_2a, pitched) equals the gather engine's to fp16 rounding
+    f16 = a.ingest_unit_f32(x)
+    a.forward(f16); b.forward(f16)
+    buf = a.plan.ops[1].dst.buf
+    la, lb = a.read_buffer(buf, f16), b.read_buffer(buf, f16)
+    assert la.shape == lb.shape == (5, 77, 77, 32)
+    assert np.abs(la - lb).max() <= 2e-3 * max(np.abs(lb).max(), 1.0)
+
+
+def test_crop_encode_pipeline_equals_direct_path(nets):
+    """The streaming public call (pinned host crops -> H2D -> K1 -> K2 -> D2H, double-buffered) returns exactly what
+    the step-by-step path returns, for every in-flight batch."""
+    import torch
+    from fire_b200 import _lib, engine
+    _, eng = nets[512]
+    B = 8
+    batches = [torch.from_numpy(_images(B, 20 + i)).pin_memory() for i in range(5)]
+    pipe = engine.CropEncodePipeline(eng, B, depth=2, normalize=True)
+    got = []
+    for i, b in enumerate(batches):
+        t = pipe.submit(b)
+        if i >= 1:
+            got.append(pipe.result(t - 1).clone())
+    got.append(pipe.result(len(batches) - 1).clone())
+    boxes = torch.tensor([[0, 0, 160, 160]] * B, dtype=torch.int32, device="cuda")
+    fid = torch.arange(B, dtype=torch.int32, device="cuda")
+    desc = torch.tensor([[i * 76800, 160, 160, 480] for i in range(B)], dtype=torch.int64, device="cuda")
+    for b, g in zip(batches, got):
+        f16, _, _ = engine.preprocess_boxes(b.cuda(), desc, boxes, fid, _lib.PRE_REFERENCE, True, False)
+        _, l2 = eng.forward(f16, want_l2=True)
+        assert torch.equal(l2.cpu(), g)
+
+
 def test_forward_argument_errors(nets):
     import torch
     from fire_b200 import _lib
