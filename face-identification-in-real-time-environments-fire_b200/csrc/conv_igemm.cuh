@@ -18,8 +18,10 @@
 //   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=bn_tile, K=16) into one of TWO TMEM accumulators,
 //               so the epilogue of tile t overlaps the main loop of tile t+1;
 //   warps 2-9   epilogue, two warps per TMEM lane quarter, 16-column chunks interleaved between them:
-//               tcgen05.ld -> cvt.rn[.relu].satfinite.f16x2 -> swizzled smem staging -> TMA store (one lane per quarter)
-//               at a channel offset of the destination buffer (concat for free); rows past M are clipped by the TMA;
+//               tcgen05.ld -> cvt.rn[.relu].satfinite.f16x2 -> swizzled smem staging (double-buffered, handed over
+//               through mbarriers);
+//   warp 18     TMA stores of the staged tile (one box of 128 rows per 64 columns) at a channel offset of the
+//               destination buffer (concat for free); rows past M are clipped by the TMA;
 //   warps 10-17 k x k / strided / padded layers: A-gather producers - 16-byte cp.async (zero-fill for padding and
 //               the K tail) straight into the 128-byte-swizzled layout the UMMA descriptor expects, each thread's
 //               cp.async.mbarrier.arrive.noinc signalling the stage when its copies land.
@@ -43,7 +45,8 @@ constexpr int CONV_FIRST_EPI_WARP = 2;
 constexpr int CONV_FIRST_HELPER_WARP = CONV_FIRST_EPI_WARP + CONV_EPI_WARPS;      // 10
 constexpr int CONV_HELPER_WARPS = 8;
 constexpr int CONV_HELPER_THREADS = CONV_HELPER_WARPS * 32;                       // 256
-constexpr int CONV_THREADS = 32 * (CONV_FIRST_HELPER_WARP + CONV_HELPER_WARPS);   // 576
+constexpr int CONV_STORE_WARP = CONV_FIRST_HELPER_WARP + CONV_HELPER_WARPS;      // 18: issues the TMA stores
+constexpr int CONV_THREADS = 32 * (CONV_STORE_WARP + 1);                          // 608
 constexpr int CONV_MAX_ISSUERS = 4;                                               // warp 0 + helper warps 10..12
 constexpr int CONV_ROWS_PER_GATHER_THREAD = CONV_BM / (CONV_HELPER_THREADS / 8);  // 4
 constexpr int CONV_A_STAGE_BYTES = CONV_BM * 128;
@@ -76,7 +79,7 @@ __host__ __device__ inline ConvSmem conv_smem_layout(int stages, int bn, int cou
   o = (o + 1023) & ~1023u;
   L.ident = o; o += n_res ? 64 * 128 : 0;                   // 64 x 64 identity, 128-byte swizzle
   L.out = o;   o += 2 * 4 * 32 * (bn < CONV_PASS_COLS ? bn : CONV_PASS_COLS) * 2;   // [2 buffers][4 quarters] staging for the TMA store
-  L.bars = o;  o += 256;
+  L.bars = o;  o += 320;
   L.total = o;
   return L;
 }
@@ -157,7 +160,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   uint64_t* acc_full = empty + p.stages;      // [2]
   uint64_t* acc_empty = acc_full + 2;         // [2]
   uint64_t* bias_ready = acc_empty + 2;       // the bias operand has landed in shared memory (filled after the setup barrier)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_ready + 1);
+  uint64_t* out_full = bias_ready + 1;        // [2] staging buffer written by the epilogue warps
+  uint64_t* out_empty = out_full + 2;         // [2] staging buffer read by the TMA store
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -177,12 +182,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], full_count); mbar_init(&empty[s], 1); }
       for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], CONV_EPI_WARPS * 32); }
       mbar_init(bias_ready, CONV_EPI_WARPS * 32);
+      for (int b = 0; b < 2; ++b) { mbar_init(&out_full[b], CONV_EPI_WARPS * 32); mbar_init(&out_empty[b], 1); }
       fence_barrier_init();
     }
     __syncwarp();
     tmem_alloc_rt(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
   }
-  if (warp >= CONV_FIRST_EPI_WARP) {
+  if (warp >= CONV_FIRST_EPI_WARP && warp < CONV_STORE_WARP) {
     // constant MMA operands (weights-side data: safe to read before the dependency wait)
     const int t = threadIdx.x - CONV_FIRST_EPI_WARP * 32;                 // 0..511
     if (t < CONV_BM) reinterpret_cast<uint4*>(smem + L.ones)[t] = make_uint4(0x3C003C00u, 0u, 0u, 0u);   // {1.0h, 1.0h, 0...}
@@ -314,13 +320,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     // ---------------------------------------------------------------- epilogue (8 warps, 2 per TMEM lane quarter)
     const int quarter = warp & 3, half = (warp - CONV_FIRST_EPI_WARP) >> 2;
     const bool relu = p.flags & CF_RELU;
-    const bool leader = half == 0 && lane == 0;                 // issues this quarter's TMA stores
     const int pass_cols = min(p.bn_tile, CONV_PASS_COLS);
-    const int rowbytes = p.box_cols * 2, box_bytes = 32 * rowbytes, chunks_per_box = p.box_cols >> 4;
-    const uint32_t swz = p.box_cols == 64 ? (lane & 7) : p.box_cols == 32 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
-    const uint32_t stage_buf_bytes = static_cast<uint32_t>(4 * 32 * pass_cols * 2);                 // one staging buffer (4 quarters)
-    const uint32_t my_stage0 = smem_u32(smem + L.out) + static_cast<uint32_t>(quarter * 32 * pass_cols * 2);
-    uint32_t sbuf = 0;                                          // staging buffer of the next pass (alternates)
+    const int rowbytes = p.box_cols * 2, box_bytes = CONV_BM * rowbytes, chunks_per_box = p.box_cols >> 4;
+    const int m_row = quarter * 32 + lane;                      // accumulator row of this thread
+    const uint32_t swz = p.box_cols == 64 ? (m_row & 7) : p.box_cols == 32 ? ((m_row >> 1) & 3) : ((m_row >> 2) & 1);
+    const uint32_t stage_buf_bytes = static_cast<uint32_t>(CONV_BM * pass_cols * 2);                // one staging buffer: [boxes][128 rows][rowbytes]
+    const uint32_t stage0 = smem_u32(smem + L.out);
+    int pc = 0;                                                 // pass counter: staging buffer pc & 1
     const bool do_store = !(p.flags & CF_DBG_NOSTORE);
     {
       // bias operand (a weight: no dependency wait needed); only needed by the LAST MMA of the first tile, so it is
@@ -330,7 +336,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       fence_proxy_async_smem();
       mbar_arrive(bias_ready);
     }
-    if (p.pdl && (leader || out_f32)) pdl_wait();               // output writes must not overtake readers of the previous layers
+    if (p.pdl && out_f32) pdl_wait();                           // output writes must not overtake readers of the previous layers
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
@@ -364,14 +370,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         mbar_arrive(&acc_empty[buf]);
         continue;
       }
-      for (int cg = 0; cg < p.bn_tile; cg += CONV_PASS_COLS) {
+      for (int cg = 0; cg < p.bn_tile; cg += CONV_PASS_COLS, ++pc) {
         const int cols = min(CONV_PASS_COLS, p.bn_tile - cg);
         const int n_chunks = cols >> 4;
-        const uint32_t my_stage = my_stage0 + sbuf * stage_buf_bytes;
-        const uint32_t my_row = my_stage + static_cast<uint32_t>(lane * rowbytes);
-        sbuf ^= 1;
-        if (leader) bulk_wait_read_1();                         // the stores issued two passes ago have left this staging buffer
-        named_bar_sync(1 + quarter, 64);
+        const int ob = pc & 1;
+        const uint32_t my_row = stage0 + static_cast<uint32_t>(ob) * stage_buf_bytes + static_cast<uint32_t>(m_row * rowbytes);
+        mbar_wait(&out_empty[ob], ((pc >> 1) & 1) ^ 1, 16);     // the store issued two passes ago has left this staging buffer
         uint32_t ra[16], rb[16];
         int c = half;
         __syncwarp();
@@ -400,18 +404,45 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           mbar_arrive(&acc_empty[buf]);
         }
         fence_proxy_async_smem();                               // staging writes -> visible to the TMA (async proxy)
-        named_bar_sync(1 + quarter, 64);
-        if (leader && do_store && m0 + quarter * 32 < p.M_total) {
-          const int n_boxes = cols / p.box_cols;
-          for (int b = 0; b < n_boxes; ++b)
-            tma_store_2d(&tmap_out, my_stage + static_cast<uint32_t>(b * box_bytes), n0 + cg + b * p.box_cols, m0 + quarter * 32);
-          bulk_commit_group();
-        }
+        mbar_arrive(&out_full[ob]);
       }
     }
-    if (leader) bulk_wait_all();                                // stores complete before the CTA exits
     if (threadIdx.x == CONV_FIRST_EPI_WARP * 32) CONV_TRACE(6);
-  } else if (!p.tma_a) {
+  } else if (warp == CONV_STORE_WARP) {
+    // ---------------------------------------------------------------- TMA store warp
+    if (!out_f32) {
+      const int pass_cols = min(p.bn_tile, CONV_PASS_COLS);
+      const int box_bytes = CONV_BM * p.box_cols * 2;
+      const uint32_t stage_buf_bytes = static_cast<uint32_t>(CONV_BM * pass_cols * 2);
+      const uint32_t stage0 = smem_u32(smem + L.out);
+      const bool do_store = !(p.flags & CF_DBG_NOSTORE);
+      if (p.pdl) pdl_wait();                                    // output writes must not overtake readers of the previous layers
+      int pc = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = fdiv(tile, p.d_ntiles);
+        const int n0 = (tile - mt * p.n_tiles) * p.bn_tile, m0 = mt * CONV_BM;
+        for (int cg = 0; cg < p.bn_tile; cg += CONV_PASS_COLS, ++pc) {
+          const int cols = min(CONV_PASS_COLS, p.bn_tile - cg);
+          const int ob = pc & 1;
+          mbar_wait(&out_full[ob], (pc >> 1) & 1, 17);
+          if (elect_one()) {
+            if (do_store) {
+              const int n_boxes = cols / p.box_cols;
+              for (int b = 0; b < n_boxes; ++b)
+                tma_store_2d(&tmap_out, stage0 + static_cast<uint32_t>(ob) * stage_buf_bytes + static_cast<uint32_t>(b * box_bytes),
+                             n0 + cg + b * p.box_cols, m0);
+            }
+            bulk_commit_group();
+            bulk_wait_read_all();                               // staging buffer read: hand it back
+            mbar_arrive(&out_empty[ob]);
+          }
+          __syncwarp();
+        }
+      }
+      if (elect_one()) bulk_wait_all();                         // stores complete before the CTA exits
+      __syncwarp();
+    }
+  } else if (!p.tma_a && warp < CONV_STORE_WARP) {
     // ---------------------------------------------------------------- A gather producers (8 warps)
     const int g = threadIdx.x - CONV_FIRST_HELPER_WARP * 32;   // 0..255
     const int chunk = g & 7, rbase = g >> 3;                    // 8 lanes cover one 128-byte row; rows rbase + 32*i

@@ -541,7 +541,7 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
       }
       if (!(o.flags & CF_OUT_F32)) {
         const __half* dst = static_cast<const __half*>(buf_ptr(net, o.dst_buf, B, in, ws, out_raw)) + o.dst_coff;
-        int rc = make_tmap_f16_2d_ex(&r.tmap_out, dst, M, (uint64_t)o.cout, (uint64_t)db.C * 2, (uint32_t)r.box_cols, 32);
+        int rc = make_tmap_f16_2d_ex(&r.tmap_out, dst, M, (uint64_t)o.cout, (uint64_t)db.C * 2, (uint32_t)r.box_cols, CONV_BM);
         if (rc != FIRE_OK) return rc;
       }
     }

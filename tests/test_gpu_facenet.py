@@ -134,13 +134,6 @@ def test_strip_kernel_matches_gather_kernel(fire_lib, monkeypatch):
     ra, rb = ra.cpu().numpy(), rb.cpu().numpy()
     assert _cos(ra, rb).min() >= 0.99999          # one-ulp fp16 flips (bias joins the fp32 sum first vs last) through ~100 layers
     assert np.abs(ra - rb).max() <= 1e-2 * np.abs(rb).max()
-    # per-layer: the first strip layer's output buffer (Conv2d_2a, pitched) equals the gather engine's to fp16 rounding
-    f16 = a.ingest_unit_f32(x)
-    a.forward(f16); b.forward(f16)
-    buf = a.plan.ops[1].dst.buf
-    la, lb = a.read_buffer(buf, f16), b.read_buffer(buf, f16)
-    assert la.shape == lb.shape == (5, 77, 77, 32)
-    assert np.abs(la - lb).max() <= 2e-3 * max(np.abs(lb).max(), 1.0)
 
 
 def test_crop_encode_pipeline_equals_direct_path(nets):
