@@ -16,8 +16,8 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "fire_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("fire_oracle.c", "hnsw_oracle.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.run(["make", "-C", _HERE, "-s", "-B"], check=True)
     return _SO
 
@@ -39,6 +39,17 @@ def lib():
         L.fire_oracle_crop_preprocess.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_long] + \
             [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p]
         L.fire_oracle_crop_preprocess.restype = ctypes.c_int
+        L.fire_hnsw_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint]
+        L.fire_hnsw_create.restype = ctypes.c_void_p
+        L.fire_hnsw_destroy.argtypes = [ctypes.c_void_p]
+        L.fire_hnsw_destroy.restype = None
+        L.fire_hnsw_add.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.fire_hnsw_add.restype = ctypes.c_int
+        L.fire_hnsw_count.argtypes = [ctypes.c_void_p]
+        L.fire_hnsw_count.restype = ctypes.c_int
+        L.fire_hnsw_query.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                      ctypes.c_void_p]
+        L.fire_hnsw_query.restype = ctypes.c_int
         _lib = L
     return _lib
 
@@ -103,3 +114,42 @@ def crop_preprocess(frame: np.ndarray, box) -> tuple:
     rc = lib().fire_oracle_crop_preprocess(frame.ctypes.data, frame.shape[0], frame.shape[1], frame.strides[0],
                                            x, y, w, h, u8.ctypes.data, f32.ctypes.data)
     return rc, u8, f32
+
+
+class HnswOracle:
+    """hnswlib.Index(space='cosine') restated (oracle/hnsw_oracle.c): the APPROXIMATE index the reference queries
+    (modules/hnsw_manager.py:20,29-30: max_elements 100000, ef_construction 200, M 16, ef 200).  Used only to report
+    recall@k of the reference's index against the exact result."""
+
+    def __init__(self, dim: int, max_elements: int = 100000, M: int = 16, ef_construction: int = 200, seed: int = 100):
+        self.dim, self.ef = dim, 10                      # hnswlib's default ef until set_ef() is called
+        self._h = lib().fire_hnsw_create(dim, max_elements, M, ef_construction, seed)
+
+    def set_ef(self, ef: int):
+        self.ef = int(ef)
+
+    def add_items(self, rows: np.ndarray):
+        rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, self.dim)
+        for r in rows:                                    # the reference adds one row per call (hnsw_manager.py:127,137)
+            if lib().fire_hnsw_add(self._h, r.ctypes.data) < 0:
+                raise RuntimeError("index full")
+
+    def get_current_count(self) -> int:
+        return int(lib().fire_hnsw_count(self._h))
+
+    def knn_query(self, q: np.ndarray, k: int = 1):
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.dim)
+        labels = np.empty((q.shape[0], k), dtype=np.int64)
+        dists = np.empty((q.shape[0], k), dtype=np.float32)
+        rc = lib().fire_hnsw_query(self._h, q.ctypes.data, q.shape[0], k, self.ef, labels.ctypes.data, dists.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("Cannot return the results in a contiguous 2D array. Probably ef or M is too small")
+        return labels.astype(np.uint64), dists
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().fire_hnsw_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
