@@ -148,7 +148,8 @@ static int pick_bn_tile(int cout, int m_tiles, int nkb, int sms, bool residual) 
   double best_cost = 1e30;
   for (int d = 16; d <= 256 && d <= cout; d += 16) {
     if (cout % d) continue;
-    if (residual && d % 64) continue;                                 // residual K-blocks are 64 columns wide
+    if (residual && (d % 64 || d > 128)) continue;                    // residual K-blocks are 64 columns wide; 128 beat 256 in the
+                                                                      // sweep (tools/tune_bn.py): one staging pass per tile
     const long long tiles = (long long)m_tiles * (cout / d);
     const long long waves = (tiles + sms - 1) / sms;
     const double fill = (16384.0 + 128.0 * d) / 32.0;
@@ -502,7 +503,16 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
         }
       }
       const bool residual = (o.flags & CF_RESIDUAL) != 0;
-      const int bn = pick_bn_tile(o.cout, r.m_tiles, o.k_pad / 64, sms, residual);
+      int bn = pick_bn_tile(o.cout, r.m_tiles, o.k_pad / 64, sms, residual);
+      if (const char* e = getenv("FIRE_B200_BN")) {            // tuning experiments: "op:bn,op:bn,..."
+        const int me = (int)(&r - net->ops.data());
+        for (const char* q = e; q && *q;) {
+          int op = -1, v = 0;
+          if (sscanf(q, "%d:%d", &op, &v) == 2 && op == me && v >= 16 && v <= 256 && v % 16 == 0 && o.cout % v == 0 && (!residual || v % 64 == 0)) bn = v;
+          q = strchr(q, ',');
+          if (q) ++q;
+        }
+      }
       if (bn != r.bn_tile) {
         int rc = make_tmap_f16_2d(&r.tmap_w, net->d_weights + o.w_off, (uint64_t)o.cout, (uint64_t)o.k_pad,
                                   (uint64_t)o.k_pad * 2, (uint32_t)bn);
