@@ -180,9 +180,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     if (lane == 0) {
       const uint32_t full_count = p.tma_a ? 1u : 1u + CONV_HELPER_THREADS;
       for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], full_count); mbar_init(&empty[s], 1); }
-      for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], CONV_EPI_WARPS * 32); }
-      mbar_init(bias_ready, CONV_EPI_WARPS * 32);
-      for (int b = 0; b < 2; ++b) { mbar_init(&out_full[b], CONV_EPI_WARPS * 32); mbar_init(&out_empty[b], 1); }
+      // one arrival per epilogue WARP (256 per-thread arrivals on one barrier word serialise: ~250 cycles per barrier)
+      for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], CONV_EPI_WARPS); }
+      mbar_init(bias_ready, CONV_EPI_WARPS);
+      for (int b = 0; b < 2; ++b) { mbar_init(&out_full[b], CONV_EPI_WARPS); mbar_init(&out_empty[b], 1); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -334,7 +335,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       uint4* s_bias = reinterpret_cast<uint4*>(smem + L.bias);
       for (int i = threadIdx.x - CONV_FIRST_EPI_WARP * 32; i < p.cout; i += CONV_EPI_WARPS * 32) s_bias[i] = __ldg(p.bias16 + i);
       fence_proxy_async_smem();
-      mbar_arrive(bias_ready);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bias_ready);
     }
     if (p.pdl && out_f32) pdl_wait();                           // output writes must not overtake readers of the previous layers
     int lt = 0;
@@ -365,9 +367,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             }
           }
         }
-        __syncwarp();
         tc_fence_before();
-        mbar_arrive(&acc_empty[buf]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
         continue;
       }
       for (int cg = 0; cg < p.bn_tile; cg += CONV_PASS_COLS, ++pc) {
@@ -398,13 +400,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             conv_stage_chunk(rb, relu, my_row + static_cast<uint32_t>(box * box_bytes), static_cast<uint32_t>(2 * cb), swz);
           }
         }
-        if (cg + CONV_PASS_COLS >= p.bn_tile) {                 // accumulator fully read: hand it back before storing
-          __syncwarp();
-          tc_fence_before();
-          mbar_arrive(&acc_empty[buf]);
-        }
+        tc_fence_before();
         fence_proxy_async_smem();                               // staging writes -> visible to the TMA (async proxy)
-        mbar_arrive(&out_full[ob]);
+        __syncwarp();
+        if (lane == 0) {
+          if (cg + CONV_PASS_COLS >= p.bn_tile) mbar_arrive(&acc_empty[buf]);   // accumulator fully read: hand it back
+          mbar_arrive(&out_full[ob]);
+        }
       }
     }
     if (threadIdx.x == CONV_FIRST_EPI_WARP * 32) CONV_TRACE(6);

@@ -93,8 +93,9 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-      for (int b = 0; b < STRIP_MAX_ACC; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], CONV_EPI_WARPS * 32); }
-      for (int b = 0; b < 2; ++b) { mbar_init(&out_full[b], CONV_EPI_WARPS * 32); mbar_init(&out_empty[b], 1); }
+      // one arrival per epilogue WARP (256 per-thread arrivals on one barrier word serialise: ~250 cycles per barrier)
+      for (int b = 0; b < STRIP_MAX_ACC; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], CONV_EPI_WARPS / 2); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&out_full[b], CONV_EPI_WARPS / 2); mbar_init(&out_empty[b], 1); }
       mbar_init(w_full, 1);
       fence_barrier_init();
     }
@@ -245,8 +246,10 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       if (lane == 0) CONV_TRACE(4);
     }
   } else if (warp < CONV_FIRST_EPI_WARP + CONV_EPI_WARPS) {
-    // ---------------------------------------------------------------- epilogue (8 warps, 2 per TMEM lane quarter)
-    const int quarter = warp & 3, half = (warp - CONV_FIRST_EPI_WARP) >> 2;
+    // ---------------------------------------------------------------- epilogue: two groups of 4 warps (one per TMEM lane quarter);
+    // group g takes the tiles with lt & 1 == g and owns staging buffer g, so the fixed per-tile latencies (two barrier
+    // waits, TMEM load, fences) of consecutive tiles overlap
+    const int quarter = warp & 3, group = (warp - CONV_FIRST_EPI_WARP) >> 2;
     const bool relu = p.flags & CF_RELU;
     const int rowbytes = p.box_cols * 2, chunks_per_box = p.box_cols >> 4;
     const int box_bytes = CONV_BM * rowbytes;                   // one column box of the whole 128-row tile
@@ -257,9 +260,10 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const uint32_t stage_buf_bytes = static_cast<uint32_t>(CONV_BM * p.cout * 2);
     const uint32_t stage0 = smem_u32(smem + L.out);
     long long te[3] = {0, 0, 0};
-    const bool prof = p.trace != nullptr && (p.flags & CF_DBG_PHASES) && threadIdx.x == CONV_FIRST_EPI_WARP * 32;
+    const bool prof = p.trace != nullptr && (p.flags & CF_DBG_PHASES) && threadIdx.x == CONV_FIRST_EPI_WARP * 32;     // group 0's tiles only
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      if ((lt & 1) != group) continue;
       const int buf = lt & (p.n_acc - 1), ob = lt & 1;
       const uint32_t stage = stage0 + static_cast<uint32_t>(ob) * stage_buf_bytes;
       long long c0 = prof ? clock64() : 0, c1;
@@ -272,7 +276,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       if (active) {
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * p.cout);
         const uint32_t my_row = stage + static_cast<uint32_t>(m * rowbytes);
-        for (int c = half; c < n_chunks; c += 2) {
+        for (int c = 0; c < n_chunks; ++c) {
           uint32_t ra[16];
           __syncwarp();
           tmem_ld_32x16(taddr + static_cast<uint32_t>(c * 16), ra);
@@ -281,11 +285,10 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           conv_stage_chunk(ra, relu, my_row + static_cast<uint32_t>(box * box_bytes), static_cast<uint32_t>(2 * cb), swz);
         }
       }
-      __syncwarp();
       tc_fence_before();
-      mbar_arrive(&acc_empty[buf]);
       fence_proxy_async_smem();                                 // staging writes -> visible to the TMA (async proxy)
-      mbar_arrive(&out_full[ob]);
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&acc_empty[buf]); mbar_arrive(&out_full[ob]); }
       if (prof) { c1 = clock64(); te[2] += c1 - c0; }
     }
     if (prof) {
@@ -313,8 +316,8 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           }
         }
         bulk_commit_group();
-        bulk_wait_read_all();                                   // staging buffer read: hand it back
-        mbar_arrive(&out_empty[ob]);
+        bulk_wait_read_all();                                   // staging buffer read: hand it back (keeping a store in flight
+        mbar_arrive(&out_empty[ob]);                            // measured slower: it queues behind the patch loads)
       }
       __syncwarp();
     }

@@ -20,7 +20,7 @@
 namespace fire {
 
 constexpr int OP_CONV = 1, OP_MAXPOOL = 2, OP_GAP = 3;
-constexpr uint32_t BLOB_VERSION = 4;
+constexpr uint32_t BLOB_VERSION = 5;
 
 #pragma pack(push, 1)
 struct BlobHeader {
@@ -36,7 +36,7 @@ struct BlobBuf {
 };
 struct BlobOp {
   int32_t kind, src_buf, src_coff, dst_buf, dst_coff, res_buf, res_coff, H, W, Ho, Wo, kh, kw, stride, pad_h, pad_w, cin,
-      cout, k_pad, flags, bn_tile, pad;
+      cout, k_pad, flags, bn_tile, flop_k;      // flop_k: real K for FLOP accounting (0 = kh * kw * cin)
   int64_t w_off, b_off;
 };
 #pragma pack(pop)
@@ -108,13 +108,23 @@ __global__ void l2norm_kernel(const float* __restrict__ in, float* __restrict__ 
   }
 }
 
-// float NHWC3 in [0,1] -> fp16 NHWC8 pixel scale (x*255; exact for x = k/255), channels 3..7 = 0
-__global__ void ingest_f32_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n_pix) {
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_pix;
+// float NHWC3 in [0,1] -> the network input: fp16 space-to-depth [80][80][16], pixel scale (x*255; exact for x = k/255),
+// channel (dy*2+dx)*3+c of position (Y,X) = pixel (2Y+dy, 2X+dx), channels 12..15 zero.  One thread per position.
+__global__ void ingest_f32_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n_pos) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_pos;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float a = in[i * 3] * 255.0f, b = in[i * 3 + 1] * 255.0f, c = in[i * 3 + 2] * 255.0f;
-    uint4 q = make_uint4(pack_f16x2_sat(a, b), pack_f16x2_sat(c, 0.f), 0u, 0u);
-    *reinterpret_cast<uint4*>(out + i * 8) = q;
+    const long long b = i / 6400;
+    const int r = static_cast<int>(i - b * 6400), Y = r / 80, X = r - Y * 80;
+    float v[12];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const float* src = in + ((b * 160 + 2 * Y + dy) * 160 + 2 * X) * 3;      // two adjacent pixels = 6 floats
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v[dy * 6 + k] = src[k] * 255.0f;
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + i * 16);
+    o[0] = make_uint4(pack_f16x2_sat(v[0], v[1]), pack_f16x2_sat(v[2], v[3]), pack_f16x2_sat(v[4], v[5]), pack_f16x2_sat(v[6], v[7]));
+    o[1] = make_uint4(pack_f16x2_sat(v[8], v[9]), pack_f16x2_sat(v[10], v[11]), 0u, 0u);
   }
 }
 
@@ -285,7 +295,7 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
       }
       r.bias16_off = bias16_off;
       bias16_off += (size_t)o.cout * 16;
-      r.flops_per_image = 2.0 * o.Ho * o.Wo * (double)o.cout * o.kh * o.kw * o.cin;
+      r.flops_per_image = 2.0 * o.Ho * o.Wo * (double)o.cout * (o.flop_k > 0 ? o.flop_k : o.kh * o.kw * o.cin);
       net->flops_per_image += r.flops_per_image;
     }
     net->ops.push_back(r);
@@ -673,9 +683,9 @@ int fire_facenet_read_buffer(fire_net_t* net, int buf, int B, const void* in_f16
 
 int fire_ingest_f32(const float* in_nhwc3, int B, void* out_f16, fire_stream_t stream) {
   if (!in_nhwc3 || !out_f16 || B <= 0) return fail(FIRE_ERR_ARG, "fire_ingest_f32: bad arguments");
-  const long long n_pix = (long long)B * 160 * 160;
-  const int blocks = (int)std::min<long long>((n_pix + 255) / 256, 148 * 32);
-  ingest_f32_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(in_nhwc3, static_cast<__half*>(out_f16), n_pix);
+  const long long n_pos = (long long)B * 80 * 80;
+  const int blocks = (int)std::min<long long>((n_pos + 255) / 256, 148 * 32);
+  ingest_f32_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(in_nhwc3, static_cast<__half*>(out_f16), n_pos);
   FIRE_LAUNCH_CHECK("ingest_f32_kernel");
   count_launch();
   return FIRE_OK;

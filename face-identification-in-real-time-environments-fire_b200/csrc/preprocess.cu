@@ -10,9 +10,8 @@
 // reference does before dividing by 255.  FIRE_PRE_NORTHSTAR is the additive mode named by the
 // north star: float half-pixel bilinear + per-crop prewhiten (davidsandberg facenet.prewhiten).
 //
-// Layout: frames are uint8 HWC3 in HBM; the output is the network's input layout, fp16 NHWC with
-// the 3 channels padded to 8 (one 16-byte vector per pixel, pixel scale 0..255), so each thread
-// finishes with one coalesced 16-byte store.  The kernel is HBM/L2-bound integer/byte work; it
+// Layout: frames are uint8 HWC3 in HBM; the output is the network's input layout, fp16 space-to-depth
+// [80][80][16] (2 x 2 pixel blocks, 12 channels used, pixel scale 0..255; see store_s2d), 204.8 KB per crop.  The kernel is HBM/L2-bound integer/byte work; it
 // deliberately stays off the tensor cores.
 #include <cfloat>
 
@@ -107,13 +106,27 @@ __device__ __forceinline__ void linear_entry(int d, int ssize, double scale, dou
   e.a1 = min(32767, __float2int_rn(__fmul_rn(f, 2048.f)));
 }
 
-__device__ __forceinline__ void store_pixel(int v0, int v1, int v2, size_t pix, __half* out_f16, float* out_f32) {
-  if (out_f16) {
-    uint4 q = make_uint4(pack_f16x2_sat(static_cast<float>(v0), static_cast<float>(v1)),
-                         pack_f16x2_sat(static_cast<float>(v2), 0.f), 0u, 0u);
-    *reinterpret_cast<uint4*>(out_f16 + pix * 8) = q;
+// Network-input layout (space-to-depth, see fire_b200/netplan.py): fp16 [box][80][80][16]; position (Y, X) holds the
+// 2 x 2 pixel block (2Y + dy, 2X + dx) as channels (dy * 2 + dx) * 3 + c, channels 12..15 zero.  Lanes 2j / 2j+1 of
+// a warp hold horizontally adjacent pixels, so the even lane collects its neighbour's three values with one shuffle
+// round and writes 12 contiguous bytes; the even lane of an odd row also writes the 8 bytes of zero padding.
+// MUST be called by all 32 lanes of the warp (it shuffles).
+__device__ __forceinline__ void store_s2d(float a0, float a1, float a2, int box, int dy, int dx, __half* out_f16) {
+  const float b0 = __shfl_xor_sync(0xffffffffu, a0, 1), b1 = __shfl_xor_sync(0xffffffffu, a1, 1), b2 = __shfl_xor_sync(0xffffffffu, a2, 1);
+  if ((dx & 1) == 0) {
+    uint32_t* q = reinterpret_cast<uint32_t*>(out_f16 + ((static_cast<size_t>(box) * (PRE_OUT / 2) + (dy >> 1)) * (PRE_OUT / 2) + (dx >> 1)) * 16 +
+                                              (dy & 1) * 6);
+    q[0] = pack_f16x2_sat(a0, a1);
+    q[1] = pack_f16x2_sat(a2, b0);
+    q[2] = pack_f16x2_sat(b1, b2);
+    if (dy & 1) { q[3] = 0u; q[4] = 0u; }             // halfs 12..15 (q points at half 6 here)
   }
+}
+
+__device__ __forceinline__ void store_pixel(int v0, int v1, int v2, int box, int dy, int dx, __half* out_f16, float* out_f32) {
+  if (out_f16) store_s2d(static_cast<float>(v0), static_cast<float>(v1), static_cast<float>(v2), box, dy, dx, out_f16);
   if (out_f32) {
+    const size_t pix = (static_cast<size_t>(box) * PRE_OUT + dy) * PRE_OUT + dx;
     out_f32[pix * 3 + 0] = __fdiv_rn(static_cast<float>(v0), 255.0f);
     out_f32[pix * 3 + 1] = __fdiv_rn(static_cast<float>(v1), 255.0f);
     out_f32[pix * 3 + 2] = __fdiv_rn(static_cast<float>(v2), 255.0f);
@@ -235,7 +248,7 @@ preprocess_reference_kernel(const uint8_t* __restrict__ frames, const int64_t* _
       }
     }
     if (swap_rb) { const int tmp = v[0]; v[0] = v[2]; v[2] = tmp; }
-    store_pixel(v[0], v[1], v[2], (static_cast<size_t>(box) * PRE_OUT + dy) * PRE_OUT + dx, out_f16, out_f32);
+    store_pixel(v[0], v[1], v[2], box, dy, dx, out_f16, out_f32);
   }
 }
 
@@ -281,7 +294,7 @@ preprocess_northstar_kernel(const uint8_t* __restrict__ frames, const int64_t* _
   const size_t pix0 = static_cast<size_t>(box) * PRE_OUT * PRE_OUT;
   if (g.mode == PM_EMPTY) {
     for (int t = threadIdx.x; t < PRE_OUT * PRE_OUT; t += NS_THREADS) {
-      if (out_f16) *reinterpret_cast<uint4*>(out_f16 + (pix0 + t) * 8) = make_uint4(0, 0, 0, 0);
+      if (out_f16 && t < PRE_OUT * PRE_OUT / 2) *reinterpret_cast<uint4*>(out_f16 + pix0 * 4 + static_cast<size_t>(t) * 8) = make_uint4(0, 0, 0, 0);   // 80*80*16 halfs
       if (out_f32) { out_f32[(pix0 + t) * 3] = 0.f; out_f32[(pix0 + t) * 3 + 1] = 0.f; out_f32[(pix0 + t) * 3 + 2] = 0.f; }
     }
     return;
@@ -317,9 +330,7 @@ preprocess_northstar_kernel(const uint8_t* __restrict__ frames, const int64_t* _
 #pragma unroll
     for (int c = 0; c < 3; ++c) y[c] = (v[c] - mean) * inv;
     if (swap_rb) { const float tmp = y[0]; y[0] = y[2]; y[2] = tmp; }
-    if (out_f16)
-      *reinterpret_cast<uint4*>(out_f16 + (pix0 + t) * 8) =
-          make_uint4(pack_f16x2_sat(y[0] * 255.f, y[1] * 255.f), pack_f16x2_sat(y[2] * 255.f, 0.f), 0u, 0u);
+    if (out_f16) store_s2d(y[0] * 255.f, y[1] * 255.f, y[2] * 255.f, box, t / PRE_OUT, t % PRE_OUT, out_f16);
     if (out_f32) { out_f32[(pix0 + t) * 3] = y[0]; out_f32[(pix0 + t) * 3 + 1] = y[1]; out_f32[(pix0 + t) * 3 + 2] = y[2]; }
   }
 }

@@ -12,7 +12,9 @@ import numpy as np
 
 from . import _lib
 from ._lib import FireError, check
-from .netplan import IN_C_PAD, IN_HW, Plan
+from .netplan import IN_HW, Plan
+
+NET_HW, NET_C = IN_HW // 2, 16          # network input: space-to-depth fp16 [B, 80, 80, 16] (netplan.Plan, csrc/preprocess.cu)
 from . import weights as W
 
 
@@ -69,11 +71,12 @@ class FaceNetEngine:
         return self._ws.data_ptr() + off, self._ws.numel() - off
 
     def forward(self, x_f16, want_l2: bool = True, out_raw=None, out_l2=None):
-        """x_f16: cuda fp16 [B,160,160,8] pixel-scale network input -> (raw [B,D] f32, l2 [B,D] f32 or None)."""
+        """x_f16: cuda fp16 [B,80,80,16] space-to-depth pixel-scale network input (what preprocess_boxes / ingest_unit_f32
+        return; pixels_to_network_input() builds it from a plain image batch) -> (raw [B,D] f32, l2 [B,D] f32 or None)."""
         torch = _torch()
         assert x_f16.is_cuda and x_f16.dtype == torch.float16 and x_f16.is_contiguous()
         B = x_f16.shape[0]
-        assert tuple(x_f16.shape[1:]) == (IN_HW, IN_HW, IN_C_PAD), x_f16.shape
+        assert tuple(x_f16.shape[1:]) == (NET_HW, NET_HW, NET_C), x_f16.shape
         raw = out_raw if out_raw is not None else torch.empty(B, self.D, dtype=torch.float32, device=self.device)
         l2 = (out_l2 if out_l2 is not None else torch.empty(B, self.D, dtype=torch.float32, device=self.device)) if want_l2 else None
         ws_ptr, ws_bytes = self._workspace(B)
@@ -82,11 +85,11 @@ class FaceNetEngine:
         return raw, l2
 
     def ingest_unit_f32(self, x_f32):
-        """cuda float32 [B,160,160,3] in the reference's [0,1] scale -> fp16 [B,160,160,8] network input."""
+        """cuda float32 [B,160,160,3] in the reference's [0,1] scale -> fp16 [B,80,80,16] network input."""
         torch = _torch()
         assert x_f32.is_cuda and x_f32.dtype == torch.float32 and x_f32.is_contiguous()
         B = x_f32.shape[0]
-        out = torch.empty(B, IN_HW, IN_HW, IN_C_PAD, dtype=torch.float16, device=self.device)
+        out = torch.empty(B, NET_HW, NET_HW, NET_C, dtype=torch.float16, device=self.device)
         check(_lib.lib().fire_ingest_f32(_ptr(x_f32), B, _ptr(out), _lib.stream_ptr()))
         return out
 
@@ -113,6 +116,25 @@ class FaceNetEngine:
         check(_lib.lib().fire_facenet_read_buffer(self._h, buf, B, _ptr(x_f16), ws_ptr, out.ctypes.data, out.nbytes))
         return out[:, :, :b.W, :].astype(np.float32)          # drop the row-pitch padding of pitched buffers
 
+
+
+def pixels_to_network_input(x):
+    """torch [B,160,160,C>=3] pixel-scale values (any float/int dtype) -> fp16 [B,80,80,16] space-to-depth network input:
+    channel (dy*2+dx)*3+c of position (Y,X) = pixel (2Y+dy, 2X+dx), channel c.  Plain torch (tests / tools only; the
+    product path gets this layout straight out of fire_preprocess / fire_ingest_f32)."""
+    torch = _torch()
+    B = x.shape[0]
+    y = x[..., :3].reshape(B, NET_HW, 2, NET_HW, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(B, NET_HW, NET_HW, 12)
+    out = torch.zeros(B, NET_HW, NET_HW, NET_C, dtype=torch.float16, device=x.device)
+    out[..., :12] = y.to(torch.float16)
+    return out
+
+
+def network_input_to_pixels(f16):
+    """Inverse of pixels_to_network_input: fp16 [B,80,80,16] -> float32 [B,160,160,3] (also returns the 4 padding channels)."""
+    B = f16.shape[0]
+    y = f16[..., :12].float().reshape(B, NET_HW, NET_HW, 2, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(B, IN_HW, IN_HW, 3)
+    return y, f16[..., 12:].float()
 
 
 class CropEncodePipeline:
@@ -265,12 +287,12 @@ def knn_merge(dists, ids):
 def preprocess_boxes(frames, frame_desc, boxes, box_frame, mode: int = _lib.PRE_REFERENCE, want_f16: bool = True,
                      want_f32: bool = False):
     """K1.  frames: cuda uint8 (flat or [F,H,W,3]); frame_desc: cuda int64 [F,4] (offset,H,W,stride);
-    boxes: cuda int32 [n,4] xywh; box_frame: cuda int32 [n].  Returns (f16 [n,160,160,8] | None,
+    boxes: cuda int32 [n,4] xywh; box_frame: cuda int32 [n].  Returns (f16 [n,80,80,16] network input | None,
     f32 [n,160,160,3] | None, status int32 [n])."""
     torch = _torch()
     n = boxes.shape[0]
     dev = frames.device
-    f16 = torch.empty(n, IN_HW, IN_HW, IN_C_PAD, dtype=torch.float16, device=dev) if want_f16 else None
+    f16 = torch.empty(n, NET_HW, NET_HW, NET_C, dtype=torch.float16, device=dev) if want_f16 else None
     f32 = torch.empty(n, IN_HW, IN_HW, 3, dtype=torch.float32, device=dev) if want_f32 else None
     status = torch.empty(n, dtype=torch.int32, device=dev)
     check(_lib.lib().fire_preprocess(_ptr(frames), _ptr(frame_desc), frame_desc.shape[0], _ptr(boxes), _ptr(box_frame), n,

@@ -91,6 +91,7 @@ class Op:
     w_off: int = 0               # byte offset of the packed [cout][k_pad] fp16 weights
     b_off: int = 0               # byte offset of the fp32 bias
     label: str = ""
+    s2d: bool = False            # first conv only: executed as a 2x2 stride-1 conv over the space-to-depth input (see Plan)
 
     @property
     def k_real(self) -> int:
@@ -118,10 +119,18 @@ def _pick_bn_tile(cout: int) -> int:
 
 
 class Plan:
-    def __init__(self, D: int, fuse_siblings: bool = True, reuse_buffers: bool = True, pitched: bool = True):
+    def __init__(self, D: int, fuse_siblings: bool = True, reuse_buffers: bool = True, pitched: bool = True,
+                 s2d_input: bool = True):
         assert D in (128, 512)
         self.D = D
         self.pitched = pitched
+        # s2d_input: the network input is handed over space-to-depth, [B, 80, 80, 16] fp16 with channel
+        # (dy * 2 + dx) * 3 + c of position (Y, X) = pixel (2Y + dy, 2X + dx), channel c (12 used, 4 zero).  The
+        # stride-2 3x3 first conv then IS a stride-1 2x2 conv with K = 64 over that tensor (taps (a, b) cover
+        # rows 2a..2a+1, cols 2b..2b+1 of the 3x3 window; the 4th row/column gets zero weights), which the
+        # strip kernel runs without im2col.  The Plan keeps describing the logical 3x3/2 conv; weights.pack()
+        # writes the transformed op into the blob.
+        self.s2d_input = s2d_input
         self.fuse = fuse_siblings
         self.reuse = reuse_buffers
         self.bufs: List[Buf] = []
@@ -185,7 +194,9 @@ class Plan:
     def _build(self):
         B = self._buf
         x = self.whole(self.in_buf)
-        t = B(79, 79, 32); self.conv("Conv2d_1a_3x3", x, self.whole(t), 3, 3, 2, cin_real=3, in_scale=1.0 / 255.0); x = self.whole(t)
+        t = B(79, 79, 32, Wp=80 if self.s2d_input else 0)
+        self.conv("Conv2d_1a_3x3", x, self.whole(t), 3, 3, 2, cin_real=3, in_scale=1.0 / 255.0).s2d = self.s2d_input
+        x = self.whole(t)
         t = B(77, 77, 32, Wp=79); self.conv("Conv2d_2a_3x3", x, self.whole(t), 3, 3); x = self.whole(t)
         t = B(77, 77, 64, Wp=79); self.conv("Conv2d_2b_3x3", x, self.whole(t), 3, 3, same=True); x = self.whole(t)
         t = B(38, 38, 64); self.maxpool(x, self.whole(t), "MaxPool_3a_3x3"); x = self.whole(t)

@@ -19,7 +19,7 @@ import numpy as np
 from .netplan import BN_EPS, OP_CONV, Plan
 
 MAGIC = b"FIREB200"
-BLOB_VERSION = 4
+BLOB_VERSION = 5
 
 HEADER_DT = np.dtype([("magic", "S8"), ("version", "<i4"), ("D", "<i4"), ("n_ops", "<i4"), ("n_bufs", "<i4"),
                       ("ws_bytes_per_image", "<i8"), ("weights_off", "<i8"), ("weights_bytes", "<i8"),
@@ -30,7 +30,7 @@ OP_DT = np.dtype([("kind", "<i4"), ("src_buf", "<i4"), ("src_coff", "<i4"), ("ds
                   ("res_buf", "<i4"), ("res_coff", "<i4"), ("H", "<i4"), ("W", "<i4"), ("Ho", "<i4"), ("Wo", "<i4"),
                   ("kh", "<i4"), ("kw", "<i4"), ("stride", "<i4"), ("pad_h", "<i4"), ("pad_w", "<i4"),
                   ("cin", "<i4"), ("cout", "<i4"), ("k_pad", "<i4"), ("flags", "<i4"), ("bn_tile", "<i4"),
-                  ("pad", "<i4"), ("w_off", "<i8"), ("b_off", "<i8")])
+                  ("flop_k", "<i4"), ("w_off", "<i8"), ("b_off", "<i8")])
 
 
 F16_MAX = 65504.0
@@ -171,6 +171,27 @@ def fold_conv(op, tensors: dict):
     return np.concatenate(rows, 0), np.concatenate(biases, 0)
 
 
+S2D_C = 16          # channels of the space-to-depth network input: (dy, dx, c) -> (dy * 2 + dx) * 3 + c, 12 used
+S2D_K = 64          # K of the equivalent 2x2 conv: tap (a, b) * 16 + channel
+
+
+def s2d_weights(Wg: np.ndarray, cin: int) -> np.ndarray:
+    """[cout, 3*3*cin] (tap-major, channel-minor, first conv) -> [cout, 64] for the 2x2 stride-1 conv over the
+    space-to-depth input: W2[(a*2+b)*16 + (dy*2+dx)*3 + c] = W[(2a+dy), (2b+dx), c], zero where the 4x4 footprint
+    leaves the 3x3 window."""
+    cout = Wg.shape[0]
+    w3 = Wg.reshape(cout, 3, 3, cin)
+    out = np.zeros((cout, 2, 2, S2D_C), dtype=np.float32)
+    for a in range(2):
+        for b in range(2):
+            for dy in range(2):
+                for dx in range(2):
+                    r, c_ = 2 * a + dy, 2 * b + dx
+                    if r < 3 and c_ < 3:
+                        out[:, a, b, (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3] = w3[:, r, c_, :3]
+    return out.reshape(cout, S2D_K)
+
+
 def pack(plan: Plan, tensors: dict) -> bytes:
     """Serialise plan + folded bf16 weights into the blob `fire_facenet_create` parses."""
     chunks, pos = [], 0
@@ -188,20 +209,32 @@ def pack(plan: Plan, tensors: dict) -> bytes:
         if op.kind != OP_CONV:
             continue
         W, b = fold_conv(op, tensors)
-        Wp = np.zeros((op.cout, op.k_pad), dtype=np.uint16)
+        if op.s2d:
+            W = s2d_weights(W, op.cin)
+        k_pad = S2D_K if op.s2d else op.k_pad
+        Wp = np.zeros((op.cout, k_pad), dtype=np.uint16)
         Wp[:, :W.shape[1]] = f32_to_f16_bits(W)
         op.w_off = put(Wp)
         op.b_off = put(b)
 
     bufs = np.zeros(len(plan.bufs), dtype=BUF_DT)
+    s2d = any(o.s2d for o in plan.ops)
     for i, b in enumerate(plan.bufs):
+        if s2d and i == plan.in_buf:                       # the engine sees the space-to-depth tensor
+            bufs[i] = (b.H // 2, b.W // 2, S2D_C, b.elt, 0, 1, 0)
+            continue
         bufs[i] = (b.H, b.W, b.C, b.elt, max(b.offset, 0), int(b.external), b.Wp)
     ops = np.zeros(len(plan.ops), dtype=OP_DT)
     for i, o in enumerate(plan.ops):
         res_buf, res_coff = (o.res.buf, o.res.c_off) if o.res is not None else (-1, 0)
+        flop_k = o.kh * o.kw * o.cin_real if o.kind == OP_CONV else 0
+        if o.s2d:                                          # 3x3 / stride 2 over [160,160,8]  ==  2x2 / stride 1 over [80,80,16]
+            ops[i] = (o.kind, o.src.buf, 0, o.dst.buf, o.dst.c_off, res_buf, res_coff, o.H // 2, o.W // 2, o.Ho, o.Wo,
+                      2, 2, 1, 0, 0, S2D_C, o.cout, S2D_K, o.flags, o.bn_tile, flop_k, o.w_off, o.b_off)
+            continue
         ops[i] = (o.kind, o.src.buf, o.src.c_off, o.dst.buf, o.dst.c_off, res_buf, res_coff, o.H, o.W, o.Ho, o.Wo,
                   o.kh, o.kw, o.stride, o.pad_h, o.pad_w, o.cin, o.cout, o.k_pad if o.kind == OP_CONV else 0,
-                  o.flags, o.bn_tile, 0, o.w_off, o.b_off)
+                  o.flags, o.bn_tile, flop_k, o.w_off, o.b_off)
     hdr = np.zeros(1, dtype=HEADER_DT)
     meta = HEADER_DT.itemsize + bufs.nbytes + ops.nbytes
     weights_off = (meta + 255) // 256 * 256

@@ -60,8 +60,9 @@ uint64_t fire_launch_count(void);          /* number of kernels this library has
  *               then the far edge is clipped to the frame (numpy slicing).  Empty crops produce an
  *               all-zero output and status 1 in box_status.
  * box_frame   : int32 [n_boxes] frame index of every box
- * out_f16     : fp16 [n_boxes][160][160][8]  network input: pixel-scale (0..255 == 0..1 in the
- *               reference), channels 3..7 zero.                       (may be NULL)
+ * out_f16     : fp16 [n_boxes][80][80][16]  network input, space-to-depth: position (Y, X) holds the 2 x 2 pixel
+ *               block (2Y + dy, 2X + dx) as channels (dy * 2 + dx) * 3 + c, channels 12..15 zero; pixel scale
+ *               (0..255 == 0..1 in the reference).                     (may be NULL)
  * out_f32     : float [n_boxes][160][160][3] exactly what preprocess_for_encoder returns (may be NULL)
  * box_status  : int32 [n_boxes] 0 = ok, 1 = empty crop (may be NULL)
  */
@@ -69,7 +70,7 @@ int fire_preprocess(const uint8_t* frames, const int64_t* frame_desc, int n_fram
                     const int32_t* box_frame, int n_boxes, int mode, void* out_f16, float* out_f32,
                     int32_t* box_status, fire_stream_t stream);
 
-/* float NHWC [B][160][160][3] in the reference's [0,1] scale -> fp16 [B][160][160][8] network input */
+/* float NHWC [B][160][160][3] in the reference's [0,1] scale -> fp16 [B][80][80][16] network input (layout above) */
 int fire_ingest_f32(const float* in_nhwc3, int B, void* out_f16, fire_stream_t stream);
 
 /* ---- K2: FaceNet (Inception-ResNet-v1) forward  (facenet_gpu.py:116-129) -------------------- */
@@ -80,7 +81,7 @@ int fire_facenet_dim(const fire_net_t* net);                    /* 128 or 512 */
 size_t fire_facenet_workspace(const fire_net_t* net, int B);    /* bytes of scratch forward() needs */
 double fire_facenet_flops(const fire_net_t* net);               /* algorithmic FLOP per image */
 int fire_facenet_num_ops(const fire_net_t* net);
-/* in_f16: fp16 [B][160][160][8]; out_raw: float [B][D] un-normalised (what encode() returns);
+/* in_f16: fp16 [B][80][80][16] (fire_preprocess / fire_ingest_f32 output); out_raw: float [B][D] un-normalised (what encode() returns);
  * out_l2: float [B][D] rows divided by their L2 norm (face_recognition.py:225-229), may be NULL. */
 int fire_facenet_forward(fire_net_t* net, const void* in_f16, int B, float* out_raw, float* out_l2,
                          void* workspace, size_t ws_bytes, fire_stream_t stream);

@@ -51,8 +51,20 @@ def run_plan(plan: Plan, blob: bytes, x_pix_nhwc8: np.ndarray, store_f16: bool =
             src = view(op.src.buf)[..., op.src.c_off:op.src.c_off + op.src.c]
             dstv = view(op.dst.buf)
             if op.kind == OP_CONV:
-                wb = np.frombuffer(blob, dtype=np.uint16, count=op.cout * op.k_pad, offset=wbase + op.w_off)
-                wf = W.f16_bits_to_f32(wb.reshape(op.cout, op.k_pad)[:, :op.k_real])
+                if op.s2d:      # packed as the 2x2 conv over the space-to-depth input: undo, the emulator feeds NHWC8
+                    wb = np.frombuffer(blob, dtype=np.uint16, count=op.cout * W.S2D_K, offset=wbase + op.w_off)
+                    w2 = W.f16_bits_to_f32(wb.reshape(op.cout, W.S2D_K)).reshape(op.cout, 2, 2, W.S2D_C)
+                    w3 = np.zeros((op.cout, 3, 3, op.cin), dtype=np.float32)
+                    for a in range(2):
+                        for b_ in range(2):
+                            for dy in range(2):
+                                for dx in range(2):
+                                    if 2 * a + dy < 3 and 2 * b_ + dx < 3:
+                                        w3[:, 2 * a + dy, 2 * b_ + dx, :3] = w2[:, a, b_, (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3]
+                    wf = w3.reshape(op.cout, -1)
+                else:
+                    wb = np.frombuffer(blob, dtype=np.uint16, count=op.cout * op.k_pad, offset=wbase + op.w_off)
+                    wf = W.f16_bits_to_f32(wb.reshape(op.cout, op.k_pad)[:, :op.k_real])
                 bias = np.frombuffer(blob, dtype=np.float32, count=op.cout, offset=wbase + op.b_off)
                 k = torch.from_numpy(wf.reshape(op.cout, op.kh, op.kw, op.cin).transpose(0, 3, 1, 2).copy())
                 y = F.conv2d(src.permute(0, 3, 1, 2), k, torch.from_numpy(bias.copy()), stride=op.stride,

@@ -165,7 +165,7 @@ def test_forward_argument_errors(nets):
     from fire_b200 import _lib
     from fire_b200._lib import FireError
     _, eng = nets[128]
-    x = torch.zeros(1, 160, 160, 8, dtype=torch.float16, device="cuda")
+    x = torch.zeros(1, 80, 80, 16, dtype=torch.float16, device="cuda")
     out = torch.zeros(1, 128, device="cuda")
     with pytest.raises(FireError):
         _lib.check(_lib.lib().fire_facenet_forward(eng._h, x.data_ptr(), 1, out.data_ptr(), None, x.data_ptr(), 16, None))

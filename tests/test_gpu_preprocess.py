@@ -32,7 +32,8 @@ def test_reference_mode_bit_exact(fire_lib, oracle_native):
     flat, desc = engine.frames_to_device(frames)
     bt = torch.tensor(boxes, dtype=torch.int32).cuda(); ft = torch.tensor(bf, dtype=torch.int32).cuda()
     f16, f32, status = engine.preprocess_boxes(flat, desc, bt, ft, _lib.PRE_REFERENCE, True, True)
-    f16 = f16.float().cpu().numpy(); f32 = f32.cpu().numpy(); status = status.cpu().numpy()
+    f16, f16_pad = engine.network_input_to_pixels(f16)          # space-to-depth network input -> [n,160,160,3] pixels + padding
+    f16 = f16.cpu().numpy(); f16_pad = f16_pad.cpu().numpy(); f32 = f32.cpu().numpy(); status = status.cpu().numpy()
     n_live = 0
     for i, (b, f) in enumerate(zip(boxes, bf)):
         rc, u8, want = oracle_native.crop_preprocess(frames[f], b)
@@ -41,7 +42,7 @@ def test_reference_mode_bit_exact(fire_lib, oracle_native):
             assert not f32[i].any() and not f16[i].any()
             continue
         assert np.array_equal(f32[i], want), (i, b)                                  # bit-exact float32 (u8 / 255)
-        assert np.array_equal(f16[i][..., :3], u8.astype(np.float32)) and not f16[i][..., 3:].any()
+        assert np.array_equal(f16[i], u8.astype(np.float32)) and not f16_pad[i].any()
         x, y, w, h = (max(0, v) for v in b)                                          # face_recognition.py:412-417
         crop = frames[f][y:y + h, x:x + w]
         live = cv2.resize(crop, (160, 160), interpolation=cv2.INTER_AREA).astype(np.float32) / 255.0
@@ -62,7 +63,7 @@ def test_swap_rb_and_northstar(fire_lib):
     assert torch.equal(a.flip(-1), b)
     # north-star mode: float half-pixel bilinear + prewhiten, against a numpy restatement (tolerance: fp32 order)
     f16, y, _ = engine.preprocess_boxes(flat, desc, bt, ft, _lib.PRE_NORTHSTAR, True, True)
-    y = y.cpu().numpy(); f16 = f16.float().cpu().numpy()
+    y = y.cpu().numpy(); f16 = engine.network_input_to_pixels(f16)[0].cpu().numpy()
     for i, (x0, y0, w, h) in enumerate(boxes):
         crop = frame[y0:y0 + h, x0:x0 + w].astype(np.float32)
         fx = np.clip((np.arange(160, dtype=np.float32) + 0.5) * np.float32(w / 160) - 0.5, 0, w - 1)
@@ -77,4 +78,4 @@ def test_swap_rb_and_northstar(fire_lib):
         want = (img - mean) / max(std, 1.0 / np.sqrt(img.size))
         assert np.abs(y[i] - want).max() < 2e-4                                      # tolerance: fp32 vs fp64 statistics
         assert abs(float(y[i].mean())) < 1e-4 and abs(float(y[i].std()) - 1.0) < 1e-3
-        assert np.abs(f16[i][..., :3] - 255.0 * want).max() < 0.5 + 255.0 * 2e-4 + 1.0   # fp16 rounding of 255*y (|.|<2048 -> ulp<=1)
+        assert np.abs(f16[i] - 255.0 * want).max() < 0.5 + 255.0 * 2e-4 + 1.0   # fp16 rounding of 255*y (|.|<2048 -> ulp<=1)

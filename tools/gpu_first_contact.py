@@ -73,7 +73,8 @@ def stage_pre():
     b = torch.tensor(boxes, dtype=torch.int32).cuda(); bf = torch.zeros(len(boxes), dtype=torch.int32).cuda()
     f16, f32, status = engine.preprocess_boxes(flat, desc, b, bf, _lib.PRE_REFERENCE, True, True)
     torch.cuda.synchronize()
-    f32 = f32.cpu().numpy(); f16 = f16.float().cpu().numpy(); status = status.cpu().numpy()
+    f16, f16_pad = engine.network_input_to_pixels(f16)
+    f32 = f32.cpu().numpy(); f16 = f16.cpu().numpy(); f16_pad = f16_pad.cpu().numpy(); status = status.cpu().numpy()
     nbad = 0
     for i, (x, y, w, h) in enumerate(boxes):
         x, y, w, h = max(0, x), max(0, y), max(0, w), max(0, h)
@@ -82,8 +83,8 @@ def stage_pre():
             assert status[i] == 1; continue
         ref = cv2.resize(crop, (160, 160), interpolation=cv2.INTER_AREA).astype(np.float32) / 255.0
         d = int((ref != f32[i]).sum()); nbad += d
-        d16 = int((np.rint(ref * 255) != f16[i][..., :3]).sum())
-        print(f"pre box {boxes[i]} crop {crop.shape[:2]}: f32 mismatches {d}, f16 mismatches {d16}, pad nonzero {int((f16[i][..., 3:] != 0).sum())}")
+        d16 = int((np.rint(ref * 255) != f16[i]).sum())
+        print(f"pre box {boxes[i]} crop {crop.shape[:2]}: f32 mismatches {d}, f16 mismatches {d16}, pad nonzero {int((f16_pad[i] != 0).sum())}")
     assert nbad == 0
 
 
@@ -109,7 +110,7 @@ def stage_conv_layers():
     u8 = W.calibration_images(B, seed=11)
     xin = np.zeros((B, 160, 160, 8), np.float32); xin[..., :3] = u8
     ref_out, ref_bufs = plan_emu.run_plan(plan, blob, xin, honor_offsets=False, return_buffers=True)
-    x = torch.from_numpy(xin).cuda().half().contiguous()
+    x = engine.pixels_to_network_input(torch.from_numpy(xin).cuda())
     raw, l2 = eng.forward(x)
     torch.cuda.synchronize()
     worst = 0.0

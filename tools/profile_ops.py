@@ -16,8 +16,7 @@ from fire_b200.netplan import OP_CONV        # noqa: E402
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 D = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 eng = engine.FaceNetEngine(D, W.synthetic_weights(D, 1234, calibrate=False))
-x = torch.randint(0, 256, (B, 160, 160, 8), device="cuda").half()
-x[..., 3:] = 0
+x = engine.pixels_to_network_input(torch.randint(0, 256, (B, 160, 160, 3), device="cuda"))
 for _ in range(3):
     eng.forward(x)
 ms = np.zeros(eng.num_ops)

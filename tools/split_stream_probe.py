@@ -15,8 +15,7 @@ from fire_b200 import engine, weights as W   # noqa: E402
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 lanes_list = [int(a) for a in sys.argv[2:]] or [1, 2, 4]
 tensors = W.synthetic_weights(512, 1234, calibrate=False)
-x = torch.randint(0, 256, (B, 160, 160, 8), device="cuda").half()
-x[..., 3:] = 0
+x = engine.pixels_to_network_input(torch.randint(0, 256, (B, 160, 160, 3), device="cuda"))
 for lanes in lanes_list:
     engs = [engine.FaceNetEngine(512, tensors) for _ in range(lanes)]
     streams = [torch.cuda.Stream() for _ in range(lanes)]

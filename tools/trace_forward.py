@@ -14,8 +14,7 @@ from fire_b200 import engine, weights as W   # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 eng = engine.FaceNetEngine(512, W.synthetic_weights(512, 1234, calibrate=False))
-x = torch.randint(0, 256, (B, 160, 160, 8), device="cuda").half()
-x[..., 3:] = 0
+x = engine.pixels_to_network_input(torch.randint(0, 256, (B, 160, 160, 3), device="cuda"))
 for i in range(3):
     if i == 2:
         print("# ---- third forward (warm) ----", file=sys.stderr)
