@@ -158,8 +158,11 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------------
 def run_fire(args):
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line (NCCL prints its version there)
+    # stdout must carry exactly ONE JSON line: anything a library prints on fd 1 (NCCL's version banner does) is sent to
+    # stderr for the duration of the run; the real stdout comes back just before rank 0 prints the result.
+    sys.stdout.flush()
+    saved_stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     rank, world, local = dist_env()
@@ -396,7 +399,10 @@ def run_fire(args):
                         "d2h_bytes_per_step": BATCH * D * 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "wall_ms_per_step": wall_dev / args.steps,
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity, "knn": knn, "frames": frames_blk}
+        sys.stdout.flush()
+        os.dup2(saved_stdout_fd, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
