@@ -91,6 +91,13 @@ def test_config2_facenet512_batch256(nets):
     r1, _ = eng.encode_unit_f32(torch.from_numpy(x[130:131]).cuda())
     r3, _ = eng.encode_unit_f32(torch.from_numpy(x[129:132]).cuda())
     assert np.array_equal(r1.cpu().numpy()[0], got[130]) and np.array_equal(r3.cpu().numpy()[1], got[130])
+    # ragged batch sizes (partial tiles everywhere, fewer tiles than SMs / more images than the bench batch)
+    for lo, hi in ((100, 137), (0, 211)):
+        rb, _ = eng.encode_unit_f32(torch.from_numpy(x[lo:hi]).cuda())
+        assert np.array_equal(rb.cpu().numpy(), got[lo:hi])
+    big = np.concatenate([x, x[:44]])                           # B = 300
+    rbig, _ = eng.encode_unit_f32(torch.from_numpy(big).cuda())
+    assert np.array_equal(rbig.cpu().numpy()[:256], got) and np.array_equal(rbig.cpu().numpy()[256:], got[:44])
 
 
 def test_golden_embeddings(nets):
