@@ -5,7 +5,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Headline (BASELINE.json configs[1]): FaceNet512 on batches of 256 uint8 160x160 crops per GPU.
-One "step" = one pass of the hot path over one batch: crop/resize/normalise kernel (K1) -> the 105
+One "step" = one pass of the hot path over one batch: crop/resize/normalise kernel (K1) -> the 100
 tcgen05 convolutions (implicit GEMM + halo-strip) + pools + tail (K2) -> L2-normalised embeddings.
   value : embeds/s with the uint8 crops already resident in HBM (device-timed, CUDA events)
   e2e   : the same through the public streaming call (fire_b200.engine.CropEncodePipeline.submit):
@@ -251,7 +251,7 @@ def run_fire(args):
         cos = (got * ref).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(ref, axis=1))
         parity = {"min_cos_vs_fp32_oracle": float(cos.min()), "images": 8}
 
-    # roofline of the dominant kernel family (the tcgen05 convolutions): algorithmic FLOP of the 105 conv launches of one
+    # roofline of the dominant kernel family (the tcgen05 convolutions): algorithmic FLOP of the 100 conv launches of one
     # step / the device time those launches take inside the timed step.  The step is timed live above; the convs' SHARE
     # of it comes from a per-op CUDA-event pass over the same batch (and is cross-checked by the ncu launch list in
     # profiles/): conv time in the step = ms_per_step * share.

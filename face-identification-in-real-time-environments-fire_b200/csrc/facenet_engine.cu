@@ -5,7 +5,7 @@
 // the op list, the buffer table (per-image offsets into one workspace arena, live ranges already
 // resolved) and the BN-folded fp16 weights; this file uploads the weights once, builds their TMA
 // descriptors once, and on every forward() enqueues one kernel per op on the caller's stream:
-//   conv_igemm_kernel (tcgen05)  x 105,  maxpool3x3s2_kernel x 3,  gap_kernel x 1,  l2norm_kernel x 1.
+//   conv_igemm_kernel x 88 + conv_strip_kernel x 12 (tcgen05),  maxpool3x3s2_kernel x 3,  gap_kernel x 1,  l2norm_kernel x 1.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>

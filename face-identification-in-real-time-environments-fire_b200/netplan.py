@@ -64,6 +64,9 @@ class ConvPart:
     cout: int
     bn: bool               # True: Conv(no bias)+BN ; False: conv with bias ("up")
     scale: float = 1.0     # residual scale folded into an "up" conv
+    cin_off: int = 0       # grouped fusion: this part reads input channels [cin_off, cin_off + cin_len) of the op's
+    cin_len: int = 0       # source slice (0 = all of them); its rows get zero weights for the other channels
+    cin_perm: Optional[List[int]] = None   # our input channel i is Keras input channel cin_perm[i] (concat stored in another order)
 
 
 @dataclass
@@ -105,7 +108,7 @@ class Op:
     def macs_per_image(self) -> int:
         if self.kind != OP_CONV:
             return 0
-        return self.Ho * self.Wo * self.cout * self.kh * self.kw * self.cin_real
+        return sum(self.Ho * self.Wo * p.cout * self.kh * self.kw * (p.cin_len or self.cin_real) for p in self.parts)
 
 
 def _pick_bn_tile(cout: int) -> int:
@@ -253,19 +256,30 @@ class Plan:
         p = f"Block35_{i}"
         B = self._buf
         if self.fuse:
-            # X = [b1_mid 32 | b2_mid 32 | b0 32 | b1_out 32 | b2_out 32]; up reads X[64:160]
-            X = B(17, 17, 160)
+            # X = [b1_mid 32 | b2_mid 32 | b0 32 | b2_out 32 | b1_out 32 | b2_t 32]
+            #   heads          -> X[0:96]                     (one 256->96 GEMM)
+            #   3x3 (grouped)  :  X[0:64]  -> X[128:192]      (Branch_1 0b and Branch_2 0b in ONE launch: block-diagonal weights)
+            #   Branch_2 0c    :  X[160:192] -> X[96:128]
+            #   up reads the concat X[64:160] = [b0 | b2_out | b1_out] (Keras order is b0, b1, b2: channel permutation folded
+            #   into the up conv's weights)
+            X = B(17, 17, 192)
             self.conv([ConvPart(f"{p}_Branch_1_Conv2d_0a_1x1", 32, True),
                        ConvPart(f"{p}_Branch_2_Conv2d_0a_1x1", 32, True),
                        ConvPart(f"{p}_Branch_0_Conv2d_1x1", 32, True)], x, Slice(X, 0, 96), label=f"{p}_heads")
-            b1m, b2m, cat = Slice(X, 0, 32), Slice(X, 32, 32), Slice(X, 64, 96)
-            b1o, b2o = Slice(X, 96, 32), Slice(X, 128, 32)
-        else:
-            X = B(17, 17, 96)
-            self.conv(f"{p}_Branch_0_Conv2d_1x1", x, Slice(X, 0, 32))
-            t1 = B(17, 17, 32); self.conv(f"{p}_Branch_1_Conv2d_0a_1x1", x, self.whole(t1)); b1m = self.whole(t1)
-            t2 = B(17, 17, 32); self.conv(f"{p}_Branch_2_Conv2d_0a_1x1", x, self.whole(t2)); b2m = self.whole(t2)
-            cat, b1o, b2o = self.whole(X), Slice(X, 32, 32), Slice(X, 64, 32)
+            self.conv([ConvPart(f"{p}_Branch_1_Conv2d_0b_3x3", 32, True, cin_off=0, cin_len=32),
+                       ConvPart(f"{p}_Branch_2_Conv2d_0b_3x3", 32, True, cin_off=32, cin_len=32)],
+                      Slice(X, 0, 64), Slice(X, 128, 64), 3, 3, same=True, label=f"{p}_Branch_12_Conv2d_0b_3x3")
+            self.conv(f"{p}_Branch_2_Conv2d_0c_3x3", Slice(X, 160, 32), Slice(X, 96, 32), 3, 3, same=True)
+            y = B(17, 17, 256)
+            perm = list(range(0, 32)) + list(range(64, 96)) + list(range(32, 64))
+            self.conv([ConvPart(f"{p}_Conv2d_1x1", 256, False, 0.17, cin_perm=perm)], Slice(X, 64, 96), self.whole(y), relu=True, res=x,
+                      label=f"{p}_up")
+            return self.whole(y)
+        X = B(17, 17, 96)
+        self.conv(f"{p}_Branch_0_Conv2d_1x1", x, Slice(X, 0, 32))
+        t1 = B(17, 17, 32); self.conv(f"{p}_Branch_1_Conv2d_0a_1x1", x, self.whole(t1)); b1m = self.whole(t1)
+        t2 = B(17, 17, 32); self.conv(f"{p}_Branch_2_Conv2d_0a_1x1", x, self.whole(t2)); b2m = self.whole(t2)
+        cat, b1o, b2o = self.whole(X), Slice(X, 32, 32), Slice(X, 64, 32)
         self.conv(f"{p}_Branch_1_Conv2d_0b_3x3", b1m, b1o, 3, 3, same=True)
         t = B(17, 17, 32); self.conv(f"{p}_Branch_2_Conv2d_0b_3x3", b2m, self.whole(t), 3, 3, same=True)
         self.conv(f"{p}_Branch_2_Conv2d_0c_3x3", self.whole(t), b2o, 3, 3, same=True)
@@ -353,7 +367,7 @@ class Plan:
                 if p.name == "Bottleneck":
                     s["Bottleneck/kernel"] = (o.cin, p.cout)
                 else:
-                    s[p.name + "/kernel"] = (o.kh, o.kw, o.cin_real, p.cout)
+                    s[p.name + "/kernel"] = (o.kh, o.kw, p.cin_len or o.cin_real, p.cout)
                 if p.bn:
                     for q in ("beta", "moving_mean", "moving_variance"):
                         s[f"{p.name}_BatchNorm/{q}"] = (p.cout,)

@@ -153,6 +153,13 @@ def fold_conv(op, tensors: dict):
         if k.ndim == 2:                      # Dense [cin, cout] -> 1x1 HWIO
             k = k.reshape(1, 1, *k.shape)
         kh, kw, cin_real, cout = k.shape
+        if p.cin_perm is not None:           # our concat order differs from Keras': gather the kernel's input channels
+            k = k[:, :, np.asarray(p.cin_perm), :]
+        if p.cin_len:                        # grouped fusion: this part only sees a sub-range of the op's input channels
+            assert (kh, kw, cout) == (op.kh, op.kw, p.cout) and cin_real == p.cin_len, (p.name, k.shape)
+            full = np.zeros((kh, kw, op.cin_real, cout), dtype=np.float32)
+            full[:, :, p.cin_off:p.cin_off + p.cin_len, :] = k
+            k, cin_real = full, op.cin_real
         assert (kh, kw, cout) == (op.kh, op.kw, p.cout) and cin_real == op.cin_real, (p.name, k.shape)
         if p.bn:
             var = np.asarray(tensors[p.name + "_BatchNorm/moving_variance"], dtype=np.float32)
@@ -227,7 +234,7 @@ def pack(plan: Plan, tensors: dict) -> bytes:
     ops = np.zeros(len(plan.ops), dtype=OP_DT)
     for i, o in enumerate(plan.ops):
         res_buf, res_coff = (o.res.buf, o.res.c_off) if o.res is not None else (-1, 0)
-        flop_k = o.kh * o.kw * o.cin_real if o.kind == OP_CONV else 0
+        flop_k = o.macs_per_image // (o.Ho * o.Wo * o.cout) if o.kind == OP_CONV else 0      # real MACs per output element
         if o.s2d:                                          # 3x3 / stride 2 over [160,160,8]  ==  2x2 / stride 1 over [80,80,16]
             ops[i] = (o.kind, o.src.buf, 0, o.dst.buf, o.dst.c_off, res_buf, res_coff, o.H // 2, o.W // 2, o.Ho, o.Wo,
                       2, 2, 1, 0, 0, S2D_C, o.cout, S2D_K, o.flags, o.bn_tile, flop_k, o.w_off, o.b_off)

@@ -122,7 +122,10 @@ def test_unfused_plan_matches_fused(fire_lib):
     a, b = engine.FaceNetEngine(128, t, fuse_siblings=True), engine.FaceNetEngine(128, t, fuse_siblings=False)
     x = torch.from_numpy(_images(6, 9).astype(np.float32) / 255.0).cuda()
     ra, _ = a.encode_unit_f32(x); rb, _ = b.encode_unit_f32(x)
-    assert torch.equal(ra, rb)                                 # horizontal fusion only regroups output channels
+    # horizontal fusion regroups output channels (bit-identical); the grouped Block35 3x3 launch also stores the branch
+    # concat in another channel order, which permutes the K summation order of the up conv: equal to fp32 rounding
+    ra, rb = ra.cpu().numpy(), rb.cpu().numpy()
+    assert _cos(ra, rb).min() >= 0.99999 and np.abs(ra - rb).max() <= 1e-2 * np.abs(rb).max()
 
 
 def test_strip_kernel_matches_gather_kernel(fire_lib, monkeypatch):

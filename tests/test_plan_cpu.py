@@ -28,7 +28,7 @@ def test_macs_and_tensor_names_match_the_oracle_graph():
             p = Plan(D, fuse_siblings=fuse)
             assert p.macs_per_image() == macs
             assert p.keras_tensor_shapes() == weight_shapes(D)
-    assert len(Plan(512, fuse_siblings=False).conv_ops()) == 133 and len(Plan(512).conv_ops()) == 105
+    assert len(Plan(512, fuse_siblings=False).conv_ops()) == 133 and len(Plan(512).conv_ops()) == 100
 
 
 def test_buffer_reuse_never_overlaps_live_buffers():
