@@ -14,6 +14,7 @@
 // [80][80][16] (2 x 2 pixel blocks, 12 channels used, pixel scale 0..255; see store_s2d), 204.8 KB per crop.  The kernel is HBM/L2-bound integer/byte work; it
 // deliberately stays off the tensor cores.
 #include <cfloat>
+#include <cmath>
 
 #include "fire_common.cuh"
 #include "fire_internal.h"
@@ -335,9 +336,130 @@ preprocess_northstar_kernel(const uint8_t* __restrict__ frames, const int64_t* _
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Aligned crop of the enrol path: cv2.warpAffine(image, M, (160, 160)) with INTER_LINEAR and a
+// constant zero border, exactly as OpenCV computes it (imgwarp.cpp): the forward 2x3 matrix is inverted in double,
+// source coordinates are 10-bit fixed point with 5 interpolation bits, the four taps are blended with the 15-bit
+// weight table of remapBilinear.  Reference call sites: yunet_face_detector.py:135-160 (and the MediaPipe /
+// RetinaFace twins), followed by [:, :, ::-1] (swap_rb).  Double arithmetic uses explicit _rn intrinsics: the host
+// code this must match bit for bit is compiled without FMA contraction.
+__device__ short g_warp_tab[1024 * 4];          // BilinearTab_i, built on the host by build_warp_tab()
+
+__global__ void __launch_bounds__(PRE_OUT)
+align_warp_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict__ frame_desc, const double* __restrict__ matrices,
+                  const int32_t* __restrict__ face_frame, int swap_rb, uint8_t* __restrict__ out_u8, __half* __restrict__ out_f16) {
+  __shared__ double sM[6];
+  const int face = blockIdx.x, x = threadIdx.x;
+  const int64_t* fd = frame_desc + 4 * static_cast<long long>(face_frame[face]);
+  const uint8_t* __restrict__ src = frames + fd[0];
+  const int sh = static_cast<int>(fd[1]), sw = static_cast<int>(fd[2]);
+  const long long sstride = fd[3];
+  if (threadIdx.x == 0) {
+    const double* Mf = matrices + 6 * static_cast<long long>(face);
+    double M0 = Mf[0], M1 = Mf[1], M2 = Mf[2], M3 = Mf[3], M4 = Mf[4], M5 = Mf[5];
+    double D = __dsub_rn(__dmul_rn(M0, M4), __dmul_rn(M1, M3));
+    D = D != 0 ? __ddiv_rn(1.0, D) : 0.0;
+    const double A11 = __dmul_rn(M4, D), A22 = __dmul_rn(M0, D);
+    M0 = A11; M1 = __dmul_rn(M1, -D);
+    M3 = __dmul_rn(M3, -D); M4 = A22;
+    const double b1 = __dsub_rn(__dmul_rn(-M0, M2), __dmul_rn(M1, M5));
+    const double b2 = __dsub_rn(__dmul_rn(-M3, M2), __dmul_rn(M4, M5));
+    sM[0] = M0; sM[1] = M1; sM[2] = b1; sM[3] = M3; sM[4] = M4; sM[5] = b2;
+  }
+  __syncthreads();
+  const double M0 = sM[0], M1 = sM[1], M2 = sM[2], M3 = sM[3], M4 = sM[4], M5 = sM[5];
+  const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(M0, static_cast<double>(x)), 1024.0));
+  const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(M3, static_cast<double>(x)), 1024.0));
+  const int y_begin = blockIdx.y * PRE_ROWS_PER_BLOCK;
+  for (int y = y_begin; y < y_begin + PRE_ROWS_PER_BLOCK; ++y) {
+    const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(M1, static_cast<double>(y)), M2), 1024.0)) + 16;
+    const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(M4, static_cast<double>(y)), M5), 1024.0)) + 16;
+    const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+    const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
+    const short* w = g_warp_tab + ((Y & 31) * 32 + (X & 31)) * 4;
+    const int w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+    int v[3] = {0, 0, 0};
+    if (static_cast<unsigned>(sx) < static_cast<unsigned>(sw - 1) && static_cast<unsigned>(sy) < static_cast<unsigned>(sh - 1)) {
+      const uint8_t* s0 = src + static_cast<long long>(sy) * sstride + sx * 3;
+      const uint8_t* s1 = s0 + sstride;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = (s0[c] * w0 + s0[c + 3] * w1 + s1[c] * w2 + s1[c + 3] * w3 + (1 << 14)) >> 15;
+    } else if (!(sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0)) {
+      const bool x0ok = sx >= 0 && sx < sw, x1ok = sx + 1 >= 0 && sx + 1 < sw, y0ok = sy >= 0 && sy < sh, y1ok = sy + 1 >= 0 && sy + 1 < sh;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int p0 = (x0ok && y0ok) ? src[static_cast<long long>(sy) * sstride + sx * 3 + c] : 0;
+        const int p1 = (x1ok && y0ok) ? src[static_cast<long long>(sy) * sstride + (sx + 1) * 3 + c] : 0;
+        const int p2 = (x0ok && y1ok) ? src[static_cast<long long>(sy + 1) * sstride + sx * 3 + c] : 0;
+        const int p3 = (x1ok && y1ok) ? src[static_cast<long long>(sy + 1) * sstride + (sx + 1) * 3 + c] : 0;
+        v[c] = ((p0 * w0 + p1 * w1 + p2 * w2 + p3 * w3 + (1 << 14)) >> 15) & 0xFF;
+      }
+    }
+    if (swap_rb) { const int t = v[0]; v[0] = v[2]; v[2] = t; }
+    if (out_u8) {
+      uint8_t* o = out_u8 + ((static_cast<size_t>(face) * PRE_OUT + y) * PRE_OUT + x) * 3;
+      o[0] = static_cast<uint8_t>(v[0]); o[1] = static_cast<uint8_t>(v[1]); o[2] = static_cast<uint8_t>(v[2]);
+    }
+    if (out_f16) store_s2d(static_cast<float>(v[0]), static_cast<float>(v[1]), static_cast<float>(v[2]), face, y, x, out_f16);
+  }
+}
+
+// BilinearTab_i of OpenCV's remap, built exactly like initInterTab2D does (see oracle/warp_oracle.c for the fix-up quirk)
+static void build_warp_tab(short* flat /* [1024 * 4 + 8] */) {
+  for (int i = 0; i < 1024 * 4 + 8; ++i) flat[i] = 0;
+  for (int i = 0; i < 32; ++i) {
+    const float xi = static_cast<float>(i) * (1.f / 32);
+    const float ty[2] = {1.f - xi, xi};
+    for (int j = 0; j < 32; ++j) {
+      const float xj = static_cast<float>(j) * (1.f / 32);
+      const float tx[2] = {1.f - xj, xj};
+      short* it = flat + (i * 32 + j) * 4;
+      int isum = 0;
+      for (int k1 = 0; k1 < 2; ++k1)
+        for (int k2 = 0; k2 < 2; ++k2) {
+          const int q = static_cast<int>(lrintf(ty[k1] * tx[k2] * 32768.f));
+          it[k1 * 2 + k2] = static_cast<short>(q > 32767 ? 32767 : (q < -32768 ? -32768 : q));
+          isum += it[k1 * 2 + k2];
+        }
+      if (isum != 32768) {
+        const int diff = isum - 32768;
+        int Mk = 3, mk = 3;
+        for (int idx = 3; idx <= 6; ++idx) {
+          if (it[idx] < it[mk]) mk = idx;
+          else if (it[idx] > it[Mk]) Mk = idx;
+        }
+        if (diff < 0) it[Mk] = static_cast<short>(it[Mk] - diff);
+        else it[mk] = static_cast<short>(it[mk] - diff);
+      }
+    }
+  }
+}
+
 }  // namespace fire
 
 using namespace fire;
+
+extern "C" int fire_align_warp(const uint8_t* frames, const int64_t* frame_desc, int n_frames, const double* matrices,
+                               const int32_t* face_frame, int n_faces, int swap_rb, uint8_t* out_u8, void* out_f16,
+                               fire_stream_t stream) {
+  if (!frames || !frame_desc || !matrices || !face_frame) return fail(FIRE_ERR_ARG, "fire_align_warp: NULL argument");
+  if (!out_u8 && !out_f16) return fail(FIRE_ERR_ARG, "fire_align_warp: no output requested");
+  if (n_faces <= 0 || n_frames <= 0) return fail(FIRE_ERR_ARG, "fire_align_warp: n_faces=%d n_frames=%d", n_faces, n_frames);
+  static bool tab_ready = false;
+  if (!tab_ready) {
+    short flat[1024 * 4 + 8];
+    build_warp_tab(flat);
+    FIRE_CUDA(cudaMemcpyToSymbol(g_warp_tab, flat, sizeof(short) * 1024 * 4));
+    tab_ready = true;
+  }
+  dim3 grid(n_faces, PRE_OUT / PRE_ROWS_PER_BLOCK);
+  align_warp_kernel<<<grid, PRE_OUT, 0, static_cast<cudaStream_t>(stream)>>>(frames, frame_desc, matrices, face_frame, swap_rb ? 1 : 0, out_u8,
+                                                                              static_cast<__half*>(out_f16));
+  FIRE_LAUNCH_CHECK("align_warp_kernel");
+  count_launch();
+  return FIRE_OK;
+}
 
 extern "C" int fire_preprocess(const uint8_t* frames, const int64_t* frame_desc, int n_frames, const int32_t* boxes_xywh,
                                const int32_t* box_frame, int n_boxes, int mode, void* out_f16, float* out_f32,

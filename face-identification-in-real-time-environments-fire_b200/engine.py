@@ -301,6 +301,24 @@ def preprocess_boxes(frames, frame_desc, boxes, box_frame, mode: int = _lib.PRE_
     return f16, f32, status
 
 
+def align_warp(frames, frame_desc, matrices, face_frame, swap_rb: bool = True, output: str = "uint8"):
+    """fire_align_warp: frames cuda uint8, frame_desc cuda int64 [F,4], matrices cuda float64 [n,6] (forward 2x3, as
+    getAffineTransform returns them), face_frame cuda int32 [n].  output "uint8" -> numpy [n,160,160,3]; "device" ->
+    cuda fp16 network input [n,80,80,16]; "both" -> (cuda uint8 [n,160,160,3], cuda fp16 [n,80,80,16])."""
+    torch = _torch()
+    n = matrices.shape[0]
+    assert matrices.dtype == torch.float64 and matrices.is_contiguous() and tuple(matrices.shape) == (n, 6)
+    dev = frames.device
+    u8 = torch.empty(n, IN_HW, IN_HW, 3, dtype=torch.uint8, device=dev) if output in ("uint8", "both") else None
+    f16 = torch.empty(n, NET_HW, NET_HW, NET_C, dtype=torch.float16, device=dev) if output in ("device", "both") else None
+    check(_lib.lib().fire_align_warp(_ptr(frames), _ptr(frame_desc), frame_desc.shape[0], _ptr(matrices), _ptr(face_frame), n,
+                                     1 if swap_rb else 0, _ptr(u8) if u8 is not None else None, _ptr(f16) if f16 is not None else None,
+                                     _lib.stream_ptr()))
+    if output == "uint8":
+        return u8.cpu().numpy()
+    return f16 if output == "device" else (u8, f16)
+
+
 def frames_to_device(frames_np):
     """[F,H,W,3] uint8 numpy (or list of HxWx3 arrays of differing sizes) -> (cuda uint8 flat, cuda int64 desc [F,4])."""
     torch = _torch()

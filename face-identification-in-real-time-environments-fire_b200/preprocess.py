@@ -111,3 +111,66 @@ def crop_resize_normalize(frames, boxes, box_frame=None, mode: str = "reference"
         return f16, status
     _, f32, status = engine.preprocess_boxes(flat, desc, boxes_t, bf, m, want_f16=False, want_f32=True)
     return f32.cpu().numpy(), status.cpu().numpy()
+
+
+# Alignment targets of the reference's extract_faces: left eye, right eye, nose tip in the 160 x 160 crop
+# (yunet_face_detector.py:143-147; identical in the MediaPipe and RetinaFace detectors)
+ALIGN_DST = np.float32([(0.35 * 160, 0.35 * 160), (0.65 * 160, 0.35 * 160), (0.5 * 160, 0.55 * 160)])
+
+
+def get_affine_transform(src_pts, dst_pts) -> np.ndarray:
+    """cv2.getAffineTransform bit for bit: the 6 x 6 system solved with OpenCV's LU elimination (partial pivoting,
+    `d = -1/a_ii; row_j += (a_ji * d) * row_i`, back substitution `s -= a_ik * x_k; x_i = s / a_ii`), all in float64 on
+    float32 inputs.  Returns the forward 2 x 3 matrix (float64)."""
+    s = np.asarray(src_pts, dtype=np.float32).reshape(3, 2)
+    d = np.asarray(dst_pts, dtype=np.float32).reshape(3, 2)
+    a = [[0.0] * 6 for _ in range(6)]
+    b = [0.0] * 6
+    for i in range(3):
+        x, y = float(s[i, 0]), float(s[i, 1])
+        a[2 * i][0:3] = [x, y, 1.0]
+        a[2 * i + 1][3:6] = [x, y, 1.0]
+        b[2 * i], b[2 * i + 1] = float(d[i, 0]), float(d[i, 1])
+    m, eps = 6, 2.220446049250313e-16 * 100
+    for i in range(m):
+        k = i
+        for j in range(i + 1, m):
+            if abs(a[j][i]) > abs(a[k][i]):
+                k = j
+        if abs(a[k][i]) < eps:
+            return np.zeros((2, 3), dtype=np.float64)
+        if k != i:
+            a[i][i:], a[k][i:] = a[k][i:], a[i][i:]
+            b[i], b[k] = b[k], b[i]
+        dd = -1 / a[i][i]
+        for j in range(i + 1, m):
+            alpha = a[j][i] * dd
+            for kk in range(i + 1, m):
+                a[j][kk] += alpha * a[i][kk]
+            b[j] += alpha * b[i]
+    for i in range(m - 1, -1, -1):
+        acc = b[i]
+        for k in range(i + 1, m):
+            acc -= a[i][k] * b[k]
+        b[i] = acc / a[i][i]
+    return np.array(b, dtype=np.float64).reshape(2, 3)
+
+
+def align_faces(frames, landmarks, face_frame=None, swap_rb: bool = True, output: str = "uint8"):
+    """Aligned 160 x 160 crops of the enrol path, on the B200: for every face
+        M = getAffineTransform([left_eye, right_eye, nose], ALIGN_DST);  crop = warpAffine(frame, M, (160, 160))[:, :, ::-1]
+    exactly as the reference's extract_faces(align=True) does with cv2 (yunet_face_detector.py:135-165).
+
+    frames    : uint8 [F,H,W,3] array or list of HxWx3 arrays
+    landmarks : [n,3,2] points in the order the reference passes them to getAffineTransform (left eye, right eye, nose)
+    swap_rb   : apply the final [:, :, ::-1] (True = what extract_faces returns)
+    output    : "uint8" -> numpy uint8 [n,160,160,3];  "device" -> cuda fp16 network input [n,80,80,16] for the engine
+    """
+    import torch
+    from . import engine
+    lm = np.asarray(landmarks, dtype=np.float32).reshape(-1, 3, 2)
+    n = lm.shape[0]
+    mats = np.stack([get_affine_transform(lm[i], ALIGN_DST) for i in range(n)]).reshape(n, 6)
+    flat, desc = engine.frames_to_device(frames)
+    ff = np.zeros(n, dtype=np.int32) if face_frame is None else np.asarray(face_frame, dtype=np.int32)
+    return engine.align_warp(flat, desc, torch.from_numpy(mats).to(flat.device), torch.from_numpy(ff).to(flat.device), swap_rb, output)

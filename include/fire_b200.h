@@ -6,6 +6,7 @@
  *
  *   fire_preprocess        <- cv2.resize(INTER_AREA) + /255      modules/encoder.py:19-27
  *                             crop slice                         modules/face_recognition.py:412-420
+ *   fire_align_warp        <- cv2.getAffineTransform + warpAffine  yunet_face_detector.py:135-160 (enrol path)
  *   fire_ingest_f32        <- the NHWC float batch handed to     modules/encoder.py:16-17
  *   fire_facenet_*         <- onnxruntime InferenceSession.run   facenet_gpu.py:72,127
  *   fire_knn_create/add    <- hnswlib Index.init_index/add_items modules/hnsw_manager.py:29,127,137
@@ -69,6 +70,16 @@ uint64_t fire_launch_count(void);          /* number of kernels this library has
 int fire_preprocess(const uint8_t* frames, const int64_t* frame_desc, int n_frames, const int32_t* boxes_xywh,
                     const int32_t* box_frame, int n_boxes, int mode, void* out_f16, float* out_f32,
                     int32_t* box_status, fire_stream_t stream);
+
+/* Aligned crop of the enrol path: cv2.warpAffine(image, M, (160, 160)) (INTER_LINEAR, constant 0 border) bit for bit,
+ * optionally followed by the reference's [:, :, ::-1]            yunet_face_detector.py:135-165 (and the MediaPipe /
+ * RetinaFace twins).  matrices: double [n_faces][6], the FORWARD 2x3 matrix cv2.getAffineTransform returns (the host
+ * shim computes it with the same LU elimination, fire_b200/preprocess.py); face_frame: int32 [n_faces].
+ * out_u8: uint8 [n_faces][160][160][3] (what extract_faces returns), out_f16: the network input of those crops
+ * (layout above); either may be NULL. */
+int fire_align_warp(const uint8_t* frames, const int64_t* frame_desc, int n_frames, const double* matrices,
+                    const int32_t* face_frame, int n_faces, int swap_rb, uint8_t* out_u8, void* out_f16,
+                    fire_stream_t stream);
 
 /* float NHWC [B][160][160][3] in the reference's [0,1] scale -> fp16 [B][80][80][16] network input (layout above) */
 int fire_ingest_f32(const float* in_nhwc3, int B, void* out_f16, fire_stream_t stream);

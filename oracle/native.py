@@ -16,7 +16,7 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("fire_oracle.c", "hnsw_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("fire_oracle.c", "hnsw_oracle.c", "warp_oracle.c")]
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.run(["make", "-C", _HERE, "-s", "-B"], check=True)
     return _SO
@@ -39,6 +39,11 @@ def lib():
         L.fire_oracle_crop_preprocess.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_long] + \
             [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p]
         L.fire_oracle_crop_preprocess.restype = ctypes.c_int
+        L.fire_oracle_get_affine.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.fire_oracle_get_affine.restype = ctypes.c_int
+        L.fire_oracle_warp_affine_u8c3.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_void_p,
+                                                   ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.fire_oracle_warp_affine_u8c3.restype = ctypes.c_int
         L.fire_hnsw_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint]
         L.fire_hnsw_create.restype = ctypes.c_void_p
         L.fire_hnsw_destroy.argtypes = [ctypes.c_void_p]
@@ -114,6 +119,25 @@ def crop_preprocess(frame: np.ndarray, box) -> tuple:
     rc = lib().fire_oracle_crop_preprocess(frame.ctypes.data, frame.shape[0], frame.shape[1], frame.strides[0],
                                            x, y, w, h, u8.ctypes.data, f32.ctypes.data)
     return rc, u8, f32
+
+
+def get_affine_transform(src_pts, dst_pts) -> np.ndarray:
+    """cv2.getAffineTransform restated (oracle/warp_oracle.c): float32 [3,2] point pairs -> float64 [2,3]."""
+    s = np.ascontiguousarray(src_pts, dtype=np.float32).reshape(3, 2)
+    d = np.ascontiguousarray(dst_pts, dtype=np.float32).reshape(3, 2)
+    M = np.zeros(6, dtype=np.float64)
+    lib().fire_oracle_get_affine(s.ctypes.data, d.ctypes.data, M.ctypes.data)
+    return M.reshape(2, 3)
+
+
+def warp_affine(image: np.ndarray, M: np.ndarray, dsize=(160, 160)) -> np.ndarray:
+    """cv2.warpAffine(image, M, dsize) restated: INTER_LINEAR, BORDER_CONSTANT 0, uint8 HWC3."""
+    image = np.ascontiguousarray(image, dtype=np.uint8)
+    M = np.ascontiguousarray(M, dtype=np.float64).reshape(6)
+    out = np.zeros((dsize[1], dsize[0], 3), dtype=np.uint8)
+    lib().fire_oracle_warp_affine_u8c3(image.ctypes.data, image.shape[0], image.shape[1], image.strides[0], M.ctypes.data,
+                                       out.ctypes.data, dsize[1], dsize[0])
+    return out
 
 
 class HnswOracle:

@@ -79,3 +79,34 @@ def test_swap_rb_and_northstar(fire_lib):
         assert np.abs(y[i] - want).max() < 2e-4                                      # tolerance: fp32 vs fp64 statistics
         assert abs(float(y[i].mean())) < 1e-4 and abs(float(y[i].std()) - 1.0) < 1e-3
         assert np.abs(f16[i] - 255.0 * want).max() < 0.5 + 255.0 * 2e-4 + 1.0   # fp16 rounding of 255*y (|.|<2048 -> ulp<=1)
+
+
+def test_aligned_crops_match_cv2_warp_affine_bitwise(fire_lib):
+    """SURVEY 8(f) row 1 - the enrol path's aligned crop (yunet_face_detector.py:135-165): getAffineTransform +
+    warpAffine(image, M, (160,160)) + [:, :, ::-1], on the B200, bit for bit against the live cv2."""
+    import cv2
+    import torch
+    from fire_b200 import engine
+    from fire_b200.preprocess import ALIGN_DST, align_faces
+    rng = np.random.default_rng(9)
+    frames = [_frame(1080, 1920, 1), _frame(480, 640, 2), _frame(200, 300, 3)]
+    lms, ff = [], []
+    for t in range(40):
+        f = t % 3
+        H, W = frames[f].shape[:2]
+        cx, cy = rng.uniform(-30, W + 30), rng.uniform(-30, H + 30)           # some faces hang over the frame edge
+        s, ang = rng.uniform(12, 0.45 * min(H, W)), rng.uniform(-0.7, 0.7)
+        pts = np.float32([(cx - s * np.cos(ang), cy - s * np.sin(ang)), (cx + s * np.cos(ang), cy + s * np.sin(ang)),
+                          (cx + 0.7 * s * np.sin(ang), cy + 0.7 * s * np.cos(ang))])
+        lms.append(np.round(pts) if t % 2 else pts)
+        ff.append(f)
+    got = align_faces(frames, np.stack(lms), ff, swap_rb=True, output="uint8")
+    for i in range(len(lms)):
+        M = cv2.getAffineTransform(lms[i], ALIGN_DST)
+        want = cv2.warpAffine(frames[ff[i]], M, (160, 160))[:, :, ::-1]
+        assert np.array_equal(got[i], want), i
+    # the network input of those crops = preprocess_for_encoder(crop) * 255 (a 160x160 crop is copied by INTER_AREA)
+    f16 = align_faces(frames, np.stack(lms), ff, swap_rb=True, output="device")
+    pix, pad = engine.network_input_to_pixels(f16)
+    assert np.array_equal(pix.cpu().numpy(), got.astype(np.float32)) and not pad.any()
+    assert not torch.isnan(f16).any()
