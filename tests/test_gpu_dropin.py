@@ -157,3 +157,45 @@ def test_two_gpu_sharded_search_matches_single(fire_lib):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29533", os.path.join(root, "tools", "dist_knn_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DIST_KNN_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_batched_recognizer_on_the_gpu_engines(encoder, tmp_path):
+    """fire_b200.recognizer with the real sm_100a surfaces (Encoder.encode_crops, HNSWManager.query_batch): the labels of
+    a frame equal the per-face path (the orchestration logic itself is pinned against the reference's own loop on the
+    CPU, tests/test_recognizer_host.py)."""
+    import types
+    from fire_b200 import recognizer
+    from fire_b200.hnsw_manager import HNSWManager
+    frame = _frame(6)
+    boxes = [[0, 0, 160, 160], [160, 0, 160, 160], [320, 160, 160, 160], [480, 320, 160, 160], [700, 10, 50, 50]]
+    mgr = HNSWManager(512, str(tmp_path / "i"), str(tmp_path / "l"), str(tmp_path / "d"), None, max_elements=1000)
+    emb, _ = encoder.encode_crops([frame], boxes[:2])
+    for j, lab in enumerate(("alice", "bob")):
+        mgr.add_embedding(emb[j] / np.linalg.norm(emb[j]), lab, j)
+
+    class FR:                                                   # the attributes recognize_faces touches (face_recognition.py:25-172)
+        pass
+    fr = FR()
+    fr.start_time, fr.frame_index, fr.detection_interval, fr.frame_count = None, 0, 1, 0
+    fr.total_detection_time = fr.total_encoding_time = 0.0
+    fr.detect_faces = lambda image: [{'bbox': b, 'confidence': i} for i, b in enumerate(boxes)]
+    fr.face_tracker = types.SimpleNamespace(update=lambda dets: [{'id': d['confidence'], 'bbox': d['bbox']} for d in dets])
+    fr.track_id_to_label, fr.unknown_faces, fr.interested_label = {}, {}, None
+    fr.encoder, fr.embedding_dim, fr.hnsw_manager, fr.similarity_threshold = encoder, 512, mgr, 0.7
+    fr.recent_embeddings, fr.recent_labels = np.empty((0, 512), dtype=np.float32), []
+    enrolled = []
+
+    def handle_unknown(track_id, e, rename_label=None):
+        lab = f"Unknown_{len(enrolled)}"
+        enrolled.append(lab)
+        mgr.add_embedding(e, lab, 100 + len(enrolled))
+        return lab
+    fr._handle_unknown_embedding = handle_unknown
+    fr._add_to_recent_embeddings = lambda e, lab: (setattr(fr, "recent_embeddings", np.vstack([fr.recent_embeddings, e])), fr.recent_labels.append(lab))
+    fr.update_label = lambda hid, new: None
+    recognizer.install(fr)
+    out = fr.recognize_faces(frame)
+    assert [r['label'] for r in out] == ["alice", "bob", "Unknown_0", "Unknown_1"]          # the off-frame box is skipped
+    assert out[0]['confidence'] > 0.9999 and mgr.hnsw_index.get_current_count() == 4
+    again = fr.recognize_faces(frame)                            # tracked faces keep their labels without re-encoding
+    assert [r['label'] for r in again] == ["alice", "bob", "Unknown_0", "Unknown_1"] and all(r['confidence'] == 1.0 for r in again)
