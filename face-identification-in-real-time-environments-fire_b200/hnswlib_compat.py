@@ -115,7 +115,7 @@ class Index:
         labels = rows.astype(np.uint64) if self._identity else self._labels[rows]
         return labels, dist
 
-    # ---- persistence (own flat format; hnswlib's binary graph is not reproduced) -------------------
+    # ---- persistence: own flat format is written; hnswlib 0.8.0 `save_index` files are READ -----
     def save_index(self, path: str):
         n = self.get_current_count()
         rows = self._idx.rows() if n else np.zeros((0, self.dim), np.float32)
@@ -129,18 +129,51 @@ class Index:
         with open(path, "rb") as f:
             blob = f.read()
         if blob[:8] != _MAGIC:
-            raise RuntimeError("Index seems to be corrupted or unsupported (not a fire_b200 index file)")
-        dim, n, saved_max, _ef = struct.unpack("<qqqq", blob[8:40])
-        if dim != self.dim:
-            raise RuntimeError(f"Index dimensionality {dim} does not match {self.dim}")
-        labels = np.frombuffer(blob, dtype="<u8", count=n, offset=40).astype(np.uint64)
-        rows = np.frombuffer(blob, dtype="<f4", count=n * dim, offset=40 + 8 * n).reshape(n, dim)
+            labels, rows, saved_max = parse_hnswlib_binary(blob, self.dim)     # an existing FIRE storage/ tree (hnsw_manager.py:43,62)
+            n, dim = rows.shape
+        else:
+            dim, n, saved_max, _ef = struct.unpack("<qqqq", blob[8:40])
+            if dim != self.dim:
+                raise RuntimeError(f"Index dimensionality {dim} does not match {self.dim}")
+            labels = np.frombuffer(blob, dtype="<u8", count=n, offset=40).astype(np.uint64)
+            rows = np.frombuffer(blob, dtype="<f4", count=n * dim, offset=40 + 8 * n).reshape(n, dim)
         self.init_index(max(int(max_elements) if max_elements else int(saved_max), n), self.ef_construction, self.M)
         self.ef = 10                       # hnswlib does not persist ef
         if n:
             self._idx.add(np.ascontiguousarray(rows))
             self._labels = labels
             self._identity = bool(np.array_equal(labels, np.arange(n, dtype=np.uint64)))
+
+
+_HNSW_HEADER = struct.Struct("<6QiI3QdQ")      # HierarchicalNSW::saveIndex, hnswlib 0.8.0 (hnswalg.h)
+
+
+def parse_hnswlib_binary(blob: bytes, dim: int):
+    """Read the vectors and labels out of a file written by hnswlib 0.8.0 `Index.save_index` (the graph is not needed:
+    the B200 search is exact).  Layout restated from hnswalg.h `saveIndex` (the library is not vendored in the
+    reference): a 96-byte header
+        offsetLevel0, max_elements, cur_element_count, size_data_per_element, label_offset, offsetData (size_t each),
+        maxlevel (int), enterpoint (uint), maxM, maxM0, M (size_t), mult (double), ef_construction (size_t)
+    then cur_element_count level-0 records of size_data_per_element bytes
+        [uint32 link count/flags][maxM0 x uint32 links][dim x float32 vector][uint64 label]
+    then the upper-level link lists.  Cosine-space vectors are stored normalised.  Returns (labels uint64 [n],
+    rows float32 [n, dim], max_elements); elements carrying hnswlib's delete mark are dropped."""
+    if len(blob) < _HNSW_HEADER.size:
+        raise RuntimeError("Index seems to be corrupted or unsupported")
+    (off0, max_el, count, per_el, label_off, data_off, _maxlevel, _enter, maxM, maxM0, M, _mult, _efc) = _HNSW_HEADER.unpack_from(blob, 0)
+    sane = (off0 == 0 and data_off == maxM0 * 4 + 4 and label_off == data_off + dim * 4 and per_el == label_off + 8 and
+            0 < M <= 4096 and maxM == M and maxM0 == 2 * M and count <= max_el and _HNSW_HEADER.size + count * per_el <= len(blob))
+    if not sane:
+        raise RuntimeError("Index seems to be corrupted or unsupported (neither a fire_b200 nor an hnswlib 0.8.0 cosine index "
+                           f"of dimension {dim})")
+    rec = np.frombuffer(blob, dtype=np.uint8, count=count * per_el, offset=_HNSW_HEADER.size).reshape(count, per_el)
+    rows = np.ascontiguousarray(rec[:, data_off:label_off]).view("<f4").reshape(count, dim)
+    labels = np.ascontiguousarray(rec[:, label_off:label_off + 8]).view("<u8").reshape(count)
+    flags = np.ascontiguousarray(rec[:, 0:4]).view("<u4").reshape(count)
+    live = ((flags >> 16) & 1) == 0                   # DELETE_MARK lives in the third byte of the level-0 link header
+    labels, rows = labels[live].astype(np.uint64), rows[live].astype(np.float32)
+    order = np.argsort(labels, kind="stable")         # FIRE's ids are its running counter: row index == label
+    return labels[order], np.ascontiguousarray(rows[order]), int(max_el)
 
 
 class BFIndex(Index):
