@@ -269,16 +269,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
       int lt = 0, s = 0;
       uint32_t ph = 0;
+      long long tw[3] = {0, 0, 0};                               // cycles: waiting for a free accumulator / for operands / issuing
+      const bool prof = p.trace != nullptr && (p.flags & CF_DBG_PHASES);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
         const int buf = lt & 1;
         const int mt = fdiv(tile, p.d_ntiles);
         const int n0 = (tile - mt * p.n_tiles) * p.bn_tile;
+        long long c0 = prof ? clock64() : 0, c1;
         mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1, 15);
         tc_fence_after();
+        if (prof) { c1 = clock64(); tw[0] += c1 - c0; c0 = c1; }
         const uint32_t d = tmem_base + static_cast<uint32_t>(buf * p.bn_tile);
         for (int kb = 0; kb < p.nkb; ++kb) {
+          if (prof) c0 = clock64();
           mbar_wait(&full[s], ph, 12);
           tc_fence_after();
+          if (prof) { c1 = clock64(); tw[1] += c1 - c0; c0 = c1; }
           if (lt == 0 && kb == 0 && lane == 0) CONV_TRACE(3);
           if (elect_one()) {
             const uint32_t a0 = a_base + static_cast<uint32_t>(s * CONV_A_STAGE_BYTES);
@@ -290,11 +296,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             umma_commit(&empty[s]);
           }
           __syncwarp();
+          if (prof) { c1 = clock64(); tw[2] += c1 - c0; }
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         for (int j = 0; j < p.n_res; ++j) {                     // D[:, 64j .. 64j+63] += R_j * I
+          if (prof) c0 = clock64();
           mbar_wait(&full[s], ph, 18);
           tc_fence_after();
+          if (prof) { c1 = clock64(); tw[1] += c1 - c0; }
           if (elect_one()) {
             const uint32_t a0 = a_base + static_cast<uint32_t>(s * CONV_A_STAGE_BYTES);
             if (do_mma) {
@@ -316,6 +325,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         __syncwarp();
       }
       if (lane == 0) CONV_TRACE(4);
+      if (prof && lane == 0) {
+        long long* q = p.trace + 8 * 148 + blockIdx.x * 8;
+        q[0] = tw[0]; q[1] = tw[1]; q[2] = tw[2]; q[7] = lt;
+      }
     }
   } else if (warp < CONV_FIRST_HELPER_WARP) {
     // ---------------------------------------------------------------- epilogue (8 warps, 2 per TMEM lane quarter)

@@ -399,6 +399,7 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
     p.stages = r.stages; p.tma_a = r.tma_a ? 1 : 0; p.tmem_cols = r.tmem_cols;
     p.m_tiles = r.m_tiles; p.n_tiles = r.n_tiles; p.pdl = pdl ? 1 : 0;
     p.flags |= net->dbg_flags;
+    if (net->d_trace && !net->trace_all) p.flags |= CF_DBG_PHASES;
     p.n_res = r.n_res; p.box_cols = r.box_cols;
     p.n_issuers = r.n_issuers;
     p.trace = !net->d_trace ? nullptr : net->trace_all ? net->d_trace + (size_t)(&r - net->ops.data()) * 4096
@@ -653,6 +654,16 @@ int fire_facenet_profile(fire_net_t* net, const void* in_f16, int B, void* works
         double avg = 0;
         for (int c = 0; c < grid; ++c) avg += (double)q[c * 8 + k] / (double)std::max<long long>(q[c * 8 + 7], 1);
         fprintf(stderr, "    %-36s %8.0f\n", ph[k], avg / grid);
+      }
+    }
+    if (!r.strip) {
+      const char* ph[3] = {"MMA warp: wait acc_empty (epilogue)", "MMA warp: wait operands (full)", "MMA warp: issue + commit (main K-blocks)"};
+      const long long* q = &t[8 * 148];
+      fprintf(stderr, "  cycles per tile (avg over CTAs), tiles per CTA %lld:\n", q[7]);
+      for (int k = 0; k < 3; ++k) {
+        double avg = 0;
+        for (int c = 0; c < grid; ++c) avg += (double)q[c * 8 + k] / (double)std::max<long long>(q[c * 8 + 7], 1);
+        fprintf(stderr, "    %-44s %8.0f\n", ph[k], avg / grid);
       }
     }
     for (int k = 0; k < 8; ++k) {
