@@ -5,7 +5,8 @@
 // the op list, the buffer table (per-image offsets into one workspace arena, live ranges already
 // resolved) and the BN-folded fp16 weights; this file uploads the weights once, builds their TMA
 // descriptors once, and on every forward() enqueues one kernel per op on the caller's stream:
-//   conv_igemm_kernel x 88 + conv_strip_kernel x 12 (tcgen05),  maxpool3x3s2_kernel x 3,  gap_kernel x 1,  l2norm_kernel x 1.
+//   conv_igemm_kernel x 48 + conv_strip_kernel x 12 + block17_fused_kernel x 1 (tcgen05; the last one runs the 40 convs of the
+//   ten Block17 blocks), maxpool3x3s2_kernel x 3,  gap_kernel x 1,  l2norm_kernel x 1.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -15,6 +16,7 @@
 
 #include "conv_igemm.cuh"
 #include "conv_strip.cuh"
+#include "block17_fused.cuh"
 #include "fire_internal.h"
 
 namespace fire {
@@ -180,8 +182,18 @@ static FastDiv make_fastdiv(int d) {
   return f;
 }
 
+// The ten Block17 blocks as one launch (block17_fused.cuh): ops [first_op, first_op + 4 * n_blocks) of the plan.
+struct Fused17 {
+  int first_op = -1, n_blocks = 0;
+  uint8_t* d_stream = nullptr;      // n_blocks x 84 units of 16 KB: the weights in consumption order, as swizzled smem images
+  float* d_bias = nullptr;          // n_blocks x 1408 fp32
+  long long* d_trace = nullptr;     // FIRE_B200_TRACE17=1
+  B17Params prm;
+};
+
 struct fire_net {
   BlobHeader hdr;
+  Fused17 f17;
   std::vector<BlobBuf> bufs;
   std::vector<OpRt> ops;
   uint8_t* d_weights = nullptr;
@@ -205,6 +217,111 @@ static int pow2_cols(int n) {
   int c = 32;
   while (c < n) c <<= 1;
   return c;
+}
+
+
+// ---- Block17 fusion: pattern match on the plan and host-side repacking of the weights ----------------------------
+// unit images: byte offset of element (row n, k) inside a [128 x 64] SWIZZLE_128B / [256 x 32] SWIZZLE_64B operand
+static void b17_put_sw128(uint16_t* unit, const uint16_t* W, int ldw, int row0, int k0) {
+  for (int n = 0; n < 128; ++n)
+    for (int k = 0; k < 64; ++k)
+      unit[(n * 128 + (((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2) / 2] = W[(size_t)(row0 + n) * ldw + k0 + k];
+}
+static void b17_put_sw64(uint16_t* unit, const uint16_t* W, int ldw, int row0, int k0) {
+  for (int n = 0; n < 256; ++n)
+    for (int k = 0; k < 32; ++k)
+      unit[(n * 64 + (((k >> 3) ^ ((n >> 1) & 3)) << 4) + (k & 7) * 2) / 2] = W[(size_t)(row0 + n) * ldw + k0 + k];
+}
+static bool b17_match(const std::vector<BlobOp>& ops, const std::vector<BlobBuf>& bufs, size_t i) {
+  if (i + 3 >= ops.size()) return false;
+  const BlobOp &h = ops[i], &a = ops[i + 1], &b = ops[i + 2], &u = ops[i + 3];
+  auto conv = [](const BlobOp& o, int kh, int kw, int cin, int cout, int ph, int pw) {
+    return o.kind == OP_CONV && o.kh == kh && o.kw == kw && o.stride == 1 && o.cin == cin && o.cout == cout && o.pad_h == ph && o.pad_w == pw &&
+           o.H == 8 && o.W == 8 && o.Ho == 8 && o.Wo == 8 && o.k_pad == kh * kw * cin;
+  };
+  if (!conv(h, 1, 1, B17_C, 256, 0, 0) || !conv(a, 1, 7, 128, 128, 0, 3) || !conv(b, 7, 1, 128, 128, 3, 0) || !conv(u, 1, 1, 256, B17_C, 0, 0)) return false;
+  if (h.flags != CF_RELU || a.flags != CF_RELU || b.flags != CF_RELU || u.flags != (CF_RELU | CF_RESIDUAL)) return false;
+  const BlobBuf &xb = bufs[h.src_buf], &yb = bufs[u.dst_buf];
+  if (xb.C != B17_C || yb.C != B17_C || h.src_coff || u.dst_coff || (xb.Wp && xb.Wp != xb.W) || (yb.Wp && yb.Wp != yb.W)) return false;
+  if (u.res_buf != h.src_buf || u.res_coff) return false;
+  // X = [b1a | b0 | b1c]: 1x7 reads the first 128 heads columns, `up` reads [b0 | b1c]
+  if (a.src_buf != h.dst_buf || a.src_coff != h.dst_coff || b.src_buf != a.dst_buf || b.src_coff != a.dst_coff) return false;
+  if (u.src_buf != h.dst_buf || u.src_coff != h.dst_coff + 128 || b.dst_buf != h.dst_buf || b.dst_coff != h.dst_coff + 256) return false;
+  return true;
+}
+// Finds the chain and uploads its weight stream / bias table.  Returns false (fusion off) when the plan has no chain.
+static bool b17_setup(fire_net* net, const std::vector<BlobOp>& ops, const uint8_t* blob, const BlobHeader& h) {
+  Fused17& f = net->f17;
+  for (size_t i = 0; i < ops.size(); ++i) {
+    if (!b17_match(ops, net->bufs, i)) continue;
+    int n = 1;
+    while (n < B17_MAX_BLOCKS && b17_match(ops, net->bufs, i + 4 * n) && ops[i + 4 * n].src_buf == ops[i + 4 * n - 1].dst_buf) ++n;
+    f.first_op = (int)i; f.n_blocks = n;
+    break;
+  }
+  if (f.first_op < 0) return false;
+  std::vector<uint16_t> stream((size_t)f.n_blocks * B17_UNITS_PER_BLOCK * (B17_UNIT / 2));
+  std::vector<float> bias((size_t)f.n_blocks * B17_BIAS_PER_BLOCK);
+  for (int j = 0; j < f.n_blocks; ++j) {
+    const BlobOp* o = &ops[f.first_op + 4 * j];
+    const uint16_t* W[4];
+    for (int q = 0; q < 4; ++q) W[q] = reinterpret_cast<const uint16_t*>(blob + h.weights_off + o[q].w_off);
+    uint16_t* dst = stream.data() + (size_t)j * B17_UNITS_PER_BLOCK * (B17_UNIT / 2);
+    auto next = [&]() { uint16_t* r = dst; dst += B17_UNIT / 2; return r; };
+    for (int kb = 0; kb < 14; ++kb)
+      for (int half = 0; half < 2; ++half) b17_put_sw64(next(), W[0], B17_C, 0, kb * 64 + half * 32);
+    for (int q = 1; q <= 2; ++q)
+      for (int s = 0; s < 7; ++s)
+        for (int kb = 0; kb < 2; ++kb) b17_put_sw128(next(), W[q], 7 * 128, 0, s * 128 + kb * 64);
+    for (int t = 0; t < 3; ++t)
+      for (int kb = 0; kb < 4; ++kb)
+        for (int half = 0; half < 2; ++half) b17_put_sw64(next(), W[3], 256, t * 256, kb * 64 + half * 32);
+    for (int kb = 0; kb < 4; ++kb) b17_put_sw128(next(), W[3], 256, 768, kb * 64);
+    float* bd = bias.data() + (size_t)j * B17_BIAS_PER_BLOCK;
+    const int nb[4] = {256, 128, 128, B17_C};
+    for (int q = 0; q < 4; ++q) {
+      memcpy(bd, blob + h.weights_off + o[q].b_off, sizeof(float) * nb[q]);
+      bd += nb[q];
+    }
+  }
+  if (cudaMalloc(&f.d_stream, stream.size() * 2) != cudaSuccess || cudaMalloc(&f.d_bias, bias.size() * 4) != cudaSuccess ||
+      cudaMemcpy(f.d_stream, stream.data(), stream.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(f.d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaFuncSetAttribute(block17_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B17_SMEM) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(f.d_stream); cudaFree(f.d_bias);
+    f.d_stream = nullptr; f.d_bias = nullptr; f.first_op = -1; f.n_blocks = 0;
+    return false;
+  }
+  if (const char* e = getenv("FIRE_B200_TRACE17")) {
+    if (e[0] == '1') {
+      cudaMalloc(&f.d_trace, (size_t)148 * B17_MAX_BLOCKS * B17_TRACE_SLOTS * 8);
+      cudaMemset(f.d_trace, 0, (size_t)148 * B17_MAX_BLOCKS * B17_TRACE_SLOTS * 8);
+    }
+  }
+  return true;
+}
+static inline bool in_f17(const fire_net* net, size_t i) {
+  return net->f17.first_op >= 0 && (int)i >= net->f17.first_op && (int)i < net->f17.first_op + 4 * net->f17.n_blocks;
+}
+static int run_f17(fire_net* net, int B, cudaStream_t st, bool pdl) {
+  Fused17& f = net->f17;
+  f.prm.pdl = pdl ? 1 : 0;
+  f.prm.dbg = net->dbg_flags >> 16;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)std::min(f.prm.n_tiles, device_sm_count()));
+  cfg.blockDim = dim3(B17_THREADS);
+  cfg.dynamicSmemBytes = B17_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  (void)B;
+  FIRE_CUDA(cudaLaunchKernelEx(&cfg, block17_fused_kernel, f.prm));
+  count_launch();
+  return FIRE_OK;
 }
 
 extern "C" {
@@ -325,6 +442,10 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
   if (is_env) net->n_issuers = std::max(1, std::min(CONV_MAX_ISSUERS, atoi(is_env)));   // 1, 2 or 4 are used
   const char* st_env = getenv("FIRE_B200_MAX_STAGES");
   if (st_env) net->max_stages = std::max(3, std::min(12, atoi(st_env)));
+  {
+    const char* f17_env = getenv("FIRE_B200_FUSE17");
+    if (!(f17_env && f17_env[0] == '0')) b17_setup(net, ops, p, h);
+  }
   *out = net;
   return FIRE_OK;
 }
@@ -334,6 +455,7 @@ int fire_facenet_destroy(fire_net_t* net) {
   cudaFree(net->d_weights);
   cudaFree(net->d_bias16);
   cudaFree(net->d_trace);
+  cudaFree(net->f17.d_stream); cudaFree(net->f17.d_bias); cudaFree(net->f17.d_trace);
   delete net;
   return FIRE_OK;
 }
@@ -566,6 +688,20 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
         if (rc != FIRE_OK) return rc;
       }
     }
+    if (net->f17.first_op >= 0) {
+      Fused17& f = net->f17;
+      const uint64_t M = (uint64_t)B * 64;
+      for (int j = 0; j <= f.n_blocks; ++j) {
+        const BlobOp& o = j < f.n_blocks ? net->ops[f.first_op + 4 * j].op : net->ops[f.first_op + 4 * (f.n_blocks - 1) + 3].op;
+        const int buf = j < f.n_blocks ? o.src_buf : o.dst_buf;
+        const __half* ptr = static_cast<const __half*>(buf_ptr(net, buf, B, in, ws, out_raw));
+        f.prm.xptr[j] = ptr;
+        int rc = make_tmap_f16_2d(&f.prm.xmap[j], ptr, M, (uint64_t)B17_C, (uint64_t)B17_C * 2, CONV_BM);
+        if (rc != FIRE_OK) return rc;
+      }
+      f.prm.wstream = f.d_stream; f.prm.bias = f.d_bias; f.prm.n_blocks = f.n_blocks; f.prm.M_total = (int)M;
+      f.prm.n_tiles = (int)((M + CONV_BM - 1) / CONV_BM); f.prm.trace = f.d_trace;
+    }
     net->key_in = in; net->key_ws = ws; net->key_out = out_raw; net->key_B = B;
   }
   return FIRE_OK;
@@ -578,9 +714,29 @@ int fire_facenet_forward(fire_net_t* net, const void* in_f16, int B, float* out_
   int rc = prepare(net, in_f16, B, out_raw, workspace, ws_bytes);
   if (rc != FIRE_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  for (OpRt& r : net->ops) {
-    rc = run_op(net, r, B, in_f16, workspace, out_raw, st, net->pdl);
+  for (size_t i = 0; i < net->ops.size(); ++i) {
+    if (in_f17(net, i)) {
+      if ((int)i == net->f17.first_op) { rc = run_f17(net, B, st, net->pdl); if (rc != FIRE_OK) return rc; }
+      continue;
+    }
+    rc = run_op(net, net->ops[i], B, in_f16, workspace, out_raw, st, net->pdl);
     if (rc != FIRE_OK) return rc;
+  }
+  if (net->f17.d_trace) {
+    FIRE_CUDA(cudaStreamSynchronize(st));
+    std::vector<long long> t((size_t)148 * B17_MAX_BLOCKS * B17_TRACE_SLOTS);
+    cudaMemcpy(t.data(), net->f17.d_trace, t.size() * 8, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "# block17_fused CTA 0, ns since its first H.  MMA warp: H start, x landed, H issued, 1x7 start, up start, up issued, tile 2 wait, tile 2 go |"
+                    " epilogue warp 2: accH, r1, r0, acc17, r2, acc71, r3, up tiles 0..3 start, stores issued, y_done\n");
+    const long long t0 = t[0];
+    for (int j = 0; j < net->f17.n_blocks; ++j) {
+      const long long* q = &t[(size_t)j * B17_TRACE_SLOTS];
+      fprintf(stderr, "  blk %d |", j);
+      for (int k = 0; k < 8; ++k) fprintf(stderr, " %7lld", q[k] - t0);
+      fprintf(stderr, " |");
+      for (int k = 8; k <= 20; ++k) fprintf(stderr, " %7lld", q[k] - t0);
+      fprintf(stderr, "\n");
+    }
   }
   if (out_l2) {
     l2norm_kernel<<<(B + 7) / 8, 256, 0, st>>>(out_raw, out_l2, B, net->hdr.D);
@@ -595,7 +751,7 @@ int fire_facenet_forward(fire_net_t* net, const void* in_f16, int B, float* out_
     fprintf(stderr, "# op grid | first entry, setup, first full(max), last MMA commit(max), epilogue done(max), last exit [ns since op 0 entered] | span | gap to previous exit\n");
     for (size_t i = 0; i < net->ops.size(); ++i) {
       const OpRt& r = net->ops[i];
-      if (r.op.kind != OP_CONV) continue;
+      if (r.op.kind != OP_CONV || in_f17(net, i)) continue;
       const int grid = (int)std::min<long long>(r.strip ? (long long)B * r.row_blocks : (long long)r.m_tiles * r.n_tiles, device_sm_count());
       const long long* q = &t[i * 4096];
       long long e0 = 1ll << 62, su = 0, ff = 0, mc = 0, ed = 0, ex = 0;
@@ -624,7 +780,11 @@ int fire_facenet_profile(fire_net_t* net, const void* in_f16, int B, void* works
   for (auto& e : ev) cudaEventCreate(&e);
   cudaEventRecord(ev[0], st);
   for (size_t i = 0; i < net->ops.size(); ++i) {
-    rc = run_op(net, net->ops[i], B, in_f16, workspace, out_raw, st, false);   // no overlap: clean per-op times
+    if (in_f17(net, i)) {                            // the fused chain is timed as a whole and reported on its first op
+      if ((int)i == net->f17.first_op) rc = run_f17(net, B, st, false);
+    } else {
+      rc = run_op(net, net->ops[i], B, in_f16, workspace, out_raw, st, false);   // no overlap: clean per-op times
+    }
     if (rc != FIRE_OK) break;
     cudaEventRecord(ev[i + 1], st);
   }
@@ -633,6 +793,11 @@ int fire_facenet_profile(fire_net_t* net, const void* in_f16, int B, void* works
     for (size_t i = 0; i < net->ops.size(); ++i) {
       cudaEventElapsedTime(&host_ms[i], ev[i], ev[i + 1]);
       if (host_flops) host_flops[i] = net->ops[i].flops_per_image * B;
+    }
+    if (host_flops && net->f17.first_op >= 0) {      // all the chain's FLOPs belong to the launch reported on its first op
+      double sum = 0;
+      for (int q = 0; q < 4 * net->f17.n_blocks; ++q) { sum += host_flops[net->f17.first_op + q]; host_flops[net->f17.first_op + q] = 0; }
+      host_flops[net->f17.first_op] = sum;
     }
   }
   if (net->d_trace && rc == FIRE_OK && e == cudaSuccess) {

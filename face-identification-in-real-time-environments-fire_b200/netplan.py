@@ -219,8 +219,16 @@ class Plan:
         self.maxpool(x, Slice(m6, 640, 256), "Mixed_6a_pool")
         x = self.whole(m6)
 
+        # The ten Block17 blocks ping-pong between two buffers that live for the whole chain, and the chain's input
+        # stays intact until its last op: csrc/block17_fused.cuh runs the chain tile by tile in ONE launch (a CTA may
+        # start a new tile at block 1 while others are at block 10), so no chain buffer may be recycled inside it.
+        pp = [B(8, 8, 896), B(8, 8, 896)]
+        chain_first = len(self.ops)
         for i in range(1, 11):
-            x = self._block17(x, i)
+            x = self._block17(x, i, pp[(i - 1) % 2])
+        for b in pp + [m6]:
+            self.bufs[b].first = min(self.bufs[b].first, chain_first)
+            self.bufs[b].last = len(self.ops) - 1
 
         # Mixed_7a: [b0 384 | b1 256 | b2 256 | pool 896] -> 3x3x1792
         m7 = B(3, 3, 1792)
@@ -287,7 +295,7 @@ class Plan:
         self.conv([ConvPart(f"{p}_Conv2d_1x1", 256, False, 0.17)], cat, self.whole(y), relu=True, res=x, label=f"{p}_up")
         return self.whole(y)
 
-    def _block17(self, x: Slice, i: int) -> Slice:
+    def _block17(self, x: Slice, i: int, y: int) -> Slice:
         p = f"Block17_{i}"
         B = self._buf
         if self.fuse:
@@ -303,7 +311,6 @@ class Plan:
             cat, b1o = self.whole(X), Slice(X, 128, 128)
         t = B(8, 8, 128); self.conv(f"{p}_Branch_1_Conv2d_0b_1x7", b1m, self.whole(t), 1, 7, same=True)
         self.conv(f"{p}_Branch_1_Conv2d_0c_7x1", self.whole(t), b1o, 7, 1, same=True)
-        y = B(8, 8, 896)
         self.conv([ConvPart(f"{p}_Conv2d_1x1", 896, False, 0.1)], cat, self.whole(y), relu=True, res=x, label=f"{p}_up")
         return self.whole(y)
 

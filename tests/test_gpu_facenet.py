@@ -146,6 +146,29 @@ def test_strip_kernel_matches_gather_kernel(fire_lib, monkeypatch):
     assert np.abs(ra - rb).max() <= 1e-2 * np.abs(rb).max()
 
 
+@pytest.mark.parametrize("B", [1, 5, 64, 301])
+def test_block17_fused_chain_matches_layer_by_layer(fire_lib, monkeypatch, B):
+    """block17_fused_kernel (the ten Block17 blocks in one launch: intermediates in shared memory, 1x7 / 7x1 as
+    row-shifted windows, residual added in the epilogue) against the same plan run layer by layer
+    (FIRE_B200_FUSE17=0: conv_igemm_kernel x 40).  Same fp16 operands, same fp32 accumulation; bias and residual join
+    the sum in a different order.  B = 1 / 5 / 301: a half-empty tile (TMA zero fill and clipping); 301: CTAs that own two tiles."""
+    import torch
+    from fire_b200 import engine, weights as W
+    t = W.synthetic_weights(128, 5)
+    x = torch.from_numpy(_images(B, 13).astype(np.float32) / 255.0).cuda()
+    a = engine.FaceNetEngine(128, t)
+    ra, _ = a.encode_unit_f32(x)
+    ra2, _ = a.encode_unit_f32(x)
+    assert torch.equal(ra, ra2)                                    # deterministic
+    monkeypatch.setenv("FIRE_B200_FUSE17", "0")
+    b = engine.FaceNetEngine(128, t)
+    rb, _ = b.encode_unit_f32(x)
+    ra, rb = ra.cpu().numpy(), rb.cpu().numpy()
+    assert np.isfinite(ra).all()
+    assert _cos(ra, rb).min() >= 0.99999
+    assert np.abs(ra - rb).max() <= 1e-2 * np.abs(rb).max()
+
+
 def test_crop_encode_pipeline_equals_direct_path(nets):
     """The streaming public call (pinned host crops -> H2D -> K1 -> K2 -> D2H, double-buffered) returns exactly what
     the step-by-step path returns, for every in-flight batch."""

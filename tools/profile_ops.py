@@ -34,12 +34,14 @@ for i, op in enumerate(eng.plan.ops):
     if op.kind == OP_CONV:
         mode = "tma" if (op.kh == 1 and op.kw == 1 and op.stride == 1) else "gather"
         grid = (M + 127) // 128
-        tf = fl[i] / ms[i] / 1e9
+        tf = fl[i] / ms[i] / 1e9 if ms[i] > 0 else 0.0
         byts = 2 * (B * op.H * op.W * op.cin + M * op.cout + op.cout * op.k_pad)
         K = op.k_real
     else:
         mode, grid, tf, K = "pool", 0, 0.0, 0
         byts = 2 * (B * op.H * op.W * op.cin + M * op.cout)
+    if ms[i] <= 0:
+        continue                      # part of a fused launch reported on its first op (block17_fused_kernel)
     print(f"{i:3d} {op.label:38} {M:8d} {op.cout:5d} {K:5d} {mode:>6} {grid:7d} {ms[i]:8.4f} {tf:8.1f} "
           f"{byts / ms[i] / 1e6:9.0f} {100 * ms[i] / ms.sum():5.1f}")
     key = op.label.split("_")[0] if not op.label.startswith("Conv2d") else "Stem"
