@@ -30,9 +30,9 @@
 // for the N = 256 GEMMs, [128 x 64] SWIZZLE_128B for the N = 128 ones): the weight producer is a linear stream of
 // cp.async.bulk copies through a 6-slot ring, with no tensor map and no per-layer prologue.  84 units per block.
 //
-// Shared memory (229 KB): [pad][R1 k0][pad][R1 k1][pad][R2 k0][pad][R2 k1][pad] (pads 48 rows x 128 B, zero),
-// R0 (32 KB), ring U (6 x 16 KB), barriers.  While H runs, R0/R1/R2 hold nothing live: their six 16 KB data regions
-// ARE ring X.  During `up`, R2's data regions are the two TMA-store staging buffers.
+// Shared memory (227 KB): [pad][R1 k0][pad][R1 k1][pad][R2 k0][pad][R2 k1][pad] (pads 48 rows x 128 B, zero),
+// R0 (32 KB), ring U (6 x 16 KB), barriers, `up` bias.  While H runs, R0/R1/R2 hold nothing live: their 16 KB data
+// regions ARE ring X.  During `up`, R2's data regions are the epilogue warps' transposition scratch.
 // TMEM (512 columns): H -> [0,256), 1x7 -> [256,384), 7x1 -> [384,512), up tiles alternate [0,256) / [256,512).
 //
 // Warp roles: 0 and 10 weight stream (unit u belongs to issuer u % 2: the wait -> expect_tx -> copy chain of one
@@ -126,6 +126,44 @@ __device__ __forceinline__ void b17_epi_row64(uint32_t taddr, const float4 (&bq)
   tmem_ld_wait(b);
   b17_store_chunk(b, bq[12], bq[13], bq[14], bq[15], row_addr, 6u, swz);
 }
+__device__ __forceinline__ void b17_pack_chunk(uint32_t (&r)[16], float4 b0, float4 b1, float4 b2, float4 b3, uint4& lo, uint4& hi);
+// Same for the two TRANSPOSING epilogues (H -> R1, 1x7 -> R2): the eight lanes of a quarter warp own rows that are 16
+// rows apart, i.e. the same swizzle phase, so writing "unit u of my row" from all lanes is an 8-way bank conflict
+// (measured: 1.4 us instead of 0.4 us per phase).  Here lane l writes unit (i + l) & 7 at step i: the row is packed into
+// registers first and rotated by l & 7 with a three-stage select network.
+__device__ __forceinline__ void b17_sel_rot(uint4 (&v)[8], bool on, int by) {
+  uint4 t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 a = v[i], b = v[(i + by) & 7];
+    t[i] = make_uint4(on ? b.x : a.x, on ? b.y : a.y, on ? b.z : a.z, on ? b.w : a.w);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = t[i];
+}
+__device__ __forceinline__ void b17_epi_row64_rot(uint32_t taddr, const float4 (&bq)[16], uint32_t row_addr, uint32_t swz, int lane) {
+  uint32_t a[16], b[16];
+  uint4 pk[8];
+  __syncwarp();
+  tmem_ld_32x16(taddr, a);
+  tmem_ld_wait(a);
+  tmem_ld_32x16(taddr + 16, b);
+  b17_pack_chunk(a, bq[0], bq[1], bq[2], bq[3], pk[0], pk[1]);
+  tmem_ld_wait(b);
+  tmem_ld_32x16(taddr + 32, a);
+  b17_pack_chunk(b, bq[4], bq[5], bq[6], bq[7], pk[2], pk[3]);
+  tmem_ld_wait(a);
+  tmem_ld_32x16(taddr + 48, b);
+  b17_pack_chunk(a, bq[8], bq[9], bq[10], bq[11], pk[4], pk[5]);
+  tmem_ld_wait(b);
+  b17_pack_chunk(b, bq[12], bq[13], bq[14], bq[15], pk[6], pk[7]);
+  const int s = lane & 7;
+  b17_sel_rot(pk, (s & 1) != 0, 1);
+  b17_sel_rot(pk, (s & 2) != 0, 2);
+  b17_sel_rot(pk, (s & 4) != 0, 4);                  // pk[i] = unit (i + s) & 7
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sts128(row_addr + (((static_cast<uint32_t>(i + s) & 7u) ^ swz) << 4), pk[i]);
+}
 // same, packed into registers (the `up` epilogue stores to global memory)
 __device__ __forceinline__ void b17_pack_chunk(uint32_t (&r)[16], float4 b0, float4 b1, float4 b2, float4 b3, uint4& lo, uint4& hi) {
   const float4 bb[4] = {b0, b1, b2, b3};
@@ -185,7 +223,9 @@ block17_fused_kernel(const __grid_constant__ B17Params p) {
   uint64_t* r2_ready = r0_ready + 1;
   uint64_t* r3_ready = r2_ready + 1;
   uint64_t* y_done = r3_ready + 1;               // the epilogue warps have written this block's y (= the next block's x)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_done + 1);
+  uint64_t* y_part = y_done + 1;                 // [3] ... N tile t of it (columns 256 t .. 256 t + 255): the next block's x K-blocks 4 t .. 4 t + 3
+  uint64_t* up_done = y_part + 3;               // every MMA of this block has completed (R0 / R1 are free)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(up_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -201,6 +241,8 @@ block17_fused_kernel(const __grid_constant__ B17Params p) {
       mbar_init(r1_ready, CONV_EPI_WARPS); mbar_init(r0_ready, CONV_EPI_WARPS);
       mbar_init(r2_ready, CONV_EPI_WARPS); mbar_init(r3_ready, CONV_EPI_WARPS);
       mbar_init(y_done, CONV_EPI_WARPS);
+      for (int t = 0; t < 3; ++t) mbar_init(&y_part[t], CONV_EPI_WARPS);
+      mbar_init(up_done, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -254,13 +296,21 @@ block17_fused_kernel(const __grid_constant__ B17Params p) {
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int m0 = tile * CONV_BM;
       for (int j = 0; j < p.n_blocks; ++j, ++blk) {
-        if (blk > 0) { mbar_wait(y_done, (blk - 1) & 1, 32); fence_proxy_async_all(); }   // y_{j-1} (= x_j) is written, and nothing in R0/R1/R2 is live
+        // Ring X: K-blocks 0-11 cycle through R0 / R1's data rows (4 slots), which are free as soon as the previous block's
+        // last `up` MMA has completed; K-block i only needs the N tile i / 4 of the previous block's y, which its epilogue
+        // publishes tile by tile (y_part): H starts on the first tiles while that epilogue is still busy with the last ones.
+        // K-blocks 12, 13 go to R2's data rows (the epilogue's scratch) once all of y is written (y_done).
+        if (blk > 0) mbar_wait(up_done, (blk - 1) & 1, 32);
         for (int i = x_issuer; i < B17_XK; i += B17_X_ISSUERS) {
-          const int k = i >= 12 ? 2 : i >= 6 ? 1 : 0;
-          const int xs = i - k * B17_X_SLOTS;
+          const int k = i >> 2;                                 // use of the slot within this block (0..2), or 3 for the R2 slots
+          const int xs = i < 12 ? (i & 3) : i - 8;              // 0..3, 4, 5
+          if (blk > 0 && (i & 3) == 0) {
+            if (i < 12) mbar_wait(&y_part[k], (blk - 1) & 1, 32); else mbar_wait(y_done, (blk - 1) & 1, 32);
+            fence_proxy_async_all();
+          }
           const uint32_t xoff = xs == 0 ? B17_R0 : xs == 1 ? B17_R0 + B17_UNIT : xs == 2 ? B17_R1K0 : xs == 3 ? B17_R1K1 : xs == 4 ? B17_R2K0 : B17_R2K1;
-          // slots 0 and 1 are filled three times per block, the others twice: fill number (0-based) = (xs < 2 ? 3 : 2) * blk + k
-          if (k > 0) mbar_wait(&x_empty[xs], ((xs < 2 ? static_cast<uint32_t>(blk) : 0u) + k - 1) & 1, 33);
+          // slots 0-3 are filled three times per block (fill number 3 blk + k), slots 4 and 5 once
+          if (i >= 4 && i < 12) mbar_wait(&x_empty[xs], (static_cast<uint32_t>(blk) + k - 1) & 1, 33);
           if (elect_one()) {
             mbar_arrive_expect_tx(&x_full[xs], B17_UNIT);
             tma_load_2d(smem + xoff, &p.xmap[j], &x_full[xs], i * 64, m0);
@@ -283,10 +333,10 @@ block17_fused_kernel(const __grid_constant__ B17Params p) {
         tc_fence_after();
         B17_TRACE(j, 0);
         for (int i = 0; i < B17_XK; ++i) {
-          const int k = i >= 12 ? 2 : i >= 6 ? 1 : 0;
-          const int xs = i - k * B17_X_SLOTS;
+          const int k = i >> 2;
+          const int xs = i < 12 ? (i & 3) : i - 8;
           const uint32_t xaddr = xs == 0 ? r0a : xs == 1 ? r0a + B17_UNIT : xs == 2 ? r1k(0) : xs == 3 ? r1k(1) : xs == 4 ? r2k(0) : r2k(1);
-          mbar_wait(&x_full[xs], ((xs < 2 ? bpar : 0u) + k) & 1, 35);
+          mbar_wait(&x_full[xs], i < 12 ? (bpar + k) & 1 : bpar, 35);
           if (i == 0) B17_TRACE(j, 1);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -377,7 +427,10 @@ block17_fused_kernel(const __grid_constant__ B17Params p) {
               if (++us == B17_U_SLOTS) { us = 0; uph ^= 1; }
             }
           }
-          if (elect_one()) umma_commit(&accU_full[t & 1]);
+          if (elect_one()) {
+            umma_commit(&accU_full[t & 1]);
+            if (t == 3) umma_commit(up_done);
+          }
           __syncwarp();
         }
         B17_TRACE(j, 5);
@@ -414,7 +467,8 @@ block17_fused_kernel(const __grid_constant__ B17Params p) {
         for (int part = 0; part < 2; ++part) {
           const uint32_t row_addr = part == 0 ? r1k(h) + static_cast<uint32_t>(rho1 * 128) : r0a + static_cast<uint32_t>(h) * B17_UNIT + static_cast<uint32_t>(r * 128);
           const uint32_t swz = part == 0 ? (rho1 & 7) : (r & 7);
-          b17_epi_row64(tq + static_cast<uint32_t>(part * 128 + h * 64), bq, row_addr, swz);
+          if (part == 0) b17_epi_row64_rot(tq + static_cast<uint32_t>(h * 64), bq, row_addr, swz, lane);
+          else b17_epi_row64(tq + static_cast<uint32_t>(128 + h * 64), bq, row_addr, swz);
           tc_fence_before();
           fence_proxy_async_smem();
           __syncwarp();
@@ -431,7 +485,8 @@ block17_fused_kernel(const __grid_constant__ B17Params p) {
           if (warp == CONV_FIRST_EPI_WARP) B17_TRACE(j, 11 + 2 * conv);
           const uint32_t row_addr = conv == 0 ? r2k(h) + static_cast<uint32_t>(rho2 * 128) : r1k(h) + static_cast<uint32_t>(rnat * 128);
           const uint32_t swz = conv == 0 ? (rho2 & 7) : (rnat & 7);
-          b17_epi_row64(tq + static_cast<uint32_t>(256 + conv * 128 + h * 64), bq, row_addr, swz);
+          if (conv == 0) b17_epi_row64_rot(tq + static_cast<uint32_t>(256 + h * 64), bq, row_addr, swz, lane);
+          else b17_epi_row64(tq + static_cast<uint32_t>(384 + h * 64), bq, row_addr, swz);
           tc_fence_before();
           fence_proxy_async_smem();
           __syncwarp();
@@ -521,6 +576,11 @@ block17_fused_kernel(const __grid_constant__ B17Params p) {
             for (int i = 0; i < 8; ++i) {
               const uint4 v = lds128(sc_co + static_cast<uint32_t>(i * 512 + ((pc ^ ((4 * i + lr0) & 7)) << 4)));
               if (grow0 + 4 * i + lr0 < p.M_total && !(p.dbg & 2)) st_global_v4(yg + static_cast<size_t>(4 * i) * B17_C + g * 64, v);
+            }
+            if (last && t < 3) {                                // this warp's share of N tile t is on its way to y
+              fence_proxy_async_all();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&y_part[t]);
             }
           }
         }
