@@ -251,7 +251,8 @@ def run_fire(args):
         cos = (got * ref).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(ref, axis=1))
         parity = {"min_cos_vs_fp32_oracle": float(cos.min()), "images": 8}
 
-    # roofline of the dominant kernel family (the tcgen05 convolutions): algorithmic FLOP of the 100 conv launches of one
+    # roofline of the dominant kernel family (the tcgen05 convolutions: conv_igemm_kernel, conv_strip_kernel and the two
+    # fused residual-block chains block35_fused_kernel / block17_fused_kernel): algorithmic FLOP of the conv launches of one
     # step / the device time those launches take inside the timed step.  The step is timed live above; the convs' SHARE
     # of it comes from a per-op CUDA-event pass over the same batch (and is cross-checked by the ncu launch list in
     # profiles/): conv time in the step = ms_per_step * share.
@@ -266,7 +267,8 @@ def run_fire(args):
         step_ms = ms_dev / args.steps
         conv_ms_in_step = step_ms * share
         achieved = conv_fl / (conv_ms_in_step * 1e-3) / 1e12
-        roofline = {"kernel": f"conv_igemm_kernel + conv_strip_kernel ({int(conv.sum())} launches/step)", "bound": "tensor",
+        roofline = {"kernel": f"tcgen05 conv kernels: conv_igemm + conv_strip + block35_fused + block17_fused ({int(conv.sum())} launches/step for the plan's 100 convs)",
+                    "bound": "tensor",
                     "achieved": achieved, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tensor_tflops"],
                     "peak_source": f"{peaks['src']} bf16 sustained (MEASURED_PEAKS.json); fp16 runs on the same kind::f16 pipe",
                     "traffic": None, "conv_share_of_step": share, "conv_ms_in_step": conv_ms_in_step,

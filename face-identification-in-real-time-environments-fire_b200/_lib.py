@@ -38,6 +38,7 @@ _SIGNATURES = {
     "fire_facenet_workspace": (C.c_size_t, [C.c_void_p, C.c_int]),
     "fire_facenet_flops": (C.c_double, [C.c_void_p]),
     "fire_facenet_num_ops": (C.c_int, [C.c_void_p]),
+    "fire_facenet_num_launches": (C.c_int, [C.c_void_p]),
     "fire_facenet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_size_t, C.c_void_p]),
     "fire_facenet_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,

@@ -17,6 +17,7 @@
 #include "conv_igemm.cuh"
 #include "conv_strip.cuh"
 #include "block17_fused.cuh"
+#include "block35_fused.cuh"
 #include "fire_internal.h"
 
 namespace fire {
@@ -191,9 +192,19 @@ struct Fused17 {
   B17Params prm;
 };
 
+// The five Block35 blocks as one launch (block35_fused.cuh): ops [first_op, first_op + 4 * n_blocks).
+struct Fused35 {
+  int first_op = -1, n_blocks = 0;
+  uint8_t* d_stream = nullptr;      // n_blocks x 19 units of 16 KB
+  float* d_bias = nullptr;          // n_blocks x 448 fp32
+  long long* d_trace = nullptr;     // FIRE_B200_TRACE35=1
+  B35Params prm;
+};
+
 struct fire_net {
   BlobHeader hdr;
   Fused17 f17;
+  Fused35 f35;
   std::vector<BlobBuf> bufs;
   std::vector<OpRt> ops;
   uint8_t* d_weights = nullptr;
@@ -324,6 +335,111 @@ static int run_f17(fire_net* net, int B, cudaStream_t st, bool pdl) {
   return FIRE_OK;
 }
 
+// ---- Block35 fusion ------------------------------------------------------------------------------------------------
+// generic operand images: `rows` x 64 K (128-byte rows, SWIZZLE_128B) / `rows` x 32 K (64-byte rows, SWIZZLE_64B);
+// kmap (optional) = source K column of our K column
+static void b35_put_sw128(uint16_t* unit, const uint16_t* W, int ldw, int row0, int rows, int k0, const int* kmap = nullptr) {
+  for (int n = 0; n < rows; ++n)
+    for (int k = 0; k < 64; ++k)
+      unit[(n * 128 + (((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2) / 2] = W[(size_t)(row0 + n) * ldw + (kmap ? kmap[k0 + k] : k0 + k)];
+}
+static void b35_put_sw64(uint16_t* unit, const uint16_t* W, int ldw, int row0, int rows, int k0, const int* kmap = nullptr) {
+  for (int n = 0; n < rows; ++n)
+    for (int k = 0; k < 32; ++k)
+      unit[(n * 64 + (((k >> 3) ^ ((n >> 1) & 3)) << 4) + (k & 7) * 2) / 2] = W[(size_t)(row0 + n) * ldw + (kmap ? kmap[k0 + k] : k0 + k)];
+}
+static bool b35_match(const std::vector<BlobOp>& ops, const std::vector<BlobBuf>& bufs, size_t i) {
+  if (i + 3 >= ops.size()) return false;
+  const BlobOp &h = ops[i], &a = ops[i + 1], &b = ops[i + 2], &u = ops[i + 3];
+  auto conv = [](const BlobOp& o, int k, int cin, int cout) {
+    return o.kind == OP_CONV && o.kh == k && o.kw == k && o.stride == 1 && o.cin == cin && o.cout == cout && o.pad_h == k / 2 && o.pad_w == k / 2 &&
+           o.H == 17 && o.W == 17 && o.Ho == 17 && o.Wo == 17 && o.k_pad == (k * k * cin + 63) / 64 * 64;
+  };
+  if (!conv(h, 1, B35_C, 96) || !conv(a, 3, 64, 64) || !conv(b, 3, 32, 32) || !conv(u, 1, 96, B35_C)) return false;
+  if (h.flags != CF_RELU || a.flags != CF_RELU || b.flags != CF_RELU || u.flags != (CF_RELU | CF_RESIDUAL)) return false;
+  const BlobBuf &xb = bufs[h.src_buf], &yb = bufs[u.dst_buf];
+  if (xb.C != B35_C || yb.C != B35_C || h.src_coff || u.dst_coff || (xb.Wp && xb.Wp != xb.W) || (yb.Wp && yb.Wp != yb.W)) return false;
+  if (u.res_buf != h.src_buf || u.res_coff) return false;
+  // X = [b1a | b2a | b0 | b2c | b1b | b2b] (netplan._block35): conv1 X[0:64] -> X[128:192], conv2 X[160:192] -> X[96:128], up reads X[64:160]
+  const int X = h.dst_buf, c0 = h.dst_coff;
+  if (a.src_buf != X || a.src_coff != c0 || a.dst_buf != X || a.dst_coff != c0 + 128) return false;
+  if (b.src_buf != X || b.src_coff != c0 + 160 || b.dst_buf != X || b.dst_coff != c0 + 96) return false;
+  if (u.src_buf != X || u.src_coff != c0 + 64) return false;
+  return true;
+}
+static bool b35_setup(fire_net* net, const std::vector<BlobOp>& ops, const uint8_t* blob, const BlobHeader& h) {
+  Fused35& f = net->f35;
+  for (size_t i = 0; i < ops.size(); ++i) {
+    if (!b35_match(ops, net->bufs, i)) continue;
+    int n = 1;
+    while (n < B35_MAX_BLOCKS && b35_match(ops, net->bufs, i + 4 * n) && ops[i + 4 * n].src_buf == ops[i + 4 * n - 1].dst_buf) ++n;
+    f.first_op = (int)i; f.n_blocks = n;
+    break;
+  }
+  if (f.first_op < 0) return false;
+  std::vector<uint16_t> stream((size_t)f.n_blocks * B35_WSLOTS_PER_BLOCK * (B35_UNIT / 2), 0);
+  std::vector<float> bias((size_t)f.n_blocks * B35_BIAS_PER_BLOCK);
+  // the plan's `up` reads [b0 | b2c | b1b]; the kernel's A operand is [b0 | b1b | b2c]
+  int kmap[96];
+  for (int k = 0; k < 32; ++k) { kmap[k] = k; kmap[32 + k] = 64 + k; kmap[64 + k] = 32 + k; }
+  for (int j = 0; j < f.n_blocks; ++j) {
+    const BlobOp* o = &ops[f.first_op + 4 * j];
+    const uint16_t* W[4];
+    for (int q = 0; q < 4; ++q) W[q] = reinterpret_cast<const uint16_t*>(blob + h.weights_off + o[q].w_off);
+    uint16_t* base = stream.data() + (size_t)j * B35_WSLOTS_PER_BLOCK * (B35_UNIT / 2);
+    auto unit = [&](int slot) { return base + (size_t)slot * (B35_UNIT / 2); };
+    for (int kb = 0; kb < 4; ++kb) b35_put_sw128(unit(kb), W[0], o[0].k_pad, 0, 96, kb * 64);
+    for (int t = 0; t < 9; ++t) b35_put_sw128(unit(4 + t), W[1], o[1].k_pad, 0, 64, t * 64);
+    for (int t = 0; t < 9; ++t) b35_put_sw64(unit(t < 5 ? 13 : 14) + (size_t)(t < 5 ? t : t - 5) * 1024, W[2], o[2].k_pad, 0, 32, t * 32);
+    for (int nh = 0; nh < 2; ++nh) {
+      b35_put_sw128(unit(15 + 2 * nh), W[3], o[3].k_pad, nh * 128, 128, 0, kmap);
+      b35_put_sw64(unit(16 + 2 * nh), W[3], o[3].k_pad, nh * 128, 128, 64, kmap);
+    }
+    float* bd = bias.data() + (size_t)j * B35_BIAS_PER_BLOCK;
+    const int nb[4] = {96, 64, 32, B35_C};
+    for (int q = 0; q < 4; ++q) {
+      memcpy(bd, blob + h.weights_off + o[q].b_off, sizeof(float) * nb[q]);
+      bd += nb[q];
+    }
+  }
+  if (cudaMalloc(&f.d_stream, stream.size() * 2) != cudaSuccess || cudaMalloc(&f.d_bias, bias.size() * 4) != cudaSuccess ||
+      cudaMemcpy(f.d_stream, stream.data(), stream.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(f.d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaFuncSetAttribute(block35_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B35_SMEM) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(f.d_stream); cudaFree(f.d_bias);
+    f.d_stream = nullptr; f.d_bias = nullptr; f.first_op = -1; f.n_blocks = 0;
+    return false;
+  }
+  if (const char* e = getenv("FIRE_B200_TRACE35")) {
+    if (e[0] == '1') {
+      cudaMalloc(&f.d_trace, (size_t)148 * 16 * 24 * 8);
+      cudaMemset(f.d_trace, 0, (size_t)148 * 16 * 24 * 8);
+    }
+  }
+  return true;
+}
+static inline bool in_f35(const fire_net* net, size_t i) {
+  return net->f35.first_op >= 0 && (int)i >= net->f35.first_op && (int)i < net->f35.first_op + 4 * net->f35.n_blocks;
+}
+static int run_f35(fire_net* net, cudaStream_t st, bool pdl) {
+  Fused35& f = net->f35;
+  f.prm.pdl = pdl ? 1 : 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)std::min(f.prm.n_images, device_sm_count()));
+  cfg.blockDim = dim3(B35_THREADS);
+  cfg.dynamicSmemBytes = B35_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  FIRE_CUDA(cudaLaunchKernelEx(&cfg, block35_fused_kernel, f.prm));
+  count_launch();
+  return FIRE_OK;
+}
+
 extern "C" {
 
 int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
@@ -445,6 +561,8 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
   {
     const char* f17_env = getenv("FIRE_B200_FUSE17");
     if (!(f17_env && f17_env[0] == '0')) b17_setup(net, ops, p, h);
+    const char* f35_env = getenv("FIRE_B200_FUSE35");
+    if (!(f35_env && f35_env[0] == '0')) b35_setup(net, ops, p, h);
   }
   *out = net;
   return FIRE_OK;
@@ -456,12 +574,20 @@ int fire_facenet_destroy(fire_net_t* net) {
   cudaFree(net->d_bias16);
   cudaFree(net->d_trace);
   cudaFree(net->f17.d_stream); cudaFree(net->f17.d_bias); cudaFree(net->f17.d_trace);
+  cudaFree(net->f35.d_stream); cudaFree(net->f35.d_bias); cudaFree(net->f35.d_trace);
   delete net;
   return FIRE_OK;
 }
 
 int fire_facenet_dim(const fire_net_t* net) { return net ? net->hdr.D : 0; }
 int fire_facenet_num_ops(const fire_net_t* net) { return net ? (int)net->ops.size() : 0; }
+int fire_facenet_num_launches(const fire_net_t* net) {
+  if (!net) return 0;
+  int n = (int)net->ops.size();
+  if (net->f17.first_op >= 0) n -= 4 * net->f17.n_blocks - 1;
+  if (net->f35.first_op >= 0) n -= 4 * net->f35.n_blocks - 1;
+  return n;
+}
 double fire_facenet_flops(const fire_net_t* net) { return net ? net->flops_per_image : 0.0; }
 
 size_t fire_facenet_workspace(const fire_net_t* net, int B) {
@@ -702,6 +828,19 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
       f.prm.wstream = f.d_stream; f.prm.bias = f.d_bias; f.prm.n_blocks = f.n_blocks; f.prm.M_total = (int)M;
       f.prm.n_tiles = (int)((M + CONV_BM - 1) / CONV_BM); f.prm.trace = f.d_trace;
     }
+    if (net->f35.first_op >= 0) {
+      Fused35& f = net->f35;
+      const uint64_t M = (uint64_t)B * B35_POS;
+      for (int j = 0; j <= f.n_blocks; ++j) {
+        const BlobOp& o = j < f.n_blocks ? net->ops[f.first_op + 4 * j].op : net->ops[f.first_op + 4 * (f.n_blocks - 1) + 3].op;
+        const int buf = j < f.n_blocks ? o.src_buf : o.dst_buf;
+        const __half* ptr = static_cast<const __half*>(buf_ptr(net, buf, B, in, ws, out_raw));
+        f.prm.xptr[j] = ptr;
+        int rc = make_tmap_f16_2d(&f.prm.xmap[j], ptr, M, (uint64_t)B35_C, (uint64_t)B35_C * 2, CONV_BM);
+        if (rc != FIRE_OK) return rc;
+      }
+      f.prm.wstream = f.d_stream; f.prm.bias = f.d_bias; f.prm.n_blocks = f.n_blocks; f.prm.n_images = B; f.prm.trace = f.d_trace;
+    }
     net->key_in = in; net->key_ws = ws; net->key_out = out_raw; net->key_B = B;
   }
   return FIRE_OK;
@@ -719,8 +858,29 @@ int fire_facenet_forward(fire_net_t* net, const void* in_f16, int B, float* out_
       if ((int)i == net->f17.first_op) { rc = run_f17(net, B, st, net->pdl); if (rc != FIRE_OK) return rc; }
       continue;
     }
+    if (in_f35(net, i)) {
+      if ((int)i == net->f35.first_op) { rc = run_f35(net, st, net->pdl); if (rc != FIRE_OK) return rc; }
+      continue;
+    }
     rc = run_op(net, net->ops[i], B, in_f16, workspace, out_raw, st, net->pdl);
     if (rc != FIRE_OK) return rc;
+  }
+  if (net->f35.d_trace) {
+    FIRE_CUDA(cudaStreamSynchronize(st));
+    std::vector<long long> t((size_t)148 * 16 * 24);
+    cudaMemcpy(t.data(), net->f35.d_trace, t.size() * 8, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "# block35_fused CTA 0, ns since its first H.  MMA warp: H start, H issued, conv1 start, conv1 issued, conv2 start, conv2 issued, up start, up issued |"
+                    " epilogue warp 2: accH[0], hready[2], acc1[0], conv1 epi done, acc2[0], aup_ready[2], up tiles 0..2 start, stores issued, y_done\n");
+    const long long t0 = t[0];
+    for (int j = 0; j < 2 * net->f35.n_blocks && j < 16; ++j) {
+      const long long* q = &t[(size_t)j * 24];
+      if (!q[0]) break;
+      fprintf(stderr, "  blk %2d |", j);
+      for (int k = 0; k < 8; ++k) fprintf(stderr, " %7lld", q[k] - t0);
+      fprintf(stderr, " |");
+      for (int k = 8; k <= 18; ++k) fprintf(stderr, " %7lld", q[k] - t0);
+      fprintf(stderr, " | up epilogue cycles (12 steps): fill+ldg %lld, acc wait %lld, first tmem ld %lld, chunks %lld, write-back %lld\n", q[19], q[20], q[21], q[22], q[23]);
+    }
   }
   if (net->f17.d_trace) {
     FIRE_CUDA(cudaStreamSynchronize(st));
@@ -751,7 +911,7 @@ int fire_facenet_forward(fire_net_t* net, const void* in_f16, int B, float* out_
     fprintf(stderr, "# op grid | first entry, setup, first full(max), last MMA commit(max), epilogue done(max), last exit [ns since op 0 entered] | span | gap to previous exit\n");
     for (size_t i = 0; i < net->ops.size(); ++i) {
       const OpRt& r = net->ops[i];
-      if (r.op.kind != OP_CONV || in_f17(net, i)) continue;
+      if (r.op.kind != OP_CONV || in_f17(net, i) || in_f35(net, i)) continue;
       const int grid = (int)std::min<long long>(r.strip ? (long long)B * r.row_blocks : (long long)r.m_tiles * r.n_tiles, device_sm_count());
       const long long* q = &t[i * 4096];
       long long e0 = 1ll << 62, su = 0, ff = 0, mc = 0, ed = 0, ex = 0;
@@ -782,6 +942,8 @@ int fire_facenet_profile(fire_net_t* net, const void* in_f16, int B, void* works
   for (size_t i = 0; i < net->ops.size(); ++i) {
     if (in_f17(net, i)) {                            // the fused chain is timed as a whole and reported on its first op
       if ((int)i == net->f17.first_op) rc = run_f17(net, B, st, false);
+    } else if (in_f35(net, i)) {
+      if ((int)i == net->f35.first_op) rc = run_f35(net, st, false);
     } else {
       rc = run_op(net, net->ops[i], B, in_f16, workspace, out_raw, st, false);   // no overlap: clean per-op times
     }
@@ -798,6 +960,11 @@ int fire_facenet_profile(fire_net_t* net, const void* in_f16, int B, void* works
       double sum = 0;
       for (int q = 0; q < 4 * net->f17.n_blocks; ++q) { sum += host_flops[net->f17.first_op + q]; host_flops[net->f17.first_op + q] = 0; }
       host_flops[net->f17.first_op] = sum;
+    }
+    if (host_flops && net->f35.first_op >= 0) {
+      double sum = 0;
+      for (int q = 0; q < 4 * net->f35.n_blocks; ++q) { sum += host_flops[net->f35.first_op + q]; host_flops[net->f35.first_op + q] = 0; }
+      host_flops[net->f35.first_op] = sum;
     }
   }
   if (net->d_trace && rc == FIRE_OK && e == cudaSuccess) {

@@ -50,6 +50,7 @@ class FaceNetEngine:
         self._ws_B = 0
         self.flops_per_image = float(_lib.lib().fire_facenet_flops(self._h))
         self.num_ops = int(_lib.lib().fire_facenet_num_ops(self._h))
+        self.num_launches = int(_lib.lib().fire_facenet_num_launches(self._h))   # fused chains count once
 
     def close(self):
         if getattr(self, "_h", None):

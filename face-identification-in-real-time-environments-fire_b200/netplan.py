@@ -207,8 +207,14 @@ class Plan:
         t = B(36, 36, 192); self.conv("Conv2d_4a_3x3", x, self.whole(t), 3, 3); x = self.whole(t)
         trunk = B(17, 17, 256); self.conv("Conv2d_4b_3x3", x, self.whole(trunk), 3, 3, 2); x = self.whole(trunk)
 
+        # same for the five Block35 blocks (csrc/block35_fused.cuh: one launch, one image per CTA pass)
+        pp35 = [B(17, 17, 256), B(17, 17, 256)]
+        chain35_first = len(self.ops)
         for i in range(1, 6):
-            x = self._block35(x, i)
+            x = self._block35(x, i, pp35[(i - 1) % 2])
+        for b in pp35 + [trunk]:
+            self.bufs[b].first = min(self.bufs[b].first, chain35_first)
+            self.bufs[b].last = len(self.ops) - 1
 
         # Mixed_6a: [b0 384 | b1 256 | pool 256] -> 8x8x896
         m6 = B(8, 8, 896)
@@ -260,7 +266,7 @@ class Plan:
         self.conv([ConvPart("Bottleneck", self.D, True)], self.whole(g), self.whole(self.out_buf),
                   relu=False, out_f32=True, label="Bottleneck")
 
-    def _block35(self, x: Slice, i: int) -> Slice:
+    def _block35(self, x: Slice, i: int, y: int) -> Slice:
         p = f"Block35_{i}"
         B = self._buf
         if self.fuse:
@@ -278,7 +284,6 @@ class Plan:
                        ConvPart(f"{p}_Branch_2_Conv2d_0b_3x3", 32, True, cin_off=32, cin_len=32)],
                       Slice(X, 0, 64), Slice(X, 128, 64), 3, 3, same=True, label=f"{p}_Branch_12_Conv2d_0b_3x3")
             self.conv(f"{p}_Branch_2_Conv2d_0c_3x3", Slice(X, 160, 32), Slice(X, 96, 32), 3, 3, same=True)
-            y = B(17, 17, 256)
             perm = list(range(0, 32)) + list(range(64, 96)) + list(range(32, 64))
             self.conv([ConvPart(f"{p}_Conv2d_1x1", 256, False, 0.17, cin_perm=perm)], Slice(X, 64, 96), self.whole(y), relu=True, res=x,
                       label=f"{p}_up")
@@ -291,7 +296,6 @@ class Plan:
         self.conv(f"{p}_Branch_1_Conv2d_0b_3x3", b1m, b1o, 3, 3, same=True)
         t = B(17, 17, 32); self.conv(f"{p}_Branch_2_Conv2d_0b_3x3", b2m, self.whole(t), 3, 3, same=True)
         self.conv(f"{p}_Branch_2_Conv2d_0c_3x3", self.whole(t), b2o, 3, 3, same=True)
-        y = B(17, 17, 256)
         self.conv([ConvPart(f"{p}_Conv2d_1x1", 256, False, 0.17)], cat, self.whole(y), relu=True, res=x, label=f"{p}_up")
         return self.whole(y)
 

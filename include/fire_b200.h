@@ -92,6 +92,9 @@ int fire_facenet_dim(const fire_net_t* net);                    /* 128 or 512 */
 size_t fire_facenet_workspace(const fire_net_t* net, int B);    /* bytes of scratch forward() needs */
 double fire_facenet_flops(const fire_net_t* net);               /* algorithmic FLOP per image */
 int fire_facenet_num_ops(const fire_net_t* net);
+/* Kernel launches one forward() enqueues for the plan's ops (without the optional L2-norm launch): ops inside a fused
+ * chain (block17_fused_kernel, block35_fused_kernel) share one launch. */
+int fire_facenet_num_launches(const fire_net_t* net);
 /* in_f16: fp16 [B][80][80][16] (fire_preprocess / fire_ingest_f32 output); out_raw: float [B][D] un-normalised (what encode() returns);
  * out_l2: float [B][D] rows divided by their L2 norm (face_recognition.py:225-229), may be NULL. */
 int fire_facenet_forward(fire_net_t* net, const void* in_f16, int B, float* out_raw, float* out_l2,

@@ -162,6 +162,30 @@ def test_block17_fused_chain_matches_layer_by_layer(fire_lib, monkeypatch, B):
     assert torch.equal(ra, ra2)                                    # deterministic
     monkeypatch.setenv("FIRE_B200_FUSE17", "0")
     b = engine.FaceNetEngine(128, t)
+    assert b.num_launches - a.num_launches == 39                   # 40 conv launches became one
+    rb, _ = b.encode_unit_f32(x)
+    ra, rb = ra.cpu().numpy(), rb.cpu().numpy()
+    assert np.isfinite(ra).all()
+    assert _cos(ra, rb).min() >= 0.99999
+    assert np.abs(ra - rb).max() <= 1e-2 * np.abs(rb).max()
+
+
+@pytest.mark.parametrize("B", [1, 7, 149, 300])
+def test_block35_fused_chain_matches_layer_by_layer(fire_lib, monkeypatch, B):
+    """block35_fused_kernel (the five Block35 blocks in one launch, one image per CTA pass: 3x3 convs as row-shifted
+    windows of a pitched zero-bordered copy in shared memory) against the same plan run layer by layer
+    (FIRE_B200_FUSE35=0: conv_igemm_kernel x 20).  B = 149 / 300: CTAs that own two / three images."""
+    import torch
+    from fire_b200 import engine, weights as W
+    t = W.synthetic_weights(128, 6)
+    x = torch.from_numpy(_images(B, 17).astype(np.float32) / 255.0).cuda()
+    a = engine.FaceNetEngine(128, t)
+    ra, _ = a.encode_unit_f32(x)
+    ra2, _ = a.encode_unit_f32(x)
+    assert torch.equal(ra, ra2)
+    monkeypatch.setenv("FIRE_B200_FUSE35", "0")
+    b = engine.FaceNetEngine(128, t)
+    assert b.num_launches - a.num_launches == 19                   # 20 conv launches became one
     rb, _ = b.encode_unit_f32(x)
     ra, rb = ra.cpu().numpy(), rb.cpu().numpy()
     assert np.isfinite(ra).all()

@@ -40,7 +40,7 @@ for i, op in enumerate(eng.plan.ops):
     else:
         mode, grid, tf, K = "pool", 0, 0.0, 0
         byts = 2 * (B * op.H * op.W * op.cin + M * op.cout)
-    if ms[i] <= 0:
+    if op.kind == OP_CONV and fl[i] == 0:
         continue                      # part of a fused launch reported on its first op (block17_fused_kernel)
     print(f"{i:3d} {op.label:38} {M:8d} {op.cout:5d} {K:5d} {mode:>6} {grid:7d} {ms[i]:8.4f} {tf:8.1f} "
           f"{byts / ms[i] / 1e6:9.0f} {100 * ms[i] / ms.sum():5.1f}")
