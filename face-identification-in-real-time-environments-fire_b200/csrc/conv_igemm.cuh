@@ -89,13 +89,15 @@ struct ConvParams {
   void* out;         int out_ld, out_coff;    // CF_OUT_F32 only (fp16 outputs go through tmap_out)
   const uint4* bias16;                        // [cout] x {hi, lo, 0...} fp16
   int H, W, Ho, Wo, kh, kw, stride, pad_h, pad_w;
-  int cin, cout, k_real, nkb, flags, bn_tile, M_total, stages, tma_a, tmem_cols;
+  int cin, cout, k_real, nkb, flags, bn_tile, M_total, stages, tma_a, tmem_cols;   // tma_a: 0 = cp.async gather, 1 = tiled 2-D TMA (1x1), 2 = im2col TMA
   int m_tiles, n_tiles, pdl;
   int n_res;                    // residual K-blocks per tile (bn_tile / 64 when CF_RESIDUAL, else 0)
   int box_cols;                 // columns per TMA-store box: 64 / 32 / 16 (128B / 64B / 32B swizzle)
   long long* trace;             // debug timeline: [gridDim.x][8] globaltimer stamps (nullptr = off)
   int n_issuers;                // TMA issuing threads (1, 2 or 4; divides `stages`), stage g is issued by thread g % n_issuers
   FastDiv d_howo, d_wo, d_cin, d_kw, d_ntiles;
+  int cpb;                      // tma_a == 2: 64-channel slices per tap (cin / 64)
+  FastDiv d_cpb;
 };
 
 __device__ __forceinline__ void tmem_alloc_rt(uint32_t* smem_slot, uint32_t cols) {
@@ -230,6 +232,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
           const int mt = fdiv(tile, p.d_ntiles);
           const int n0 = (tile - mt * p.n_tiles) * p.bn_tile, m0 = mt * CONV_BM;
+          int bw = 0, bh = 0, bn_img = 0;                          // im2col: input-space base pixel of the tile's first output pixel
+          if (p.tma_a == 2) {
+            bn_img = fdiv(m0, p.d_howo);
+            const int rem = m0 - bn_img * (p.Ho * p.Wo), ho = fdiv(rem, p.d_wo);
+            bw = (rem - ho * p.Wo) * p.stride - p.pad_w;
+            bh = ho * p.stride - p.pad_h;
+          }
           for (int kb = 0; kb < nk_total; ++kb, ++g) {
             if (pass == 0 && g >= prefill) break;
             if (turn == issuer) {
@@ -241,7 +250,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                     mbar_arrive_expect_tx(&full[s], tx);
                     tma_load_2d_hint(sB + static_cast<size_t>(s) * b_stage_bytes, &tmap_w, &full[s], kb * 64, n0, kEvictLast);
                   }
-                  if (p.tma_a && pass == 1) tma_load_2d(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES, &tmap_a, &full[s], kb * 64, m0);
+                  if (p.tma_a == 1 && pass == 1) tma_load_2d(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES, &tmap_a, &full[s], kb * 64, m0);
+                  if (p.tma_a == 2 && pass == 1) {               // k x k layer, cin % 64 == 0: K-block kb = (tap, 64-channel slice)
+                    const int tap = fdiv(kb, p.d_cpb), c0 = (kb - tap * p.cpb) * 64;
+                    const int r = fdiv(tap, p.d_kw), sx = tap - r * p.kw;
+                    tma_load_im2col_4d(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES, &tmap_a, &full[s], c0, bw, bh, bn_img,
+                                       static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
+                  }
                 } else if (pass == 1) {                           // residual K-block: [128 rows x 64 channels] of x
                   mbar_arrive_expect_tx(&full[s], CONV_A_STAGE_BYTES);
                   tma_load_2d(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES, &tmap_res, &full[s], n0 + (kb - p.nkb) * 64, m0);

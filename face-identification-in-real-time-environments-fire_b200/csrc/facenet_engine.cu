@@ -142,6 +142,7 @@ struct OpRt {
   CUtensorMap tmap_res;   // residual matrix (up convs): box 64 columns x 128 rows
   CUtensorMap tmap_out;   // output slice, box = box_cols x 32 rows (TMA store)
   bool tma_a = false;
+  bool im2col = false;    // k x k layer whose A operand comes through an im2col tensor map (ConvParams::tma_a == 2)
   int bn_tile = 0, stages = 0, n_issuers = 1, tmem_cols = 0, m_tiles = 0, n_tiles = 0;
   int n_res = 0, box_cols = 64;
   bool strip = false;     // stride-1 k x k layer run by conv_strip_kernel (halo patch + shifted descriptors)
@@ -522,6 +523,8 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
                     o.cout, o.k_pad, o.cin);
       }
       r.tma_a = (o.kh == 1 && o.kw == 1 && o.stride == 1 && o.pad_h == 0 && o.pad_w == 0);
+      r.im2col = !r.tma_a && o.kh == o.kw && o.kh > 1 && o.pad_h == o.pad_w && o.cin % 64 == 0 && o.k_pad == o.kh * o.kw * o.cin &&
+                 !(o.flags & (CF_RESIDUAL | CF_OUT_F32));
       if ((o.flags & CF_RESIDUAL) && (!r.tma_a || o.cout % 64)) {
         cudaFree(net->d_weights); cudaFree(net->d_bias16); delete net;
         return fail(FIRE_ERR_ARG, "fire_facenet_create: residual is supported on 1x1/stride-1 convs with cout %% 64 == 0");
@@ -544,6 +547,9 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
     net->trace_op = atoi(tr_env);
     cudaMalloc(&net->d_trace, 8 * 8 * 512);
     cudaMemset(net->d_trace, 0, 8 * 8 * 512);
+  }
+  if (const char* e = getenv("FIRE_B200_IM2COL")) {
+    if (e[0] == '0') for (OpRt& r : net->ops) r.im2col = false;      // A/B experiments and the parity test: cp.async gather instead
   }
   const char* sp_env = getenv("FIRE_B200_STRIP");
   net->use_strip = !(sp_env && sp_env[0] == '0');
@@ -644,7 +650,8 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
     p.H = o.H; p.W = o.W; p.Ho = o.Ho; p.Wo = o.Wo; p.kh = o.kh; p.kw = o.kw; p.stride = o.stride;
     p.pad_h = o.pad_h; p.pad_w = o.pad_w; p.cin = o.cin; p.cout = o.cout; p.k_real = o.kh * o.kw * o.cin;
     p.nkb = o.k_pad / 64; p.flags = o.flags; p.bn_tile = r.bn_tile; p.M_total = B * o.Ho * o.Wo;
-    p.stages = r.stages; p.tma_a = r.tma_a ? 1 : 0; p.tmem_cols = r.tmem_cols;
+    p.stages = r.stages; p.tma_a = r.tma_a ? 1 : (r.im2col ? 2 : 0); p.tmem_cols = r.tmem_cols;
+    p.cpb = std::max(1, o.cin / 64); p.d_cpb = make_fastdiv(p.cpb);
     p.m_tiles = r.m_tiles; p.n_tiles = r.n_tiles; p.pdl = pdl ? 1 : 0;
     p.flags |= net->dbg_flags;
     if (net->d_trace && !net->trace_all) p.flags |= CF_DBG_PHASES;
@@ -664,7 +671,7 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    FIRE_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, r.tmap_w, r.tma_a ? r.tmap_a : r.tmap_w, r.n_res ? r.tmap_res : r.tmap_w,
+    FIRE_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, r.tmap_w, (r.tma_a || r.im2col) ? r.tmap_a : r.tmap_w, r.n_res ? r.tmap_res : r.tmap_w,
                                  (o.flags & CF_OUT_F32) ? r.tmap_w : r.tmap_out, p));
   } else if (o.kind == OP_MAXPOOL) {
     const long long total = (long long)B * o.Ho * o.Wo * (o.cin / 8);
@@ -787,7 +794,7 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
       if (r.stages < 2) return fail(FIRE_ERR_UNSUPPORTED, "conv tile %d does not fit shared memory", bn);
       // TMA issuing threads (1x1 layers): the ring depth is rounded down to a multiple of their number (see conv_igemm.cuh)
       r.n_issuers = 1;
-      if (r.tma_a && net->n_issuers > 1) {
+      if ((r.tma_a || r.im2col) && net->n_issuers > 1) {
         if (r.stages > 4 && r.stages % 4 && r.stages % 3) --r.stages;        // 5 -> 4, 7 -> 6: a ring the issuers can share
         for (int j = std::min(net->n_issuers, CONV_MAX_ISSUERS); j >= 2; --j)
           if (r.stages % j == 0) { r.n_issuers = j; break; }
@@ -800,6 +807,11 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
       if (r.tma_a) {
         const __half* src = static_cast<const __half*>(buf_ptr(net, o.src_buf, B, in, ws, out_raw)) + o.src_coff;
         int rc = make_tmap_f16_2d(&r.tmap_a, src, M, (uint64_t)o.cin, (uint64_t)sb.C * 2, CONV_BM);
+        if (rc != FIRE_OK) return rc;
+      } else if (r.im2col) {
+        if (buf_wp(sb) != sb.W) return fail(FIRE_ERR_UNSUPPORTED, "im2col conv over a pitched buffer");
+        const __half* src = static_cast<const __half*>(buf_ptr(net, o.src_buf, B, in, ws, out_raw)) + o.src_coff;
+        int rc = make_tmap_f16_im2col(&r.tmap_a, src, (uint64_t)o.cin, (uint64_t)o.W, (uint64_t)o.H, (uint64_t)B, (uint64_t)sb.C, o.kh, o.pad_h, o.stride);
         if (rc != FIRE_OK) return rc;
       }
       if (r.n_res) {

@@ -121,6 +121,34 @@ int make_tmap_f16_pos3d(CUtensorMap* out, const void* base, uint64_t C, uint64_t
   return FIRE_OK;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
+                                   const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tmap_f16_im2col(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint64_t ld_elems,
+                         int k, int pad, int stride) {
+  static EncodeIm2colFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+      return fail(FIRE_ERR_CUDA, "cuTensorMapEncodeIm2col not available from the driver");
+    fn = reinterpret_cast<EncodeIm2colFn>(p);
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld_elems & 7) || C % 64)
+    return fail(FIRE_ERR_ARG, "im2col tensor map: base/stride must be 16-byte aligned, channels a multiple of 64");
+  cuuint64_t gdim[4] = {C, W, H, N};
+  cuuint64_t gstride[3] = {ld_elems * 2, W * ld_elems * 2, H * W * ld_elems * 2};
+  // base pixels run over [-pad, dim - 1 + pad - (k - 1)] in both spatial dimensions (dilation 1)
+  int lower[2] = {-pad, -pad};
+  int upper[2] = {pad - (k - 1), pad - (k - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstride, lower, upper, 64, 128, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FIRE_ERR_CUDA, "cuTensorMapEncodeIm2col failed with CUresult %d", (int)r);
+  return FIRE_OK;
+}
+
 int device_sm_count() {
   static int n = 0;
   if (n) return n;

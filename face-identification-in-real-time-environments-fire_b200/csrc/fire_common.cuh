@@ -118,6 +118,18 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // named barrier among `count` threads (count a multiple of 32); id 0 is __syncthreads
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
+// im2col load (4-D NHWC tensor map built with cuTensorMapEncodeIm2col): `pixelsPerColumn` output pixels starting at the
+// input-space base pixel (w, h, n) = (wo * stride - pad, ho * stride - pad, n), traversed along W, then H, then N inside the
+// map's bounding box, each read at filter-tap offset (off_w, off_h); `channelsPerPixel` channels from c.  Padding and
+// pixels past the last image read as zero.  The shared-memory tile is [pixels][channels], swizzled like a tiled box.
+__device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c, int w, int h, int n,
+                                                   uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
 // 4D tiled load / store (coordinates inner -> outer: c, w, h, n); out-of-range elements load as zero / are not stored.
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(

@@ -193,6 +193,24 @@ def test_block35_fused_chain_matches_layer_by_layer(fire_lib, monkeypatch, B):
     assert np.abs(ra - rb).max() <= 1e-2 * np.abs(rb).max()
 
 
+@pytest.mark.parametrize("B", [2, 37, 130])
+def test_im2col_tma_operand_is_bit_identical_to_gather(fire_lib, monkeypatch, B):
+    """k x k layers with Cin % 64 == 0 (Conv2d_4b, Mixed_6a, Mixed_7a) fetch their A operand with im2col-mode TMA loads
+    (one instruction per (tap, 64-channel slice) and 128 output pixels; padding, stride and the ragged last tile are the
+    tensor map's business) instead of the cp.async gather warps: the same bytes land in the same swizzled tile, so the
+    embeddings must be bit-identical."""
+    import torch
+    from fire_b200 import engine, weights as W
+    t = W.synthetic_weights(128, 10)
+    x = torch.from_numpy(_images(B, 31).astype(np.float32) / 255.0).cuda()
+    a = engine.FaceNetEngine(128, t)
+    ra, _ = a.encode_unit_f32(x)
+    monkeypatch.setenv("FIRE_B200_IM2COL", "0")
+    b = engine.FaceNetEngine(128, t)
+    rb, _ = b.encode_unit_f32(x)
+    assert torch.equal(ra, rb)
+
+
 def test_crop_encode_pipeline_equals_direct_path(nets):
     """The streaming public call (pinned host crops -> H2D -> K1 -> K2 -> D2H, double-buffered) returns exactly what
     the step-by-step path returns, for every in-flight batch."""
