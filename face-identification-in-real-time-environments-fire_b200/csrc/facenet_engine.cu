@@ -523,7 +523,7 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
                     o.cout, o.k_pad, o.cin);
       }
       r.tma_a = (o.kh == 1 && o.kw == 1 && o.stride == 1 && o.pad_h == 0 && o.pad_w == 0);
-      r.im2col = !r.tma_a && o.kh == o.kw && o.kh > 1 && o.pad_h == o.pad_w && o.cin % 64 == 0 && o.k_pad == o.kh * o.kw * o.cin &&
+      r.im2col = !r.tma_a && o.kh * o.kw > 1 && o.cin % 64 == 0 && o.k_pad == o.kh * o.kw * o.cin &&
                  !(o.flags & (CF_RESIDUAL | CF_OUT_F32));
       if ((o.flags & CF_RESIDUAL) && (!r.tma_a || o.cout % 64)) {
         cudaFree(net->d_weights); cudaFree(net->d_bias16); delete net;
@@ -811,7 +811,7 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
       } else if (r.im2col) {
         if (buf_wp(sb) != sb.W) return fail(FIRE_ERR_UNSUPPORTED, "im2col conv over a pitched buffer");
         const __half* src = static_cast<const __half*>(buf_ptr(net, o.src_buf, B, in, ws, out_raw)) + o.src_coff;
-        int rc = make_tmap_f16_im2col(&r.tmap_a, src, (uint64_t)o.cin, (uint64_t)o.W, (uint64_t)o.H, (uint64_t)B, (uint64_t)sb.C, o.kh, o.pad_h, o.stride);
+        int rc = make_tmap_f16_im2col(&r.tmap_a, src, (uint64_t)o.cin, (uint64_t)o.W, (uint64_t)o.H, (uint64_t)B, (uint64_t)sb.C, o.kw, o.kh, o.pad_w, o.pad_h, o.stride);
         if (rc != FIRE_OK) return rc;
       }
       if (r.n_res) {

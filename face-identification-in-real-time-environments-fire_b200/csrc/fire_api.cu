@@ -126,7 +126,7 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int make_tmap_f16_im2col(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint64_t ld_elems,
-                         int k, int pad, int stride) {
+                         int kw, int kh, int pad_w, int pad_h, int stride) {
   static EncodeIm2colFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -139,9 +139,10 @@ int make_tmap_f16_im2col(CUtensorMap* out, const void* base, uint64_t C, uint64_
     return fail(FIRE_ERR_ARG, "im2col tensor map: base/stride must be 16-byte aligned, channels a multiple of 64");
   cuuint64_t gdim[4] = {C, W, H, N};
   cuuint64_t gstride[3] = {ld_elems * 2, W * ld_elems * 2, H * W * ld_elems * 2};
-  // base pixels run over [-pad, dim - 1 + pad - (k - 1)] in both spatial dimensions (dilation 1)
-  int lower[2] = {-pad, -pad};
-  int upper[2] = {pad - (k - 1), pad - (k - 1)};
+  // base pixels run over [-pad, dim - 1 + pad - (k - 1)] in each spatial dimension (dilation 1); corner arrays are {W, H}
+  // like every other array of the tensor map (verified on the 1x3 / 3x1 layers of Block8)
+  int lower[2] = {-pad_w, -pad_h};
+  int upper[2] = {pad_w - (kw - 1), pad_h - (kh - 1)};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstride, lower, upper, 64, 128, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -49,10 +49,10 @@ int make_tmap_f16_nhwc(CUtensorMap* out, const void* base, uint64_t C, uint64_t 
 int make_tmap_f16_pos3d(CUtensorMap* out, const void* base, uint64_t C, uint64_t positions, uint64_t N, uint64_t ld_elems,
                         uint32_t box_c, uint32_t box_pos);
 
-// im2col view {C, W, H, N} of an NHWC fp16 buffer for a k x k convolution (square kernel, symmetric padding `pad`, stride
+// im2col view {C, W, H, N} of an NHWC fp16 buffer for a kh x kw convolution (padding pad_h / pad_w on both sides, stride
 // `stride`): 64 channels x 128 output pixels per load, 128-byte swizzle (conv_igemm.cuh, tma_a == 2).
 int make_tmap_f16_im2col(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint64_t ld_elems,
-                         int k, int pad, int stride);
+                         int kw, int kh, int pad_w, int pad_h, int stride);
 
 int device_sm_count();
 
