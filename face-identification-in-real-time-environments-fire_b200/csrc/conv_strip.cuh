@@ -20,11 +20,14 @@
 // consumer reads (their tensor maps end at Wo).
 #pragma once
 
+#include <type_traits>
+
 #include "conv_igemm.cuh"
 
 namespace fire {
 
-constexpr int STRIP_THREADS = 32 * (3 + CONV_EPI_WARPS);     // warp 0 producer, warp 1 MMA, warps 2-9 epilogue, warp 10 TMA stores
+constexpr int STRIP_MMA_WARPS = 2;                           // warps 1 and 11
+constexpr int STRIP_THREADS = 32 * (3 + CONV_EPI_WARPS + STRIP_MMA_WARPS - 1);   // warp 0 producer, warps 1 / 11 MMA, warps 2-9 epilogue, warp 10 TMA stores
 constexpr int STRIP_MAX_ACC = 8;                             // TMEM accumulators (tiles in flight between MMA and epilogue)
 
 struct StripSmem {
@@ -57,6 +60,10 @@ struct StripParams {
                           //    buffer has row pitch Wbox, so the garbage columns land in its padding); 0: R whole rows
   int Ho;
   int a_stage_bytes, stages, tmem_cols, flags, pdl, box_cols;
+  int n_mma_warps;        // MMA issuing warps (1 or 2): tile i of an interleaved group belongs to warp i % n_mma_warps.  One thread
+                          // issues a tcgen05.mma every ~110 cycles whatever its size; issuers in different warps overlap
+                          // (tools/umma_probe.cu part 6: N <= 64, 4 accumulators: 120 / 77 cycles per MMA with 1 / 2 threads).
+                          // Measured: Conv2d_2a 100 -> 77 us, Conv2d_2b 112 -> 92 us with two; four warps were slower (118 / 121 us)
   int n_acc;              // TMEM accumulators (power of two, <= STRIP_MAX_ACC); the MMA warp interleaves n_acc / 2 tiles
   long long* trace;
   FastDiv d_rowblocks, d_wbox;
@@ -143,8 +150,12 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
+  } else if (warp == 1 || (warp > CONV_FIRST_EPI_WARP + CONV_EPI_WARPS && warp - (CONV_FIRST_EPI_WARP + CONV_EPI_WARPS) < p.n_mma_warps)) {
+    // ---------------------------------------------------------------- MMA issuers
+    // `mw` (which tiles of a group this warp owns) is a COMPILE-TIME constant of each instantiation: predicates derived
+    // from threadIdx are not provably warp-uniform, and ptxas then wraps every tcgen05.mma in its serialisation loop again.
+    auto mma_role = [&](auto n_mw_c, auto mw_c) {
+    constexpr int n_mw = decltype(n_mw_c)::value, mw = decltype(mw_c)::value;
     // The WHOLE warp runs the loop (so every address/descriptor stays in uniform registers) and one elected lane
     // issues: a divergent `if (lane == 0)` body makes ptxas wrap every tcgen05.mma in an ELECT + 7 x R2UR +
     // BRA.U.ANY serialisation loop, which costs ~100-200 cycles per MMA (tools/umma_probe.cu part 5/6).
@@ -170,27 +181,27 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       for (int lt0 = 0; lt0 < my_tiles; lt0 += G) {
         const int cnt = min(G, my_tiles - lt0);
         long long c0 = prof ? clock64() : 0, c1;
-        for (int i = 0; i < cnt; ++i) {
+        for (int i = mw; i < cnt; i += n_mw) {                  // this warp's tiles of the group: i = mw (mod n_mw)
           const int l = lt0 + i;
           mbar_wait(&acc_empty[l & (p.n_acc - 1)], (static_cast<uint32_t>(l / p.n_acc) & 1u) ^ 1u, 23);
         }
         tc_fence_after();
         if (prof) { c1 = clock64(); tm[0] += c1 - c0; c0 = c1; }
         if (elect_one()) {
-          for (int i = 0; i < cnt; ++i)
+          for (int i = mw; i < cnt; i += n_mw)
             umma_f16(tmem_base + static_cast<uint32_t>(((lt0 + i) & (p.n_acc - 1)) * p.cout), ones_desc, bias_desc, idesc, 0u);   // D = ones * bias^T
         }
         {
           int si = s;
           uint32_t phi = ph;
           for (int i = 0; i < cnt; ++i) {
-            mbar_wait(&a_full[si], phi, 24);
+            if (i % n_mw == mw) mbar_wait(&a_full[si], phi, 24);
             if (++si == p.stages) { si = 0; phi ^= 1; }
           }
         }
         tc_fence_after();
         if (prof) { c1 = clock64(); tm[1] += c1 - c0; c0 = c1; }
-        if (lt0 == 0 && lane == 0) CONV_TRACE(3);
+        if (lt0 == 0 && lane == 0 && mw == 0) CONV_TRACE(3);
         if (elect_one()) {
           const uint32_t a_ring = smem_u32(sA);
           uint32_t tile_base[STRIP_MAX_ACC / 2], tile_acc[STRIP_MAX_ACC / 2];   // per tile of the group: A start address, accumulator
@@ -214,7 +225,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             const uint64_t bdesc = b_desc_hi | static_cast<uint64_t>((b_addr & 0x3FFFF) >> 4);
 #pragma unroll
             for (int i = 0; i < STRIP_MAX_ACC / 2; ++i) {
-              if (i < cnt) {
+              if (i < cnt && i % n_mw == mw) {
                 const uint32_t a_addr = tile_base[i] + tap_off + static_cast<uint32_t>(c0 * 2);
                 umma_f16(tile_acc[i], a_desc_hi | static_cast<uint64_t>((a_addr & 0x3FFFF) >> 4), bdesc, idesc, 1u);
               }
@@ -229,8 +240,10 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           }
           int si = s;
           for (int i = 0; i < cnt; ++i) {
-            umma_commit(&a_empty[si]);
-            umma_commit(&acc_full[(lt0 + i) & (p.n_acc - 1)]);
+            if (i % n_mw == mw) {
+              umma_commit(&a_empty[si]);
+              umma_commit(&acc_full[(lt0 + i) & (p.n_acc - 1)]);
+            }
             if (++si == p.stages) si = 0;
           }
         }
@@ -239,12 +252,18 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         for (int i = 0; i < cnt; ++i)
           if (++s == p.stages) { s = 0; ph ^= 1; }
       }
-      if (prof && lane == 0) {
+      if (prof && lane == 0 && mw == 0) {
         long long* q = p.trace + 8 * 148 + blockIdx.x * 8;
         q[0] = tm[0]; q[1] = tm[1]; q[2] = tm[2]; q[7] = my_tiles;
       }
-      if (lane == 0) CONV_TRACE(4);
+      if (lane == 0 && mw == 0) CONV_TRACE(4);
     }
+    };
+    using std::integral_constant;
+    const int mwi = warp == 1 ? 0 : warp - (CONV_FIRST_EPI_WARP + CONV_EPI_WARPS);
+    if (p.n_mma_warps == 1) mma_role(integral_constant<int, 1>{}, integral_constant<int, 0>{});
+    else if (mwi == 0) mma_role(integral_constant<int, 2>{}, integral_constant<int, 0>{});
+    else mma_role(integral_constant<int, 2>{}, integral_constant<int, 1>{});
   } else if (warp < CONV_FIRST_EPI_WARP + CONV_EPI_WARPS) {
     // ---------------------------------------------------------------- epilogue: two groups of 4 warps (one per TMEM lane quarter);
     // group g takes the tiles with lt & 1 == g and owns staging buffer g, so the fixed per-tile latencies (two barrier
@@ -296,7 +315,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       q[3] = te[0]; q[4] = te[1]; q[5] = te[2];
     }
     if (threadIdx.x == CONV_FIRST_EPI_WARP * 32) CONV_TRACE(6);
-  } else {
+  } else if (warp == CONV_FIRST_EPI_WARP + CONV_EPI_WARPS) {
     // ---------------------------------------------------------------- TMA store warp: one 4-D store per column box of a tile
     const int rowbytes = p.box_cols * 2, box_bytes = CONV_BM * rowbytes, n_boxes = p.cout / p.box_cols;
     const uint32_t stage_buf_bytes = static_cast<uint32_t>(CONV_BM * p.cout * 2);

@@ -217,6 +217,7 @@ struct fire_net {
   bool gather_l1 = false; // cp.async.ca instead of .cg for the A gather (FIRE_B200_GATHER_L1=1)
   int max_stages = 8;
   int n_issuers = CONV_MAX_ISSUERS;   // TMA issuing threads per CTA in 1x1 layers (FIRE_B200_ISSUERS=1|2|4)
+  int strip_mma_warps = STRIP_MMA_WARPS;   // FIRE_B200_STRIP_MMAW=1|2|4: MMA issuing warps of conv_strip_kernel
   bool use_strip = true;    // FIRE_B200_STRIP=0 forces the gather path for every k x k layer (A/B experiments)
   bool trace_all = false;   // FIRE_B200_TRACE_ALL=1: forward() records every conv's timeline, synchronises and prints it
   long long* d_trace = nullptr; int trace_op = -1;   // FIRE_B200_TRACE_OP=<op index>: in-kernel timeline of that op (profile only)
@@ -551,6 +552,7 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
   if (const char* e = getenv("FIRE_B200_IM2COL")) {
     if (e[0] == '0') for (OpRt& r : net->ops) r.im2col = false;      // A/B experiments and the parity test: cp.async gather instead
   }
+  if (const char* e = getenv("FIRE_B200_STRIP_MMAW")) net->strip_mma_warps = atoi(e) >= 2 ? 2 : 1;
   const char* sp_env = getenv("FIRE_B200_STRIP");
   net->use_strip = !(sp_env && sp_env[0] == '0');
   const char* ta_env = getenv("FIRE_B200_TRACE_ALL");
@@ -626,6 +628,8 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
       q.a_stage_bytes = r.a_stage_bytes; q.stages = r.stages; q.tmem_cols = r.tmem_cols; q.flags = o.flags | net->dbg_flags;
       if (net->d_trace && !net->trace_all) q.flags |= CF_DBG_PHASES;
       q.pdl = pdl ? 1 : 0; q.box_cols = r.box_cols; q.n_acc = r.n_acc;
+      // two issuing warps pay off when the main loop is long enough to be issue-bound (Conv2d_2a / 2b: 18 K steps; 1a has 4)
+      q.n_mma_warps = (q.k16_steps >= 8 && r.n_acc >= 4) ? std::min(net->strip_mma_warps, 2) : 1;
       q.trace = !net->d_trace ? nullptr : net->trace_all ? net->d_trace + (size_t)(&r - net->ops.data()) * 4096
                 : (&r == &net->ops[net->trace_op] ? net->d_trace : nullptr);
       q.d_rowblocks = make_fastdiv(r.row_blocks);

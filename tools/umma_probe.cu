@@ -614,6 +614,105 @@ static void part6() {
   cudaFree(dout);
 }
 
+// ------------------------------------------------------------------------------------------------ part 7
+// cta_group::2: does ONE tcgen05.mma that spans a CTA pair (M = 256, each SM holds 128 rows of A and half of B) cost the
+// same ~85-130 cycles as the single-CTA M = 128 instruction?  If so, the small-N strip layers (N = 32 / 64) would do twice
+// the work per instruction.  Leader CTA issues, tcgen05.commit multicasts the completion to both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_2cta_kernel(int N, int n_mma, int n_acc, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 64 * 1024;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  for (int i = threadIdx.x; i < 128 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  fence_proxy_async_smem();
+  __syncthreads();
+  cluster_sync_all();
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t rank = cluster_ctarank();
+  if (threadIdx.x == 0) {
+    long long best = 1ll << 60;
+    for (int rep = 0; rep < 5; ++rep) {
+      if (rank == 0) {
+        const uint32_t idesc = umma_idesc_f16(256, N);
+        const long long t0 = clock64();
+        for (int j = 0; j < n_mma; ++j)
+          for (int a = 0; a < n_acc; ++a)
+            umma_f16_2cta(tmem + a * N, umma_desc_sw128(smem_u32(sA) + (j & 3) * 32 + a * 16384), umma_desc_sw128(smem_u32(sB) + (j & 3) * 32), idesc,
+                          j ? 1u : 0u);
+        umma_commit_2cta(&bar);
+        mbar_wait(&bar, rep & 1, 9);
+        const long long t1 = clock64();
+        if (rep >= 1 && t1 - t0 < best) best = t1 - t0;
+      } else {
+        mbar_wait(&bar, rep & 1, 10);                 // the multicast commit arrives here too
+      }
+    }
+    if (rank == 0) out[blockIdx.x / 2] = best;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (threadIdx.x < 32) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+static void part7() {
+  printf("== part 7: n tcgen05.mma.cta_group::2 (M=256 over a CTA pair, K=16) per accumulator, n_acc accumulators, one issuing thread ==\n");
+  CK(cudaFuncSetAttribute(umma_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 130 * 1024));
+  long long* dout;
+  CK(cudaMalloc(&dout, 64));
+  for (int N : {32, 64, 128, 256}) {
+    for (int n_acc : {1, 2, 4}) {
+      if (n_acc * N > 512) continue;
+      printf("  N=%-3d accumulators %d:", N, n_acc);
+      for (int n : {18, 36}) {
+        umma_2cta_kernel<<<2, 128, 130 * 1024>>>(N, n, n_acc, dout);
+        CK(cudaDeviceSynchronize());
+        long long h = 0;
+        CK(cudaMemcpy(&h, dout, 8, cudaMemcpyDeviceToHost));
+        printf("  n=%-2d %5lld (%.0f clk per MMA = per 2 x 128 rows)", n, h, (double)h / (n * n_acc));
+      }
+      printf("\n");
+    }
+  }
+  cudaFree(dout);
+}
+
 int main(int argc, char** argv) {
   const int which = argc > 1 ? atoi(argv[1]) : 3;
   CK(cudaSetDevice(0));
@@ -623,5 +722,6 @@ int main(int argc, char** argv) {
   if (which & 8) part4();
   if (which & 16) part5();
   if (which & 32) part6();
+  if (which & 64) part7();
   return 0;
 }
