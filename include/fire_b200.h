@@ -100,10 +100,13 @@ int fire_facenet_num_launches(const fire_net_t* net);
 int fire_facenet_forward(fire_net_t* net, const void* in_f16, int B, float* out_raw, float* out_l2,
                          void* workspace, size_t ws_bytes, fire_stream_t stream);
 /* Profiling aid: runs forward with a CUDA-event pair around every op; host_ms[n_ops] gets the
- * per-op device time, host_flops[n_ops] the per-op algorithmic FLOP (0 for pools).  Synchronises. */
+ * per-op device time, host_flops[n_ops] the per-op algorithmic FLOP (0 for pools).  Synchronises.
+ * A fused chain (fire_facenet_num_launches) is reported on its first op: time and FLOP of the whole launch there, 0 on the rest. */
 int fire_facenet_profile(fire_net_t* net, const void* in_f16, int B, void* workspace, size_t ws_bytes,
                          float* host_ms, double* host_flops, int n_ops, fire_stream_t stream);
-/* Debug aid: copy an internal activation buffer (index into the plan's buffer table) to the host as fp16. */
+/* Debug aid: copy an internal activation buffer (index into the plan's buffer table) to the host as fp16.  Buffers that
+ * only exist inside a fused chain (the branch tensors of Block17 / Block35) are never written unless the chain runs layer
+ * by layer (FIRE_B200_FUSE17=0 / FIRE_B200_FUSE35=0); the arena also recycles dead buffers. */
 int fire_facenet_read_buffer(fire_net_t* net, int buf, int B, const void* in_f16, const void* workspace,
                              void* host_out, size_t bytes);
 
