@@ -24,6 +24,8 @@
 // u % 2).  TMEM: accumulators of tile mt at columns 128 mt (+96 for conv2); `up` alternates [0,256) / [256,512).
 #pragma once
 
+#include <type_traits>
+
 #include "block17_fused.cuh"
 
 namespace fire {
@@ -105,12 +107,12 @@ block35_fused_kernel(const __grid_constant__ B35Params p) {
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < B35_SLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+      for (int s = 0; s < B35_SLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }       // a slot is released by two commits
       for (int t = 0; t < 3; ++t) {
         mbar_init(&accH_full[t], 1); mbar_init(&acc1_full[t], 1); mbar_init(&acc2_full[t], 1);
         mbar_init(&hready[t], CONV_EPI_WARPS); mbar_init(&b2ready[t], CONV_EPI_WARPS / 2); mbar_init(&aup_ready[t], CONV_EPI_WARPS);
       }
-      for (int b = 0; b < 2; ++b) { mbar_init(&accU_full[b], 1); mbar_init(&accU_empty[b], CONV_EPI_WARPS); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&accU_full[b], 2); mbar_init(&accU_empty[b], CONV_EPI_WARPS); }   // one arrival per N half
       mbar_init(y_done, CONV_EPI_WARPS);
       fence_barrier_init();
     }
@@ -159,50 +161,76 @@ block35_fused_kernel(const __grid_constant__ B35Params p) {
         }
       }
     }
-  } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
+  } else if (warp == 1 || warp == 11) {
+    // ---------------------------------------------------------------- MMA issuers (two warps)
+    // One thread issues a tcgen05.mma every ~110 cycles whatever its size and these GEMMs have N <= 128, so ONE issuer
+    // is the bottleneck of H / conv1 / conv2; issuers in different warps overlap (tools/umma_probe.cu part 6).  The
+    // three M tiles have independent accumulators: warp 1 owns tiles 0 and 2, warp 11 tile 1 (in `up`: the first / second
+    // N half of every tile).  Both walk the same unit
+    // sequence and BOTH wait for every fill, also of the units only the other warp reads: mbarrier waits are by phase
+    // PARITY, so a warp that skipped a fill of a slot could take the fill before it for the one it is waiting for (the
+    // ring wraps every six units; this was an intermittent wrong result), and BOTH commit once on every slot's `empty`
+    // barrier (count 2), so neither can fall a whole ring behind the producer either.  `mw`
+    // is a compile-time constant of each instantiation (predicates derived from threadIdx are not provably warp-uniform:
+    // ptxas would serialise every MMA).
+    auto mma_role = [&](auto mw_c) {
+    constexpr int mw = decltype(mw_c)::value;
     const uint32_t idesc96 = umma_idesc_f16(CONV_BM, 96), idesc64 = umma_idesc_f16(CONV_BM, 64), idesc32 = umma_idesc_f16(CONV_BM, 32),
                    idesc128 = umma_idesc_f16(CONV_BM, 128);
     int slot = 0, blk = 0;
     uint32_t ph = 0;
     auto next_slot = [&]() { if (++slot == B35_SLOTS) { slot = 0; ph ^= 1; } };
+    auto owns = [&](int idx) { return (idx & 1) == mw; };
+    // every warp commits exactly once on every unit's `empty` barrier: after its MMAs if it read the slot, at once otherwise
+    auto release_slot = [&]() {
+      if (elect_one()) umma_commit(&empty[slot]);
+      __syncwarp();
+    };
     for (int img = blockIdx.x; img < p.n_images; img += gridDim.x) {
       for (int j = 0; j < p.n_blocks; ++j, ++blk) {
         const uint32_t bpar = blk & 1;
         // ---- H: D[mt] (TMEM columns 128 mt .. +95) = x[mt] * Wh^T
         if (blk > 0) { mbar_wait(&accU_empty[0], 1, 63); mbar_wait(&accU_empty[1], (blk - 1) & 1, 64); }   // the previous `up` has left TMEM
         tc_fence_after();
-        B35_TRACE(0);
+        if (mw == 0) B35_TRACE(0);
         for (int kb = 0; kb < 4; ++kb) {
           mbar_wait(&full[slot], ph, 65);
           const int wslot = slot;
           next_slot();
-          for (int mt = 0; mt < 3; ++mt) {
-            mbar_wait(&full[slot], ph, 66);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t a0 = ring + static_cast<uint32_t>(slot) * B35_UNIT, b0 = ring + static_cast<uint32_t>(wslot) * B35_UNIT;
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16(tmem_base + static_cast<uint32_t>(mt * 128), umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc96, (kb | k) != 0 ? 1u : 0u);
-              umma_commit(&empty[slot]);
-              if (mt == 2) umma_commit(&empty[wslot]);
-              if (kb == 3) umma_commit(&accH_full[mt]);
+          for (int mt = 0; mt < 3; ++mt) {
+            mbar_wait(&full[slot], ph, 66);             // BOTH warps observe every fill in order (see above), the owner issues
+            if (owns(mt)) {
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t a0 = ring + static_cast<uint32_t>(slot) * B35_UNIT, b0 = ring + static_cast<uint32_t>(wslot) * B35_UNIT;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(tmem_base + static_cast<uint32_t>(mt * 128), umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc96, (kb | k) != 0 ? 1u : 0u);
+                umma_commit(&empty[slot]);
+                if (kb == 3) umma_commit(&accH_full[mt]);
+              }
+              __syncwarp();
+            } else {
+              if (elect_one()) umma_commit(&empty[slot]);
+              __syncwarp();
             }
-            __syncwarp();
             next_slot();
           }
+          if (elect_one()) umma_commit(&empty[wslot]);
+          __syncwarp();
         }
-        B35_TRACE(1);
+        if (mw == 0) B35_TRACE(1);
         // ---- conv1: nine taps, each a K = 64 MMA on P12 shifted by r * 18 + s rows
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(&full[slot], ph, 67);
           tc_fence_after();
           const int r = tap / 3, s = tap - 3 * r;
+#pragma unroll
           for (int mt = 0; mt < 3; ++mt) {
-            if (tap == 0) {                                     // tile mt reads P12 rows written by the H epilogues of tiles mt and mt + 1
-              if (mt == 0) mbar_wait(&hready[0], bpar, 68);
-              if (mt < 2) mbar_wait(&hready[mt + 1], bpar, 68);
+            if (!owns(mt)) continue;
+            if (tap == 0) {                                     // tile mt reads P12 rows q - 19 in [128 mt - 19, 128 mt + 147): all three H epilogues
+              for (int t = 0; t < 3; ++t) mbar_wait(&hready[t], bpar, 68);
               tc_fence_after();
               if (mt == 0) B35_TRACE(2);
             }
@@ -211,22 +239,23 @@ block35_fused_kernel(const __grid_constant__ B35Params p) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_f16(tmem_base + static_cast<uint32_t>(mt * 128), umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc64, (tap | k) != 0 ? 1u : 0u);
-              if (mt == 2) umma_commit(&empty[slot]);
               if (tap == 8) umma_commit(&acc1_full[mt]);
             }
             __syncwarp();
           }
+          release_slot();
           next_slot();
         }
-        B35_TRACE(3);
+        if (mw == 0) B35_TRACE(3);
         // ---- conv2: nine taps, K = 32, on channels 0-31 of P12 (now b2b); two weight units (taps 0-4, 5-8)
         for (int tap = 0; tap < 9; ++tap) {
           if (tap == 0 || tap == 5) { mbar_wait(&full[slot], ph, 69); tc_fence_after(); }
           const int r = tap / 3, s = tap - 3 * r, tl = tap < 5 ? tap : tap - 5;
+#pragma unroll
           for (int mt = 0; mt < 3; ++mt) {
+            if (!owns(mt)) continue;
             if (tap == 0) {
-              if (mt == 0) mbar_wait(&b2ready[0], bpar, 70);
-              if (mt < 2) mbar_wait(&b2ready[mt + 1], bpar, 70);
+              for (int t = 0; t < 3; ++t) mbar_wait(&b2ready[t], bpar, 70);
               tc_fence_after();
               if (mt == 0) B35_TRACE(4);
             }
@@ -236,50 +265,60 @@ block35_fused_kernel(const __grid_constant__ B35Params p) {
 #pragma unroll
               for (int k = 0; k < 2; ++k)
                 umma_f16(tmem_base + static_cast<uint32_t>(mt * 128 + 96), umma_desc_sw128(a0 + k * 32), umma_desc_swz(b0 + k * 32, 64), idesc32, (tap | k) != 0 ? 1u : 0u);
-              if (mt == 2 && (tap == 4 || tap == 8)) umma_commit(&empty[slot]);
               if (tap == 8) umma_commit(&acc2_full[mt]);
             }
             __syncwarp();
           }
-          if (tap == 4 || tap == 8) next_slot();
-        }
-        B35_TRACE(5);
-        // ---- up: per M tile D[128 x 256] = [AU0 | AU1] * Wu^T in two N halves
-        for (int t = 0; t < 3; ++t) mbar_wait(&aup_ready[t], bpar, 71);
-        tc_fence_after();
-        B35_TRACE(6);
-        for (int mt = 0; mt < 3; ++mt) {
-          if (mt == 2) { mbar_wait(&accU_empty[0], 0, 72); tc_fence_after(); }      // `up` of tile 0 has been read
-          const uint32_t d = tmem_base + static_cast<uint32_t>((mt & 1) * 256);
-          for (int nh = 0; nh < 2; ++nh) {
-            mbar_wait(&full[slot], ph, 73);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t a0 = au0 + static_cast<uint32_t>(mt) * 16384u, b0 = ring + static_cast<uint32_t>(slot) * B35_UNIT;
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16(d + static_cast<uint32_t>(nh * 128), umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc128, k != 0 ? 1u : 0u);
-              umma_commit(&empty[slot]);
-            }
-            __syncwarp();
-            next_slot();
-            mbar_wait(&full[slot], ph, 74);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t a0 = au1 + static_cast<uint32_t>(mt) * 8192u, b0 = ring + static_cast<uint32_t>(slot) * B35_UNIT;
-#pragma unroll
-              for (int k = 0; k < 2; ++k)
-                umma_f16(d + static_cast<uint32_t>(nh * 128), umma_desc_swz(a0 + k * 32, 64), umma_desc_swz(b0 + k * 32, 64), idesc128, 1u);
-              umma_commit(&empty[slot]);
-              if (nh == 1) umma_commit(&accU_full[mt & 1]);
-            }
-            __syncwarp();
+          if (tap == 4 || tap == 8) {
+            release_slot();
             next_slot();
           }
         }
-        B35_TRACE(7);
+        if (mw == 0) B35_TRACE(5);
+        // ---- up: per M tile D[128 x 256] = [AU0 | AU1] * Wu^T in two N halves
+        for (int t = 0; t < 3; ++t) mbar_wait(&aup_ready[t], bpar, 71);
+        tc_fence_after();
+        if (mw == 0) B35_TRACE(6);
+        for (int mt = 0; mt < 3; ++mt) {
+          if (mt == 2) { mbar_wait(&accU_empty[0], 0, 72); tc_fence_after(); }      // `up` of tile 0 has been read
+          const uint32_t d = tmem_base + static_cast<uint32_t>((mt & 1) * 256);
+#pragma unroll
+          for (int nh = 0; nh < 2; ++nh) {
+            mbar_wait(&full[slot], ph, 73);
+            if (owns(nh)) {
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t a0 = au0 + static_cast<uint32_t>(mt) * 16384u, b0 = ring + static_cast<uint32_t>(slot) * B35_UNIT;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(d + static_cast<uint32_t>(nh * 128), umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc128, k != 0 ? 1u : 0u);
+              }
+              __syncwarp();
+            }
+            release_slot();
+            next_slot();
+            mbar_wait(&full[slot], ph, 74);
+            if (owns(nh)) {
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t a0 = au1 + static_cast<uint32_t>(mt) * 8192u, b0 = ring + static_cast<uint32_t>(slot) * B35_UNIT;
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                  umma_f16(d + static_cast<uint32_t>(nh * 128), umma_desc_swz(a0 + k * 32, 64), umma_desc_swz(b0 + k * 32, 64), idesc128, 1u);
+                umma_commit(&accU_full[mt & 1]);                // one of two arrivals per tile (one per N half)
+              }
+              __syncwarp();
+            }
+            release_slot();
+            next_slot();
+          }
+        }
+        if (mw == 0) B35_TRACE(7);
       }
     }
+    };
+    if (warp == 1) mma_role(std::integral_constant<int, 0>{});
+    else mma_role(std::integral_constant<int, 1>{});
   } else if (warp >= CONV_FIRST_EPI_WARP && warp < CONV_FIRST_EPI_WARP + CONV_EPI_WARPS) {
     // ---------------------------------------------------------------- epilogue (8 warps: TMEM lane quarter x half)
     const int quarter = warp & 3, h = (warp - CONV_FIRST_EPI_WARP) >> 2;
@@ -342,7 +381,7 @@ block35_fused_kernel(const __grid_constant__ B35Params p) {
         }
         // ---- conv1: half 0 takes b1b (columns 0-31 -> AU0 channels 32-63) tile by tile; half 1 takes b2b (columns 32-63 ->
         // P12 channels 0-31, over b1a) once EVERY conv1 MMA has completed (they all read b1a)
-        if (h == 1) mbar_wait(&acc1_full[2], bpar, 76);
+        if (h == 1) { for (int t = 0; t < 3; ++t) mbar_wait(&acc1_full[t], bpar, 76); }     // each commit only covers its own warp's MMAs
         for (int mt = 0; mt < 3; ++mt) {
           const int m = mt * 128 + r;
           const int y = (m * 3641) >> 16, x = m - y * B35_P;                           // m / 18
