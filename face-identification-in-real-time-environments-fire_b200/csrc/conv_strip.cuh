@@ -64,13 +64,19 @@ struct StripParams {
                           // issues a tcgen05.mma every ~110 cycles whatever its size; issuers in different warps overlap
                           // (tools/umma_probe.cu part 6: N <= 64, 4 accumulators: 120 / 77 cycles per MMA with 1 / 2 threads).
                           // Measured: Conv2d_2a 100 -> 77 us, Conv2d_2b 112 -> 92 us with two; four warps were slower (118 / 121 us)
+  int pair;               // 1: CTA pair (cluster of 2, tcgen05 cta_group::2): the pair takes the same position block of two
+                          // consecutive images; ONE M = 256 tcgen05.mma of the leader covers both tiles, each CTA holds half of the
+                          // weight rows.  A tcgen05.mma costs its issuing thread ~110 cycles whatever its size (probe part 7)
   int n_acc;              // TMEM accumulators (power of two, <= STRIP_MAX_ACC); the MMA warp interleaves n_acc / 2 tiles
   long long* trace;
   FastDiv d_rowblocks, d_wbox;
 };
 
+// kPair: CTA-pair instantiation (must be launched as clusters of 2: it contains cta_group::2 instructions, and a kernel that
+// does cannot be launched without a cluster - "cluster misconfiguration")
+template <bool kPair>
 __global__ void __launch_bounds__(STRIP_THREADS, 1)
-conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
+conv_strip_kernel_t(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
                   const __grid_constant__ CUtensorMap tmap_out, const StripParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -85,10 +91,18 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   uint64_t* out_full = acc_empty + STRIP_MAX_ACC;     // [2] staging buffer written by the epilogue warps
   uint64_t* out_empty = out_full + 2;                 // [2] staging buffer read by the TMA store
   uint64_t* w_full = out_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  uint64_t* peer_full = w_full + 1;                   // [stages] pair mode, leader: the peer CTA's patch of this stage has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_full + p.stages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b_kb_bytes = p.cout * 128;
+  constexpr bool pair = kPair;
+  const uint32_t rank = pair ? cluster_ctarank() : 0u;              // 0 = leader (issues the MMAs of the pair)
+  const int t_first = pair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int t_step = pair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  // tile t = (image or image pair q, position block tin); this CTA's image:
+  auto tile_image = [&](int q) { return pair ? 2 * q + static_cast<int>(rank) : q; };
+  const int b_rows = pair ? p.cout / 2 : p.cout;                    // weight rows held by this CTA
+  const int b_kb_bytes = b_rows * 128;
   const int in_row_bytes = p.cin * 2;
   if (threadIdx.x == 0) CONV_TRACE(0);
 
@@ -101,24 +115,31 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
       // one arrival per epilogue WARP (256 per-thread arrivals on one barrier word serialise: ~250 cycles per barrier)
-      for (int b = 0; b < STRIP_MAX_ACC; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], CONV_EPI_WARPS / 2); }
+      for (int b = 0; b < STRIP_MAX_ACC; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], pair ? CONV_EPI_WARPS : CONV_EPI_WARPS / 2); }
+      for (int s = 0; s < p.stages; ++s) mbar_init(&peer_full[s], 1);
       for (int b = 0; b < 2; ++b) { mbar_init(&out_full[b], CONV_EPI_WARPS / 2); mbar_init(&out_empty[b], 1); }
       mbar_init(w_full, 1);
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc_rt(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+    if (!pair) tmem_alloc_rt(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
   }
   if (warp >= CONV_FIRST_EPI_WARP && warp < CONV_FIRST_EPI_WARP + CONV_EPI_WARPS) {
     const int t = threadIdx.x - CONV_FIRST_EPI_WARP * 32;                 // 0..255
     uint4* s_bias = reinterpret_cast<uint4*>(smem + L.bias);
-    for (int i = t; i < p.cout; i += CONV_EPI_WARPS * 32) s_bias[i] = __ldg(p.bias16 + i);
+    for (int i = t; i < b_rows; i += CONV_EPI_WARPS * 32) s_bias[i] = __ldg(p.bias16 + rank * b_rows + i);
     if (t < CONV_BM) reinterpret_cast<uint4*>(smem + L.ones)[t] = make_uint4(0x3C003C00u, 0u, 0u, 0u);
     reinterpret_cast<uint4*>(smem + L.zero)[t] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
   }
+  if (pair) {                                       // barriers of both CTAs are initialised before anything remote touches them
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) tmem_alloc2_rt(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+  }
   tc_fence_before();
   __syncthreads();
+  if (pair) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) CONV_TRACE(1);
@@ -130,15 +151,15 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       if (elect_one()) {
         mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(p.nkb * b_kb_bytes));
         for (int kb = 0; kb < p.nkb; ++kb)
-          tma_load_2d_hint(sB + static_cast<size_t>(kb) * b_kb_bytes, &tmap_w, w_full, kb * 64, 0, kEvictLast);
+          tma_load_2d_hint(sB + static_cast<size_t>(kb) * b_kb_bytes, &tmap_w, w_full, kb * 64, static_cast<int>(rank) * b_rows, kEvictLast);
       }
       __syncwarp();
       if (p.pdl) pdl_wait();                                    // activations come from the previous layer
       const uint32_t box_bytes = static_cast<uint32_t>(in_row_bytes * p.Wbox * p.Hbox);
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n = fdiv(tile, p.d_rowblocks), tin = tile - n * p.row_blocks;
+      for (int tile = t_first; tile < p.total_tiles; tile += t_step) {
+        const int q = fdiv(tile, p.d_rowblocks), tin = tile - q * p.row_blocks, n = tile_image(q);
         const int y0 = p.flat ? fdiv(tin * CONV_BM, p.d_wbox) : tin * p.R;      // first output row of the tile
         mbar_wait(&a_empty[s], ph ^ 1, 21);
         if (elect_one()) {
@@ -146,7 +167,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           tma_load_4d(sA + static_cast<size_t>(s) * p.a_stage_bytes, &tmap_a, &a_full[s], 0, -p.pad_w, y0 - p.pad_h, n);
         }
         __syncwarp();
-        if (lane == 0 && tile == static_cast<int>(blockIdx.x)) CONV_TRACE(2);
+        if (lane == 0 && tile == t_first) CONV_TRACE(2);
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
     }
@@ -160,7 +181,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     // issues: a divergent `if (lane == 0)` body makes ptxas wrap every tcgen05.mma in an ELECT + 7 x R2UR +
     // BRA.U.ANY serialisation loop, which costs ~100-200 cycles per MMA (tools/umma_probe.cu part 5/6).
     {
-      const uint32_t idesc = umma_idesc_f16(CONV_BM, p.cout);
+      const uint32_t idesc = umma_idesc_f16(pair ? 2 * CONV_BM : CONV_BM, p.cout);
       const uint32_t ones_addr = smem_u32(smem + L.ones), zero_addr = smem_u32(smem + L.zero), bias_addr = smem_u32(smem + L.bias);
       const uint64_t ones_desc = umma_desc_nosw(ones_addr, zero_addr - ones_addr, 128);
       const uint64_t bias_desc = umma_desc_nosw(bias_addr, zero_addr - bias_addr, 128);
@@ -173,7 +194,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       // (tools/umma_probe.cu part 5/6), so G = n_acc / 2 tiles are accumulated side by side: the K loop is the outer
       // loop and the G independent accumulators the inner one.
       const int G = p.n_acc >> 1;
-      const int my_tiles = static_cast<int>(blockIdx.x) < p.total_tiles ? (p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
+      const int my_tiles = t_first < p.total_tiles ? (p.total_tiles - t_first + t_step - 1) / t_step : 0;
       int s = 0;
       uint32_t ph = 0;
       long long tm[3] = {0, 0, 0};
@@ -181,6 +202,22 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       for (int lt0 = 0; lt0 < my_tiles; lt0 += G) {
         const int cnt = min(G, my_tiles - lt0);
         long long c0 = prof ? clock64() : 0, c1;
+        if (rank != 0) {
+          // peer CTA of a pair: no MMAs here; tell the leader when this CTA's patches have landed
+          int si = s;
+          uint32_t phi = ph;
+          for (int i = 0; i < cnt; ++i) {
+            if (i % n_mw == mw) {
+              mbar_wait(&a_full[si], phi, 24);
+              if (lane == 0) mbar_arrive_remote_relaxed(&peer_full[si], 0u);
+              __syncwarp();
+            }
+            if (++si == p.stages) { si = 0; phi ^= 1; }
+          }
+          for (int i = 0; i < cnt; ++i)
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+          continue;
+        }
         for (int i = mw; i < cnt; i += n_mw) {                  // this warp's tiles of the group: i = mw (mod n_mw)
           const int l = lt0 + i;
           mbar_wait(&acc_empty[l & (p.n_acc - 1)], (static_cast<uint32_t>(l / p.n_acc) & 1u) ^ 1u, 23);
@@ -188,14 +225,19 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         tc_fence_after();
         if (prof) { c1 = clock64(); tm[0] += c1 - c0; c0 = c1; }
         if (elect_one()) {
-          for (int i = mw; i < cnt; i += n_mw)
-            umma_f16(tmem_base + static_cast<uint32_t>(((lt0 + i) & (p.n_acc - 1)) * p.cout), ones_desc, bias_desc, idesc, 0u);   // D = ones * bias^T
+          for (int i = mw; i < cnt; i += n_mw) {                // D = ones * bias^T
+            const uint32_t dacc = tmem_base + static_cast<uint32_t>(((lt0 + i) & (p.n_acc - 1)) * p.cout);
+            if (pair) umma_f16_2cta(dacc, ones_desc, bias_desc, idesc, 0u); else umma_f16(dacc, ones_desc, bias_desc, idesc, 0u);
+          }
         }
         {
           int si = s;
           uint32_t phi = ph;
           for (int i = 0; i < cnt; ++i) {
-            if (i % n_mw == mw) mbar_wait(&a_full[si], phi, 24);
+            if (i % n_mw == mw) {
+              mbar_wait(&a_full[si], phi, 24);
+              if (pair) mbar_wait(&peer_full[si], phi, 28);
+            }
             if (++si == p.stages) { si = 0; phi ^= 1; }
           }
         }
@@ -209,7 +251,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             int si = s;
 #pragma unroll
             for (int i = 0; i < STRIP_MAX_ACC / 2; ++i) {
-              const int tile_i = static_cast<int>(blockIdx.x) + (lt0 + i) * static_cast<int>(gridDim.x);
+              const int tile_i = t_first + (lt0 + i) * t_step;
               const int tin = tile_i - fdiv(tile_i, p.d_rowblocks) * p.row_blocks;
               const int f0 = tin * CONV_BM;
               // flat mode: the tile starts (f0 mod Wbox) rows into its patch
@@ -227,7 +269,8 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             for (int i = 0; i < STRIP_MAX_ACC / 2; ++i) {
               if (i < cnt && i % n_mw == mw) {
                 const uint32_t a_addr = tile_base[i] + tap_off + static_cast<uint32_t>(c0 * 2);
-                umma_f16(tile_acc[i], a_desc_hi | static_cast<uint64_t>((a_addr & 0x3FFFF) >> 4), bdesc, idesc, 1u);
+                if (pair) umma_f16_2cta(tile_acc[i], a_desc_hi | static_cast<uint64_t>((a_addr & 0x3FFFF) >> 4), bdesc, idesc, 1u);
+                else umma_f16(tile_acc[i], a_desc_hi | static_cast<uint64_t>((a_addr & 0x3FFFF) >> 4), bdesc, idesc, 1u);
               }
             }
             c0 += 16;
@@ -241,8 +284,8 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           int si = s;
           for (int i = 0; i < cnt; ++i) {
             if (i % n_mw == mw) {
-              umma_commit(&a_empty[si]);
-              umma_commit(&acc_full[(lt0 + i) & (p.n_acc - 1)]);
+              if (pair) { umma_commit_2cta(&a_empty[si]); umma_commit_2cta(&acc_full[(lt0 + i) & (p.n_acc - 1)]); }   // both CTAs
+              else { umma_commit(&a_empty[si]); umma_commit(&acc_full[(lt0 + i) & (p.n_acc - 1)]); }
             }
             if (++si == p.stages) si = 0;
           }
@@ -281,7 +324,7 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     long long te[3] = {0, 0, 0};
     const bool prof = p.trace != nullptr && (p.flags & CF_DBG_PHASES) && threadIdx.x == CONV_FIRST_EPI_WARP * 32;     // group 0's tiles only
     int lt = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+    for (int tile = t_first; tile < p.total_tiles; tile += t_step, ++lt) {
       if ((lt & 1) != group) continue;
       const int buf = lt & (p.n_acc - 1), ob = lt & 1;
       const uint32_t stage = stage0 + static_cast<uint32_t>(ob) * stage_buf_bytes;
@@ -307,7 +350,10 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       tc_fence_before();
       fence_proxy_async_smem();                                 // staging writes -> visible to the TMA (async proxy)
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&acc_empty[buf]); mbar_arrive(&out_full[ob]); }
+      if (lane == 0) {
+        mbar_arrive(&out_full[ob]);
+        if (rank != 0) mbar_arrive_remote_relaxed(&acc_empty[buf], 0u); else mbar_arrive(&acc_empty[buf]);     // the leader's MMA warps own the accumulators
+      }
       if (prof) { c1 = clock64(); te[2] += c1 - c0; }
     }
     if (prof) {
@@ -322,9 +368,9 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const uint32_t stage0 = smem_u32(smem + L.out);
     if (p.pdl) pdl_wait();                                      // output writes must not overtake readers of the previous layers
     int lt = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+    for (int tile = t_first; tile < p.total_tiles; tile += t_step, ++lt) {
       const int ob = lt & 1;
-      const int n = fdiv(tile, p.d_rowblocks), tin = tile - n * p.row_blocks;
+      const int q = fdiv(tile, p.d_rowblocks), tin = tile - q * p.row_blocks, n = tile_image(q);
       mbar_wait(&out_full[ob], (lt >> 1) & 1, 27);
       if (elect_one()) {
         if (!(p.flags & CF_DBG_NOSTORE)) {
@@ -346,9 +392,10 @@ conv_strip_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (pair) cluster_sync_all();                     // the peer's accumulators and barriers are still in use until both are done
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc_rt(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+    if (pair) tmem_dealloc2_rt(tmem_base, static_cast<uint32_t>(p.tmem_cols)); else tmem_dealloc_rt(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
   if (threadIdx.x == 0) CONV_TRACE(7);
 }

@@ -147,6 +147,7 @@ struct OpRt {
   int n_res = 0, box_cols = 64;
   bool strip = false;     // stride-1 k x k layer run by conv_strip_kernel (halo patch + shifted descriptors)
   int Wbox = 0, R = 0, Hbox = 0, row_blocks = 0, a_stage_bytes = 0, n_acc = 2;
+  bool pair = false;      // strip conv run by CTA pairs (cta_group::2): weight map box = cout / 2 rows
   bool flat = false;      // strip conv with flat 128-position tiles (the destination buffer is pitched to Wbox)
   size_t bias16_off = 0;  // byte offset of this op's [cout] x {hi, lo, 0 x 6} fp16 bias rows in d_bias16
   size_t smem = 0;
@@ -218,6 +219,7 @@ struct fire_net {
   int max_stages = 8;
   int n_issuers = CONV_MAX_ISSUERS;   // TMA issuing threads per CTA in 1x1 layers (FIRE_B200_ISSUERS=1|2|4)
   int strip_mma_warps = STRIP_MMA_WARPS;   // FIRE_B200_STRIP_MMAW=1|2|4: MMA issuing warps of conv_strip_kernel
+  bool strip_pair = false;  // FIRE_B200_STRIP_PAIR=1: CTA pairs (cta_group::2) in conv_strip_kernel - correct, but measured slower
   bool use_strip = true;    // FIRE_B200_STRIP=0 forces the gather path for every k x k layer (A/B experiments)
   bool trace_all = false;   // FIRE_B200_TRACE_ALL=1: forward() records every conv's timeline, synchronises and prints it
   long long* d_trace = nullptr; int trace_op = -1;   // FIRE_B200_TRACE_OP=<op index>: in-kernel timeline of that op (profile only)
@@ -501,7 +503,8 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
   static bool attr_done = false;
   if (!attr_done) {
     e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_strip_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_strip_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       cudaFree(net->d_weights);
       delete net;
@@ -553,6 +556,7 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
     if (e[0] == '0') for (OpRt& r : net->ops) r.im2col = false;      // A/B experiments and the parity test: cp.async gather instead
   }
   if (const char* e = getenv("FIRE_B200_STRIP_MMAW")) net->strip_mma_warps = atoi(e) >= 2 ? 2 : 1;
+  if (const char* e = getenv("FIRE_B200_STRIP_PAIR")) net->strip_pair = e[0] == '1';
   const char* sp_env = getenv("FIRE_B200_STRIP");
   net->use_strip = !(sp_env && sp_env[0] == '0');
   const char* ta_env = getenv("FIRE_B200_TRACE_ALL");
@@ -623,7 +627,9 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
       q.bias16 = reinterpret_cast<const uint4*>(net->d_bias16 + r.bias16_off);
       q.cin = o.cin; q.cout = o.cout; q.kh = o.kh; q.kw = o.kw; q.pad_h = o.pad_h; q.pad_w = o.pad_w;
       q.k16_steps = o.kh * o.kw * o.cin / 16; q.nkb = o.k_pad / 64;
-      q.Wbox = r.Wbox; q.R = r.R; q.Hbox = r.Hbox; q.row_blocks = r.row_blocks; q.total_tiles = B * r.row_blocks;
+      q.Wbox = r.Wbox; q.R = r.R; q.Hbox = r.Hbox; q.row_blocks = r.row_blocks;
+      q.pair = r.pair ? 1 : 0;
+      q.total_tiles = (r.pair ? (B + 1) / 2 : B) * r.row_blocks;          // pair mode: one scheduling unit = the same position block of two images
       q.flat = r.flat ? 1 : 0; q.Ho = o.Ho; q.d_wbox = make_fastdiv(r.Wbox);
       q.a_stage_bytes = r.a_stage_bytes; q.stages = r.stages; q.tmem_cols = r.tmem_cols; q.flags = o.flags | net->dbg_flags;
       if (net->d_trace && !net->trace_all) q.flags |= CF_DBG_PHASES;
@@ -634,16 +640,27 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
                 : (&r == &net->ops[net->trace_op] ? net->d_trace : nullptr);
       q.d_rowblocks = make_fastdiv(r.row_blocks);
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3((unsigned)std::min<long long>((long long)B * r.row_blocks, device_sm_count()));
+      cfg.gridDim = r.pair ? dim3((unsigned)std::min<long long>(2LL * q.total_tiles, device_sm_count() & ~1))
+                           : dim3((unsigned)std::min<long long>((long long)B * r.row_blocks, device_sm_count()));
       cfg.blockDim = dim3(STRIP_THREADS);
       cfg.dynamicSmemBytes = r.smem;
       cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cudaLaunchAttribute attr[2];
+      int na = 0;
+      if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+      }
+      if (r.pair) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+      }
       cfg.attrs = attr;
-      cfg.numAttrs = pdl ? 1 : 0;
-      FIRE_CUDA(cudaLaunchKernelEx(&cfg, conv_strip_kernel, r.tmap_w, r.tmap_a, r.tmap_out, q));
+      cfg.numAttrs = na;
+      if (r.pair) FIRE_CUDA(cudaLaunchKernelEx(&cfg, conv_strip_kernel_t<true>, r.tmap_w, r.tmap_a, r.tmap_out, q));
+      else FIRE_CUDA(cudaLaunchKernelEx(&cfg, conv_strip_kernel_t<false>, r.tmap_w, r.tmap_a, r.tmap_out, q));
       count_launch();
       return FIRE_OK;
     }
@@ -740,8 +757,10 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
           }
           r.a_stage_bytes = (rows_alloc * o.cin * 2 + 1023) / 1024 * 1024;
           r.bn_tile = 0;                       // force a fresh weight map below
+          // CTA pairs for the issue-bound layers (>= 8 K steps per tile, two accumulators per warp): cout / 2 weight rows per CTA
+          r.pair = net->strip_pair && r.flat && B >= 2 && o.cout % 32 == 0 && o.kh * o.kw * o.cin / 16 >= 8 && (sms & ~1) >= 2;
           int rc = make_tmap_f16_2d(&r.tmap_w, net->d_weights + o.w_off, (uint64_t)o.cout, (uint64_t)o.k_pad, (uint64_t)o.k_pad * 2,
-                                    (uint32_t)o.cout);
+                                    (uint32_t)(r.pair ? o.cout / 2 : o.cout));
           if (rc != FIRE_OK) return rc;
           r.box_cols = o.cout % 64 == 0 ? 64 : (o.cout % 32 == 0 ? 32 : 16);
           const size_t fixed = strip_smem_layout(0, r.a_stage_bytes, o.k_pad / 64, o.cout).total + 1024;

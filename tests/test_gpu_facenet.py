@@ -211,6 +211,24 @@ def test_im2col_tma_operand_is_bit_identical_to_gather(fire_lib, monkeypatch, B)
     assert torch.equal(ra, rb)
 
 
+@pytest.mark.parametrize("B", [2, 9, 150])
+def test_strip_kernel_cta_pairs_are_bit_identical(fire_lib, monkeypatch, B):
+    """conv_strip_kernel_t<true> (FIRE_B200_STRIP_PAIR=1): clusters of two CTAs take the same position block of two
+    consecutive images; ONE M = 256 tcgen05.mma.cta_group::2 of the leader covers both tiles, each CTA holds half of the
+    weight rows, completions are multicast to both CTAs and the peer reports through remote mbarrier arrives.  Same
+    products in the same order per output row: bit-identical (odd B: the last image's partner is a zero-filled phantom)."""
+    import torch
+    from fire_b200 import engine, weights as W
+    t = W.synthetic_weights(128, 12)
+    x = torch.from_numpy(_images(B, 37).astype(np.float32) / 255.0).cuda()
+    a = engine.FaceNetEngine(128, t)
+    ra, _ = a.encode_unit_f32(x)
+    monkeypatch.setenv("FIRE_B200_STRIP_PAIR", "1")
+    b = engine.FaceNetEngine(128, t)
+    rb, _ = b.encode_unit_f32(x)
+    assert torch.equal(ra, rb)
+
+
 def test_crop_encode_pipeline_equals_direct_path(nets):
     """The streaming public call (pinned host crops -> H2D -> K1 -> K2 -> D2H, double-buffered) returns exactly what
     the step-by-step path returns, for every in-flight batch."""
