@@ -68,11 +68,11 @@ __device__ __forceinline__ int fdiv(int x, FastDiv f) {
 struct ConvSmem {
   uint32_t a, b, bias, ones, zero, ident, out, bars, total;
 };
-__host__ __device__ inline ConvSmem conv_smem_layout(int stages, int bn, int cout, int n_res) {
+__host__ __device__ inline ConvSmem conv_smem_layout(int stages, int bn, int cout, int n_res, bool pair = false) {
   ConvSmem L;
   uint32_t o = 0;
   L.a = o;     o += static_cast<uint32_t>(stages) * CONV_A_STAGE_BYTES;
-  L.b = o;     o += static_cast<uint32_t>(stages) * bn * 128;
+  L.b = o;     o += static_cast<uint32_t>(stages) * (pair ? bn / 2 : bn) * 128;     // a CTA of a pair holds half of the weight rows
   L.bias = o;  o += static_cast<uint32_t>(cout) * 16;       // [cout] x {hi, lo, 0 x 6} fp16: K-chunk 0 of the bias operand
   L.ones = o;  o += CONV_BM * 16;                           // [128] x {1, 1, 0 x 6}: K-chunk 0 of the ones operand
   L.zero = o;  o += 256 * 16;                               // K-chunk 1 of both (all zero)
@@ -146,14 +146,24 @@ __device__ __forceinline__ void conv_stage_chunk(const uint32_t (&r)[16], bool r
   sts128(row_addr + (((u0 + 1) ^ swz) << 4), hi);
 }
 
+// kPair: CTA-pair instantiation (clusters of two, tcgen05 cta_group::2; TMA-fed layers without residual): the pair computes
+// M = 256 x bn per MMA, each CTA loads its own A tile and HALF of the weight rows, so per MMA every SM fills and reads 16 KB
+// of shared memory instead of 24 KB - the 1-CTA ceiling of DESIGN 5.7.  Only the leader (rank 0) issues MMAs; completions
+// are multicast to both CTAs; the peer reports operand arrival and accumulator release with remote mbarrier arrives.
+template <bool kPair>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
+conv_igemm_kernel_t(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
                   const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out,
                   const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const ConvSmem L = conv_smem_layout(p.stages, p.bn_tile, p.cout, p.n_res);
-  const int b_stage_bytes = p.bn_tile * 128;
+  constexpr bool pair = kPair;
+  const uint32_t rank = pair ? cluster_ctarank() : 0u;
+  const int t_first = pair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int t_step = pair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int b_rows = pair ? p.bn_tile / 2 : p.bn_tile;
+  const ConvSmem L = conv_smem_layout(p.stages, p.bn_tile, p.cout, p.n_res, pair);
+  const int b_stage_bytes = b_rows * 128;
   uint8_t* sA = smem + L.a;
   uint8_t* sB = smem + L.b;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
@@ -164,10 +174,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   uint64_t* bias_ready = acc_empty + 2;       // the bias operand has landed in shared memory (filled after the setup barrier)
   uint64_t* out_full = bias_ready + 1;        // [2] staging buffer written by the epilogue warps
   uint64_t* out_empty = out_full + 2;         // [2] staging buffer read by the TMA store
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_empty + 2);
+  uint64_t* peer_full = out_empty + 2;        // [stages] pair mode, leader: the peer CTA's operands of this stage have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_full + (pair ? p.stages : 0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = (pair ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;     // scheduling units: (pair of) M tile(s) x N tile
+  // M tile of this CTA inside unit `tile`
+  auto unit_mt = [&](int tile) { const int q = fdiv(tile, p.d_ntiles); return pair ? 2 * q + static_cast<int>(rank) : q; };
   const int nk_total = p.nkb + p.n_res;
   const bool out_f32 = p.flags & CF_OUT_F32;
   if (threadIdx.x == 0) CONV_TRACE(0);
@@ -183,13 +196,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       const uint32_t full_count = p.tma_a ? 1u : 1u + CONV_HELPER_THREADS;
       for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], full_count); mbar_init(&empty[s], 1); }
       // one arrival per epilogue WARP (256 per-thread arrivals on one barrier word serialise: ~250 cycles per barrier)
-      for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], CONV_EPI_WARPS); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], pair ? 2 * CONV_EPI_WARPS : CONV_EPI_WARPS); }
+      if (pair) for (int s = 0; s < p.stages; ++s) mbar_init(&peer_full[s], 1);
       mbar_init(bias_ready, CONV_EPI_WARPS);
       for (int b = 0; b < 2; ++b) { mbar_init(&out_full[b], CONV_EPI_WARPS); mbar_init(&out_empty[b], 1); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc_rt(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+    if (!pair) tmem_alloc_rt(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
   }
   if (warp >= CONV_FIRST_EPI_WARP && warp < CONV_STORE_WARP) {
     // constant MMA operands (weights-side data: safe to read before the dependency wait)
@@ -206,8 +220,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     }
     fence_proxy_async_smem();
   }
+  if (pair) {                                       // barriers of both CTAs exist before anything remote touches them
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) tmem_alloc2_rt(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+  }
   tc_fence_before();
   __syncthreads();
+  if (pair) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) CONV_TRACE(1);
@@ -229,9 +249,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         if (pass == 1 && p.pdl && p.tma_a) pdl_wait();          // activations / residual come from the previous layer
         int s = 0, turn = 0, g = 0;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-          const int mt = fdiv(tile, p.d_ntiles);
-          const int n0 = (tile - mt * p.n_tiles) * p.bn_tile, m0 = mt * CONV_BM;
+        for (int tile = t_first; tile < total_tiles; tile += t_step) {
+          const int n0 = (tile - fdiv(tile, p.d_ntiles) * p.n_tiles) * p.bn_tile, m0 = unit_mt(tile) * CONV_BM;
           int bw = 0, bh = 0, bn_img = 0;                          // im2col: input-space base pixel of the tile's first output pixel
           if (p.tma_a == 2) {
             bn_img = fdiv(m0, p.d_howo);
@@ -248,7 +267,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                 if (kb < p.nkb) {
                   if (!pre || pass == 0) {
                     mbar_arrive_expect_tx(&full[s], tx);
-                    tma_load_2d_hint(sB + static_cast<size_t>(s) * b_stage_bytes, &tmap_w, &full[s], kb * 64, n0, kEvictLast);
+                    tma_load_2d_hint(sB + static_cast<size_t>(s) * b_stage_bytes, &tmap_w, &full[s], kb * 64, n0 + static_cast<int>(rank) * b_rows, kEvictLast);
                   }
                   if (p.tma_a == 1 && pass == 1) tma_load_2d(sA + static_cast<size_t>(s) * CONV_A_STAGE_BYTES, &tmap_a, &full[s], kb * 64, m0);
                   if (p.tma_a == 2 && pass == 1) {               // k x k layer, cin % 64 == 0: K-block kb = (tap, 64-channel slice)
@@ -274,8 +293,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer (whole warp loops, one elected lane issues)
-    {
-      const uint32_t idesc = umma_idesc_f16(CONV_BM, p.bn_tile);
+    if (rank == 0) {                                   // the peer CTA of a pair issues nothing: the leader's MMAs cover both
+      const uint32_t idesc = umma_idesc_f16(pair ? 2 * CONV_BM : CONV_BM, p.bn_tile);
       const uint32_t idesc64 = umma_idesc_f16(CONV_BM, 64);
       const uint32_t ones_addr = smem_u32(smem + L.ones), zero_addr = smem_u32(smem + L.zero);
       const uint32_t bias_addr = smem_u32(smem + L.bias), ident_addr = smem_u32(smem + L.ident);
@@ -286,10 +305,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       uint32_t ph = 0;
       long long tw[3] = {0, 0, 0};                               // cycles: waiting for a free accumulator / for operands / issuing
       const bool prof = p.trace != nullptr && (p.flags & CF_DBG_PHASES);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      for (int tile = t_first; tile < total_tiles; tile += t_step, ++lt) {
         const int buf = lt & 1;
-        const int mt = fdiv(tile, p.d_ntiles);
-        const int n0 = (tile - mt * p.n_tiles) * p.bn_tile;
+        const int n0 = (tile - fdiv(tile, p.d_ntiles) * p.n_tiles) * p.bn_tile;
         long long c0 = prof ? clock64() : 0, c1;
         mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1, 15);
         tc_fence_after();
@@ -298,6 +316,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         for (int kb = 0; kb < p.nkb; ++kb) {
           if (prof) c0 = clock64();
           mbar_wait(&full[s], ph, 12);
+          if (pair) mbar_wait(&peer_full[s], ph, 20);
           tc_fence_after();
           if (prof) { c1 = clock64(); tw[1] += c1 - c0; c0 = c1; }
           if (lt == 0 && kb == 0 && lane == 0) CONV_TRACE(3);
@@ -306,9 +325,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             const uint32_t b0 = b_base + static_cast<uint32_t>(s * b_stage_bytes);
             if (do_mma) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+                if (pair) umma_f16_2cta(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+                else umma_f16(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+              }
             }
-            umma_commit(&empty[s]);
+            if (pair) umma_commit_2cta(&empty[s]); else umma_commit(&empty[s]);
           }
           __syncwarp();
           if (prof) { c1 = clock64(); tw[2] += c1 - c0; }
@@ -333,9 +355,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         }
         if (lt == 0) mbar_wait(bias_ready, 0, 19);
         if (elect_one()) {                                      // D += ones * bias^T, then publish the accumulator
-          const uint32_t b_addr = bias_addr + static_cast<uint32_t>(n0) * 16;
-          umma_f16(d, ones_desc, umma_desc_nosw(b_addr, zero_addr - b_addr, 128), idesc, 1u);
-          umma_commit(&acc_full[buf]);
+          const uint32_t b_addr = bias_addr + static_cast<uint32_t>(n0) * 16;     // pair: each CTA keeps ITS half of the tile's rows here
+          if (pair) {
+            umma_f16_2cta(d, ones_desc, umma_desc_nosw(b_addr, zero_addr - b_addr, 128), idesc, 1u);
+            umma_commit_2cta(&acc_full[buf]);
+          } else {
+            umma_f16(d, ones_desc, umma_desc_nosw(b_addr, zero_addr - b_addr, 128), idesc, 1u);
+            umma_commit(&acc_full[buf]);
+          }
         }
         __syncwarp();
       }
@@ -361,17 +388,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       // bias operand (a weight: no dependency wait needed); only needed by the LAST MMA of the first tile, so it is
       // fetched here, off the critical path of the prologue
       uint4* s_bias = reinterpret_cast<uint4*>(smem + L.bias);
-      for (int i = threadIdx.x - CONV_FIRST_EPI_WARP * 32; i < p.cout; i += CONV_EPI_WARPS * 32) s_bias[i] = __ldg(p.bias16 + i);
+      for (int i = threadIdx.x - CONV_FIRST_EPI_WARP * 32; i < p.cout; i += CONV_EPI_WARPS * 32) {
+        // pair: the MMA descriptor addresses row j of an N tile at the same offset in both CTAs; the peer keeps rows bn/2.. there
+        const int j = i % p.bn_tile, src = pair ? i - j + (j + static_cast<int>(rank) * b_rows) % p.bn_tile : i;
+        s_bias[i] = __ldg(p.bias16 + src);
+      }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bias_ready);
     }
     if (p.pdl && out_f32) pdl_wait();                           // output writes must not overtake readers of the previous layers
     int lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    for (int tile = t_first; tile < total_tiles; tile += t_step, ++lt) {
       const int buf = lt & 1;
-      const int mt = fdiv(tile, p.d_ntiles);
-      const int n0 = (tile - mt * p.n_tiles) * p.bn_tile, m0 = mt * CONV_BM;
+      const int n0 = (tile - fdiv(tile, p.d_ntiles) * p.n_tiles) * p.bn_tile, m0 = unit_mt(tile) * CONV_BM;
       mbar_wait(&acc_full[buf], (lt >> 1) & 1, 14);
       tc_fence_after();
       if (lt == 0 && threadIdx.x == CONV_FIRST_EPI_WARP * 32) CONV_TRACE(5);
@@ -397,7 +427,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if (lane == 0) { if (rank != 0) mbar_arrive_remote_relaxed(&acc_empty[buf], 0u); else mbar_arrive(&acc_empty[buf]); }
         continue;
       }
       for (int cg = 0; cg < p.bn_tile; cg += CONV_PASS_COLS, ++pc) {
@@ -432,7 +462,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         fence_proxy_async_smem();                               // staging writes -> visible to the TMA (async proxy)
         __syncwarp();
         if (lane == 0) {
-          if (cg + CONV_PASS_COLS >= p.bn_tile) mbar_arrive(&acc_empty[buf]);   // accumulator fully read: hand it back
+          if (cg + CONV_PASS_COLS >= p.bn_tile) {             // accumulator fully read: hand it back (to the leader's MMA warp)
+            if (rank != 0) mbar_arrive_remote_relaxed(&acc_empty[buf], 0u); else mbar_arrive(&acc_empty[buf]);
+          }
           mbar_arrive(&out_full[ob]);
         }
       }
@@ -448,9 +480,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       const bool do_store = !(p.flags & CF_DBG_NOSTORE);
       if (p.pdl) pdl_wait();                                    // output writes must not overtake readers of the previous layers
       int pc = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = fdiv(tile, p.d_ntiles);
-        const int n0 = (tile - mt * p.n_tiles) * p.bn_tile, m0 = mt * CONV_BM;
+      for (int tile = t_first; tile < total_tiles; tile += t_step) {
+        const int n0 = (tile - fdiv(tile, p.d_ntiles) * p.n_tiles) * p.bn_tile, m0 = unit_mt(tile) * CONV_BM;
         for (int cg = 0; cg < p.bn_tile; cg += CONV_PASS_COLS, ++pc) {
           const int cols = min(CONV_PASS_COLS, p.bn_tile - cg);
           const int ob = pc & 1;
@@ -471,6 +502,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       }
       if (elect_one()) bulk_wait_all();                         // stores complete before the CTA exits
       __syncwarp();
+    }
+  } else if (pair && rank != 0 && warp == CONV_STORE_WARP - 1) {
+    // ---------------------------------------------------------------- relay (peer CTA of a pair): tell the leader when a stage of
+    // THIS CTA's operands has landed (relaxed: the data was written by the TMA and is read by the tensor cores, both async
+    // proxy; a release.cluster arrive per stage made this loop the bottleneck of the whole layer)
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = t_first; tile < total_tiles; tile += t_step) {
+      for (int kb = 0; kb < nk_total; ++kb) {
+        mbar_wait(&full[s], ph, 21);
+        if (lane == 0) mbar_arrive_remote_relaxed(&peer_full[s], 0u);
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
     }
   } else if (!p.tma_a && warp < CONV_STORE_WARP) {
     // ---------------------------------------------------------------- A gather producers (8 warps)
@@ -524,9 +569,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (pair) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc_rt(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+    if (pair) tmem_dealloc2_rt(tmem_base, static_cast<uint32_t>(p.tmem_cols)); else tmem_dealloc_rt(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
   if (threadIdx.x == 0) CONV_TRACE(7);
 }

@@ -145,6 +145,7 @@ struct OpRt {
   bool im2col = false;    // k x k layer whose A operand comes through an im2col tensor map (ConvParams::tma_a == 2)
   int bn_tile = 0, stages = 0, n_issuers = 1, tmem_cols = 0, m_tiles = 0, n_tiles = 0;
   int n_res = 0, box_cols = 64;
+  bool gpair = false;     // conv_igemm_kernel_t<true>: CTA pairs (TMA-fed layer without residual); weight map box = bn / 2 rows
   bool strip = false;     // stride-1 k x k layer run by conv_strip_kernel (halo patch + shifted descriptors)
   int Wbox = 0, R = 0, Hbox = 0, row_blocks = 0, a_stage_bytes = 0, n_acc = 2;
   bool pair = false;      // strip conv run by CTA pairs (cta_group::2): weight map box = cout / 2 rows
@@ -219,6 +220,7 @@ struct fire_net {
   int max_stages = 8;
   int n_issuers = CONV_MAX_ISSUERS;   // TMA issuing threads per CTA in 1x1 layers (FIRE_B200_ISSUERS=1|2|4)
   int strip_mma_warps = STRIP_MMA_WARPS;   // FIRE_B200_STRIP_MMAW=1|2|4: MMA issuing warps of conv_strip_kernel
+  bool igemm_pair = true;   // FIRE_B200_IGEMM_PAIR=0: no CTA pairs in conv_igemm_kernel
   bool strip_pair = false;  // FIRE_B200_STRIP_PAIR=1: CTA pairs (cta_group::2) in conv_strip_kernel - correct, but measured slower
   bool use_strip = true;    // FIRE_B200_STRIP=0 forces the gather path for every k x k layer (A/B experiments)
   bool trace_all = false;   // FIRE_B200_TRACE_ALL=1: forward() records every conv's timeline, synchronises and prints it
@@ -502,7 +504,8 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
   }
   static bool attr_done = false;
   if (!attr_done) {
-    e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    e = cudaFuncSetAttribute(conv_igemm_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_igemm_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_strip_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_strip_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
@@ -557,6 +560,7 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
   }
   if (const char* e = getenv("FIRE_B200_STRIP_MMAW")) net->strip_mma_warps = atoi(e) >= 2 ? 2 : 1;
   if (const char* e = getenv("FIRE_B200_STRIP_PAIR")) net->strip_pair = e[0] == '1';
+  if (const char* e = getenv("FIRE_B200_IGEMM_PAIR")) net->igemm_pair = e[0] != '0';
   const char* sp_env = getenv("FIRE_B200_STRIP");
   net->use_strip = !(sp_env && sp_env[0] == '0');
   const char* ta_env = getenv("FIRE_B200_TRACE_ALL");
@@ -683,17 +687,30 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
     p.d_howo = make_fastdiv(o.Ho * o.Wo); p.d_wo = make_fastdiv(o.Wo); p.d_cin = make_fastdiv(o.cin); p.d_kw = make_fastdiv(o.kw);
     p.d_ntiles = make_fastdiv(r.n_tiles);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)std::min<long long>((long long)r.m_tiles * r.n_tiles, device_sm_count()));
+    cfg.gridDim = r.gpair ? dim3((unsigned)std::min<long long>(2LL * ((r.m_tiles + 1) / 2) * r.n_tiles, device_sm_count() & ~1))
+                          : dim3((unsigned)std::min<long long>((long long)r.m_tiles * r.n_tiles, device_sm_count()));
     cfg.blockDim = dim3(CONV_THREADS);
     cfg.dynamicSmemBytes = r.smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    if (r.gpair) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    FIRE_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, r.tmap_w, (r.tma_a || r.im2col) ? r.tmap_a : r.tmap_w, r.n_res ? r.tmap_res : r.tmap_w,
-                                 (o.flags & CF_OUT_F32) ? r.tmap_w : r.tmap_out, p));
+    cfg.numAttrs = na;
+    if (r.gpair)
+      FIRE_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel_t<true>, r.tmap_w, r.tmap_a, r.tmap_w, r.tmap_out, p));
+    else
+      FIRE_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel_t<false>, r.tmap_w, (r.tma_a || r.im2col) ? r.tmap_a : r.tmap_w, r.n_res ? r.tmap_res : r.tmap_w,
+                                   (o.flags & CF_OUT_F32) ? r.tmap_w : r.tmap_out, p));
   } else if (o.kind == OP_MAXPOOL) {
     const long long total = (long long)B * o.Ho * o.Wo * (o.cin / 8);
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
@@ -806,18 +823,22 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
           if (q) ++q;
         }
       }
-      if (bn != r.bn_tile) {
+      // CTA pairs (cta_group::2): TMA-fed layers without residual whose pairs still fill the GPU
+      const bool gpair = net->igemm_pair && (r.tma_a || r.im2col) && !residual && !(o.flags & CF_OUT_F32) && bn % 32 == 0 && bn >= 64 &&
+                         (long long)((r.m_tiles + 1) / 2) * (o.cout / bn) >= (sms / 2) && o.k_pad >= 256;
+      if (bn != r.bn_tile || gpair != r.gpair) {
         int rc = make_tmap_f16_2d(&r.tmap_w, net->d_weights + o.w_off, (uint64_t)o.cout, (uint64_t)o.k_pad,
-                                  (uint64_t)o.k_pad * 2, (uint32_t)bn);
+                                  (uint64_t)o.k_pad * 2, (uint32_t)(gpair ? bn / 2 : bn));
         if (rc != FIRE_OK) return rc;
         r.bn_tile = bn;
+        r.gpair = gpair;
       }
       r.n_tiles = o.cout / bn;
       r.n_res = residual ? bn / 64 : 0;
       r.box_cols = bn % 64 == 0 ? 64 : (bn % 32 == 0 ? 32 : 16);
-      const size_t stage = CONV_A_STAGE_BYTES + (size_t)bn * 128;
-      const size_t fixed = conv_smem_layout(0, bn, o.cout, r.n_res).total + 1024;     // + alignment slack
-      r.stages = (int)std::min<size_t>(net->max_stages, (232448 - fixed) / stage);
+      const size_t stage = CONV_A_STAGE_BYTES + (size_t)(r.gpair ? bn / 2 : bn) * 128;
+      const size_t fixed = conv_smem_layout(0, bn, o.cout, r.n_res, r.gpair).total + 1024;     // + alignment slack
+      r.stages = (int)std::min<size_t>(r.gpair ? std::min(net->max_stages, 8) : net->max_stages, (232448 - fixed) / stage);
       if (r.stages < 2) return fail(FIRE_ERR_UNSUPPORTED, "conv tile %d does not fit shared memory", bn);
       // TMA issuing threads (1x1 layers): the ring depth is rounded down to a multiple of their number (see conv_igemm.cuh)
       r.n_issuers = 1;
@@ -826,7 +847,7 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
         for (int j = std::min(net->n_issuers, CONV_MAX_ISSUERS); j >= 2; --j)
           if (r.stages % j == 0) { r.n_issuers = j; break; }
       }
-      r.smem = conv_smem_layout(r.stages, bn, o.cout, r.n_res).total + 1024;
+      r.smem = conv_smem_layout(r.stages, bn, o.cout, r.n_res, r.gpair).total + 1024;
       r.tmem_cols = pow2_cols(2 * bn);
       const BlobBuf& sb = net->bufs[o.src_buf];
       const BlobBuf& db = net->bufs[o.dst_buf];

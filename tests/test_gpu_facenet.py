@@ -229,6 +229,23 @@ def test_strip_kernel_cta_pairs_are_bit_identical(fire_lib, monkeypatch, B):
     assert torch.equal(ra, rb)
 
 
+@pytest.mark.parametrize("B", [2, 65, 256])
+def test_igemm_cta_pairs_are_bit_identical(fire_lib, monkeypatch, B):
+    """conv_igemm_kernel_t<true>: the TMA-fed layers without residual (Conv2d_3b / 4b, Mixed_6a, Mixed_7a at large batch) run
+    as CTA pairs - M = 256 per tcgen05.mma.cta_group::2, each CTA loads its own activation tile and half of the weight
+    rows.  Per output row the same products in the same order as the single-CTA kernel (FIRE_B200_IGEMM_PAIR=0)."""
+    import torch
+    from fire_b200 import engine, weights as W
+    t = W.synthetic_weights(128, 14)
+    x = torch.from_numpy(_images(B, 41).astype(np.float32) / 255.0).cuda()
+    a = engine.FaceNetEngine(128, t)
+    ra, _ = a.encode_unit_f32(x)
+    monkeypatch.setenv("FIRE_B200_IGEMM_PAIR", "0")
+    b = engine.FaceNetEngine(128, t)
+    rb, _ = b.encode_unit_f32(x)
+    assert torch.equal(ra, rb)
+
+
 def test_crop_encode_pipeline_equals_direct_path(nets):
     """The streaming public call (pinned host crops -> H2D -> K1 -> K2 -> D2H, double-buffered) returns exactly what
     the step-by-step path returns, for every in-flight batch."""
