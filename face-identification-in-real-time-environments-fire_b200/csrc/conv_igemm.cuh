@@ -293,7 +293,21 @@ conv_igemm_kernel_t(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer (whole warp loops, one elected lane issues)
-    if (rank == 0) {                                   // the peer CTA of a pair issues nothing: the leader's MMAs cover both
+    if (rank != 0) {
+      // peer CTA of a pair: this warp issues nothing (the leader's MMAs cover both CTAs); it is the RELAY that tells the leader
+      // when a stage of THIS CTA's operands has landed (relaxed arrive: the data was written by the TMA / cp.async path and
+      // is read by the tensor cores; a release.cluster arrive per stage made this loop the bottleneck of the whole layer)
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = t_first; tile < total_tiles; tile += t_step) {
+        for (int kb = 0; kb < nk_total; ++kb) {
+          mbar_wait(&full[s], ph, 21);
+          if (lane == 0) mbar_arrive_remote_relaxed(&peer_full[s], 0u);
+          __syncwarp();
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    } else {                                           // leader (or single CTA)
       const uint32_t idesc = umma_idesc_f16(pair ? 2 * CONV_BM : CONV_BM, p.bn_tile);
       const uint32_t idesc64 = umma_idesc_f16(CONV_BM, 64);
       const uint32_t ones_addr = smem_u32(smem + L.ones), zero_addr = smem_u32(smem + L.zero);
@@ -503,20 +517,6 @@ conv_igemm_kernel_t(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
       if (elect_one()) bulk_wait_all();                         // stores complete before the CTA exits
       __syncwarp();
     }
-  } else if (pair && rank != 0 && warp == CONV_STORE_WARP - 1) {
-    // ---------------------------------------------------------------- relay (peer CTA of a pair): tell the leader when a stage of
-    // THIS CTA's operands has landed (relaxed: the data was written by the TMA and is read by the tensor cores, both async
-    // proxy; a release.cluster arrive per stage made this loop the bottleneck of the whole layer)
-    int s = 0;
-    uint32_t ph = 0;
-    for (int tile = t_first; tile < total_tiles; tile += t_step) {
-      for (int kb = 0; kb < nk_total; ++kb) {
-        mbar_wait(&full[s], ph, 21);
-        if (lane == 0) mbar_arrive_remote_relaxed(&peer_full[s], 0u);
-        __syncwarp();
-        if (++s == p.stages) { s = 0; ph ^= 1; }
-      }
-    }
   } else if (!p.tma_a && warp < CONV_STORE_WARP) {
     // ---------------------------------------------------------------- A gather producers (8 warps)
     const int g = threadIdx.x - CONV_FIRST_HELPER_WARP * 32;   // 0..255
@@ -528,8 +528,8 @@ conv_igemm_kernel_t(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
     if (p.pdl) pdl_wait();
     int s = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = fdiv(tile, p.d_ntiles) * CONV_BM;
+    for (int tile = t_first; tile < total_tiles; tile += t_step) {
+      const int m0 = unit_mt(tile) * CONV_BM;
       int base_off[CONV_ROWS_PER_GATHER_THREAD];
       uint32_t vmask[CONV_ROWS_PER_GATHER_THREAD];  // bits 0..7: tap rows r with ih in range; bits 8..15: tap cols s with iw in range
 #pragma unroll

@@ -221,6 +221,7 @@ struct fire_net {
   int n_issuers = CONV_MAX_ISSUERS;   // TMA issuing threads per CTA in 1x1 layers (FIRE_B200_ISSUERS=1|2|4)
   int strip_mma_warps = STRIP_MMA_WARPS;   // FIRE_B200_STRIP_MMAW=1|2|4: MMA issuing warps of conv_strip_kernel
   bool igemm_pair = true;   // FIRE_B200_IGEMM_PAIR=0: no CTA pairs in conv_igemm_kernel
+  int pair_slack = 0;       // FIRE_B200_PAIR_SLACK=n: accept layers with n pairs fewer than SMs / 2
   bool strip_pair = false;  // FIRE_B200_STRIP_PAIR=1: CTA pairs (cta_group::2) in conv_strip_kernel - correct, but measured slower
   bool use_strip = true;    // FIRE_B200_STRIP=0 forces the gather path for every k x k layer (A/B experiments)
   bool trace_all = false;   // FIRE_B200_TRACE_ALL=1: forward() records every conv's timeline, synchronises and prints it
@@ -561,6 +562,7 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
   if (const char* e = getenv("FIRE_B200_STRIP_MMAW")) net->strip_mma_warps = atoi(e) >= 2 ? 2 : 1;
   if (const char* e = getenv("FIRE_B200_STRIP_PAIR")) net->strip_pair = e[0] == '1';
   if (const char* e = getenv("FIRE_B200_IGEMM_PAIR")) net->igemm_pair = e[0] != '0';
+  if (const char* e = getenv("FIRE_B200_PAIR_SLACK")) net->pair_slack = atoi(e);
   const char* sp_env = getenv("FIRE_B200_STRIP");
   net->use_strip = !(sp_env && sp_env[0] == '0');
   const char* ta_env = getenv("FIRE_B200_TRACE_ALL");
@@ -707,7 +709,7 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
     cfg.attrs = attr;
     cfg.numAttrs = na;
     if (r.gpair)
-      FIRE_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel_t<true>, r.tmap_w, r.tmap_a, r.tmap_w, r.tmap_out, p));
+      FIRE_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel_t<true>, r.tmap_w, (r.tma_a || r.im2col) ? r.tmap_a : r.tmap_w, r.tmap_w, r.tmap_out, p));
     else
       FIRE_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel_t<false>, r.tmap_w, (r.tma_a || r.im2col) ? r.tmap_a : r.tmap_w, r.n_res ? r.tmap_res : r.tmap_w,
                                    (o.flags & CF_OUT_F32) ? r.tmap_w : r.tmap_out, p));
@@ -824,8 +826,8 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
         }
       }
       // CTA pairs (cta_group::2): TMA-fed layers without residual whose pairs still fill the GPU
-      const bool gpair = net->igemm_pair && (r.tma_a || r.im2col) && !residual && !(o.flags & CF_OUT_F32) && bn % 32 == 0 && bn >= 64 &&
-                         (long long)((r.m_tiles + 1) / 2) * (o.cout / bn) >= (sms / 2) && o.k_pad >= 256;
+      const bool gpair = net->igemm_pair && !residual && !(o.flags & CF_OUT_F32) && bn % 32 == 0 && bn >= 64 &&
+                         (long long)((r.m_tiles + 1) / 2) * (o.cout / bn) >= (sms / 2) - net->pair_slack && o.k_pad >= 256;
       if (bn != r.bn_tile || gpair != r.gpair) {
         int rc = make_tmap_f16_2d(&r.tmap_w, net->d_weights + o.w_off, (uint64_t)o.cout, (uint64_t)o.k_pad,
                                   (uint64_t)o.k_pad * 2, (uint32_t)(gpair ? bn / 2 : bn));
