@@ -57,6 +57,10 @@ _SIGNATURES = {
     "fire_knn_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
     "fire_knn_search_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    "fire_knn_search_rows": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fire_knn_search_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "fire_knn_merge_packed": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fire_knn_stats_ex": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "fire_knn_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
     "fire_knn_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -86,14 +90,11 @@ def check(rc: int) -> None:
         raise FireError(f"libfire_b200 error {rc}: {lib().fire_last_error().decode(errors='replace')}")
 
 
-_inited = set()
-
-
 def init(device: int = 0) -> None:
-    """cudaSetDevice + capability check (sm_100 required).  Raises FireError on a GPU-less host."""
-    if device not in _inited:
-        check(lib().fire_init(device))
-        _inited.add(device)
+    """cudaSetDevice + capability check (sm_100 required).  Raises FireError on a GPU-less host.  Always makes `device`
+    current: a handle lives on the device that is current when it is created (every later call on the handle switches
+    back to that device by itself)."""
+    check(lib().fire_init(device))
 
 
 def launch_count() -> int:

@@ -54,6 +54,11 @@ constexpr int B17_PAD = 48 * 128;          // 6144 B of zero rows
 constexpr int B17_UNITS_PER_BLOCK = 28 + 14 + 14 + 28;     // 84
 constexpr int B17_BIAS_PER_BLOCK = 256 + 128 + 128 + 896;  // 1408 floats: [heads | 1x7 | 7x1 | up]
 constexpr int B17_MAX_BLOCKS = 10;
+#ifdef FIRE_B200_SKIP_EXPERIMENTS
+constexpr int B17_DBG_MASK = 3;
+#else
+constexpr int B17_DBG_MASK = 0;            // the shipped library cannot skip residual loads or output stores
+#endif
 constexpr int B17_TRACE_SLOTS = 24;         // per CTA and block: 0-7 MMA warp, 8-23 epilogue warp 2
 constexpr int B17_THREADS = 32 * 12;        // 12 warps: the register file gives each thread 168 registers (14 warps: 128, with spills)
 constexpr int B17_W_ISSUERS = 2;           // warps 0, 10: unit u is issued by issuer u % 2 (2 divides the ring: a slot has one owner)
@@ -79,7 +84,7 @@ struct B17Params {
   const uint8_t* wstream;                 // n_blocks x 84 units
   const float* bias;                      // n_blocks x 1408
   int n_blocks, M_total, n_tiles, pdl;
-  int dbg;                                // timing experiments only (wrong results): 1 = no residual loads, 2 = no y stores
+  int dbg;                                // FIRE_B200_SKIP_EXPERIMENTS builds only (B17_DBG_MASK is 0 otherwise): 1 = no residual loads, 2 = no y stores
   long long* trace;                       // optional: [gridDim.x][B17_MAX_BLOCKS][B17_TRACE_SLOTS] globaltimer stamps
 };
 
@@ -522,7 +527,7 @@ block17_fused_kernel(const __grid_constant__ B17Params p) {
           uint4 rp[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            rp[i] = (grow0 + 4 * i + lr0 < p.M_total && !(p.dbg & 1)) ? ld_cg_v4(xg + static_cast<size_t>(4 * i) * B17_C + h * 64) : make_uint4(0u, 0u, 0u, 0u);
+            rp[i] = (grow0 + 4 * i + lr0 < p.M_total && !(p.dbg & B17_DBG_MASK & 1)) ? ld_cg_v4(xg + static_cast<size_t>(4 * i) * B17_C + h * 64) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
           for (int gi = 0; gi < 7; ++gi) {
             const int g = 2 * gi + h;                           // 64-column group; N tile g >> 2 (tile 3 has groups 12, 13 only)
@@ -533,7 +538,7 @@ block17_fused_kernel(const __grid_constant__ B17Params p) {
             if (gi + 1 < 7) {
 #pragma unroll
               for (int i = 0; i < 8; ++i)
-                rp[i] = (grow0 + 4 * i + lr0 < p.M_total && !(p.dbg & 1)) ? ld_cg_v4(xg + static_cast<size_t>(4 * i) * B17_C + (g + 2) * 64) : make_uint4(0u, 0u, 0u, 0u);
+                rp[i] = (grow0 + 4 * i + lr0 < p.M_total && !(p.dbg & B17_DBG_MASK & 1)) ? ld_cg_v4(xg + static_cast<size_t>(4 * i) * B17_C + (g + 2) * 64) : make_uint4(0u, 0u, 0u, 0u);
             }
             if (gi == 0 || ((g & 3) < 2)) {                     // first group of this warp in tile t
               mbar_wait(&accU_full[t & 1], (t >> 1) & 1, 47);
@@ -575,7 +580,7 @@ block17_fused_kernel(const __grid_constant__ B17Params p) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const uint4 v = lds128(sc_co + static_cast<uint32_t>(i * 512 + ((pc ^ ((4 * i + lr0) & 7)) << 4)));
-              if (grow0 + 4 * i + lr0 < p.M_total && !(p.dbg & 2)) st_global_v4(yg + static_cast<size_t>(4 * i) * B17_C + g * 64, v);
+              if (grow0 + 4 * i + lr0 < p.M_total && !(p.dbg & B17_DBG_MASK & 2)) st_global_v4(yg + static_cast<size_t>(4 * i) * B17_C + g * 64, v);
             }
             if (last && t < 3) {                                // this warp's share of N tile t is on its way to y
               fence_proxy_async_all();

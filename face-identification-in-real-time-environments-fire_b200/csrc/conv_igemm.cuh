@@ -55,7 +55,13 @@ constexpr int CONV_PASS_COLS = 128;        // columns staged per epilogue pass
 
 constexpr int CF_RELU = 1, CF_RESIDUAL = 2, CF_OUT_F32 = 4;
 constexpr int CF_DBG_PHASES = 1 << 19;     // with a trace buffer: per-role cycle accounting (strip kernel)
-constexpr int CF_DBG_NOGATHER = 1 << 16, CF_DBG_NOSTORE = 1 << 17, CF_DBG_NOMMA = 1 << 18;   // timing experiments only (wrong results)
+// Work-skipping switches for timing experiments exist only in a -DFIRE_B200_SKIP_EXPERIMENTS build; in the shipped library the
+// masks are 0, the tests below fold to constants and no code path can drop a gather, a store or an MMA.
+#ifdef FIRE_B200_SKIP_EXPERIMENTS
+constexpr int CF_DBG_NOGATHER = 1 << 16, CF_DBG_NOSTORE = 1 << 17, CF_DBG_NOMMA = 1 << 18;
+#else
+constexpr int CF_DBG_NOGATHER = 0, CF_DBG_NOSTORE = 0, CF_DBG_NOMMA = 0;
+#endif
 
 struct FastDiv {            // q = x / d for 0 <= x < 2^31  (mul = ceil(2^sh / d), sh = 31 + ceil(log2 d))
   uint32_t mul, sh;

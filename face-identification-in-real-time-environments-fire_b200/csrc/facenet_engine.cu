@@ -207,6 +207,7 @@ struct Fused35 {
 
 struct fire_net {
   BlobHeader hdr;
+  int device = 0;          // the device that was current at fire_facenet_create; every entry point runs there
   Fused17 f17;
   Fused35 f35;
   std::vector<BlobBuf> bufs;
@@ -227,7 +228,7 @@ struct fire_net {
   bool use_strip = true;    // FIRE_B200_STRIP=0 forces the gather path for every k x k layer (A/B experiments)
   bool trace_all = false;   // FIRE_B200_TRACE_ALL=1: forward() records every conv's timeline, synchronises and prints it
   long long* d_trace = nullptr; int trace_op = -1;   // FIRE_B200_TRACE_OP=<op index>: in-kernel timeline of that op (profile only)
-  int dbg_flags = 0;      // FIRE_B200_DBG: timing experiments (1 = no gather copies, 2 = no epilogue stores, 4 = no MMA)
+  int dbg_flags = 0;      // always 0 unless built with -DFIRE_B200_SKIP_EXPERIMENTS (then FIRE_B200_DBG: 1 = no gather copies, 2 = no epilogue stores, 4 = no MMA)
 };
 
 static inline int buf_wp(const BlobBuf& b) { return b.Wp > 0 ? b.Wp : b.W; }
@@ -466,6 +467,7 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
   fire_net* net = new (std::nothrow) fire_net();
   if (!net) return fail(FIRE_ERR_STATE, "out of host memory");
   net->hdr = h;
+  net->device = dev;
   net->bufs.resize(h.n_bufs);
   memcpy(net->bufs.data(), p + sizeof(BlobHeader), sizeof(BlobBuf) * h.n_bufs);
   std::vector<BlobOp> ops(h.n_ops);
@@ -504,8 +506,9 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
       return fail(FIRE_ERR_CUDA, "fire_facenet_create: bias upload failed: %s", cudaGetErrorString(e));
     }
   }
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[FIRE_MAX_DEVICES] = {};        // the shared-memory opt-in is per device (context), not per process
+  if (dev < 0 || dev >= FIRE_MAX_DEVICES) { cudaFree(net->d_weights); cudaFree(net->d_bias16); delete net; return fail(FIRE_ERR_ARG, "device %d out of range", dev); }
+  if (!attr_done[dev]) {
     e = cudaFuncSetAttribute(conv_igemm_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_igemm_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_strip_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -515,7 +518,7 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
       delete net;
       return fail(FIRE_ERR_CUDA, "cudaFuncSetAttribute(conv_igemm_kernel): %s", cudaGetErrorString(e));
     }
-    attr_done = true;
+    attr_done[dev] = true;
   }
   size_t bias16_off = 0;
   for (const BlobOp& o : ops) {
@@ -549,8 +552,10 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
   net->pdl = !(pdl_env && pdl_env[0] == '0');
   const char* l1_env = getenv("FIRE_B200_GATHER_L1");
   net->gather_l1 = l1_env && l1_env[0] == '1';
+#ifdef FIRE_B200_SKIP_EXPERIMENTS
   const char* dbg_env = getenv("FIRE_B200_DBG");
   if (dbg_env) net->dbg_flags = (atoi(dbg_env) & 7) << 16;
+#endif
   const char* tr_env = getenv("FIRE_B200_TRACE_OP");
   if (tr_env && atoi(tr_env) >= 0 && atoi(tr_env) < (int)net->ops.size()) {
     net->trace_op = atoi(tr_env);
@@ -589,6 +594,7 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
 
 int fire_facenet_destroy(fire_net_t* net) {
   if (!net) return FIRE_OK;
+  use_device(net->device);
   cudaFree(net->d_weights);
   cudaFree(net->d_bias16);
   cudaFree(net->d_trace);
@@ -913,7 +919,10 @@ extern "C" {
 
 int fire_facenet_forward(fire_net_t* net, const void* in_f16, int B, float* out_raw, float* out_l2, void* workspace,
                          size_t ws_bytes, fire_stream_t stream) {
-  int rc = prepare(net, in_f16, B, out_raw, workspace, ws_bytes);
+  if (!net) return fail(FIRE_ERR_ARG, "fire_facenet_forward: NULL handle");
+  int rc = use_device(net->device);
+  if (rc != FIRE_OK) return rc;
+  rc = prepare(net, in_f16, B, out_raw, workspace, ws_bytes);
   if (rc != FIRE_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (size_t i = 0; i < net->ops.size(); ++i) {
@@ -994,6 +1003,7 @@ int fire_facenet_forward(fire_net_t* net, const void* in_f16, int B, float* out_
 int fire_facenet_profile(fire_net_t* net, const void* in_f16, int B, void* workspace, size_t ws_bytes, float* host_ms,
                          double* host_flops, int n_ops, fire_stream_t stream) {
   if (!net || !host_ms || n_ops < (int)net->ops.size()) return fail(FIRE_ERR_ARG, "fire_facenet_profile: bad arguments");
+  { const int rc_dev = use_device(net->device); if (rc_dev != FIRE_OK) return rc_dev; }
   float* out_raw = nullptr;
   FIRE_CUDA(cudaMalloc(&out_raw, sizeof(float) * (size_t)B * net->hdr.D));
   int rc = prepare(net, in_f16, B, out_raw, workspace, ws_bytes);
@@ -1078,6 +1088,7 @@ int fire_facenet_profile(fire_net_t* net, const void* in_f16, int B, void* works
 int fire_facenet_read_buffer(fire_net_t* net, int buf, int B, const void* in_f16, const void* workspace, void* host_out,
                              size_t bytes) {
   if (!net || buf < 0 || buf >= (int)net->bufs.size() || !host_out) return fail(FIRE_ERR_ARG, "fire_facenet_read_buffer: bad arguments");
+  { const int rc_dev = use_device(net->device); if (rc_dev != FIRE_OK) return rc_dev; }
   const BlobBuf& b = net->bufs[buf];
   const size_t need = (size_t)B * b.H * buf_wp(b) * b.C * b.elt;
   if (bytes < need) return fail(FIRE_ERR_ARG, "fire_facenet_read_buffer: need %zu bytes", need);

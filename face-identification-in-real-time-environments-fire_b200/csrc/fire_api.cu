@@ -151,12 +151,21 @@ int make_tmap_f16_im2col(CUtensorMap* out, const void* base, uint64_t C, uint64_
 }
 
 int device_sm_count() {
-  static int n = 0;
-  if (n) return n;
+  static int n[FIRE_MAX_DEVICES] = {};                 // cached per device: handles may live on different GPUs of one process
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  return n;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= FIRE_MAX_DEVICES) return 148;
+  if (n[dev]) return n[dev];
+  int v = 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+  n[dev] = v;
+  return v;
+}
+
+int use_device(int device) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) == cudaSuccess && cur == device) return FIRE_OK;
+  FIRE_CUDA(cudaSetDevice(device));
+  return FIRE_OK;
 }
 
 }  // namespace fire

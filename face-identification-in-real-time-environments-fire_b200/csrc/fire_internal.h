@@ -54,7 +54,10 @@ int make_tmap_f16_pos3d(CUtensorMap* out, const void* base, uint64_t C, uint64_t
 int make_tmap_f16_im2col(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint64_t ld_elems,
                          int kw, int kh, int pad_w, int pad_h, int stride);
 
-int device_sm_count();
+constexpr int FIRE_MAX_DEVICES = 64;
+int device_sm_count();          // SM count of the CURRENT device
+// Every entry point that takes a handle runs on the handle's device: makes it current if it is not (one handle = one device).
+int use_device(int device);
 
 // Launch counter (every kernel launch of this library bumps it; bench.py reports it as gpu_launches).
 void count_launch(int n = 1);

@@ -52,9 +52,10 @@ struct KnnScanParams {
 // one warp per row; writes the fp32 normalised row and its fp16 rounding.
 // Also measures ||x^ - fp16(x^)||_2 of every row: per query into row_err[], max over gallery rows into *max_err
 // (positive floats order like their bit patterns, so atomicMax on the bits is a float max).
+// `prenormalized`: the rows are stored gallery rows (already x^), used as queries as they are (fire_knn_search_rows).
 __global__ void knn_normalize_kernel(const float* __restrict__ in, size_t n, int D, float* __restrict__ out32,
                                      __half* __restrict__ out16, size_t n_pad16, float* __restrict__ row_err,
-                                     int* __restrict__ max_err) {
+                                     int* __restrict__ max_err, int prenormalized) {
   size_t row = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (row >= n_pad16) return;
@@ -70,7 +71,7 @@ __global__ void knn_normalize_kernel(const float* __restrict__ in, size_t n, int
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  float inv = 1.0f / (sqrtf(s) + 1e-30f);
+  float inv = prenormalized ? 1.0f : 1.0f / (sqrtf(s) + 1e-30f);
   float e2 = 0.f;
   for (int c = lane * 4; c < D; c += 128) {
     float4 v = *reinterpret_cast<const float4*>(x + c);
@@ -90,6 +91,35 @@ __global__ void knn_normalize_kernel(const float* __restrict__ in, size_t n, int
     if (row_err) row_err[row] = e;
     if (max_err) atomicMax(max_err, __float_as_int(e));
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Where results go.  Either two arrays (dist f32 [Q][k], ids i64 [Q][k]) or ONE packed array of 12-byte records
+// {f32 distance, i64 id} stored as three 32-bit words - the message of the multi-GPU exchange, so that a single
+// all-gather carries both.  id = row * id_stride + id_offset maps a shard row to its global label
+// (contiguous shards: stride 1, offset = first row; interleaved shards: stride = world, offset = rank).
+struct KnnOut {
+  float* dist;
+  long long* ids;
+  int32_t* packed;
+  long long id_offset, id_stride;
+  __device__ __forceinline__ void put(size_t slot, float d, uint32_t row) const {
+    const long long id = row == 0xFFFFFFFFu ? -1ll : static_cast<long long>(row) * id_stride + id_offset;
+    if (packed) {
+      packed[slot * 3] = __float_as_int(d);
+      packed[slot * 3 + 1] = static_cast<int32_t>(static_cast<unsigned long long>(id) & 0xFFFFFFFFull);
+      packed[slot * 3 + 2] = static_cast<int32_t>(static_cast<unsigned long long>(id) >> 32);
+    } else {
+      dist[slot] = d;
+      ids[slot] = id;
+    }
+  }
+};
+
+// Padding fill: every slot = (FLT_MAX, -1).  Used when a shard holds no rows at all.
+__global__ void knn_fill_padding_kernel(KnnOut out, size_t n_slots) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_slots; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out.put(i, FLT_MAX, 0xFFFFFFFFu);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -353,9 +383,8 @@ __device__ __forceinline__ void warp_merge_lists(int G, int len, int n_out, Get 
 template <int KP>
 __global__ void knn_rerank_kernel(const float* __restrict__ qn, const float* __restrict__ g32,
                                   const float* __restrict__ cand_score, const uint32_t* __restrict__ cand_idx, int S,
-                                  int D, int Q, int k, int64_t id_offset, float slack, const float* __restrict__ q_err,
-                                  const int* __restrict__ g_max_err, float* __restrict__ out_dist,
-                                  long long* __restrict__ out_ids, uint32_t* __restrict__ flagged,
+                                  int D, int Q, int k, float slack, const float* __restrict__ q_err,
+                                  const int* __restrict__ g_max_err, KnnOut out, uint32_t* __restrict__ flagged,
                                   uint32_t* __restrict__ flagged_count) {
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -404,11 +433,12 @@ __global__ void knn_rerank_kernel(const float* __restrict__ qn, const float* __r
     if ((r & 31) == lane) {
 #pragma unroll
       for (int e = 0; e < EPL; ++e)
-        if (e == (r >> 5)) dist[e] = 1.0f - acc;
+        if (e == (r >> 5)) { const float dd = 1.0f - acc; dist[e] = dd == dd ? dd : FLT_MAX; }    // a NaN (NaN/Inf in the query) sorts last instead of poisoning the ranking
     }
   }
 
-  // rank by (distance asc, id asc); invalid entries (FLT_MAX, ~0) sort last
+  // rank by (distance asc, id asc); invalid entries (FLT_MAX, ~0) sort last and, being equal to one another, are told apart by
+  // their list position - every entry gets a distinct rank, so all k output slots are always written (padding = (FLT_MAX, -1))
   int rank[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) rank[e] = 0;
@@ -420,7 +450,7 @@ __global__ void knn_rerank_kernel(const float* __restrict__ qn, const float* __r
 #pragma unroll
     for (int e = 0; e < EPL; ++e) {
       const int me = e * 32 + lane;
-      if (me < KP && me != r && keyid_less(od, oi, dist[e], sel_idx[e])) rank[e]++;
+      if (me < KP && me != r && (keyid_less(od, oi, dist[e], sel_idx[e]) || (od == dist[e] && oi == sel_idx[e] && r < me))) rank[e]++;
     }
   }
   float kth_dist = -FLT_MAX;   // distance of rank k-1
@@ -428,9 +458,7 @@ __global__ void knn_rerank_kernel(const float* __restrict__ qn, const float* __r
   for (int e = 0; e < EPL; ++e) {
     const int me = e * 32 + lane;
     if (me < KP && rank[e] < k) {
-      out_dist[static_cast<size_t>(q) * k + rank[e]] = dist[e];
-      out_ids[static_cast<size_t>(q) * k + rank[e]] =
-          sel_idx[e] == 0xFFFFFFFFu ? -1ll : static_cast<long long>(sel_idx[e]) + id_offset;
+      out.put(static_cast<size_t>(q) * k + rank[e], dist[e], sel_idx[e]);
       if (rank[e] == k - 1) kth_dist = dist[e];
     }
   }
@@ -453,67 +481,161 @@ __global__ void knn_rerank_kernel(const float* __restrict__ qn, const float* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// Exact fp32 fallback for flagged queries.  The kernels read the flagged count on the device and
-// return at once when it is zero, so they are enqueued unconditionally (no host round trip).
-//   pass A (<= EXACT_CAP flagged queries): rows split over the blocks -> per-block partial top-k
-//           -> knn_exact_merge_kernel merges the partials and overwrites the query's output row;
-//   pass B (overflow beyond EXACT_CAP, pathological galleries): one block scans the whole shard
-//           for one query, blocks stride over the overflow queries.
+// Flagged queries (the merged-list proof failed): exact fp32 work, bounded by what the scan already knows.
+//
+//   knn_refine_kernel   one block per flagged query: the exact distances of ALL S x KP candidates the scan kept (every
+//                       split's own list, not only the merged KP best) give a new exact top-k.  A row that is in NO list
+//                       was dropped inside its own split s, so its fp16 score is <= that split's KP-th score cmin_s: split s
+//                       can still hide a true top-k row only if its list is full and cmin_s + eps >= 1 - kth.  Splits
+//                       that pass need no further work (the usual case: one split's KP-th score is far below the global
+//                       one).  Exactly one unsafe split -> work item (query, split): only that split's rows are scanned.
+//                       Two or more -> work item (query, all rows).
+//   knn_exact_scan_kernel   rows of every work item's range split over the blocks -> per-block partial top-k
+//   knn_exact_merge_kernel  per work item: partial lists (+ the candidate list, duplicates dropped) -> output row
+//   knn_exact_overflow_kernel  flagged queries beyond EXACT_CAP (pathological galleries): one block scans the whole
+//                       shard for one query.
+// All kernels read the counts on the device and return at once when there is nothing to do, so they are enqueued
+// unconditionally (no host round trip).  counters: [0] flagged queries, [1] work items.
 constexpr int EXACT_WARPS = 8;
 constexpr int EXACT_CAP = 256;
+constexpr int EXACT_MAX_BLOCKS = 296;        // partial lists per work item (+ 1 candidate list) <= 32 * KNN_MAX_LISTS_PER_LANE
 
 struct ExactSmem {
   float q[512];
   float d[EXACT_WARPS][64];
   uint32_t i[EXACT_WARPS][64];
 };
+struct KnnWorkItem {
+  uint32_t q;       // query row
+  uint32_t f;       // index into flagged[] (= slot of the candidate list in ref_dist / ref_idx)
+  int split;        // gallery split to scan, -1 = every row of the shard
+  int pad;
+};
 
-// every warp scans rows r0+warp, r0+warp+8, ... < r1 and keeps its k best in sm.d/sm.i[warp]
-__device__ __forceinline__ void exact_block_scan(ExactSmem& sm, const float* __restrict__ qn,
-                                                 const float* __restrict__ g32, uint32_t q, int D, int k, int r0,
-                                                 int r1) {
+__device__ __forceinline__ void exact_lists_reset(ExactSmem& sm, const float* __restrict__ qn, uint32_t q, int D) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __syncthreads();
   for (int c = threadIdx.x; c < D; c += blockDim.x) sm.q[c] = qn[static_cast<size_t>(q) * D + c];
   for (int j = lane; j < 64; j += 32) { sm.d[warp][j] = FLT_MAX; sm.i[warp][j] = 0xFFFFFFFFu; }
   __syncthreads();
-  for (int r = r0 + warp; r < r1; r += EXACT_WARPS) {
-    const float* gv = g32 + static_cast<size_t>(r) * D;
-    float acc = 0.f;
-    for (int c = lane * 4; c < D; c += 128) {
-      float4 b = __ldg(reinterpret_cast<const float4*>(gv + c));
-      acc = fmaf(sm.q[c], b.x, acc); acc = fmaf(sm.q[c + 1], b.y, acc);
-      acc = fmaf(sm.q[c + 2], b.z, acc); acc = fmaf(sm.q[c + 3], b.w, acc);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    const float d = 1.0f - acc;
-    if (lane == 0 && keyid_less(d, static_cast<unsigned long long>(r), sm.d[warp][k - 1], sm.i[warp][k - 1])) {
-      int j = k - 1;
-      while (j > 0 && keyid_less(d, static_cast<unsigned long long>(r), sm.d[warp][j - 1], sm.i[warp][j - 1])) {
-        sm.d[warp][j] = sm.d[warp][j - 1]; sm.i[warp][j] = sm.i[warp][j - 1]; --j;
-      }
-      sm.d[warp][j] = d; sm.i[warp][j] = static_cast<uint32_t>(r);
-    }
-    __syncwarp();
+}
+// this warp: exact distance of gallery row r, inserted into the warp's sorted list of the k best (distance asc, id asc)
+__device__ __forceinline__ void exact_consume_row(ExactSmem& sm, const float* __restrict__ g32, int D, int k, uint32_t r) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* gv = g32 + static_cast<size_t>(r) * D;
+  float acc = 0.f;
+  for (int c = lane * 4; c < D; c += 128) {
+    float4 b = __ldg(reinterpret_cast<const float4*>(gv + c));
+    acc = fmaf(sm.q[c], b.x, acc); acc = fmaf(sm.q[c + 1], b.y, acc);
+    acc = fmaf(sm.q[c + 2], b.z, acc); acc = fmaf(sm.q[c + 3], b.w, acc);
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  float d = 1.0f - acc;
+  if (!(d == d)) d = FLT_MAX;
+  if (lane == 0 && keyid_less(d, static_cast<unsigned long long>(r), sm.d[warp][k - 1], sm.i[warp][k - 1])) {
+    int j = k - 1;
+    while (j > 0 && keyid_less(d, static_cast<unsigned long long>(r), sm.d[warp][j - 1], sm.i[warp][j - 1])) {
+      sm.d[warp][j] = sm.d[warp][j - 1]; sm.i[warp][j] = sm.i[warp][j - 1]; --j;
+    }
+    sm.d[warp][j] = d; sm.i[warp][j] = r;
+  }
+  __syncwarp();
+}
+// every warp scans rows r0+warp, r0+warp+8, ... < r1 and keeps its k best in sm.d/sm.i[warp]
+__device__ __forceinline__ void exact_block_scan(ExactSmem& sm, const float* __restrict__ qn,
+                                                 const float* __restrict__ g32, uint32_t q, int D, int k, int r0,
+                                                 int r1) {
+  const int warp = threadIdx.x >> 5;
+  exact_lists_reset(sm, qn, q, D);
+  for (int r = r0 + warp; r < r1; r += EXACT_WARPS) exact_consume_row(sm, g32, D, k, static_cast<uint32_t>(r));
   __syncthreads();
 }
 
 __global__ void __launch_bounds__(EXACT_WARPS * 32)
-knn_exact_scan_kernel(const float* __restrict__ qn, const float* __restrict__ g32, int n_rows, int D, int k,
-                      const uint32_t* __restrict__ flagged, const uint32_t* __restrict__ flagged_count,
+knn_refine_kernel(const float* __restrict__ qn, const float* __restrict__ g32, const float* __restrict__ cand_score,
+                  const uint32_t* __restrict__ cand_idx, int S, int KP, int D, int k, float slack,
+                  const float* __restrict__ q_err, const int* __restrict__ g_max_err, const uint32_t* __restrict__ flagged,
+                  uint32_t* __restrict__ counters, float* __restrict__ ref_dist, uint32_t* __restrict__ ref_idx,
+                  KnnWorkItem* __restrict__ work, KnnOut out, unsigned long long* __restrict__ stats, int Q) {
+  __shared__ ExactSmem sm;
+  __shared__ float s_kth;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {               // fold this search into the handle's counters
+    stats[0] += static_cast<unsigned long long>(Q);
+    stats[1] += static_cast<unsigned long long>(counters[0]);
+  }
+  const uint32_t nf = min(counters[0], static_cast<uint32_t>(EXACT_CAP));
+  for (uint32_t f = blockIdx.x; f < nf; f += gridDim.x) {
+    const uint32_t q = flagged[f];
+    const float* cs = cand_score + static_cast<size_t>(q) * S * KP;
+    const uint32_t* ci = cand_idx + static_cast<size_t>(q) * S * KP;
+    exact_lists_reset(sm, qn, q, D);
+    const int total = S * KP;
+    for (int c = warp; c < total; c += EXACT_WARPS) {
+      const uint32_t idx = ci[c];
+      if (idx != 0xFFFFFFFFu) exact_consume_row(sm, g32, D, k, idx);     // warp-uniform
+    }
+    __syncthreads();
+    if (warp == 0) {
+      auto get = [&](int l, int pos, float& key, unsigned long long& id) { key = sm.d[l][pos]; id = sm.i[l][pos]; };
+      auto emit = [&](int r, float key, unsigned long long id, bool valid) {
+        if (lane == 0) {
+          const uint32_t row = valid ? static_cast<uint32_t>(id) : 0xFFFFFFFFu;
+          const float d = valid && row != 0xFFFFFFFFu ? key : FLT_MAX;
+          out.put(static_cast<size_t>(q) * k + r, d, row);
+          ref_dist[static_cast<size_t>(f) * 64 + r] = d;
+          ref_idx[static_cast<size_t>(f) * 64 + r] = row;
+          if (r == k - 1) s_kth = d;
+        }
+      };
+      warp_merge_lists(EXACT_WARPS, k, k, get, emit);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const float kth = s_kth;
+      const float eq = q_err[q], eg = __int_as_float(*g_max_err);
+      const float eps = (eq + eg) * 1.0005f + eq * eg + slack;
+      int unsafe = 0, first = -1;
+      for (int s0 = 0; s0 < S; s0 += 32) {
+        const int sidx = s0 + lane;
+        bool bad = false;
+        if (sidx < S) {
+          const bool full = ci[static_cast<size_t>(sidx) * KP + KP - 1] != 0xFFFFFFFFu;
+          bad = full && (cs[static_cast<size_t>(sidx) * KP + KP - 1] + eps >= 1.0f - kth);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, bad);
+        if (m && first < 0) first = s0 + __ffs(m) - 1;
+        unsafe += __popc(m);
+      }
+      if (lane == 0 && unsafe > 0) {
+        const uint32_t slot = atomicAdd(&counters[1], 1u);
+        KnnWorkItem w;
+        w.q = q; w.f = f; w.split = unsafe == 1 ? first : -1; w.pad = 0;
+        work[slot] = w;
+        atomicAdd(&stats[unsafe == 1 ? 2 : 3], 1ull);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(EXACT_WARPS * 32)
+knn_exact_scan_kernel(const float* __restrict__ qn, const float* __restrict__ g32, int n_rows, int rows_per_split, int D, int k,
+                      const KnnWorkItem* __restrict__ work, const uint32_t* __restrict__ counters,
                       float* __restrict__ part_dist, uint32_t* __restrict__ part_idx) {
   __shared__ ExactSmem sm;
   const int lane = threadIdx.x & 31;
-  const uint32_t nf = min(*flagged_count, static_cast<uint32_t>(EXACT_CAP));
-  const int rows_per_block = (n_rows + gridDim.x - 1) / gridDim.x;
-  const int r0 = blockIdx.x * rows_per_block, r1 = min(n_rows, r0 + rows_per_block);
-  for (uint32_t f = 0; f < nf; ++f) {
-    exact_block_scan(sm, qn, g32, flagged[f], D, k, r0, r1);
+  const uint32_t nw = min(counters[1], static_cast<uint32_t>(EXACT_CAP));
+  for (uint32_t w = 0; w < nw; ++w) {
+    const KnnWorkItem it = work[w];
+    const int R0 = it.split < 0 ? 0 : it.split * rows_per_split;
+    const int R1 = it.split < 0 ? n_rows : min(n_rows, R0 + rows_per_split);
+    const int rows_per_block = (R1 - R0 + gridDim.x - 1) / gridDim.x;
+    const int r0 = min(R1, R0 + static_cast<int>(blockIdx.x) * rows_per_block), r1 = min(R1, r0 + rows_per_block);
+    exact_block_scan(sm, qn, g32, it.q, D, k, r0, r1);
     if (threadIdx.x < 32) {
-      float* od = part_dist + (static_cast<size_t>(f) * gridDim.x + blockIdx.x) * k;
-      uint32_t* oi = part_idx + (static_cast<size_t>(f) * gridDim.x + blockIdx.x) * k;
+      float* od = part_dist + (static_cast<size_t>(w) * gridDim.x + blockIdx.x) * k;
+      uint32_t* oi = part_idx + (static_cast<size_t>(w) * gridDim.x + blockIdx.x) * k;
       auto get = [&](int l, int pos, float& key, unsigned long long& id) { key = sm.d[l][pos]; id = sm.i[l][pos]; };
       auto emit = [&](int r, float key, unsigned long long id, bool valid) {
         if (lane == 0) { od[r] = valid ? key : FLT_MAX; oi[r] = valid ? static_cast<uint32_t>(id) : 0xFFFFFFFFu; }
@@ -523,42 +645,46 @@ knn_exact_scan_kernel(const float* __restrict__ qn, const float* __restrict__ g3
   }
 }
 
-// merge the per-block partial lists of every pass-A query and overwrite its output row;
-// block 0 also folds this search into the handle's counters.
-__global__ void knn_exact_merge_kernel(const float* __restrict__ part_dist, const uint32_t* __restrict__ part_idx,
-                                       int nblk, int k, int64_t id_offset, const uint32_t* __restrict__ flagged,
-                                       const uint32_t* __restrict__ flagged_count, float* __restrict__ out_dist,
-                                       long long* __restrict__ out_ids, unsigned long long* __restrict__ stats, int Q) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    stats[0] += static_cast<unsigned long long>(Q);
-    stats[1] += static_cast<unsigned long long>(*flagged_count);
-  }
-  const uint32_t nf = min(*flagged_count, static_cast<uint32_t>(EXACT_CAP));
+// one warp per work item: merge the per-block partial lists (and, for a single-split item, the candidate list of the other
+// splits - rows of the scanned split appear in both, the second copy is dropped) and overwrite the query's output row
+__global__ void knn_exact_merge_kernel(const float* __restrict__ part_dist, const uint32_t* __restrict__ part_idx, int nblk, int k,
+                                       const KnnWorkItem* __restrict__ work, const uint32_t* __restrict__ counters,
+                                       const float* __restrict__ ref_dist, const uint32_t* __restrict__ ref_idx, KnnOut out) {
+  const uint32_t nw = min(counters[1], static_cast<uint32_t>(EXACT_CAP));
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
-  for (uint32_t f = blockIdx.x * wpb + (threadIdx.x >> 5); f < nf; f += gridDim.x * wpb) {
-    const uint32_t q = flagged[f];
-    const float* pd = part_dist + static_cast<size_t>(f) * nblk * k;
-    const uint32_t* pi = part_idx + static_cast<size_t>(f) * nblk * k;
-    auto get = [&](int l, int pos, float& key, unsigned long long& id) { key = pd[l * k + pos]; id = pi[l * k + pos]; };
-    auto emit = [&](int r, float key, unsigned long long id, bool valid) {
-      if (lane == 0) {
-        out_dist[static_cast<size_t>(q) * k + r] = key;
-        out_ids[static_cast<size_t>(q) * k + r] = valid && id != 0xFFFFFFFFull ? static_cast<long long>(id) + id_offset : -1ll;
-      }
+  for (uint32_t w = blockIdx.x * wpb + (threadIdx.x >> 5); w < nw; w += gridDim.x * wpb) {
+    const KnnWorkItem it = work[w];
+    const float* pd = part_dist + static_cast<size_t>(w) * nblk * k;
+    const uint32_t* pi = part_idx + static_cast<size_t>(w) * nblk * k;
+    const float* rd = ref_dist + static_cast<size_t>(it.f) * 64;
+    const uint32_t* ri = ref_idx + static_cast<size_t>(it.f) * 64;
+    const int lists = it.split < 0 ? nblk : nblk + 1;
+    auto get = [&](int l, int pos, float& key, unsigned long long& id) {
+      if (l < nblk) { key = pd[l * k + pos]; id = pi[l * k + pos]; }
+      else { key = rd[pos]; id = ri[pos]; }
     };
-    warp_merge_lists(nblk, k, k, get, emit);
+    int cnt = 0;
+    unsigned long long prev = ~0ull;
+    auto emit = [&](int r, float key, unsigned long long id, bool valid) {
+      (void)r;
+      const bool real = valid && id != 0xFFFFFFFFull;
+      if (cnt < k && (!real || id != prev)) {             // all lanes see the same stream: cnt / prev stay warp-uniform
+        if (lane == 0) out.put(static_cast<size_t>(it.q) * k + cnt, real ? key : FLT_MAX, real ? static_cast<uint32_t>(id) : 0xFFFFFFFFu);
+        ++cnt;
+      }
+      if (real) prev = id;
+    };
+    warp_merge_lists(lists, k, 2 * k, get, emit);
   }
 }
 
 __global__ void __launch_bounds__(EXACT_WARPS * 32)
 knn_exact_overflow_kernel(const float* __restrict__ qn, const float* __restrict__ g32, int n_rows, int D, int k,
-                          int64_t id_offset, const uint32_t* __restrict__ flagged,
-                          const uint32_t* __restrict__ flagged_count, float* __restrict__ out_dist,
-                          long long* __restrict__ out_ids) {
+                          const uint32_t* __restrict__ flagged, const uint32_t* __restrict__ counters, KnnOut out) {
   __shared__ ExactSmem sm;
   const int lane = threadIdx.x & 31;
-  const uint32_t total = *flagged_count;
+  const uint32_t total = counters[0];
   for (uint32_t f = EXACT_CAP + blockIdx.x; f < total; f += gridDim.x) {
     const uint32_t q = flagged[f];
     exact_block_scan(sm, qn, g32, q, D, k, 0, n_rows);
@@ -566,8 +692,8 @@ knn_exact_overflow_kernel(const float* __restrict__ qn, const float* __restrict_
       auto get = [&](int l, int pos, float& key, unsigned long long& id) { key = sm.d[l][pos]; id = sm.i[l][pos]; };
       auto emit = [&](int r, float key, unsigned long long id, bool valid) {
         if (lane == 0) {
-          out_dist[static_cast<size_t>(q) * k + r] = key;
-          out_ids[static_cast<size_t>(q) * k + r] = valid && id != 0xFFFFFFFFull ? static_cast<long long>(id) + id_offset : -1ll;
+          const bool real = valid && id != 0xFFFFFFFFull;
+          out.put(static_cast<size_t>(q) * k + r, real ? key : FLT_MAX, real ? static_cast<uint32_t>(id) : 0xFFFFFFFFu);
         }
       };
       warp_merge_lists(EXACT_WARPS, k, k, get, emit);
@@ -575,20 +701,27 @@ knn_exact_overflow_kernel(const float* __restrict__ qn, const float* __restrict_
   }
 }
 
-// multi-GPU merge: dists/ids [G][Q][k] ascending per row -> global top-k per query
-__global__ void knn_merge_kernel(const float* __restrict__ dists, const long long* __restrict__ ids, int Q, int k, int G,
-                                 float* __restrict__ out_dist, long long* __restrict__ out_ids) {
+// multi-GPU merge: G per-shard lists per query (each ascending) -> global top-k per query.  The lists come either as two
+// arrays dists/ids [G][Q][k] or as ONE array of packed 12-byte records [G][Q][k][3] (what a single all-gather delivers).
+__global__ void knn_merge_kernel(const float* __restrict__ dists, const long long* __restrict__ ids, const int32_t* __restrict__ packed,
+                                 int Q, int k, int G, float* __restrict__ out_dist, long long* __restrict__ out_ids) {
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (q >= Q) return;
   auto get = [&](int l, int pos, float& key, unsigned long long& id) {
     const size_t o = (static_cast<size_t>(l) * Q + q) * k + pos;
-    key = dists[o];
-    id = static_cast<unsigned long long>(ids[o]);
+    if (packed) {
+      key = __int_as_float(packed[o * 3]);
+      id = static_cast<unsigned long long>(static_cast<uint32_t>(packed[o * 3 + 1])) |
+           (static_cast<unsigned long long>(static_cast<uint32_t>(packed[o * 3 + 2])) << 32);
+    } else {
+      key = dists[o];
+      id = static_cast<unsigned long long>(ids[o]);
+    }
   };
   auto emit = [&](int r, float key, unsigned long long id, bool valid) {
     if (lane == 0) {
-      out_dist[static_cast<size_t>(q) * k + r] = key;
+      out_dist[static_cast<size_t>(q) * k + r] = valid ? key : FLT_MAX;
       out_ids[static_cast<size_t>(q) * k + r] = valid ? static_cast<long long>(id) : -1ll;
     }
   };
@@ -618,10 +751,13 @@ struct fire_knn {
   float* cand_score = nullptr;
   uint32_t* cand_idx = nullptr;
   uint32_t* flagged = nullptr;       // [q_cap]
-  uint32_t* flagged_count = nullptr; // [1] + stats [2] (uint64 each, separate alloc below)
-  unsigned long long* stats = nullptr;   // device: {queries_total, queries_fallback}
+  uint32_t* counters = nullptr;      // [4]: flagged queries, work items
+  unsigned long long* stats = nullptr;   // device: {queries_total, queries_flagged, single-split scans, whole-shard scans}
   float* part_dist = nullptr;
   uint32_t* part_idx = nullptr;
+  float* ref_dist = nullptr;         // [EXACT_CAP][64] exact top-k over the candidates of every flagged query
+  uint32_t* ref_idx = nullptr;
+  KnnWorkItem* work = nullptr;       // [EXACT_CAP]
   int exact_blocks = 0;
   float eps = KNN_DEFAULT_EPS;
   // staging for *_host calls
@@ -632,13 +768,14 @@ struct fire_knn {
   size_t dev_q_cap = 0, dev_o_cap = 0;
 };
 
-static int knn_ensure_scratch(fire_knn* h, int Q, int S, int KP, int k) {
+static int knn_ensure_scratch(fire_knn* h, int Q, int S, int KP) {
   const int q_pad = (Q + KNN_BM - 1) / KNN_BM * KNN_BM;
   if (q_pad > h->q_cap || S > h->s_cap || KP > h->kp_cap) {
     const int nq = std::max(q_pad, h->q_cap), ns = std::max(S, h->s_cap), nkp = std::max(KP, h->kp_cap);
     FIRE_CUDA(cudaDeviceSynchronize());
     cudaFree(h->qn32); cudaFree(h->q16); cudaFree(h->cand_score); cudaFree(h->cand_idx); cudaFree(h->flagged); cudaFree(h->q_err);
     h->q_err = nullptr; h->qn32 = nullptr; h->q16 = nullptr; h->cand_score = nullptr; h->cand_idx = nullptr; h->flagged = nullptr;
+    h->q_cap = 0; h->s_cap = 0; h->kp_cap = 0;
     FIRE_CUDA(cudaMalloc(&h->qn32, sizeof(float) * nq * h->D));
     FIRE_CUDA(cudaMalloc(&h->q_err, sizeof(float) * nq));
     FIRE_CUDA(cudaMalloc(&h->q16, sizeof(__half) * nq * h->D));
@@ -647,158 +784,53 @@ static int knn_ensure_scratch(fire_knn* h, int Q, int S, int KP, int k) {
     FIRE_CUDA(cudaMalloc(&h->flagged, sizeof(uint32_t) * nq));
     h->q_cap = nq; h->s_cap = ns; h->kp_cap = nkp;
   }
-  if (!h->flagged_count) {
-    FIRE_CUDA(cudaMalloc(&h->flagged_count, sizeof(uint32_t) * 4));
-    FIRE_CUDA(cudaMalloc(&h->stats, sizeof(unsigned long long) * 2));
-    FIRE_CUDA(cudaMemset(h->stats, 0, sizeof(unsigned long long) * 2));
-    h->exact_blocks = std::min(320, 2 * device_sm_count());
+  if (!h->counters) {
+    FIRE_CUDA(cudaMalloc(&h->counters, sizeof(uint32_t) * 4));
+    FIRE_CUDA(cudaMalloc(&h->stats, sizeof(unsigned long long) * 4));
+    FIRE_CUDA(cudaMemset(h->stats, 0, sizeof(unsigned long long) * 4));
+    h->exact_blocks = std::min(EXACT_MAX_BLOCKS, 2 * device_sm_count());
   }
   if (!h->part_dist) {
     FIRE_CUDA(cudaMalloc(&h->part_dist, sizeof(float) * EXACT_CAP * h->exact_blocks * 64));
     FIRE_CUDA(cudaMalloc(&h->part_idx, sizeof(uint32_t) * EXACT_CAP * h->exact_blocks * 64));
+    FIRE_CUDA(cudaMalloc(&h->ref_dist, sizeof(float) * EXACT_CAP * 64));
+    FIRE_CUDA(cudaMalloc(&h->ref_idx, sizeof(uint32_t) * EXACT_CAP * 64));
+    FIRE_CUDA(cudaMalloc(&h->work, sizeof(KnnWorkItem) * EXACT_CAP));
   }
-  (void)k;
   return FIRE_OK;
 }
 
 template <int KP>
 static int knn_launch_scan(fire_knn* h, const CUtensorMap& tq, const CUtensorMap& tg, const KnnScanParams& p,
                            size_t smem_bytes, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[FIRE_MAX_DEVICES] = {};        // the opt-in is per device (context), not per process
+  if (!attr_done[h->device]) {
     FIRE_CUDA(cudaFuncSetAttribute(knn_scan_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(KNN_SMEM_BUDGET + 1024)));
-    attr_done = true;
+    attr_done[h->device] = true;
   }
-  (void)h;
   knn_scan_kernel<KP><<<p.QB * p.S, KNN_THREADS, smem_bytes, st>>>(tq, tg, p);
   FIRE_LAUNCH_CHECK("knn_scan_kernel");
   count_launch();
   return FIRE_OK;
 }
 
-extern "C" {
-
-int fire_knn_create(int D, size_t capacity, fire_knn_t** out) {
-  if (!out) return fail(FIRE_ERR_ARG, "fire_knn_create: out is NULL");
-  if (D <= 0 || D % 64 != 0 || D > 512) return fail(FIRE_ERR_UNSUPPORTED, "fire_knn_create: D=%d must be a multiple of 64 in [64,512]", D);
-  if (capacity == 0 || capacity > 0x7FFFFFF0ull) return fail(FIRE_ERR_ARG, "fire_knn_create: capacity %zu out of range", capacity);
-  fire_knn* h = new (std::nothrow) fire_knn();
-  if (!h) return fail(FIRE_ERR_STATE, "out of host memory");
-  h->D = D;
-  h->capacity = capacity;
-  if (cudaGetDevice(&h->device) != cudaSuccess) { delete h; return fail(FIRE_ERR_CUDA, "no current CUDA device (no CPU fallback)"); }
-  cudaError_t e1 = cudaMalloc(&h->g32, sizeof(float) * capacity * D);
-  cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(&h->g16, sizeof(__half) * capacity * D) : e1;
-  if (e1 != cudaSuccess || e2 != cudaSuccess) {
-    cudaFree(h->g32); cudaFree(h->g16);
-    delete h;
-    return fail(FIRE_ERR_CUDA, "fire_knn_create: cudaMalloc of %zu x %d gallery failed: %s", capacity, D,
-                cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-  }
-  if (cudaMalloc(&h->g_max_err, sizeof(int)) != cudaSuccess || cudaMemset(h->g_max_err, 0, sizeof(int)) != cudaSuccess) {
-    cudaFree(h->g32); cudaFree(h->g16); cudaFree(h->g_max_err);
-    delete h;
-    return fail(FIRE_ERR_CUDA, "fire_knn_create: cudaMalloc failed");
-  }
-  *out = h;
-  return FIRE_OK;
-}
-
-int fire_knn_destroy(fire_knn_t* h) {
-  if (!h) return FIRE_OK;
-  cudaFree(h->g32); cudaFree(h->g16); cudaFree(h->g_max_err); cudaFree(h->q_err); cudaFree(h->qn32); cudaFree(h->q16); cudaFree(h->cand_score);
-  cudaFree(h->cand_idx); cudaFree(h->flagged); cudaFree(h->flagged_count); cudaFree(h->stats);
-  cudaFree(h->part_dist); cudaFree(h->part_idx);
-  if (h->stage_q) cudaFreeHost(h->stage_q);
-  if (h->stage_d) cudaFreeHost(h->stage_d);
-  if (h->stage_i) cudaFreeHost(h->stage_i);
-  if (h->stage_rows) cudaFree(h->stage_rows);
-  cudaFree(h->dev_q); cudaFree(h->dev_d); cudaFree(h->dev_i);
-  delete h;
-  return FIRE_OK;
-}
-
-int fire_knn_reset(fire_knn_t* h) {
-  if (!h) return fail(FIRE_ERR_ARG, "NULL handle");
-  h->count = 0;
-  FIRE_CUDA(cudaMemset(h->g_max_err, 0, sizeof(int)));
-  return FIRE_OK;
-}
-size_t fire_knn_count(const fire_knn_t* h) { return h ? h->count : 0; }
-size_t fire_knn_capacity(const fire_knn_t* h) { return h ? h->capacity : 0; }
-int fire_knn_dim(const fire_knn_t* h) { return h ? h->D : 0; }
-
-int fire_knn_add(fire_knn_t* h, const float* rows, size_t n, fire_stream_t stream) {
-  if (!h || (!rows && n)) return fail(FIRE_ERR_ARG, "fire_knn_add: NULL argument");
-  if (n == 0) return FIRE_OK;
-  if (h->count + n > h->capacity)
-    return fail(FIRE_ERR_STATE, "fire_knn_add: %zu + %zu rows exceed capacity %zu", h->count, n, h->capacity);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t warps_per_block = 8;
-  const size_t blocks = (n + warps_per_block - 1) / warps_per_block;
-  knn_normalize_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(rows, n, h->D, h->g32 + h->count * h->D,
-                                                                       h->g16 + h->count * h->D, n, nullptr, h->g_max_err);
-  FIRE_LAUNCH_CHECK("knn_normalize_kernel(add)");
-  count_launch();
-  h->count += n;
-  return FIRE_OK;
-}
-
-int fire_knn_add_host(fire_knn_t* h, const float* host_rows, size_t n) {
-  if (!h || (!host_rows && n)) return fail(FIRE_ERR_ARG, "fire_knn_add_host: NULL argument");
-  if (n == 0) return FIRE_OK;
-  if (h->count + n > h->capacity)
-    return fail(FIRE_ERR_STATE, "fire_knn_add_host: %zu + %zu rows exceed capacity %zu", h->count, n, h->capacity);
-  const size_t chunk_rows = std::max<size_t>(1, (64u << 20) / (sizeof(float) * h->D));
-  if (h->stage_rows_cap < std::min(n, chunk_rows)) {
-    if (h->stage_rows) cudaFree(h->stage_rows);
-  cudaFree(h->dev_q); cudaFree(h->dev_d); cudaFree(h->dev_i);
-    h->stage_rows = nullptr;
-    h->stage_rows_cap = std::min(n, chunk_rows);
-    FIRE_CUDA(cudaMalloc(&h->stage_rows, sizeof(float) * h->stage_rows_cap * h->D));
-  }
-  for (size_t off = 0; off < n; off += h->stage_rows_cap) {
-    const size_t m = std::min(h->stage_rows_cap, n - off);
-    FIRE_CUDA(cudaMemcpy(h->stage_rows, host_rows + off * h->D, sizeof(float) * m * h->D, cudaMemcpyHostToDevice));
-    int rc = fire_knn_add(h, h->stage_rows, m, nullptr);
-    if (rc != FIRE_OK) return rc;
-    FIRE_CUDA(cudaStreamSynchronize(nullptr));
-  }
-  return FIRE_OK;
-}
-
-int fire_knn_get_rows_host(fire_knn_t* h, size_t first, size_t n, float* host_out) {
-  if (!h || (!host_out && n)) return fail(FIRE_ERR_ARG, "fire_knn_get_rows_host: NULL argument");
-  if (first + n > h->count) return fail(FIRE_ERR_ARG, "fire_knn_get_rows_host: rows [%zu,%zu) beyond count %zu", first, first + n, h->count);
-  if (n == 0) return FIRE_OK;
-  FIRE_CUDA(cudaMemcpy(host_out, h->g32 + first * h->D, sizeof(float) * n * h->D, cudaMemcpyDeviceToHost));
-  return FIRE_OK;
-}
-
-int fire_knn_set_margin(fire_knn_t* h, float eps) {
-  if (!h) return fail(FIRE_ERR_ARG, "NULL handle");
-  h->eps = eps > 0.f ? eps : KNN_DEFAULT_EPS;
-  return FIRE_OK;
-}
-
-int fire_knn_stats(fire_knn_t* h, uint64_t* host_queries_total, uint64_t* host_queries_fallback) {
-  if (!h) return fail(FIRE_ERR_ARG, "NULL handle");
-  unsigned long long v[2] = {0, 0};
-  if (h->stats) FIRE_CUDA(cudaMemcpy(v, h->stats, sizeof(v), cudaMemcpyDeviceToHost));
-  if (host_queries_total) *host_queries_total = v[0];
-  if (host_queries_fallback) *host_queries_fallback = v[1];
-  return FIRE_OK;
-}
-
-int fire_knn_search(fire_knn_t* h, const float* queries, int Q, int k, int64_t id_offset, float* out_dist,
-                    int64_t* out_ids, fire_stream_t stream) {
-  if (!h || !queries || !out_dist || !out_ids) return fail(FIRE_ERR_ARG, "fire_knn_search: NULL argument");
+// The whole search: normalise the queries, tensor-core scan, exact re-rank with proof, bounded exact fallback.
+// `stored_first` >= 0: the queries are the stored (already normalised) rows [stored_first, stored_first + Q).
+// `allow_short`: k may exceed the number of stored rows; missing entries come back as (FLT_MAX, -1) (shards of a sharded gallery).
+static int knn_search_impl(fire_knn* h, const float* queries, long long stored_first, int Q, int k, const KnnOut& out, bool allow_short,
+                           cudaStream_t st) {
   if (Q <= 0) return fail(FIRE_ERR_ARG, "fire_knn_search: Q=%d", Q);
   if (k < 1 || k > 64) return fail(FIRE_ERR_UNSUPPORTED, "fire_knn_search: k=%d outside [1,64]", k);
-  if (static_cast<size_t>(k) > h->count)
+  if (static_cast<size_t>(k) > h->count && !allow_short)
     return fail(FIRE_ERR_STATE, "fire_knn_search: k=%d exceeds the %zu stored rows", k, h->count);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (h->count == 0) {                              // empty shard: nothing but padding
+    const size_t n = static_cast<size_t>(Q) * k;
+    knn_fill_padding_kernel<<<static_cast<unsigned>(std::min<size_t>((n + 255) / 256, 1024)), 256, 0, st>>>(out, n);
+    FIRE_LAUNCH_CHECK("knn_fill_padding_kernel");
+    count_launch();
+    return FIRE_OK;
+  }
   const int D = h->D, nkb = D / 64;
   const int KP = k <= 10 ? 16 : 64;
   const int n_rows = static_cast<int>(h->count);
@@ -813,15 +845,16 @@ int fire_knn_search(fire_knn_t* h, const float* queries, int Q, int k, int64_t i
   const int tiles_per_split = (tiles_total + S - 1) / S;
   S = (tiles_total + tiles_per_split - 1) / tiles_per_split;
 
-  int rc = knn_ensure_scratch(h, Q, S, KP, k);
+  int rc = knn_ensure_scratch(h, Q, S, KP);
   if (rc != FIRE_OK) return rc;
 
   // normalised queries (fp32 for the exact re-rank, fp16 tile-padded for the tensor cores)
   {
     const size_t q_pad = static_cast<size_t>(QB) * KNN_BM;
     const size_t blocks = (q_pad + 7) / 8;
-    knn_normalize_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(queries, static_cast<size_t>(Q), D, h->qn32,
-                                                                         h->q16, q_pad, h->q_err, nullptr);
+    const float* src = stored_first >= 0 ? h->g32 + static_cast<size_t>(stored_first) * D : queries;
+    knn_normalize_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(src, static_cast<size_t>(Q), D, h->qn32, h->q16, q_pad, h->q_err,
+                                                                         nullptr, stored_first >= 0 ? 1 : 0);
     FIRE_LAUNCH_CHECK("knn_normalize_kernel(query)");
     count_launch();
   }
@@ -846,59 +879,217 @@ int fire_knn_search(fire_knn_t* h, const float* queries, int Q, int k, int64_t i
   p.cand_score = h->cand_score; p.cand_idx = h->cand_idx;
   const size_t smem_bytes = 1024 + a_bytes + static_cast<size_t>(stages) * KNN_B_STAGE_BYTES + bar_bytes;
 
-  FIRE_CUDA(cudaMemsetAsync(h->flagged_count, 0, sizeof(uint32_t) * 4, st));
+  FIRE_CUDA(cudaMemsetAsync(h->counters, 0, sizeof(uint32_t) * 4, st));
   rc = KP == 16 ? knn_launch_scan<16>(h, tq, tg, p, smem_bytes, st) : knn_launch_scan<64>(h, tq, tg, p, smem_bytes, st);
   if (rc != FIRE_OK) return rc;
 
   {
     const int blocks = (Q + 7) / 8;
     if (KP == 16)
-      knn_rerank_kernel<16><<<blocks, 256, 0, st>>>(h->qn32, h->g32, h->cand_score, h->cand_idx, S, D, Q, k, id_offset, h->eps,
-                                                    h->q_err, h->g_max_err, out_dist, reinterpret_cast<long long*>(out_ids), h->flagged, h->flagged_count);
+      knn_rerank_kernel<16><<<blocks, 256, 0, st>>>(h->qn32, h->g32, h->cand_score, h->cand_idx, S, D, Q, k, h->eps, h->q_err, h->g_max_err,
+                                                    out, h->flagged, h->counters);
     else
-      knn_rerank_kernel<64><<<blocks, 256, 0, st>>>(h->qn32, h->g32, h->cand_score, h->cand_idx, S, D, Q, k, id_offset, h->eps,
-                                                    h->q_err, h->g_max_err, out_dist, reinterpret_cast<long long*>(out_ids), h->flagged, h->flagged_count);
+      knn_rerank_kernel<64><<<blocks, 256, 0, st>>>(h->qn32, h->g32, h->cand_score, h->cand_idx, S, D, Q, k, h->eps, h->q_err, h->g_max_err,
+                                                    out, h->flagged, h->counters);
     FIRE_LAUNCH_CHECK("knn_rerank_kernel");
     count_launch();
   }
-  knn_exact_scan_kernel<<<h->exact_blocks, EXACT_WARPS * 32, 0, st>>>(h->qn32, h->g32, n_rows, D, k, h->flagged,
-                                                                      h->flagged_count, h->part_dist, h->part_idx);
-  knn_exact_merge_kernel<<<32, 256, 0, st>>>(h->part_dist, h->part_idx, h->exact_blocks, k, id_offset, h->flagged,
-                                             h->flagged_count, out_dist, reinterpret_cast<long long*>(out_ids), h->stats, Q);
-  knn_exact_overflow_kernel<<<h->exact_blocks, EXACT_WARPS * 32, 0, st>>>(h->qn32, h->g32, n_rows, D, k, id_offset, h->flagged,
-                                                                          h->flagged_count, out_dist,
-                                                                          reinterpret_cast<long long*>(out_ids));
+  knn_refine_kernel<<<sms, EXACT_WARPS * 32, 0, st>>>(h->qn32, h->g32, h->cand_score, h->cand_idx, S, KP, D, k, h->eps, h->q_err, h->g_max_err,
+                                                      h->flagged, h->counters, h->ref_dist, h->ref_idx, h->work, out, h->stats, Q);
+  knn_exact_scan_kernel<<<h->exact_blocks, EXACT_WARPS * 32, 0, st>>>(h->qn32, h->g32, n_rows, p.rows_per_split, D, k, h->work, h->counters,
+                                                                      h->part_dist, h->part_idx);
+  knn_exact_merge_kernel<<<32, 256, 0, st>>>(h->part_dist, h->part_idx, h->exact_blocks, k, h->work, h->counters, h->ref_dist, h->ref_idx, out);
+  knn_exact_overflow_kernel<<<h->exact_blocks, EXACT_WARPS * 32, 0, st>>>(h->qn32, h->g32, n_rows, D, k, h->flagged, h->counters, out);
   FIRE_LAUNCH_CHECK("knn exact fallback");
-  count_launch(3);
+  count_launch(4);
   return FIRE_OK;
+}
+
+extern "C" {
+
+int fire_knn_create(int D, size_t capacity, fire_knn_t** out) {
+  if (!out) return fail(FIRE_ERR_ARG, "fire_knn_create: out is NULL");
+  if (D <= 0 || D % 64 != 0 || D > 512) return fail(FIRE_ERR_UNSUPPORTED, "fire_knn_create: D=%d must be a multiple of 64 in [64,512]", D);
+  if (capacity == 0 || capacity > 0x7FFFFFF0ull) return fail(FIRE_ERR_ARG, "fire_knn_create: capacity %zu out of range", capacity);
+  fire_knn* h = new (std::nothrow) fire_knn();
+  if (!h) return fail(FIRE_ERR_STATE, "out of host memory");
+  h->D = D;
+  h->capacity = capacity;
+  if (cudaGetDevice(&h->device) != cudaSuccess || h->device < 0 || h->device >= FIRE_MAX_DEVICES) {
+    delete h;
+    return fail(FIRE_ERR_CUDA, "no current CUDA device (no CPU fallback)");
+  }
+  cudaError_t e1 = cudaMalloc(&h->g32, sizeof(float) * capacity * D);
+  cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(&h->g16, sizeof(__half) * capacity * D) : e1;
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    cudaFree(h->g32); cudaFree(h->g16);
+    delete h;
+    return fail(FIRE_ERR_CUDA, "fire_knn_create: cudaMalloc of %zu x %d gallery failed: %s", capacity, D,
+                cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  }
+  if (cudaMalloc(&h->g_max_err, sizeof(int)) != cudaSuccess || cudaMemset(h->g_max_err, 0, sizeof(int)) != cudaSuccess) {
+    cudaFree(h->g32); cudaFree(h->g16); cudaFree(h->g_max_err);
+    delete h;
+    return fail(FIRE_ERR_CUDA, "fire_knn_create: cudaMalloc failed");
+  }
+  *out = h;
+  return FIRE_OK;
+}
+
+int fire_knn_destroy(fire_knn_t* h) {
+  if (!h) return FIRE_OK;
+  use_device(h->device);
+  cudaFree(h->g32); cudaFree(h->g16); cudaFree(h->g_max_err); cudaFree(h->q_err); cudaFree(h->qn32); cudaFree(h->q16); cudaFree(h->cand_score);
+  cudaFree(h->cand_idx); cudaFree(h->flagged); cudaFree(h->counters); cudaFree(h->stats);
+  cudaFree(h->part_dist); cudaFree(h->part_idx); cudaFree(h->ref_dist); cudaFree(h->ref_idx); cudaFree(h->work);
+  if (h->stage_q) cudaFreeHost(h->stage_q);
+  if (h->stage_d) cudaFreeHost(h->stage_d);
+  if (h->stage_i) cudaFreeHost(h->stage_i);
+  if (h->stage_rows) cudaFree(h->stage_rows);
+  cudaFree(h->dev_q); cudaFree(h->dev_d); cudaFree(h->dev_i);
+  delete h;
+  return FIRE_OK;
+}
+
+int fire_knn_reset(fire_knn_t* h) {
+  if (!h) return fail(FIRE_ERR_ARG, "NULL handle");
+  { const int rc_dev = use_device(h->device); if (rc_dev != FIRE_OK) return rc_dev; }
+  h->count = 0;
+  FIRE_CUDA(cudaMemset(h->g_max_err, 0, sizeof(int)));
+  return FIRE_OK;
+}
+size_t fire_knn_count(const fire_knn_t* h) { return h ? h->count : 0; }
+size_t fire_knn_capacity(const fire_knn_t* h) { return h ? h->capacity : 0; }
+int fire_knn_dim(const fire_knn_t* h) { return h ? h->D : 0; }
+
+int fire_knn_add(fire_knn_t* h, const float* rows, size_t n, fire_stream_t stream) {
+  if (!h || (!rows && n)) return fail(FIRE_ERR_ARG, "fire_knn_add: NULL argument");
+  { const int rc_dev = use_device(h->device); if (rc_dev != FIRE_OK) return rc_dev; }
+  if (n == 0) return FIRE_OK;
+  if (h->count + n > h->capacity)
+    return fail(FIRE_ERR_STATE, "fire_knn_add: %zu + %zu rows exceed capacity %zu", h->count, n, h->capacity);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t warps_per_block = 8;
+  const size_t blocks = (n + warps_per_block - 1) / warps_per_block;
+  knn_normalize_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(rows, n, h->D, h->g32 + h->count * h->D,
+                                                                       h->g16 + h->count * h->D, n, nullptr, h->g_max_err, 0);
+  FIRE_LAUNCH_CHECK("knn_normalize_kernel(add)");
+  count_launch();
+  h->count += n;
+  return FIRE_OK;
+}
+
+int fire_knn_add_host(fire_knn_t* h, const float* host_rows, size_t n) {
+  if (!h || (!host_rows && n)) return fail(FIRE_ERR_ARG, "fire_knn_add_host: NULL argument");
+  { const int rc_dev = use_device(h->device); if (rc_dev != FIRE_OK) return rc_dev; }
+  if (n == 0) return FIRE_OK;
+  if (h->count + n > h->capacity)
+    return fail(FIRE_ERR_STATE, "fire_knn_add_host: %zu + %zu rows exceed capacity %zu", h->count, n, h->capacity);
+  const size_t chunk_rows = std::max<size_t>(1, (64u << 20) / (sizeof(float) * h->D));
+  if (h->stage_rows_cap < std::min(n, chunk_rows)) {         // the row staging buffer is independent of the search buffers
+    if (h->stage_rows) cudaFree(h->stage_rows);
+    h->stage_rows = nullptr;
+    h->stage_rows_cap = 0;
+    FIRE_CUDA(cudaMalloc(&h->stage_rows, sizeof(float) * std::min(n, chunk_rows) * h->D));
+    h->stage_rows_cap = std::min(n, chunk_rows);
+  }
+  for (size_t off = 0; off < n; off += h->stage_rows_cap) {
+    const size_t m = std::min(h->stage_rows_cap, n - off);
+    FIRE_CUDA(cudaMemcpy(h->stage_rows, host_rows + off * h->D, sizeof(float) * m * h->D, cudaMemcpyHostToDevice));
+    int rc = fire_knn_add(h, h->stage_rows, m, nullptr);
+    if (rc != FIRE_OK) return rc;
+    FIRE_CUDA(cudaStreamSynchronize(nullptr));
+  }
+  return FIRE_OK;
+}
+
+int fire_knn_get_rows_host(fire_knn_t* h, size_t first, size_t n, float* host_out) {
+  if (!h || (!host_out && n)) return fail(FIRE_ERR_ARG, "fire_knn_get_rows_host: NULL argument");
+  { const int rc_dev = use_device(h->device); if (rc_dev != FIRE_OK) return rc_dev; }
+  if (first + n > h->count) return fail(FIRE_ERR_ARG, "fire_knn_get_rows_host: rows [%zu,%zu) beyond count %zu", first, first + n, h->count);
+  if (n == 0) return FIRE_OK;
+  FIRE_CUDA(cudaMemcpy(host_out, h->g32 + first * h->D, sizeof(float) * n * h->D, cudaMemcpyDeviceToHost));
+  return FIRE_OK;
+}
+
+int fire_knn_set_margin(fire_knn_t* h, float eps) {
+  if (!h) return fail(FIRE_ERR_ARG, "NULL handle");
+  h->eps = eps > 0.f ? eps : KNN_DEFAULT_EPS;
+  return FIRE_OK;
+}
+
+int fire_knn_stats_ex(fire_knn_t* h, uint64_t* host_out4) {
+  if (!h || !host_out4) return fail(FIRE_ERR_ARG, "fire_knn_stats_ex: NULL argument");
+  { const int rc_dev = use_device(h->device); if (rc_dev != FIRE_OK) return rc_dev; }
+  unsigned long long v[4] = {0, 0, 0, 0};
+  if (h->stats) FIRE_CUDA(cudaMemcpy(v, h->stats, sizeof(v), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 4; ++i) host_out4[i] = v[i];
+  return FIRE_OK;
+}
+
+int fire_knn_stats(fire_knn_t* h, uint64_t* host_queries_total, uint64_t* host_queries_fallback) {
+  uint64_t v[4];
+  const int rc = fire_knn_stats_ex(h, v);
+  if (rc != FIRE_OK) return rc;
+  if (host_queries_total) *host_queries_total = v[0];
+  if (host_queries_fallback) *host_queries_fallback = v[1];
+  return FIRE_OK;
+}
+
+int fire_knn_search(fire_knn_t* h, const float* queries, int Q, int k, int64_t id_offset, float* out_dist,
+                    int64_t* out_ids, fire_stream_t stream) {
+  if (!h || !queries || !out_dist || !out_ids) return fail(FIRE_ERR_ARG, "fire_knn_search: NULL argument");
+  { const int rc_dev = use_device(h->device); if (rc_dev != FIRE_OK) return rc_dev; }
+  KnnOut out{out_dist, reinterpret_cast<long long*>(out_ids), nullptr, id_offset, 1};
+  return knn_search_impl(h, queries, -1, Q, k, out, false, static_cast<cudaStream_t>(stream));
+}
+
+int fire_knn_search_rows(fire_knn_t* h, size_t first, int Q, int k, int64_t id_offset, float* out_dist, int64_t* out_ids,
+                         fire_stream_t stream) {
+  if (!h || !out_dist || !out_ids) return fail(FIRE_ERR_ARG, "fire_knn_search_rows: NULL argument");
+  { const int rc_dev = use_device(h->device); if (rc_dev != FIRE_OK) return rc_dev; }
+  if (Q <= 0 || first + static_cast<size_t>(Q) > h->count)
+    return fail(FIRE_ERR_ARG, "fire_knn_search_rows: rows [%zu,%zu) beyond count %zu", first, first + static_cast<size_t>(std::max(Q, 0)), h->count);
+  KnnOut out{out_dist, reinterpret_cast<long long*>(out_ids), nullptr, id_offset, 1};
+  return knn_search_impl(h, nullptr, static_cast<long long>(first), Q, k, out, false, static_cast<cudaStream_t>(stream));
+}
+
+int fire_knn_search_packed(fire_knn_t* h, const float* queries, int Q, int k, int64_t id_offset, int64_t id_stride,
+                           void* out_packed, fire_stream_t stream) {
+  if (!h || !queries || !out_packed) return fail(FIRE_ERR_ARG, "fire_knn_search_packed: NULL argument");
+  if (id_stride < 1) return fail(FIRE_ERR_ARG, "fire_knn_search_packed: id_stride=%lld", static_cast<long long>(id_stride));
+  { const int rc_dev = use_device(h->device); if (rc_dev != FIRE_OK) return rc_dev; }
+  KnnOut out{nullptr, nullptr, static_cast<int32_t*>(out_packed), id_offset, id_stride};
+  return knn_search_impl(h, queries, -1, Q, k, out, true, static_cast<cudaStream_t>(stream));
 }
 
 int fire_knn_search_host(fire_knn_t* h, const float* host_queries, int Q, int k, int64_t id_offset,
                          float* host_out_dist, int64_t* host_out_ids) {
   if (!h || !host_queries || !host_out_dist || !host_out_ids) return fail(FIRE_ERR_ARG, "fire_knn_search_host: NULL argument");
+  { const int rc_dev = use_device(h->device); if (rc_dev != FIRE_OK) return rc_dev; }
   if (Q <= 0 || k < 1) return fail(FIRE_ERR_ARG, "fire_knn_search_host: Q=%d k=%d", Q, k);
   const size_t qn = static_cast<size_t>(Q) * h->D, on = static_cast<size_t>(Q) * k;
   if (qn > h->stage_q_cap) {
     if (h->stage_q) cudaFreeHost(h->stage_q);
-    h->stage_q = nullptr;
+    h->stage_q = nullptr; h->stage_q_cap = 0;
     FIRE_CUDA(cudaMallocHost(&h->stage_q, sizeof(float) * qn));
     h->stage_q_cap = qn;
   }
   if (on > h->stage_o_cap) {
     if (h->stage_d) cudaFreeHost(h->stage_d);
     if (h->stage_i) cudaFreeHost(h->stage_i);
-    h->stage_d = nullptr; h->stage_i = nullptr;
+    h->stage_d = nullptr; h->stage_i = nullptr; h->stage_o_cap = 0;
     FIRE_CUDA(cudaMallocHost(&h->stage_d, sizeof(float) * on));
     FIRE_CUDA(cudaMallocHost(&h->stage_i, sizeof(long long) * on));
     h->stage_o_cap = on;
   }
   if (qn > h->dev_q_cap) {
-    cudaFree(h->dev_q); h->dev_q = nullptr;
+    cudaFree(h->dev_q); h->dev_q = nullptr; h->dev_q_cap = 0;
     FIRE_CUDA(cudaMalloc(&h->dev_q, sizeof(float) * qn));
     h->dev_q_cap = qn;
   }
   if (on > h->dev_o_cap) {
-    cudaFree(h->dev_d); cudaFree(h->dev_i); h->dev_d = nullptr; h->dev_i = nullptr;
+    cudaFree(h->dev_d); cudaFree(h->dev_i); h->dev_d = nullptr; h->dev_i = nullptr; h->dev_o_cap = 0;
     FIRE_CUDA(cudaMalloc(&h->dev_d, sizeof(float) * on));
     FIRE_CUDA(cudaMalloc(&h->dev_i, sizeof(long long) * on));
     h->dev_o_cap = on;
@@ -915,17 +1106,29 @@ int fire_knn_search_host(fire_knn_t* h, const float* host_queries, int Q, int k,
   return FIRE_OK;
 }
 
-int fire_knn_merge(const float* dists, const int64_t* ids, int Q, int k, int G, float* out_dist, int64_t* out_ids,
-                   fire_stream_t stream) {
-  if (!dists || !ids || !out_dist || !out_ids) return fail(FIRE_ERR_ARG, "fire_knn_merge: NULL argument");
+static int knn_merge_impl(const float* dists, const int64_t* ids, const void* packed, int Q, int k, int G, float* out_dist, int64_t* out_ids,
+                          fire_stream_t stream) {
+  if (!out_dist || !out_ids) return fail(FIRE_ERR_ARG, "fire_knn_merge: NULL argument");
   if (Q <= 0 || k < 1 || G < 1 || G > 32 * KNN_MAX_LISTS_PER_LANE)
     return fail(FIRE_ERR_ARG, "fire_knn_merge: Q=%d k=%d G=%d out of range", Q, k, G);
   const int blocks = (Q + 7) / 8;
-  knn_merge_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(dists, reinterpret_cast<const long long*>(ids), Q, k, G,
-                                                                           out_dist, reinterpret_cast<long long*>(out_ids));
+  knn_merge_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(dists, reinterpret_cast<const long long*>(ids),
+                                                                           static_cast<const int32_t*>(packed), Q, k, G, out_dist,
+                                                                           reinterpret_cast<long long*>(out_ids));
   FIRE_LAUNCH_CHECK("knn_merge_kernel");
   count_launch();
   return FIRE_OK;
+}
+
+int fire_knn_merge(const float* dists, const int64_t* ids, int Q, int k, int G, float* out_dist, int64_t* out_ids,
+                   fire_stream_t stream) {
+  if (!dists || !ids) return fail(FIRE_ERR_ARG, "fire_knn_merge: NULL argument");
+  return knn_merge_impl(dists, ids, nullptr, Q, k, G, out_dist, out_ids, stream);
+}
+
+int fire_knn_merge_packed(const void* packed, int Q, int k, int G, float* out_dist, int64_t* out_ids, fire_stream_t stream) {
+  if (!packed) return fail(FIRE_ERR_ARG, "fire_knn_merge_packed: NULL argument");
+  return knn_merge_impl(nullptr, nullptr, packed, Q, k, G, out_dist, out_ids, stream);
 }
 
 }  // extern "C"

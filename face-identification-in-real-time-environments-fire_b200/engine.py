@@ -265,10 +265,36 @@ class KnnIndex:
         check(_lib.lib().fire_knn_search(self._h, _ptr(queries), Q, k, id_offset, _ptr(dist), _ptr(ids), _lib.stream_ptr()))
         return dist, ids
 
+    def search_rows(self, first: int, n: int, k: int, id_offset: int = 0, out_dist=None, out_ids=None):
+        """Top-k with the STORED rows [first, first+n) as queries (bulk find_similar_embeddings, hnsw_manager.py:227-244).
+        Returns cuda tensors (dist f32 [n,k], ids int64 [n,k]); every row's first hit is itself (distance ~0)."""
+        torch = _torch()
+        dist = out_dist if out_dist is not None else torch.empty(n, k, dtype=torch.float32, device=self.device)
+        ids = out_ids if out_ids is not None else torch.empty(n, k, dtype=torch.int64, device=self.device)
+        check(_lib.lib().fire_knn_search_rows(self._h, first, n, k, id_offset, _ptr(dist), _ptr(ids), _lib.stream_ptr()))
+        return dist, ids
+
+    def search_packed(self, queries, k: int, id_offset: int = 0, id_stride: int = 1, out=None):
+        """Shard search for the multi-GPU exchange: cuda float32 queries -> cuda int32 [Q,k,3] records
+        {distance bits, id low, id high}; id = row * id_stride + id_offset; k may exceed this shard's row count
+        (missing entries = (FLT_MAX, -1))."""
+        torch = _torch()
+        assert queries.is_cuda and queries.dtype == torch.float32 and queries.is_contiguous()
+        Q = queries.numel() // self.dim
+        rec = out if out is not None else torch.empty(Q, k, 3, dtype=torch.int32, device=self.device)
+        check(_lib.lib().fire_knn_search_packed(self._h, _ptr(queries), Q, k, id_offset, id_stride, _ptr(rec), _lib.stream_ptr()))
+        return rec
+
     def stats(self) -> Tuple[int, int]:
         a, b = C.c_uint64(), C.c_uint64()
         check(_lib.lib().fire_knn_stats(self._h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
+
+    def stats_ex(self) -> Tuple[int, int, int, int]:
+        """(queries, queries whose merged-list proof failed, of those: single-split exact scans, whole-shard exact scans)."""
+        v = (C.c_uint64 * 4)()
+        check(_lib.lib().fire_knn_stats_ex(self._h, v))
+        return tuple(int(x) for x in v)
 
     def set_margin(self, eps: float):
         check(_lib.lib().fire_knn_set_margin(self._h, eps))
@@ -282,6 +308,18 @@ def knn_merge(dists, ids):
     od = torch.empty(Q, k, dtype=torch.float32, device=dists.device)
     oi = torch.empty(Q, k, dtype=torch.int64, device=dists.device)
     check(_lib.lib().fire_knn_merge(_ptr(dists), _ptr(ids), Q, k, G, _ptr(od), _ptr(oi), _lib.stream_ptr()))
+    return od, oi
+
+
+def knn_merge_packed(records, out_dist=None, out_ids=None):
+    """records: cuda int32 [G,Q,k,3] (G shards' KnnIndex.search_packed results, e.g. straight out of one all_gather)
+    -> global top-k (dist f32 [Q,k], ids int64 [Q,k])."""
+    torch = _torch()
+    G, Q, k, three = records.shape
+    assert three == 3 and records.is_contiguous() and records.dtype == torch.int32
+    od = out_dist if out_dist is not None else torch.empty(Q, k, dtype=torch.float32, device=records.device)
+    oi = out_ids if out_ids is not None else torch.empty(Q, k, dtype=torch.int64, device=records.device)
+    check(_lib.lib().fire_knn_merge_packed(_ptr(records), Q, k, G, _ptr(od), _ptr(oi), _lib.stream_ptr()))
     return od, oi
 
 

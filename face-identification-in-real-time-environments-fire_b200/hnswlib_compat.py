@@ -115,15 +115,42 @@ class Index:
         labels = rows.astype(np.uint64) if self._identity else self._labels[rows]
         return labels, dist
 
-    # ---- persistence: own flat format is written; hnswlib 0.8.0 `save_index` files are READ -----
+    def knn_query_rows(self, first: int, n: int, k: int = 1):
+        """knn_query with the STORED rows [first, first+n) as the queries (additive; fire_knn_search_rows): what
+        knn_query(original vector of row i) returns for every i in the range, in one GPU pass."""
+        if self._idx is None or k > self._idx.count:
+            raise RuntimeError("Cannot return the results in a contiguous 2D array. Probably ef or M is too small")
+        dist, rows = self._idx.search_rows(first, n, k)
+        dist = dist.cpu().numpy() if hasattr(dist, "cpu") else np.asarray(dist)
+        rows = rows.cpu().numpy() if hasattr(rows, "cpu") else np.asarray(rows)
+        labels = rows.astype(np.uint64) if self._identity else self._labels[rows]
+        return labels, dist
+
+    # ---- persistence (SURVEY 8(f) row 2): the file is an hnswlib 0.8.0 `save_index` image in BOTH directions, so a storage/
+    # tree written here still opens with the reference's hnswlib.load_index (a roll-back does not lose the gallery) ---------
     def save_index(self, path: str):
         n = self.get_current_count()
         rows = self._idx.rows() if n else np.zeros((0, self.dim), np.float32)
+        links = self._knn_graph(n, 2 * self.M)
         with open(path, "wb") as f:
-            f.write(_MAGIC)
-            f.write(struct.pack("<qqqq", self.dim, n, self.max_elements, self.ef))
-            f.write(self._labels.astype("<u8").tobytes())
-            f.write(rows.astype("<f4").tobytes())
+            f.write(write_hnswlib_binary(self._labels, rows, links, self.max_elements, self.M, self.ef_construction))
+
+    def _knn_graph(self, n: int, max_links: int) -> np.ndarray:
+        """Level-0 links of the exported graph: every element's exact nearest neighbours (the GPU search finds them in a
+        few tiled passes).  An exact k-NN graph is what HNSW's construction approximates on its bottom layer."""
+        k = min(max_links, n - 1)
+        if k <= 0:
+            return np.zeros((n, 0), dtype=np.uint32)
+        out = np.empty((n, k), dtype=np.uint32)
+        for first in range(0, n, 8192):
+            m = min(8192, n - first)
+            _, nb = self._idx.search_rows(first, m, k + 1)
+            nb = nb.cpu().numpy() if hasattr(nb, "cpu") else np.asarray(nb)
+            me = np.arange(first, first + m)[:, None]
+            keep = nb != me                                        # drop the row itself (an exact duplicate may sit before it)
+            keep[keep.sum(1) > k, -1] = False                      # no self hit among k+1 (k+1 duplicates): drop the farthest
+            out[first:first + m] = nb[keep].reshape(m, k)
+        return out
 
     def load_index(self, path: str, max_elements: int = 0, allow_replace_deleted: bool = False):
         with open(path, "rb") as f:
@@ -146,6 +173,30 @@ class Index:
 
 
 _HNSW_HEADER = struct.Struct("<6QiI3QdQ")      # HierarchicalNSW::saveIndex, hnswlib 0.8.0 (hnswalg.h)
+
+
+def write_hnswlib_binary(labels: np.ndarray, rows: np.ndarray, links: np.ndarray, max_elements: int, M: int = 16,
+                         ef_construction: int = 200) -> bytes:
+    """The inverse of `parse_hnswlib_binary`: an hnswlib 0.8.0 `save_index` image (layout documented there) of a one-level
+    graph - every element on level 0, entry point 0, level-0 neighbour lists = `links` (uint32 [n, <= 2M] internal ids),
+    no upper-level lists (one zero uint32 per element)."""
+    n, dim = rows.shape
+    maxM0 = 2 * M
+    assert links.shape[0] == n and links.shape[1] <= maxM0
+    data_off = maxM0 * 4 + 4
+    label_off = data_off + dim * 4
+    per_el = label_off + 8
+    rec = np.zeros((n, per_el), dtype=np.uint8)
+    if n:
+        head = np.zeros((n, 1 + maxM0), dtype="<u4")
+        head[:, 0] = links.shape[1]
+        head[:, 1:1 + links.shape[1]] = links
+        rec[:, :data_off] = head.view(np.uint8).reshape(n, data_off)
+        rec[:, data_off:label_off] = np.ascontiguousarray(rows, dtype="<f4").view(np.uint8).reshape(n, dim * 4)
+        rec[:, label_off:] = np.ascontiguousarray(labels, dtype="<u8").view(np.uint8).reshape(n, 8)
+    header = _HNSW_HEADER.pack(0, max(int(max_elements), n), n, per_el, label_off, data_off, 0 if n else -1, 0 if n else 0xFFFFFFFF,
+                               M, maxM0, M, 1.0 / np.log(M), ef_construction)
+    return header + rec.tobytes() + np.zeros(n, dtype="<u4").tobytes()
 
 
 def parse_hnswlib_binary(blob: bytes, dim: int):

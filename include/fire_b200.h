@@ -128,11 +128,30 @@ int fire_knn_search(fire_knn_t* h, const float* queries, int Q, int k, int64_t i
                     int64_t* out_ids, fire_stream_t stream);
 int fire_knn_search_host(fire_knn_t* h, const float* host_queries, int Q, int k, int64_t id_offset,
                          float* host_out_dist, int64_t* host_out_ids);
+/* Same search with the STORED rows [first, first+Q) as the queries, used as they are (they were normalised when they were
+ * added, which is exactly what knn_query would make of the vector the row came from).  This is the bulk form of the
+ * reference's find_similar_embeddings loop in shrink_db_ids (modules/face_recognition.py:265-315, hnsw_manager.py:227-244:
+ * one top-50 query per stored embedding); the caller tiles first/Q over the gallery. */
+int fire_knn_search_rows(fire_knn_t* h, size_t first, int Q, int k, int64_t id_offset, float* out_dist, int64_t* out_ids,
+                         fire_stream_t stream);
+/* Shard form for the multi-GPU exchange: results as ONE array of 12-byte records, int32 [Q][k][3] =
+ * {distance bits, id low word, id high word}, so a single all-gather carries distances and ids; id = row * id_stride +
+ * id_offset (contiguous shards: stride 1, offset = first global row; interleaved shards: stride = world size, offset =
+ * rank).  Unlike fire_knn_search, k may exceed the rows this shard holds (an empty or tiny shard of a sharded gallery):
+ * missing entries are (FLT_MAX, -1), which fire_knn_merge* sorts last. */
+int fire_knn_search_packed(fire_knn_t* h, const float* queries, int Q, int k, int64_t id_offset, int64_t id_stride,
+                           void* out_packed, fire_stream_t stream);
 /* Merge G partial results (dists/ids laid out [G][Q][k], each row ascending) into the global top-k. */
 int fire_knn_merge(const float* dists, const int64_t* ids, int Q, int k, int G, float* out_dist,
                    int64_t* out_ids, fire_stream_t stream);
+/* Same merge over packed records [G][Q][k][3] as written by fire_knn_search_packed and gathered with one all-gather. */
+int fire_knn_merge_packed(const void* packed, int Q, int k, int G, float* out_dist, int64_t* out_ids,
+                          fire_stream_t stream);
 /* Counters: queries answered so far / queries that needed the exact fp32 fallback scan. */
 int fire_knn_stats(fire_knn_t* h, uint64_t* host_queries_total, uint64_t* host_queries_fallback);
+/* host_out4 = {queries answered, queries whose merged-list proof failed (exact re-rank of every split's candidates),
+ * of those: queries that then scanned ONE gallery split, queries that scanned the whole shard}. */
+int fire_knn_stats_ex(fire_knn_t* h, uint64_t* host_out4);
 /* Test hook: widen the fp16-filter safety margin (default: 3e-5 on top of the measured fp16 rounding bound) to force the fallback path. */
 int fire_knn_set_margin(fire_knn_t* h, float eps);
 

@@ -54,8 +54,26 @@ def test_hnswlib_binary_loads_into_the_dropin(tmp_path, monkeypatch, oracle_nati
     (tmp_path / "junk.bin").write_bytes(b"\x01" * 500)
     with pytest.raises(RuntimeError):
         hnswlib_compat.Index(space="cosine", dim=128).load_index(str(tmp_path / "junk.bin"))
-    # and what the drop-in saves itself still round-trips
+    # what the drop-in saves is an hnswlib 0.8.0 image too (a roll-back to the reference must not lose the gallery):
+    # same header arithmetic, every element on level 0, neighbour lists = the exact 2M nearest rows, no self links
     idx.save_index(str(tmp_path / "own.bin"))
+    blob = (tmp_path / "own.bin").read_bytes()
+    hdr = hnswlib_compat._HNSW_HEADER.unpack_from(blob, 0)
+    n, per_el, label_off, data_off = hdr[2], hdr[3], hdr[4], hdr[5]
+    assert (hdr[0], n, hdr[8], hdr[9], hdr[10]) == (0, 299, 16, 32, 16) and hdr[6] == 0 and hdr[7] == 0
+    assert len(blob) == hnswlib_compat._HNSW_HEADER.size + n * per_el + 4 * n            # + one empty upper-level list per element
+    rec = np.frombuffer(blob, np.uint8, n * per_el, hnswlib_compat._HNSW_HEADER.size).reshape(n, per_el)
+    head = np.ascontiguousarray(rec[:, :data_off]).view("<u4").reshape(n, 33)
+    assert np.all(head[:, 0] == 32) and np.all(head[:, 1:] < n) and not np.any(head[:, 1:] == np.arange(n)[:, None])
+    stored = np.ascontiguousarray(rec[:, data_off:label_off]).view("<f4").reshape(n, 128)
+    want_nb = np.argsort(-(stored @ stored.T) + 2 * np.eye(n), axis=1)[:, :32]           # brute-force neighbours, self pushed last
+    assert np.mean([len(set(head[i, 1:]) & set(want_nb[i])) for i in range(n)]) > 31.9
     again = hnswlib_compat.Index(space="cosine", dim=128)
     again.load_index(str(tmp_path / "own.bin"))
     assert again.get_current_count() == 299 and np.array_equal(again.knn_query(q, k=5)[0], lab)
+    # files written by round 1 of this package (private FIREKNN1 layout) still load
+    old = tmp_path / "old.bin"
+    old.write_bytes(b"FIREKNN1" + struct.pack("<qqqq", 128, 3, 1000, 10) + np.arange(3, dtype="<u8").tobytes() + rows[:3].astype("<f4").tobytes())
+    legacy = hnswlib_compat.Index(space="cosine", dim=128)
+    legacy.load_index(str(old))
+    assert legacy.get_current_count() == 3 and legacy.knn_query(rows[1], k=1)[0][0][0] == 1

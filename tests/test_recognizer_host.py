@@ -140,3 +140,55 @@ def test_batched_recognizer_equals_the_reference_loop(ref_world, tmp_path, renam
     assert st_a["unknown"].keys() == st_b["unknown"].keys()
     for k in st_a["unknown"]:
         assert st_a["unknown"][k][0] == st_b["unknown"][k][0] and np.array_equal(st_a["unknown"][k][1], st_b["unknown"][k][1])
+
+
+def test_bulk_shrink_db_ids_equals_the_reference_loop(ref_world, tmp_path):
+    """HNSWManager.shrink_db_ids (all neighbour lists from tiled GPU passes, fire_knn_search_rows) leaves
+    labels and SQLite exactly as the REAL FaceRecognition.shrink_db_ids (modules/face_recognition.py:265-315) does."""
+    import sqlite3
+    from fire_b200.hnsw_manager import HNSWManager
+    frm = ref_world
+    rng = np.random.default_rng(9)
+    centers = rng.standard_normal((12, D)).astype(np.float32)
+    centers /= np.linalg.norm(centers, axis=1, keepdims=True)
+    people, vecs, labels = [], [], []
+    for i in range(160):
+        c = int(rng.integers(0, 12))
+        v = centers[c] + float(rng.choice([0.02, 0.05, 0.12])) * rng.standard_normal(D).astype(np.float32)
+        # clusters 0-7: one known name each plus unknowns; 8-9: two different known names (conflict); 10-11: unknowns only
+        if c < 8:
+            lab = f"person{c}" if rng.random() < 0.3 else f"Unknown_{i:08x}"
+        elif c < 10:
+            lab = f"person{c}{'ab'[int(rng.integers(0, 2))]}" if rng.random() < 0.5 else f"Unknown_{i:08x}"
+        else:
+            lab = f"Unknown_{i:08x}"
+        vecs.append((v * float(rng.uniform(0.5, 3))).astype(np.float32)); labels.append(lab)   # un-normalised on purpose (M2)
+
+    (tmp_path / "ref").mkdir(); (tmp_path / "new").mkdir()
+    fr = frm.FaceRecognition(detector_type="yunet", encoder_model_type="128", encoder_mode="cpu_optimized",
+                             sqlite_db_path=str(tmp_path / "ref" / "f.db"), hnsw_index_path=str(tmp_path / "ref" / "i.bin"),
+                             hnsw_labels_path=str(tmp_path / "ref" / "l.pkl"), hnsw_db_ids_path=str(tmp_path / "ref" / "d.pkl"))
+    for v, lab in zip(vecs, labels):
+        fr.hnsw_manager.add_embedding(v, lab, fr._add_to_sqlite(lab, v))
+    fr.shrink_db_ids(0.75)
+    want_labels = list(fr.hnsw_manager.hnsw_labels)
+    want_db = [r[0] for r in fr.db_manager.cursor.execute("SELECT label FROM faces ORDER BY id")]
+    fr.close()
+
+    conn = sqlite3.connect(str(tmp_path / "new" / "f.db"))
+    cur = conn.cursor()
+    cur.execute("CREATE TABLE faces (id INTEGER PRIMARY KEY AUTOINCREMENT, label TEXT NOT NULL, embedding BLOB NOT NULL)")
+    mgr = HNSWManager(D, str(tmp_path / "new" / "i.bin"), str(tmp_path / "new" / "l.pkl"), str(tmp_path / "new" / "d.pkl"), None)
+    for v, lab in zip(vecs, labels):
+        cur.execute("INSERT INTO faces (label, embedding) VALUES (?, ?)", (lab, v.tobytes()))
+        mgr.add_embedding(v, lab, cur.lastrowid)
+    conn.commit()
+    lists = mgr.find_similar_all(0.75, tile=64)
+    for hid in (0, 17, 159):                                                   # the bulk lists == the per-row call of the reference API
+        e = mgr._get_embedding_from_db_id(mgr.hnsw_db_ids[hid], cur)
+        assert [int(x) for x in lists[hid]] == [int(x) for x in mgr.find_similar_embeddings(e, 0.75)]
+    merges = mgr.shrink_db_ids(cur, conn, 0.75)
+    assert merges >= 8 and len(set(want_labels)) < len(set(labels))           # the scenario really merges groups
+    assert mgr.hnsw_labels == want_labels
+    assert [r[0] for r in cur.execute("SELECT label FROM faces ORDER BY id")] == want_db
+    assert any(l.startswith("person8") for l in want_labels) and len({l for l in want_labels if l.startswith("person8")}) == 2   # conflict kept
