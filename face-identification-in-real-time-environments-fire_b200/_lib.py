@@ -29,6 +29,9 @@ _SIGNATURES = {
     "fire_launch_count": (C.c_uint64, []),
     "fire_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fire_roi_meta_bytes": (C.c_size_t, [C.c_int]),
+    "fire_pack_rois_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t,
+                                      C.POINTER(C.c_size_t), C.c_int]),
     "fire_align_warp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
     "fire_ingest_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

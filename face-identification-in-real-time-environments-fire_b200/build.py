@@ -18,7 +18,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 OBJ_DIR = os.path.join(PKG_DIR, "_obj")
 LIB_PATH = os.path.join(PKG_DIR, "libfire_b200.so")
-SOURCES = ["fire_api.cu", "knn.cu", "preprocess.cu", "facenet_engine.cu"]
+SOURCES = ["fire_api.cu", "knn.cu", "preprocess.cu", "roi_upload.cu", "facenet_engine.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-Xptxas", "-v"]
 

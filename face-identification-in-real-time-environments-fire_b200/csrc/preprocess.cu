@@ -124,31 +124,116 @@ __device__ __forceinline__ void store_s2d(float a0, float a1, float a2, int box,
   }
 }
 
-__device__ __forceinline__ void store_pixel(int v0, int v1, int v2, int box, int dy, int dx, __half* out_f16, float* out_f32) {
-  if (out_f16) store_s2d(static_cast<float>(v0), static_cast<float>(v1), static_cast<float>(v2), box, dy, dx, out_f16);
-  if (out_f32) {
-    const size_t pix = (static_cast<size_t>(box) * PRE_OUT + dy) * PRE_OUT + dx;
-    out_f32[pix * 3 + 0] = __fdiv_rn(static_cast<float>(v0), 255.0f);
-    out_f32[pix * 3 + 1] = __fdiv_rn(static_cast<float>(v1), 255.0f);
-    out_f32[pix * 3 + 2] = __fdiv_rn(static_cast<float>(v2), 255.0f);
+// One output pixel of cv::resize(INTER_AREA) on 8UC3 (every branch resize.cpp can take for this call), re-quantised to
+// uint8 like the reference does before dividing by 255.  `src` / `st` address the crop: pixel (sy, sx) channel c is
+// src[sy * st + sx * 3 + c]; they point either at the frame in HBM or at the CTA's staged copy in shared memory.
+__device__ __forceinline__ void reference_pixel(int mode, const CropGeom& g, const uint8_t* __restrict__ src, long long st, int dx, int dy,
+                                                const AreaEntry& eax, const AreaEntry& eay, const LinEntry& elx, const LinEntry& ely, int xmax,
+                                                int (&v)[3]) {
+  v[0] = v[1] = v[2] = 0;
+  if (mode == PM_COPY) {
+    const uint8_t* s = src + dy * st + dx * 3;
+    v[0] = s[0]; v[1] = s[1]; v[2] = s[2];
+  } else if (mode == PM_FAST) {
+    const int ix = g.iscale_x, iy = g.iscale_y;
+    int sum[3] = {0, 0, 0};
+    for (int yy = 0; yy < iy; ++yy) {
+      const uint8_t* s = src + static_cast<long long>(dy * iy + yy) * st + static_cast<long long>(dx) * ix * 3;
+      for (int xx = 0; xx < ix; ++xx) { sum[0] += s[xx * 3]; sum[1] += s[xx * 3 + 1]; sum[2] += s[xx * 3 + 2]; }
+    }
+    if (ix == 2 && iy == 2) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = (sum[c] + 2) >> 2;
+    } else {
+      const float scale = 1.f / static_cast<float>(ix * iy);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = min(255, max(0, __float2int_rn(__fmul_rn(static_cast<float>(sum[c]), scale))));
+    }
+  } else if (mode == PM_AREA) {
+    const AreaEntry ex = eax;
+    const AreaEntry ey = eay;
+    float sum[3] = {0.f, 0.f, 0.f};
+    bool first = true;
+    const int ny = ey.has_left + ey.n_mid + ey.has_right;
+    for (int j = 0; j < ny; ++j) {
+      int sy; float beta;
+      if (ey.has_left && j == 0) { sy = ey.s_left; beta = ey.a_left; }
+      else if (j - ey.has_left < ey.n_mid) { sy = ey.s_mid0 + j - ey.has_left; beta = ey.a_mid; }
+      else { sy = ey.s_right; beta = ey.a_right; }
+      const uint8_t* s = src + static_cast<long long>(sy) * st;
+      float buf[3] = {0.f, 0.f, 0.f};
+      if (ex.has_left) {
+        const uint8_t* q = s + ex.s_left * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) buf[c] = __fadd_rn(buf[c], __fmul_rn(static_cast<float>(q[c]), ex.a_left));
+      }
+      for (int k = 0; k < ex.n_mid; ++k) {
+        const uint8_t* q = s + (ex.s_mid0 + k) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) buf[c] = __fadd_rn(buf[c], __fmul_rn(static_cast<float>(q[c]), ex.a_mid));
+      }
+      if (ex.has_right) {
+        const uint8_t* q = s + ex.s_right * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) buf[c] = __fadd_rn(buf[c], __fmul_rn(static_cast<float>(q[c]), ex.a_right));
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        sum[c] = first ? __fmul_rn(beta, buf[c]) : __fadd_rn(sum[c], __fmul_rn(beta, buf[c]));
+      first = false;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = min(255, max(0, __float2int_rn(sum[c])));
+  } else if (mode == PM_LINEAR) {
+    const LinEntry ex = elx;
+    const LinEntry ey = ely;
+    const int r0 = min(max(ey.ofs, 0), g.ch - 1), r1 = min(max(ey.ofs + 1, 0), g.ch - 1);
+    const uint8_t* s0 = src + static_cast<long long>(r0) * st + ex.ofs * 3;
+    const uint8_t* s1 = src + static_cast<long long>(r1) * st + ex.ofs * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      int h0, h1;
+      if (dx < xmax) {
+        h0 = s0[c] * ex.a0 + s0[3 + c] * ex.a1;
+        h1 = s1[c] * ex.a0 + s1[3 + c] * ex.a1;
+      } else {
+        h0 = s0[c] * 2048; h1 = s1[c] * 2048;
+      }
+      v[c] = ((((ey.a0 * (h0 >> 4)) >> 16) + ((ey.a1 * (h1 >> 4)) >> 16) + 2) >> 2) & 0xFF;
+    }
   }
 }
+
+// One CTA = one box x 16 output rows.
+//   1. thread 0 applies the crop rule; the span tables of the 160 output columns and 16 output rows are built in shared memory;
+//   2. the source rows this row block needs are STAGED in shared memory with 16-byte loads (one coalesced uint4 per lane
+//      along the row, from the 16-byte-aligned address below the crop's first byte to the one above its last; the few
+//      chunks that would cross the frame's own bytes are read bytewise) - every source byte crosses HBM/L2 -> SM once per
+//      row block, whatever the tap overlap.  Blocks whose span does not fit (very large boxes) read the frame directly;
+//   3. one thread finishes one network-input POSITION (the 2 x 2 pixel block of the space-to-depth layout): 4 pixels ->
+//      16 fp16 channels -> one aligned 32-byte store; a warp writes 1 KB of consecutive bytes.
+constexpr int PRE_STAGE_BYTES = 64 * 1024;
 
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_reference_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict__ frame_desc,
                             const int32_t* __restrict__ boxes, const int32_t* __restrict__ box_frame, int swap_rb,
                             __half* __restrict__ out_f16, float* __restrict__ out_f32, int32_t* __restrict__ status) {
+  extern __shared__ __align__(16) uint8_t stage[];
   __shared__ CropGeom g;
   __shared__ AreaEntry ax[PRE_OUT];
   __shared__ AreaEntry ay[PRE_ROWS_PER_BLOCK];
   __shared__ LinEntry lx[PRE_OUT];
   __shared__ LinEntry ly[PRE_ROWS_PER_BLOCK];
-  __shared__ int s_xmax;
+  __shared__ int s_xmax, s_row_lo, s_row_hi;
+  __shared__ long long s_frame_lo, s_frame_hi;     // byte range of the frame inside `frames`
 
   const int box = blockIdx.x;
   const int dy0 = blockIdx.y * PRE_ROWS_PER_BLOCK;
   if (threadIdx.x == 0) {
-    crop_geometry(frames, frame_desc + 4 * static_cast<long long>(box_frame[box]), boxes + 4 * box, g);
+    const int64_t* fd = frame_desc + 4 * static_cast<long long>(box_frame[box]);
+    crop_geometry(frames, fd, boxes + 4 * box, g);
+    s_frame_lo = fd[0];
+    s_frame_hi = fd[0] + fd[1] * fd[3];
     s_xmax = PRE_OUT;
     if (status && blockIdx.y == 0) status[box] = g.mode == PM_EMPTY ? 1 : 0;
   }
@@ -170,86 +255,93 @@ preprocess_reference_kernel(const uint8_t* __restrict__ frames, const int64_t* _
     }
   }
   __syncthreads();
-  const int xmax = s_xmax;
-  const uint8_t* __restrict__ src = g.base;
-  const long long st = g.stride;
-
-  for (int t = threadIdx.x; t < PRE_ROWS_PER_BLOCK * PRE_OUT; t += PRE_THREADS) {
-    const int ry = t / PRE_OUT, dx = t - ry * PRE_OUT, dy = dy0 + ry;
-    int v[3] = {0, 0, 0};
-    if (mode == PM_COPY) {
-      const uint8_t* s = src + dy * st + dx * 3;
-      v[0] = s[0]; v[1] = s[1]; v[2] = s[2];
-    } else if (mode == PM_FAST) {
-      const int ix = g.iscale_x, iy = g.iscale_y;
-      int sum[3] = {0, 0, 0};
-      for (int yy = 0; yy < iy; ++yy) {
-        const uint8_t* s = src + static_cast<long long>(dy * iy + yy) * st + static_cast<long long>(dx) * ix * 3;
-        for (int xx = 0; xx < ix; ++xx) { sum[0] += s[xx * 3]; sum[1] += s[xx * 3 + 1]; sum[2] += s[xx * 3 + 2]; }
+  if (threadIdx.x == 0) {                       // source rows [lo, hi) this row block reads
+    int lo = 0, hi = 0;
+    if (mode == PM_COPY) { lo = dy0; hi = dy0 + PRE_ROWS_PER_BLOCK; }
+    else if (mode == PM_FAST) { lo = dy0 * g.iscale_y; hi = (dy0 + PRE_ROWS_PER_BLOCK) * g.iscale_y; }
+    else if (mode == PM_AREA) {
+      lo = g.ch; hi = 0;
+      for (int i = 0; i < PRE_ROWS_PER_BLOCK; ++i) {
+        const AreaEntry& e = ay[i];
+        if (e.has_left) { lo = min(lo, e.s_left); hi = max(hi, e.s_left + 1); }
+        if (e.n_mid > 0) { lo = min(lo, e.s_mid0); hi = max(hi, e.s_mid0 + e.n_mid); }
+        if (e.has_right) { lo = min(lo, e.s_right); hi = max(hi, e.s_right + 1); }
       }
-      if (ix == 2 && iy == 2) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) v[c] = (sum[c] + 2) >> 2;
-      } else {
-        const float scale = 1.f / static_cast<float>(ix * iy);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) v[c] = min(255, max(0, __float2int_rn(__fmul_rn(static_cast<float>(sum[c]), scale))));
-      }
-    } else if (mode == PM_AREA) {
-      const AreaEntry ex = ax[dx];
-      const AreaEntry ey = ay[ry];
-      float sum[3] = {0.f, 0.f, 0.f};
-      bool first = true;
-      const int ny = ey.has_left + ey.n_mid + ey.has_right;
-      for (int j = 0; j < ny; ++j) {
-        int sy; float beta;
-        if (ey.has_left && j == 0) { sy = ey.s_left; beta = ey.a_left; }
-        else if (j - ey.has_left < ey.n_mid) { sy = ey.s_mid0 + j - ey.has_left; beta = ey.a_mid; }
-        else { sy = ey.s_right; beta = ey.a_right; }
-        const uint8_t* s = src + static_cast<long long>(sy) * st;
-        float buf[3] = {0.f, 0.f, 0.f};
-        if (ex.has_left) {
-          const uint8_t* q = s + ex.s_left * 3;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) buf[c] = __fadd_rn(buf[c], __fmul_rn(static_cast<float>(q[c]), ex.a_left));
-        }
-        for (int k = 0; k < ex.n_mid; ++k) {
-          const uint8_t* q = s + (ex.s_mid0 + k) * 3;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) buf[c] = __fadd_rn(buf[c], __fmul_rn(static_cast<float>(q[c]), ex.a_mid));
-        }
-        if (ex.has_right) {
-          const uint8_t* q = s + ex.s_right * 3;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) buf[c] = __fadd_rn(buf[c], __fmul_rn(static_cast<float>(q[c]), ex.a_right));
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          sum[c] = first ? __fmul_rn(beta, buf[c]) : __fadd_rn(sum[c], __fmul_rn(beta, buf[c]));
-        first = false;
-      }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) v[c] = min(255, max(0, __float2int_rn(sum[c])));
     } else if (mode == PM_LINEAR) {
-      const LinEntry ex = lx[dx];
-      const LinEntry ey = ly[ry];
-      const int r0 = min(max(ey.ofs, 0), g.ch - 1), r1 = min(max(ey.ofs + 1, 0), g.ch - 1);
-      const uint8_t* s0 = src + static_cast<long long>(r0) * st + ex.ofs * 3;
-      const uint8_t* s1 = src + static_cast<long long>(r1) * st + ex.ofs * 3;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        int h0, h1;
-        if (dx < xmax) {
-          h0 = s0[c] * ex.a0 + s0[3 + c] * ex.a1;
-          h1 = s1[c] * ex.a0 + s1[3 + c] * ex.a1;
-        } else {
-          h0 = s0[c] * 2048; h1 = s1[c] * 2048;
-        }
-        v[c] = ((((ey.a0 * (h0 >> 4)) >> 16) + ((ey.a1 * (h1 >> 4)) >> 16) + 2) >> 2) & 0xFF;
+      lo = g.ch; hi = 0;
+      for (int i = 0; i < PRE_ROWS_PER_BLOCK; ++i) {
+        const int r0 = min(max(ly[i].ofs, 0), g.ch - 1), r1 = min(max(ly[i].ofs + 1, 0), g.ch - 1);
+        lo = min(lo, r0); hi = max(hi, r1 + 1);
       }
     }
-    if (swap_rb) { const int tmp = v[0]; v[0] = v[2]; v[2] = tmp; }
-    store_pixel(v[0], v[1], v[2], box, dy, dx, out_f16, out_f32);
+    s_row_lo = max(0, min(lo, g.ch)); s_row_hi = max(s_row_lo, min(hi, g.ch));
+  }
+  __syncthreads();
+  const int xmax = s_xmax;
+  const uint8_t* __restrict__ src = g.base;
+  long long st = g.stride;
+
+  if (mode != PM_EMPTY) {
+    // stage rows [row_lo, row_hi) x bytes [0, cw * 3) of the crop; smem row r holds the 16-byte-aligned span around them
+    const int row_lo = s_row_lo, n_rows = s_row_hi - s_row_lo;
+    const int lead = static_cast<int>(reinterpret_cast<uintptr_t>(g.base) & 15);      // same for every row iff the stride is a multiple of 16
+    const int pitch = (lead + g.cw * 3 + 15) & ~15;
+    if ((g.stride & 15) == 0 && n_rows > 0 && static_cast<long long>(n_rows) * pitch <= PRE_STAGE_BYTES) {
+      const int chunks = pitch >> 4;
+      const uint8_t* row0 = g.base - lead + static_cast<long long>(row_lo) * g.stride;
+      const uint8_t* f_lo = frames + s_frame_lo;
+      const uint8_t* f_hi = frames + s_frame_hi;
+      for (int i = threadIdx.x; i < n_rows * chunks; i += PRE_THREADS) {
+        const int r = i / chunks, c = i - r * chunks;
+        const uint8_t* gp = row0 + static_cast<long long>(r) * g.stride + c * 16;
+        uint4 q;
+        if (gp >= f_lo && gp + 16 <= f_hi) {
+          q = __ldg(reinterpret_cast<const uint4*>(gp));
+        } else {                                 // the chunk hangs over the frame's first / last byte
+          uint8_t b[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) b[k] = (gp + k >= f_lo && gp + k < f_hi) ? gp[k] : static_cast<uint8_t>(0);
+          q = *reinterpret_cast<uint4*>(b);
+        }
+        *reinterpret_cast<uint4*>(stage + static_cast<size_t>(r) * pitch + c * 16) = q;
+      }
+      __syncthreads();
+      src = stage + lead - static_cast<long long>(row_lo) * pitch;      // crop-relative addressing into the staged rows
+      st = pitch;
+    }
+  }
+
+  constexpr int POS_W = PRE_OUT / 2;
+  for (int t = threadIdx.x; t < (PRE_ROWS_PER_BLOCK / 2) * POS_W; t += PRE_THREADS) {
+    const int yl = t / POS_W, X = t - yl * POS_W;
+    float h[12];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int ry = 2 * yl + a, dx = 2 * X + b;
+        int v[3];
+        reference_pixel(mode, g, src, st, dx, dy0 + ry, ax[dx], ay[ry], lx[dx], ly[ry], xmax, v);
+        if (swap_rb) { const int tmp = v[0]; v[0] = v[2]; v[2] = tmp; }
+        h[(a * 2 + b) * 3 + 0] = static_cast<float>(v[0]);
+        h[(a * 2 + b) * 3 + 1] = static_cast<float>(v[1]);
+        h[(a * 2 + b) * 3 + 2] = static_cast<float>(v[2]);
+      }
+    const int Y = (dy0 >> 1) + yl;
+    if (out_f16) {
+      uint4* o = reinterpret_cast<uint4*>(out_f16 + ((static_cast<size_t>(box) * POS_W + Y) * POS_W + X) * 16);
+      o[0] = make_uint4(pack_f16x2_sat(h[0], h[1]), pack_f16x2_sat(h[2], h[3]), pack_f16x2_sat(h[4], h[5]), pack_f16x2_sat(h[6], h[7]));
+      o[1] = make_uint4(pack_f16x2_sat(h[8], h[9]), pack_f16x2_sat(h[10], h[11]), 0u, 0u);
+    }
+    if (out_f32) {
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        float2* o = reinterpret_cast<float2*>(out_f32 + ((static_cast<size_t>(box) * PRE_OUT + 2 * Y + a) * PRE_OUT + 2 * X) * 3);
+        o[0] = make_float2(__fdiv_rn(h[a * 6 + 0], 255.0f), __fdiv_rn(h[a * 6 + 1], 255.0f));
+        o[1] = make_float2(__fdiv_rn(h[a * 6 + 2], 255.0f), __fdiv_rn(h[a * 6 + 3], 255.0f));
+        o[2] = make_float2(__fdiv_rn(h[a * 6 + 4], 255.0f), __fdiv_rn(h[a * 6 + 5], 255.0f));
+      }
+    }
   }
 }
 
@@ -472,7 +564,14 @@ extern "C" int fire_preprocess(const uint8_t* frames, const int64_t* frame_desc,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (m == FIRE_PRE_REFERENCE) {
     dim3 grid(n_boxes, PRE_OUT / PRE_ROWS_PER_BLOCK);
-    preprocess_reference_kernel<<<grid, PRE_THREADS, 0, st>>>(frames, frame_desc, boxes_xywh, box_frame, swap,
+    static bool attr_done[FIRE_MAX_DEVICES] = {};
+    int dev = 0;
+    FIRE_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < FIRE_MAX_DEVICES && !attr_done[dev]) {
+      FIRE_CUDA(cudaFuncSetAttribute(preprocess_reference_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PRE_STAGE_BYTES));
+      attr_done[dev] = true;
+    }
+    preprocess_reference_kernel<<<grid, PRE_THREADS, PRE_STAGE_BYTES, st>>>(frames, frame_desc, boxes_xywh, box_frame, swap,
                                                               static_cast<__half*>(out_f16), out_f32, box_status);
   } else if (m == FIRE_PRE_NORTHSTAR) {
     preprocess_northstar_kernel<<<n_boxes, NS_THREADS, 0, st>>>(frames, frame_desc, boxes_xywh, box_frame, swap,

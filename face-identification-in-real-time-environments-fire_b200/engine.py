@@ -340,6 +340,73 @@ def preprocess_boxes(frames, frame_desc, boxes, box_frame, mode: int = _lib.PRE_
     return f16, f32, status
 
 
+def pack_rois(frames_host, frame_desc_host, boxes_host, box_frame_host, out_host, threads: int = 4) -> int:
+    """fire_pack_rois_host: crop rectangles of `boxes_host` (int32 [n,4] xywh, the reference's clamp rule) out of host frames
+    (uint8, flat or [F,H,W,3]; frame_desc_host int64 [F,4] = offset, H, W, row stride) into the staging buffer `out_host`
+    (uint8, 16-byte aligned, ideally pinned), tables first.  numpy arrays or CPU torch tensors.  Returns the bytes used.
+    Pure host work (no GPU needed): staging for the upload, not compute."""
+    def addr(a):
+        return a.ctypes.data if isinstance(a, np.ndarray) else int(a.data_ptr())
+
+    def nbytes(a):
+        return a.nbytes if isinstance(a, np.ndarray) else a.numel() * a.element_size()
+    n = int(boxes_host.shape[0])
+    used = C.c_size_t(0)
+    check(_lib.lib().fire_pack_rois_host(addr(frames_host), addr(frame_desc_host), int(frame_desc_host.shape[0]), addr(boxes_host),
+                                         addr(box_frame_host), n, addr(out_host), nbytes(out_host), C.byref(used), threads))
+    return int(used.value)
+
+
+def roi_views(buf, n: int):
+    """The tables at the head of a packed ROI buffer (host or device tensor): (frame_desc int64 [n,4], boxes int32 [n,4],
+    box_frame int32 [n])."""
+    torch = _torch() if buf.is_cuda else __import__("torch")
+    desc = buf[:32 * n].view(torch.int64).view(n, 4)
+    boxes = buf[32 * n:48 * n].view(torch.int32).view(n, 4)
+    bframe = buf[48 * n:52 * n].view(torch.int32)
+    return desc, boxes, bframe
+
+
+class RoiStager:
+    """Upload only what the crops read (BASELINE configs[4]): per step, the crop rectangles of all boxes are packed on the
+    host into a pinned buffer (fire_pack_rois_host) and moved with ONE host->device copy on a copy stream, `depth` slots
+    deep so that the upload of step i+1 runs under the kernels of step i.  `submit` returns the device arguments of
+    preprocess_boxes; results are bit-identical to uploading the whole frames."""
+
+    def __init__(self, max_bytes: int, depth: int = 2, device: int = 0, threads: int = 4):
+        torch = _torch()
+        self.device = torch.device("cuda", device)
+        self.depth, self.threads, self.n = max(2, depth), threads, 0
+        self.host = [torch.empty(max_bytes, dtype=torch.uint8).pin_memory() for _ in range(self.depth)]
+        self.dev = [torch.empty(max_bytes, dtype=torch.uint8, device=self.device) for _ in range(self.depth)]
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.ev_in = [torch.cuda.Event() for _ in range(self.depth)]
+        self.ev_free = [torch.cuda.Event() for _ in range(self.depth)]
+        self.last_bytes = 0
+
+    def submit(self, frames_host, frame_desc_host, boxes_host, box_frame_host):
+        """-> (frames, frame_desc, boxes, box_frame) cuda tensors for preprocess_boxes, valid until `depth` later submits;
+        call `release()` once the kernels reading them are enqueued."""
+        torch = _torch()
+        slot = self.n % self.depth
+        n = int(boxes_host.shape[0])
+        if self.n >= self.depth:
+            self.ev_in[slot].synchronize()                      # the copy out of this pinned slot (depth submits ago) has finished
+            self.copy_stream.wait_event(self.ev_free[slot])     # and the kernels that read the device slot are done
+        used = pack_rois(frames_host, frame_desc_host, boxes_host, box_frame_host, self.host[slot], self.threads)
+        self.last_bytes = used
+        with torch.cuda.stream(self.copy_stream):
+            self.dev[slot][:used].copy_(self.host[slot][:used], non_blocking=True)
+            self.ev_in[slot].record(self.copy_stream)
+        torch.cuda.current_stream().wait_event(self.ev_in[slot])
+        self._slot = slot
+        self.n += 1
+        return (self.dev[slot],) + roi_views(self.dev[slot], n)
+
+    def release(self):
+        self.ev_free[self._slot].record(_torch().cuda.current_stream())
+
+
 def align_warp(frames, frame_desc, matrices, face_frame, swap_rb: bool = True, output: str = "uint8"):
     """fire_align_warp: frames cuda uint8, frame_desc cuda int64 [F,4], matrices cuda float64 [n,6] (forward 2x3, as
     getAffineTransform returns them), face_frame cuda int32 [n].  output "uint8" -> numpy [n,160,160,3]; "device" ->

@@ -71,6 +71,18 @@ int fire_preprocess(const uint8_t* frames, const int64_t* frame_desc, int n_fram
                     const int32_t* box_frame, int n_boxes, int mode, void* out_f16, float* out_f32,
                     int32_t* box_status, fire_stream_t stream);
 
+/* ROI upload for frame-sized inputs (BASELINE configs[4]): HOST-side packing of the crop rectangles of every box (the
+ * crop rule above applied on the host, like the reference's image[y:y+h, x:x+w]) into one pinned staging buffer, so that only
+ * the pixels a crop reads cross PCIe instead of whole frames.  host_packed receives, from offset 0, the tables
+ * int64 frame_desc[n][4] | int32 boxes[n][4] | int32 box_frame[n] (fire_roi_meta_bytes(n) bytes in all) and then the
+ * rectangles (rows padded to 16 bytes).  After ONE copy of *bytes_used bytes to a device buffer D, call
+ * fire_preprocess(D, (int64*)D, n, (int32*)(D + 32 n), (int32*)(D + 48 n), n, ...): results are bit-identical to passing the
+ * whole frames.  n_threads worker threads do the row copies (staging only - there is no compute here). */
+size_t fire_roi_meta_bytes(int n_boxes);
+int fire_pack_rois_host(const uint8_t* host_frames, const int64_t* host_frame_desc, int n_frames,
+                        const int32_t* host_boxes_xywh, const int32_t* host_box_frame, int n_boxes,
+                        uint8_t* host_packed, size_t host_packed_bytes, size_t* bytes_used, int n_threads);
+
 /* Aligned crop of the enrol path: cv2.warpAffine(image, M, (160, 160)) (INTER_LINEAR, constant 0 border) bit for bit,
  * optionally followed by the reference's [:, :, ::-1]            yunet_face_detector.py:135-165 (and the MediaPipe /
  * RetinaFace twins).  matrices: double [n_faces][6], the FORWARD 2x3 matrix cv2.getAffineTransform returns (the host

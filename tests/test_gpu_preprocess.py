@@ -110,3 +110,38 @@ def test_aligned_crops_match_cv2_warp_affine_bitwise(fire_lib):
     pix, pad = engine.network_input_to_pixels(f16)
     assert np.array_equal(pix.cpu().numpy(), got.astype(np.float32)) and not pad.any()
     assert not torch.isnan(f16).any()
+
+
+def test_staged_loads_unaligned_frames_and_roi_upload(fire_lib, oracle_native):
+    """The kernel stages source rows with 16-byte loads: frames that start at an odd byte (chunks hanging over the first /
+    last byte of the allocation) still give the oracle's bytes; and the ROI upload (fire_pack_rois_host + ONE copy) is
+    bit-identical to uploading whole frames (configs[4])."""
+    import torch
+    from fire_b200 import _lib, engine
+    rng = np.random.default_rng(21)
+    frames = [_frame(270, 480, 4), _frame(128, 208, 7)]                 # strides 1440 and 624: multiples of 16 -> staged path
+    boxes = np.array([[0, 0, 160, 160], [0, 0, 480, 270], [320, 110, 160, 160], [300, 100, 200, 200], [-10, -10, 100, 90], [470, 260, 50, 50],
+                      [0, 0, 208, 128], [48, 0, 160, 128], [100, 64, 108, 64], [5, 5, 33, 41], [600, 5, 20, 20]] +
+                     [[int(rng.integers(-20, 440)), int(rng.integers(-20, 250)), int(rng.integers(20, 300)), int(rng.integers(20, 300))] for _ in range(30)],
+                     dtype=np.int32)
+    bf = np.array([0] * 6 + [1] * 5 + [0] * 30, dtype=np.int32)
+    prefix = 5                                                           # frames start at byte 5 of the allocation
+    flat = np.concatenate([np.zeros(prefix, np.uint8)] + [f.reshape(-1) for f in frames])
+    desc = np.array([[prefix, 270, 480, 1440], [prefix + frames[0].size, 128, 208, 624]], dtype=np.int64)
+    dev = torch.from_numpy(flat).cuda()
+    bt, ft = torch.from_numpy(boxes).cuda(), torch.from_numpy(bf).cuda()
+    f16, f32, status = engine.preprocess_boxes(dev, torch.from_numpy(desc).cuda(), bt, ft, _lib.PRE_REFERENCE, True, True)
+    torch.cuda.synchronize()
+    for i, b in enumerate(boxes):
+        rc, u8, want = oracle_native.crop_preprocess(frames[bf[i]], b)
+        assert int(status[i]) == rc and np.array_equal(f32[i].cpu().numpy(), want), (i, b)
+    # ROI upload: same boxes through the stager, twice (both slots), bit-identical outputs
+    stager = engine.RoiStager(max_bytes=8 << 20, depth=2)
+    host_flat = torch.from_numpy(flat).pin_memory()
+    for _ in range(3):
+        d_frames, d_desc, d_boxes, d_bf = stager.submit(host_flat, desc, boxes, bf)
+        g16, g32, gst = engine.preprocess_boxes(d_frames, d_desc, d_boxes, d_bf, _lib.PRE_REFERENCE, True, True)
+        stager.release()
+        torch.cuda.synchronize()
+        assert torch.equal(g16, f16) and torch.equal(g32, f32) and torch.equal(gst, status)
+    assert stager.last_bytes < flat.nbytes * 6                           # rectangles, not frames (boxes overlap, so not < 1x here)
