@@ -1,19 +1,26 @@
 #!/usr/bin/env python
 """bench.py - FIRE identification hot path on B200: FaceNet512 embeds/s (+ cosine top-10 QPS).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl fire|reference] [--no-knn]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl fire|reference] [--no-knn] [--no-frames] [--no-cpu]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Headline (BASELINE.json configs[1]): FaceNet512 on batches of 256 uint8 160x160 crops per GPU.
 One "step" = one pass of the hot path over one batch: crop/resize/normalise kernel (K1) -> the 100
-tcgen05 convolutions (implicit GEMM + halo-strip) + pools + tail (K2) -> L2-normalised embeddings.
-  value : embeds/s with the uint8 crops already resident in HBM (device-timed, CUDA events)
-  e2e   : the same through the public streaming call (fire_b200.engine.CropEncodePipeline.submit):
-          pinned host uint8 crops -> H2D -> K1 -> K2 -> D2H float32 embeddings, every step (H2D double-buffered)
-  knn   : BASELINE.json configs[2]/[3]: exact cosine top-10, 4096 queries, 1M x 512 (N=1) and 10M x 512
-          (row-sharded over the N ranks, NCCL all_gather + merge) -> QPS, with its own roofline
+tcgen05 convolutions (implicit GEMM + halo-strip + fused residual chains) + pools + tail (K2) -> L2-normalised embeddings.
+  value     : embeds/s with the uint8 crops already resident in HBM (device-timed, CUDA events, exactly K steps)
+  sustained : the same loop run for >= 1 s when K steps are shorter than that (clocks sampled over both)
+  e2e       : the same through the public streaming call (fire_b200.engine.CropEncodePipeline.submit):
+              pinned host uint8 crops -> H2D -> K1 -> K2 -> D2H float32 embeddings, every step (H2D double-buffered)
+  roofline  : algorithmic FLOP of one step / the step's own device time (every launch of the step counted against the
+              tensor peak: a lower bound for the convolution kernels), per-family figures next to it
+  knn       : configs[2]/[3]: exact cosine top-10, 4096 queries, 1M x 512 (N=1) and 10M x 512 (row-sharded over the N
+              ranks, one NCCL all_gather of packed records + merge, exchange pipelined under the scan) -> QPS with its
+              roofline, its CPU baseline, the small-batch (Q = 1..256, HBM-bound) regime, and a parity block against
+              the BFIndex oracle on a 256-query subset (sharded result at N > 1)
+  frames    : configs[4]: 1080p frames x 8 boxes -> ROI upload -> K1 -> FaceNet512 -> top-1 vs 1M gallery, with
+              enrolled faces planted so that accept/reject decisions and labels are compared with the CPU chain
 `--impl reference` times the reference's CPU path restated (oracle/: cv2 INTER_AREA + torch-CPU
-Inception-ResNet-v1 at batch 1 per face like modules/encoder.py:26) on the host cores.
+Inception-ResNet-v1 at batch 1 per face like modules/encoder.py:26) on the host cores, on the same config.
 """
 from __future__ import annotations
 
@@ -34,6 +41,15 @@ import numpy as np  # noqa: E402
 METRIC = "FaceNet512 embeds/s (160x160 crops)"
 BATCH = 256
 D = 512
+N_ROT = 4
+
+
+def bench_config(world: int) -> dict:
+    """The workload both arms are quoted on (BASELINE.json configs[1])."""
+    return {"workload": "FaceNet512 batch-256 uint8 160x160 crops per GPU (BASELINE configs[1]): K1 preprocess + K2 conv stack + L2 norm",
+            "batch_per_gpu": BATCH, "global_batch": BATCH * world, "weights": "synthetic seed 1234 (real ONNX is a git-LFS pointer)",
+            "l2": f"inputs rotate over {N_ROT} batches; activations (~1.5 MB/img, 394 MB/step) exceed the 126 MB L2",
+            "parallelism": f"dp{world}"}
 
 
 def load_peaks():
@@ -44,6 +60,15 @@ def load_peaks():
         return {"tensor_tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "tensor_burst": d.get("bf16_tflops"),
                 "hbm_gbs": d.get("hbm_gbs"), "src": "measured"}
     return {"tensor_tflops": 1400.0, "tensor_burst": 1590.0, "hbm_gbs": 6650.0, "src": "fallback"}
+
+
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures of this round."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return None
 
 
 class ClockSampler:
@@ -85,10 +110,7 @@ class ClockSampler:
 
 
 def dist_env():
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
 def make_crops(n_batches: int, seed: int = 2):
@@ -128,6 +150,22 @@ def cpu_reference_embeds(n_faces: int, threads: int):
     return n_faces / dt, dt
 
 
+def cpu_reference_knn(n_rows: int, n_queries: int, k: int, threads: int):
+    """hnswlib.BFIndex(space='cosine').knn_query restated in C (oracle/fire_oracle.c, the library's own loop order: one
+    full scan per query, queries spread over the threads like its ParallelFor).  Returns (QPS, seconds)."""
+    from oracle import native
+    rng = np.random.default_rng(3)
+    ora = native.BFIndexOracle(D)
+    ora.rows = native.normalize(rng.standard_normal((n_rows, D), dtype=np.float32))
+    ora.labels = np.arange(n_rows, dtype=np.uint64)
+    q = rng.standard_normal((n_queries, D), dtype=np.float32)
+    ora.knn_query(q[:threads], k, num_threads=threads)                       # warm-up (page in the rows)
+    t = time.perf_counter()
+    ora.knn_query(q, k, num_threads=threads)
+    dt = time.perf_counter() - t
+    return n_queries / dt, dt
+
+
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
@@ -146,17 +184,30 @@ def run_reference(args):
     line = {"metric": METRIC, "value": v, "unit": "embeds/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "FaceNet512 batch-256 crops (configs[1]); reference arm = bounded sample of "
-                                   f"{per_step} faces/step at batch 1 like modules/encoder.py:26", "weights": "synthetic seed 1234"},
+            "config": bench_config(world),
             "cpu_baseline": {"value": v, "unit": "embeds/s", "cores": threads, "kind": "port",
-                             "sample": f"{per_step} faces per step, batch 1 per face, cv2 INTER_AREA + torch-CPU fp32 oracle "
-                                       "(stand-in for onnxruntime 1.20.1 CPU EP, which is not installable here)"},
+                             "sample": f"bounded sample of the config's workload: {per_step} of the 256 faces per step, batch 1 per face like "
+                                       "modules/encoder.py:26, cv2 INTER_AREA + torch-CPU fp32 oracle (stand-in for onnxruntime 1.20.1 CPU EP, "
+                                       "which is not installable here); a per-face rate, so it scales to the full batch"},
             "e2e": {"value": v, "unit": "embeds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "torch_threads": torch.get_num_threads()}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------------
+def check_ids(got_i, got_d, ol, od, k):
+    """ids bit-exact vs the oracle except ties within 1e-5; distances within 5e-6.  Returns (ok, mismatching ids, max |dd|)."""
+    ol = ol.astype(np.int64)
+    dd = float(np.abs(got_d - od).max())
+    bad = np.argwhere(got_i != ol)
+    ok = dd < 5e-6
+    for qi, j in bad:
+        near = [od[qi, jj] for jj in (j - 1, j + 1) if 0 <= jj < k]
+        if not any(abs(od[qi, j] - v) < 1e-5 for v in near):
+            ok = False
+    return ok, int(len(bad)), dd
+
+
 def run_fire(args):
     # stdout must carry exactly ONE JSON line: anything a library prints on fd 1 (NCCL's version banner does) is sent to
     # stderr for the duration of the run; the real stdout comes back just before rank 0 prints the result.
@@ -173,7 +224,9 @@ def run_fire(args):
     from fire_b200.dist import ShardedGallery, shard_bounds
     _lib.init(local)
     peaks = load_peaks()
+    traffic = load_traffic()
     dev = torch.device("cuda", local)
+    host_threads = os.cpu_count() or 1
 
     def barrier():
         if world > 1:
@@ -190,8 +243,7 @@ def run_fire(args):
     # ---------------- FaceNet512, B=256 per GPU -------------------------------------------------
     tensors = W.synthetic_weights(D, 1234)
     eng = engine.FaceNetEngine(D, tensors, device=local)
-    n_rot = 4
-    host_batches = make_crops(n_rot, seed=2 + rank)
+    host_batches = make_crops(N_ROT, seed=2 + rank)
     pinned = [torch.from_numpy(b).pin_memory() for b in host_batches]
     dev_batches = [p.to(dev) for p in pinned]
     boxes = torch.tensor([[0, 0, 160, 160]] * BATCH, dtype=torch.int32, device=dev)
@@ -201,7 +253,7 @@ def run_fire(args):
     l2 = torch.empty(BATCH, D, dtype=torch.float32, device=dev)
 
     def step_device(i):
-        f16, _, _ = engine.preprocess_boxes(dev_batches[i % n_rot], desc, boxes, frame_ids, _lib.PRE_REFERENCE, True, False)
+        f16, _, _ = engine.preprocess_boxes(dev_batches[i % N_ROT], desc, boxes, frame_ids, _lib.PRE_REFERENCE, True, False)
         eng.forward(f16, want_l2=True, out_raw=raw, out_l2=l2)
 
     pipe = engine.CropEncodePipeline(eng, BATCH, depth=2, normalize=True)
@@ -210,7 +262,7 @@ def run_fire(args):
         # the public streaming call: pinned host crops -> H2D (copy stream) -> K1 -> K2 -> D2H of the embeddings; the
         # H2D of step i+1 overlaps the kernels of step i.  Every step's result lands in pinned host memory before the
         # closing synchronize of the timed region.
-        pipe.submit(pinned[i % n_rot])
+        pipe.submit(pinned[i % N_ROT])
 
     def timed(step_fn, steps, warmup):
         for i in range(warmup):
@@ -233,6 +285,18 @@ def run_fire(args):
         sampler.start()
         time.sleep(0.5)                      # let nvidia-smi start streaming before the timed region
     ms_dev, wall_dev, launches = timed(step_device, args.steps, args.warmup)
+    # the contract's K steps can be a few tens of milliseconds: the same loop again for >= 1 s, so that the sustained rate and
+    # the clocks under load are on record too (same kernels, same inputs; reported next to `value`, never instead of it)
+    sustained = None
+    long_steps = int(max(args.steps, np.ceil(1100.0 / max(ms_dev / args.steps, 1e-3))))
+    if world > 1:
+        t = torch.tensor([long_steps], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        long_steps = int(t.item())
+    if ms_dev < 1000.0:
+        ms_long, _, _ = timed(step_device, long_steps, 0)
+        sustained = {"value": world * BATCH * long_steps / (ms_long * 1e-3), "unit": "embeds/s", "steps": long_steps,
+                     "timed_region_s": ms_long * 1e-3, "ms_per_step": ms_long / long_steps}
     if rank == 0:
         time.sleep(0.15)
     clocks = sampler.stop() if rank == 0 else None
@@ -251,30 +315,69 @@ def run_fire(args):
         cos = (got * ref).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(ref, axis=1))
         parity = {"min_cos_vs_fp32_oracle": float(cos.min()), "images": 8}
 
-    # roofline of the dominant kernel family (the tcgen05 convolutions: conv_igemm_kernel, conv_strip_kernel and the two
-    # fused residual-block chains block35_fused_kernel / block17_fused_kernel): algorithmic FLOP of the conv launches of one
-    # step / the device time those launches take inside the timed step.  The step is timed live above; the convs' SHARE
-    # of it comes from a per-op CUDA-event pass over the same batch (and is cross-checked by the ncu launch list in
-    # profiles/): conv time in the step = ms_per_step * share.
+    # ---------------- roofline ----------------------------------------------------------------------------------------
+    # Direct: the step's algorithmic FLOP (2.8353 GFLOP x 256 images) over the step's OWN device time as timed
+    # above - every launch of the step (K1, 42 tensor launches, pools, GAP, L2 norm) is charged to the tensor roofline, so this
+    # is a lower bound for the convolution kernels and needs no share from a separate pass.  `families` adds the per-family
+    # picture from one serialised per-op event pass (no overlap between launches: it overstates small launches) and the live
+    # HBM figures of K1.
     roofline = None
     if rank == 0:
+        step_ms = ms_dev / args.steps
+        flop_step = eng.flops_per_image * BATCH
+        achieved = flop_step / (step_ms * 1e-3) / 1e12
         f16, _, _ = engine.preprocess_boxes(dev_batches[0], desc, boxes, frame_ids, _lib.PRE_REFERENCE, True, False)
         eng.profile(f16)
         ms_ops, fl_ops = eng.profile(f16)
         conv = fl_ops > 0
-        conv_ms, conv_fl = float(ms_ops[conv].sum()), float(fl_ops[conv].sum())
-        share = conv_ms / (float(ms_ops.sum()) + 1e-9)
-        step_ms = ms_dev / args.steps
-        conv_ms_in_step = step_ms * share
-        achieved = conv_fl / (conv_ms_in_step * 1e-3) / 1e12
-        roofline = {"kernel": f"tcgen05 conv kernels: conv_igemm + conv_strip + block35_fused + block17_fused ({int(conv.sum())} launches/step for the plan's 100 convs)",
-                    "bound": "tensor",
-                    "achieved": achieved, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tensor_tflops"],
+        labels = [o.label for o in eng.plan.ops]
+        pool_ms = float(sum(m for m, o in zip(ms_ops, eng.plan.ops) if o.kind != 1))
+        pool_bytes = 0.0
+        for o in eng.plan.ops:
+            if o.kind != 1:
+                sb, db = eng.plan.bufs[o.src.buf], eng.plan.bufs[o.dst.buf]
+                pool_bytes += BATCH * 2.0 * (o.H * (sb.Wp or sb.W) * o.cin + o.Ho * o.Wo * o.cout)
+
+        def k1_gbs(frames_t, desc_t, boxes_t, bf_t, bytes_per_call, reps=50):
+            for _ in range(5):
+                engine.preprocess_boxes(frames_t, desc_t, boxes_t, bf_t, _lib.PRE_REFERENCE, True, False)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                engine.preprocess_boxes(frames_t, desc_t, boxes_t, bf_t, _lib.PRE_REFERENCE, True, False)
+            b.record()
+            torch.cuda.synchronize()
+            us = a.elapsed_time(b) * 1e3 / reps
+            return {"us_per_launch": us, "algorithmic_bytes": bytes_per_call, "achieved_GBps": bytes_per_call / (us * 1e-6) / 1e9,
+                    "frac_of_hbm": bytes_per_call / (us * 1e-6) / 1e9 / peaks["hbm_gbs"]}
+        out_bytes = 80 * 80 * 16 * 2
+        k1_copy = k1_gbs(dev_batches[0], desc, boxes, frame_ids, BATCH * (160 * 160 * 3 + out_bytes))
+        # configs[4]-sized boxes (w, h in [48, 400]) out of 1080p frames resident in HBM
+        rng4 = np.random.default_rng(5)
+        fr4 = torch.randint(0, 256, (8, 1080, 1920, 3), dtype=torch.uint8, device=dev)
+        bx4 = np.stack([rng4.integers(0, 1500, BATCH), rng4.integers(0, 660, BATCH), rng4.integers(48, 401, BATCH), rng4.integers(48, 401, BATCH)], 1).astype(np.int32)
+        d4 = torch.tensor([[i * 1080 * 1920 * 3, 1080, 1920, 5760] for i in range(8)], dtype=torch.int64, device=dev)
+        k1_boxes = k1_gbs(fr4, d4, torch.from_numpy(bx4).to(dev), torch.arange(BATCH, dtype=torch.int32, device=dev) % 8,
+                          float((bx4[:, 2].astype(np.int64) * bx4[:, 3] * 3).sum() + BATCH * out_bytes))
+        del fr4
+        roofline = {"kernel": "the step's tensor launches: conv_igemm + conv_strip + block35_fused + block17_fused "
+                              f"({int(conv.sum())} launches for the plan's 100 convs), timed as the whole step",
+                    "bound": "tensor", "achieved": achieved, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["tensor_tflops"], "frac_of_burst_peak": achieved / peaks["tensor_burst"],
                     "peak_source": f"{peaks['src']} bf16 sustained (MEASURED_PEAKS.json); fp16 runs on the same kind::f16 pipe",
-                    "traffic": None, "conv_share_of_step": share, "conv_ms_in_step": conv_ms_in_step,
-                    "conv_ms_serialised_per_op_events": conv_ms, "all_ops_ms_serialised_per_op_events": float(ms_ops.sum()),
-                    "algorithmic_flop_per_step": conv_fl, "algorithmic_flop_per_launch_avg": conv_fl / int(conv.sum()),
-                    "avg_launch_us_in_step": conv_ms_in_step * 1e3 / int(conv.sum())}
+                    "how": "algorithmic FLOP per step / (device ms of the timed region / steps); no share from a separate pass",
+                    "algorithmic_flop_per_step": flop_step, "algorithmic_flop_per_launch_avg": flop_step / int(conv.sum()),
+                    "step_ms": step_ms, "avg_launch_us_in_step": step_ms * 1e3 / max(1, launches // args.steps),
+                    "traffic": (traffic or {}).get("conv_family_dram_bytes_per_launch_avg"),
+                    "traffic_detail": traffic,
+                    "families": {
+                        "tensor_kernels_serialised": {"ms": float(ms_ops[conv].sum()), "TFLOPs": float(fl_ops[conv].sum()) / (float(ms_ops[conv].sum()) * 1e-3) / 1e12,
+                                                      "note": "per-op CUDA events, launches serialised (no PDL overlap): overstates short launches"},
+                        "pools_gap_serialised": {"ms": pool_ms, "algorithmic_bytes": pool_bytes, "achieved_GBps": pool_bytes / (pool_ms * 1e-3) / 1e9,
+                                                 "frac_of_hbm": pool_bytes / (pool_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+                        "k1_preprocess_160x160_copy": k1_copy, "k1_preprocess_configs4_boxes": k1_boxes,
+                        "by_stage_ms_serialised": {s: float(sum(m for m, l in zip(ms_ops, labels) if l.startswith(s)))
+                                                   for s in ("Conv2d", "MaxPool", "Block35", "Mixed_6a", "Block17", "Mixed_7a", "Block8", "AvgPool", "Bottleneck")}}}
 
     # ---------------- exact cosine top-10 ---------------------------------------------------------------
     knn = None
@@ -284,19 +387,27 @@ def run_fire(args):
         gq = torch.Generator(device=dev)
         gq.manual_seed(4)
         queries = torch.randn(Q, D, generator=gq, device=dev)
+
+        def rows(lo_, hi_):
+            g = torch.Generator(device=dev)
+            g.manual_seed(1000 + lo_)
+            return torch.randn(hi_ - lo_, D, generator=g, device=dev)
+
+        def chunk_starts(n_total, world_):
+            """(lo, hi) of every enrolment chunk of every rank: the gallery is a deterministic function of these."""
+            out = []
+            for r in range(world_):
+                lo, hi = shard_bounds(n_total, world_, r)
+                out += [(c0, min(hi, c0 + 1_000_000)) for c0 in range(lo, hi, 1_000_000)]
+            return out
+
         for name, n_total in (("1M", 1_000_000), ("10M", 10_000_000)):
             if name == "1M" and world > 1:
                 continue
             lo, hi = shard_bounds(n_total, world, rank)
             gal = ShardedGallery(D, hi - lo, rank, world, device=local)
-
-            def rows(lo_, hi_):
-                g = torch.Generator(device=dev)
-                g.manual_seed(1000 + lo_)
-                return torch.randn(hi_ - lo_, D, generator=g, device=dev)
-            # enrol in chunks to bound the temporary
-            gal.id_offset, gal.total = lo, n_total
-            for c0 in range(lo, hi, 1_000_000):
+            gal.id_offset, gal.total, gal.bulk_total = lo, n_total, n_total
+            for c0 in range(lo, hi, 1_000_000):                    # enrol in chunks to bound the temporary
                 gal.local.add(rows(c0, min(hi, c0 + 1_000_000)))
             torch.cuda.synchronize()
             steps = max(3, min(20, args.steps // 4))
@@ -314,78 +425,159 @@ def run_fire(args):
             qps = Q / (ms * 1e-3)
             flops = 2.0 * Q * n_total * D
             tf = flops / (ms * 1e-3) / 1e12 / world
-            tot, fb = gal.local.stats()
-            knn[name] = {"metric": f"cosine top-10 QPS, {name} x 512 gallery, 4096-query batch", "value": qps, "unit": "queries/s",
-                         "ms_per_batch": ms, "n_gpus": world, "gallery_rows": n_total, "queries": Q, "k": k,
-                         "launches_per_batch": (_lib.launch_count() - l0) // steps,
-                         "fallback_queries_fraction": fb / max(tot, 1),
-                         "roofline": {"kernel": "knn_scan_kernel<16>", "bound": "tensor", "achieved": tf, "peak": peaks["tensor_tflops"],
-                                      "unit": "TFLOP/s", "frac": tf / peaks["tensor_tflops"], "per_gpu": True,
-                                      "note": "whole search (normalise+scan+rerank+fallback) over algorithmic 2*Q*N*D"}}
+            tot, fb, one_split, whole = gal.local.stats_ex()
+            blk = {"metric": f"cosine top-10 QPS, {name} x 512 gallery, 4096-query batch", "value": qps, "unit": "queries/s",
+                   "ms_per_batch": ms, "n_gpus": world, "gallery_rows": n_total, "queries": Q, "k": k,
+                   "launches_per_batch": (_lib.launch_count() - l0) // steps,
+                   "exchange": None if world == 1 else "one all_gather of packed 12-byte records per query chunk, 2 chunks: chunk 0's exchange + merge run under chunk 1's scan",
+                   "flagged_queries_fraction": fb / max(tot, 1), "single_split_rescans": one_split, "whole_shard_rescans": whole,
+                   "roofline": {"kernel": "knn_scan_kernel<16>", "bound": "tensor", "achieved": tf, "peak": peaks["tensor_tflops"],
+                                "unit": "TFLOP/s", "frac": tf / peaks["tensor_tflops"], "per_gpu": True,
+                                "traffic": (traffic or {}).get("knn_scan_dram_bytes_per_launch"),
+                                "note": "whole search (normalise+scan+rerank+fallback+exchange) over algorithmic 2*Q*N*D"}}
+            # ---- parity on a 256-query subset against the BFIndex oracle over ALL rows; at N > 1 this is
+            # the SHARDED result (local scans + all_gather + merge) checked on hardware.  Rank 0 regenerates the gallery chunk by
+            # chunk (same seeds as the enrolment), the oracle answers per chunk, the per-chunk lists are merged on the host.
+            if rank == 0 and not args.no_cpu and (name == "1M" or world > 1):     # 10M at N=1 runs the kernels 1M already checked
+                from oracle import native
+                t_par = time.perf_counter()
+                sel = np.arange(0, Q, Q // 256)[:256]
+                qs = queries[torch.from_numpy(sel).to(dev)].cpu().numpy()
+                best_d = np.full((256, k), np.inf, np.float32)
+                best_i = np.full((256, k), -1, np.int64)
+                for c0, c1 in chunk_starts(n_total, world):
+                    ora = native.BFIndexOracle(D)
+                    ora.rows = native.normalize(rows(c0, c1).cpu().numpy())
+                    ora.labels = np.arange(c0, c1, dtype=np.uint64)
+                    ol, od = ora.knn_query(qs, k, num_threads=host_threads, blocked=True)
+                    cat_d = np.concatenate([best_d, od], 1)
+                    cat_i = np.concatenate([best_i, ol.astype(np.int64)], 1)
+                    order = np.lexsort((cat_i, cat_d), axis=1)[:, :k]
+                    best_d, best_i = np.take_along_axis(cat_d, order, 1), np.take_along_axis(cat_i, order, 1)
+                ok, n_bad, max_dd = check_ids(ii[torch.from_numpy(sel).to(dev)].cpu().numpy(), dd[torch.from_numpy(sel).to(dev)].cpu().numpy(),
+                                              best_i, best_d, k)
+                blk["parity"] = {"checked_queries": 256, "rows": n_total, "sharded_over": world, "ids_equal_except_1e-5_ties": ok,
+                                 "ids_differing_inside_tie_window": n_bad, "max_abs_dist_diff": max_dd, "oracle": "C BFIndex restatement, all rows",
+                                 "seconds": time.perf_counter() - t_par}
+            knn[name] = blk
+            if name == "1M":
+                # ---- the regime the reference actually runs: a handful of queries per call (hnsw_manager.py:147: one).  The scan is
+                # HBM-bound there (below Q ~ 218): one pass over the fp16 gallery copy per call.
+                small = {}
+                gal_bytes = n_total * D * 2.0
+                for qn in (1, 8, 32, 256):
+                    qsub = queries[:qn].contiguous()
+                    od_, oi_ = torch.empty(qn, k, dtype=torch.float32, device=dev), torch.empty(qn, k, dtype=torch.int64, device=dev)
+                    for _ in range(5):
+                        gal.local.search(qsub, k, out_dist=od_, out_ids=oi_)
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    reps = 50
+                    a.record()
+                    for _ in range(reps):
+                        gal.local.search(qsub, k, out_dist=od_, out_ids=oi_)
+                    b.record()
+                    torch.cuda.synchronize()
+                    us = a.elapsed_time(b) * 1e3 / reps
+                    small[f"Q{qn}"] = {"us_per_call": us, "qps": qn / (us * 1e-6), "achieved_GBps": gal_bytes / (us * 1e-6) / 1e9,
+                                       "frac_of_hbm": gal_bytes / (us * 1e-6) / 1e9 / peaks["hbm_gbs"]}
+                knn["1M_small_batch"] = {"metric": "cosine top-10 latency / QPS at small query batches, 1M x 512 gallery", "bound": "hbm",
+                                         "algorithmic_bytes_per_call": gal_bytes, "peak_GBps": peaks["hbm_gbs"], **small}
+                if rank == 0 and not args.no_cpu:
+                    v, dt = cpu_reference_knn(n_total, 64, k, host_threads)
+                    knn["1M"]["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": host_threads, "kind": "port",
+                                                 "sample": f"64 of the 4096 queries against all 1M rows, {dt:.1f} s; C restatement of hnswlib.BFIndex "
+                                                           "cosine search (one scan per query, queries over the threads) = stand-in for hnswlib 0.8.0"}
             gal.local.close()
             del gal
             torch.cuda.empty_cache()
 
-
     # ---------------- configs[4]: 1080p frames + fixed YuNet-style boxes -> preprocess -> FaceNet512 -> top-1 match ---------
     frames_blk = None
     if not args.no_frames:
-        from fire_b200.engine import KnnIndex
+        from fire_b200.engine import KnnIndex, RoiStager
         F, PER = 32, 8                                   # 32 frames x 8 boxes = 256 faces per step and GPU
+        NF = F * PER
         rng = np.random.default_rng(5 + rank)
-        small = rng.integers(0, 256, (F, 135, 240, 3), dtype=np.uint8)
-        frames_np = np.ascontiguousarray(np.repeat(np.repeat(small, 8, axis=1), 8, axis=2))          # smooth 1080x1920 content
+        small_f = rng.integers(0, 256, (F, 135, 240, 3), dtype=np.uint8)
+        frames_np = np.ascontiguousarray(np.repeat(np.repeat(small_f, 8, axis=1), 8, axis=2))          # smooth 1080x1920 content
         frames_pin = torch.from_numpy(frames_np).pin_memory()
-        bx = np.zeros((F * PER, 4), dtype=np.int32)
-        bx[:, 2] = rng.integers(48, 401, F * PER); bx[:, 3] = rng.integers(48, 401, F * PER)
-        bx[:, 0] = rng.integers(-40, 1920 - 40, F * PER); bx[:, 1] = rng.integers(-40, 1080 - 40, F * PER)   # some cross the edges / start negative
-        boxes5 = torch.from_numpy(bx).to(dev)
-        bf5 = torch.arange(F * PER, dtype=torch.int32, device=dev) // PER
-        desc5 = torch.tensor([[i * 1080 * 1920 * 3, 1080, 1920, 1920 * 3] for i in range(F)], dtype=torch.int64, device=dev)
+        bx = np.zeros((NF, 4), dtype=np.int32)
+        bx[:, 2] = rng.integers(48, 401, NF); bx[:, 3] = rng.integers(48, 401, NF)
+        bx[:, 0] = rng.integers(-40, 1920 - 40, NF); bx[:, 1] = rng.integers(-40, 1080 - 40, NF)   # some cross the edges / start negative
+        bf = (np.arange(NF, dtype=np.int32) // PER).astype(np.int32)
+        desc5 = np.array([[i * 1080 * 1920 * 3, 1080, 1920, 1920 * 3] for i in range(F)], dtype=np.int64)
+        # enrolled faces: for n_chk faces the CPU chain (oracle crop + /255, fp32 oracle FaceNet, L2 norm) gives the embedding; a
+        # gallery row at a chosen cosine to it (0.9 / 0.72 accept, 0.68 / 0.5 reject at the CLI threshold 0.7) is planted at row j
+        n_chk = 24 if (rank == 0 and not args.no_cpu) else 0
+        planted, cpu_emb = None, None
+        if n_chk:
+            from oracle import native
+            from oracle.facenet_ref import facenet_forward, l2_normalize_rows
+            crops = np.stack([native.crop_preprocess(frames_np[bf[j]], bx[j])[2] for j in range(n_chk)])
+            cpu_emb = l2_normalize_rows(facenet_forward(tensors, crops))
+            prng = np.random.default_rng(99)
+            planted = np.empty((n_chk, D), np.float32)
+            for j in range(n_chk):
+                c = (0.9, 0.72, 0.68, 0.5)[j % 4]
+                r = prng.standard_normal(D).astype(np.float32)
+                r -= r.dot(cpu_emb[j]) * cpu_emb[j]
+                r /= np.linalg.norm(r)
+                planted[j] = c * cpu_emb[j] + np.sqrt(1 - c * c) * r
         gal5 = KnnIndex(D, 1_000_000, device=local)
         g5 = torch.Generator(device=dev); g5.manual_seed(77)
-        gal5.add(torch.randn(1_000_000, D, generator=g5, device=dev))
-        stage5 = [torch.empty(tuple(frames_pin.shape), dtype=torch.uint8, device=dev) for _ in range(2)]
-        copy5 = torch.cuda.Stream(device=dev)
-        ev_in = [torch.cuda.Event() for _ in range(2)]
-        ev_free = [torch.cuda.Event() for _ in range(2)]
-        raw5 = torch.empty(F * PER, D, dtype=torch.float32, device=dev)
-        l25 = torch.empty(F * PER, D, dtype=torch.float32, device=dev)
-        out_d = torch.empty(F * PER, 1, dtype=torch.float32).pin_memory()
-        out_i = torch.empty(F * PER, 1, dtype=torch.int64).pin_memory()
+        if n_chk:
+            gal5.add(torch.from_numpy(planted).to(dev))
+        gal5.add(torch.randn(1_000_000 - n_chk, D, generator=g5, device=dev))
+        stager = RoiStager(max_bytes=int(NF * (400 * 1216 + 512) + 65536), depth=2, device=local, threads=4)
+        raw5 = torch.empty(NF, D, dtype=torch.float32, device=dev)
+        l25 = torch.empty(NF, D, dtype=torch.float32, device=dev)
+        dd5 = torch.empty(NF, 1, dtype=torch.float32, device=dev)
+        ii5 = torch.empty(NF, 1, dtype=torch.int64, device=dev)
+        out_d = torch.empty(NF, 1, dtype=torch.float32).pin_memory()
+        out_i = torch.empty(NF, 1, dtype=torch.int64).pin_memory()
 
         def step_frames(i):
-            b = i % 2
-            main = torch.cuda.current_stream()
-            copy5.wait_event(ev_free[b])
-            with torch.cuda.stream(copy5):
-                stage5[b].copy_(frames_pin, non_blocking=True)
-                ev_in[b].record(copy5)
-            main.wait_event(ev_in[b])
-            f16, _, status = engine.preprocess_boxes(stage5[b], desc5, boxes5, bf5, _lib.PRE_REFERENCE, True, False)
-            ev_free[b].record(main)
+            # host: pack the crop rectangles of the 256 boxes (fire_pack_rois_host) -> ONE H2D copy -> K1 -> K2 -> top-1 -> D2H
+            d_frames, d_desc, d_boxes, d_bf = stager.submit(frames_pin, desc5, bx, bf)
+            f16, _, status = engine.preprocess_boxes(d_frames, d_desc, d_boxes, d_bf, _lib.PRE_REFERENCE, True, False)
+            stager.release()
             eng.forward(f16, want_l2=True, out_raw=raw5, out_l2=l25)
-            dd, ii = gal5.search(l25, 1)
-            out_d.copy_(dd, non_blocking=True); out_i.copy_(ii, non_blocking=True)
+            gal5.search(l25, 1, out_dist=dd5, out_ids=ii5)
+            out_d.copy_(dd5, non_blocking=True); out_i.copy_(ii5, non_blocking=True)
 
         fsteps = max(5, min(30, args.steps // 5))
         ms_f, _, _ = timed(step_frames, fsteps, 3)
         accepted = int(((1.0 - out_d.numpy()[:, 0]) > 0.7).sum())          # strict >, face_recognition.py:462-463
-        frames_blk = {"metric": "configs[4]: 1080p frames, 8 fixed boxes each -> K1 -> FaceNet512 -> cosine top-1 vs 1M gallery (replicated), thr 0.7",
-                      "frames_per_s": world * F * fsteps / (ms_f * 1e-3), "faces_per_s": world * F * PER * fsteps / (ms_f * 1e-3),
+        frames_blk = {"metric": "configs[4]: 1080p frames, 8 fixed boxes each -> ROI upload -> K1 -> FaceNet512 -> cosine top-1 vs 1M gallery (replicated), thr 0.7",
+                      "frames_per_s": world * F * fsteps / (ms_f * 1e-3), "faces_per_s": world * NF * fsteps / (ms_f * 1e-3),
                       "ms_per_step": ms_f / fsteps, "frames_per_step_per_gpu": F, "boxes_per_frame": PER, "n_gpus": world,
-                      "h2d_bytes_per_step": int(frames_pin.numel()), "h2d_GBps_per_gpu": frames_pin.numel() / (ms_f / fsteps * 1e-3) / 1e9,
-                      "d2h_bytes_per_step": F * PER * 12, "accepted_faces_last_step": accepted,
-                      "note": "host frames pinned; H2D double-buffered on a copy stream; the step is PCIe-bound (6.2 MB per frame)"}
+                      "h2d_bytes_per_step": int(stager.last_bytes), "h2d_GBps_per_gpu": stager.last_bytes / (ms_f / fsteps * 1e-3) / 1e9,
+                      "whole_frame_bytes_per_step": int(frames_pin.numel()),
+                      "d2h_bytes_per_step": NF * 12, "accepted_faces_last_step": accepted,
+                      "note": "host frames pinned; per step the crop rectangles are packed on the host (4 threads) and uploaded with one copy, "
+                              "double-buffered on a copy stream (round 1 uploaded whole frames: 199 MB per step)"}
+        if n_chk:
+            # decisions and labels of the GPU chain vs the CPU chain (oracle crop -> oracle FaceNet -> BFIndex oracle top-1 over the
+            # same 1M rows), for the faces with an enrolled neighbour
+            from oracle import native
+            ora = native.BFIndexOracle(D)
+            ora.rows = gal5.rows()
+            ora.labels = np.arange(1_000_000, dtype=np.uint64)
+            ol, od = ora.knn_query(cpu_emb, 1, num_threads=host_threads, blocked=True)
+            gpu_i, gpu_d = out_i.numpy()[:n_chk, 0], out_d.numpy()[:n_chk, 0]
+            cpu_acc, gpu_acc = (1.0 - od[:, 0]) > 0.7, (1.0 - gpu_d) > 0.7
+            frames_blk["parity"] = {"faces_checked": n_chk, "labels_equal_cpu_chain": bool(np.array_equal(gpu_i, ol[:, 0].astype(np.int64))),
+                                    "decisions_equal_cpu_chain": bool(np.array_equal(cpu_acc, gpu_acc)), "accepted_cpu_chain": int(cpu_acc.sum()),
+                                    "accepted_gpu_chain": int(gpu_acc.sum()), "max_abs_cosine_diff": float(np.abs(gpu_d - od[:, 0]).max()),
+                                    "planted_cosines": [0.9, 0.72, 0.68, 0.5]}
         gal5.close()
-        del gal5, stage5
+        del gal5, stager
         torch.cuda.empty_cache()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
-        v, dt = cpu_reference_embeds(800, threads)
-        cpu_baseline = {"value": v, "unit": "embeds/s", "cores": threads, "kind": "port",
+        v, dt = cpu_reference_embeds(800, host_threads)
+        cpu_baseline = {"value": v, "unit": "embeds/s", "cores": host_threads, "kind": "port",
                         "sample": f"800 faces at batch 1 (reference behaviour, modules/encoder.py:26), {dt:.1f} s; torch-CPU fp32 "
                                   "restatement of the graph = stand-in for onnxruntime-CPU (not installable offline)"}
 
@@ -393,13 +585,10 @@ def run_fire(args):
         line = {"metric": METRIC, "value": value, "unit": "embeds/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16", "data": "synthetic",
-                "config": {"workload": "FaceNet512 batch-256 uint8 160x160 crops per GPU (BASELINE configs[1]): K1 preprocess + K2 conv stack + L2 norm",
-                           "batch_per_gpu": BATCH, "global_batch": BATCH * world, "weights": "synthetic seed 1234 (real ONNX is a git-LFS pointer)",
-                           "l2": f"inputs rotate over {n_rot} batches; activations (~1.5 MB/img, 394 MB/step) exceed the 126 MB L2",
-                           "parallelism": f"dp{world}"},
+                "config": bench_config(world),
                 "e2e": {"value": e2e_value, "unit": "embeds/s", "h2d_bytes_per_step": BATCH * 160 * 160 * 3,
                         "d2h_bytes_per_step": BATCH * D * 4, "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches), "wall_ms_per_step": wall_dev / args.steps,
+                "gpu_launches": int(launches), "wall_ms_per_step": wall_dev / args.steps, "sustained": sustained,
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity, "knn": knn, "frames": frames_blk}
         sys.stdout.flush()
         os.dup2(saved_stdout_fd, 1)
@@ -413,7 +602,7 @@ def run_fire(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=800)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="fire", choices=["fire", "reference"])
     ap.add_argument("--no-knn", action="store_true")
@@ -421,6 +610,8 @@ def main():
     ap.add_argument("--no-frames", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "fire" else args.warmup
+    if args.impl == "reference" and args.steps > 50:
+        args.steps = 20                       # the CPU arm's default: 20 steps x 16 faces (a few seconds per step)
     if args.impl == "reference":
         run_reference(args)
     else:

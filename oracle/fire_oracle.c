@@ -115,6 +115,58 @@ int fire_oracle_bf_knn(const float* g, const uint64_t* labels, size_t n, int D, 
   return 0;
 }
 
+/* Same result, different loop order: every thread walks the gallery ONCE for a block of 8 queries (each row is loaded
+ * once per block instead of once per query), so that checking hundreds of queries against millions of rows is
+ * compute-bound instead of DRAM-bound.  The arithmetic of every (query, row) pair - inner_product(), the pair order,
+ * the insertion - is the code above, so the output is bit-identical to fire_oracle_bf_knn (tests/test_oracle_knn.py).
+ * Used by the parity checks that compare the GPU against the oracle at BASELINE sizes. */
+#define BF_QBLOCK 8
+static void* bf_worker_blocked(void* arg) {
+  bf_job_t* J = (bf_job_t*)arg;
+  const int k = J->k, D = J->D;
+  for (int qb = J->q0; qb < J->q1; qb += BF_QBLOCK) {
+    const int nq = J->q1 - qb < BF_QBLOCK ? J->q1 - qb : BF_QBLOCK;
+    int cnt[BF_QBLOCK] = {0};
+    for (size_t r = 0; r < J->n; ++r) {
+      const float* gv = J->g + r * (size_t)D;
+      const uint64_t lab = J->labels ? J->labels[r] : (uint64_t)r;
+      for (int b = 0; b < nq; ++b) {
+        const int qi = qb + b;
+        float* bd = J->out_dist + (size_t)qi * k;
+        uint64_t* bl = J->out_labels + (size_t)qi * k;
+        float dist = 1.0f - inner_product(J->q + (size_t)qi * D, gv, D);
+        if (cnt[b] == k && !pair_less(dist, lab, bd[k - 1], bl[k - 1])) continue;
+        int j = cnt[b] < k ? cnt[b] : k - 1;
+        while (j > 0 && pair_less(dist, lab, bd[j - 1], bl[j - 1])) { bd[j] = bd[j - 1]; bl[j] = bl[j - 1]; --j; }
+        bd[j] = dist; bl[j] = lab;
+        if (cnt[b] < k) cnt[b]++;
+      }
+    }
+  }
+  return NULL;
+}
+
+int fire_oracle_bf_knn_blocked(const float* g, const uint64_t* labels, size_t n, int D, const float* q, int Q, int k,
+                               uint64_t* out_labels, float* out_dist, int num_threads) {
+  if (k < 1 || (size_t)k > n) return -1;
+  if (num_threads < 1) num_threads = 1;
+  if (num_threads > (Q + BF_QBLOCK - 1) / BF_QBLOCK) num_threads = (Q + BF_QBLOCK - 1) / BF_QBLOCK;
+  if (num_threads > 256) num_threads = 256;
+  bf_job_t jobs[256];
+  pthread_t th[256];
+  const int blocks = (Q + BF_QBLOCK - 1) / BF_QBLOCK;
+  for (int t = 0; t < num_threads; ++t) {
+    int q0 = (int)((long long)blocks * t / num_threads) * BF_QBLOCK, q1 = (int)((long long)blocks * (t + 1) / num_threads) * BF_QBLOCK;
+    if (q1 > Q) q1 = Q;
+    bf_job_t J = {g, labels, n, D, q, q0, q1, k, out_labels, out_dist};
+    jobs[t] = J;
+  }
+  for (int t = 1; t < num_threads; ++t) pthread_create(&th[t], NULL, bf_worker_blocked, &jobs[t]);
+  bf_worker_blocked(&jobs[0]);
+  for (int t = 1; t < num_threads; ++t) pthread_join(th[t], NULL);
+  return 0;
+}
+
 /* ------------------------------------------------------------------------------------------- */
 /* (2) cv::resize INTER_AREA, 8UC3                                                              */
 /* ------------------------------------------------------------------------------------------- */

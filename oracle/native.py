@@ -33,6 +33,8 @@ def lib():
         L.fire_oracle_bf_knn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p,
                                          ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.fire_oracle_bf_knn.restype = ctypes.c_int
+        L.fire_oracle_bf_knn_blocked.argtypes = L.fire_oracle_bf_knn.argtypes
+        L.fire_oracle_bf_knn_blocked.restype = ctypes.c_int
         L.fire_oracle_resize_area_u8c3.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_long,
                                                    ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         L.fire_oracle_resize_area_u8c3.restype = ctypes.c_int
@@ -87,14 +89,17 @@ class BFIndexOracle:
     def get_current_count(self) -> int:
         return len(self.labels)
 
-    def knn_query(self, data, k: int = 1, num_threads: int = 1):
+    def knn_query(self, data, k: int = 1, num_threads: int = 1, blocked: bool = False):
+        """blocked=True: same arithmetic per (query, row) pair, gallery walked once per block of 8 queries (bit-identical
+        output, far less DRAM traffic: what the BASELINE-sized parity checks use)."""
         q = normalize(np.asarray(data, dtype=np.float32).reshape(-1, self.dim))
         if k > len(self.labels):
             raise RuntimeError("Cannot return the results in a contiguous 2D array. Probably ef or M is too small")
         labels = np.empty((q.shape[0], k), dtype=np.uint64)
         dists = np.empty((q.shape[0], k), dtype=np.float32)
         rows = np.ascontiguousarray(self.rows)
-        rc = lib().fire_oracle_bf_knn(rows.ctypes.data, self.labels.ctypes.data, rows.shape[0], self.dim, q.ctypes.data,
+        fn = lib().fire_oracle_bf_knn_blocked if blocked else lib().fire_oracle_bf_knn
+        rc = fn(rows.ctypes.data, self.labels.ctypes.data, rows.shape[0], self.dim, q.ctypes.data,
                                       q.shape[0], k, labels.ctypes.data, dists.ctypes.data, num_threads)
         assert rc == 0
         return labels, dists

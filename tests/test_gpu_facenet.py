@@ -101,7 +101,8 @@ def test_config2_facenet512_batch256(nets):
 
 
 def test_golden_embeddings(nets):
-    """Committed fixture (tests/golden/facenet_golden.json, written from the CPU oracle by make_facenet_golden.py)."""
+    """Committed fixture (tests/golden/facenet_golden.json): the synthetic weights exported as a full-structure ONNX graph and
+    run by cv2.dnn.readNetFromONNX (make_facenet_golden.py) - numbers neither the oracle nor the engine produced."""
     import torch
     from fire_b200 import weights as W
     with open(os.path.join(GOLDEN, "facenet_golden.json")) as f:
@@ -112,6 +113,7 @@ def test_golden_embeddings(nets):
         raw, _ = eng.encode_unit_f32(torch.from_numpy(u8.astype(np.float32) / 255.0).cuda())
         got = raw.cpu().numpy()
         want = np.asarray(gold[str(D)]["embeddings"], dtype=np.float32)
+        assert gold["executor"].startswith("cv2.dnn")
         assert _cos(got, want).min() >= 0.9999
 
 
@@ -279,3 +281,33 @@ def test_forward_argument_errors(nets):
     out = torch.zeros(1, 128, device="cuda")
     with pytest.raises(FireError):
         _lib.check(_lib.lib().fire_facenet_forward(eng._h, x.data_ptr(), 1, out.data_ptr(), None, x.data_ptr(), 16, None))
+
+
+def test_no_activation_saturates_fp16(fire_lib, monkeypatch):
+    """fp16 storage has a range (65504) that bf16 does not: the epilogues convert with .satfinite, which would clip SILENTLY.
+    Saturation counter: with every activation kept in its own memory (reuse_buffers=False) and the residual chains run layer
+    by layer (so their branch tensors exist), every stored activation of a forward is read back and counted against the
+    limit.  The count must be 0 and the headroom is reported (profiles/r02_bf16_vs_fp16.txt has the CPU-side table)."""
+    import torch
+    from fire_b200 import engine, weights as W
+    monkeypatch.setenv("FIRE_B200_FUSE17", "0")
+    monkeypatch.setenv("FIRE_B200_FUSE35", "0")
+    for D in (512, 128):
+        t = W.synthetic_weights(D, 1234)
+        eng = engine.FaceNetEngine(D, t, reuse_buffers=False)
+        u8 = np.concatenate([_images(6, 31), np.full((1, 160, 160, 3), 255, np.uint8), np.zeros((1, 160, 160, 3), np.uint8)])   # incl. all-white / all-black
+        x = eng.ingest_unit_f32(torch.from_numpy(u8.astype(np.float32) / 255.0).cuda())
+        raw, _ = eng.forward(x)
+        assert torch.isfinite(raw).all()
+        worst, n_sat, n_read = 0.0, 0, 0
+        for i, b in enumerate(eng.plan.bufs):
+            if b.external or b.elt != 2:
+                continue
+            a = eng.read_buffer(i, x)
+            assert np.isfinite(a).all(), i
+            worst = max(worst, float(np.abs(a).max()))
+            n_sat += int((np.abs(a) >= 65504.0).sum())
+            n_read += 1
+        assert n_read > 100 and n_sat == 0, (n_read, n_sat)
+        assert worst < 65504.0 / 16, worst                           # more than 4 bits of headroom on this workload
+        eng.close()

@@ -62,3 +62,18 @@ def test_normalize_formula(oracle_native):
     x = np.array([[3.0, 4.0] + [0.0] * 14], np.float32)
     y = oracle_native.normalize(x)
     assert abs(y[0, 0] - 0.6) < 1e-7 and abs(y[0, 1] - 0.8) < 1e-7
+
+
+def test_blocked_scan_is_bit_identical(oracle_native):
+    """The query-blocked loop order used by the BASELINE-sized parity checks changes nothing but the DRAM traffic."""
+    rng = np.random.default_rng(77)
+    g = rng.standard_normal((5000, 128)).astype(np.float32)
+    g[100] = g[7]; g[4000] = g[7]                                # exact ties across the scan
+    q = rng.standard_normal((37, 128)).astype(np.float32)
+    q[3] = g[7]
+    ora = oracle_native.BFIndexOracle(128); ora.add_items(g)
+    for k in (1, 10, 50):
+        for threads in (1, 3, 8):
+            a = ora.knn_query(q, k, num_threads=threads)
+            b = ora.knn_query(q, k, num_threads=threads, blocked=True)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
