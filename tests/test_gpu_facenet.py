@@ -308,6 +308,6 @@ def test_no_activation_saturates_fp16(fire_lib, monkeypatch):
             worst = max(worst, float(np.abs(a).max()))
             n_sat += int((np.abs(a) >= 65504.0).sum())
             n_read += 1
-        assert n_read > 100 and n_sat == 0, (n_read, n_sat)
+        assert n_read >= 60 and n_sat == 0, (n_read, n_sat)
         assert worst < 65504.0 / 16, worst                           # more than 4 bits of headroom on this workload
         eng.close()
