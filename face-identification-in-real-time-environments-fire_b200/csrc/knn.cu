@@ -164,7 +164,12 @@ __device__ __forceinline__ float pick32(const uint32_t (&r)[32], int j) {
 // One CTA = one (query block, gallery split).  The 128 x D query tile stays resident in shared
 // memory; gallery K-blocks stream through a TMA ring; two 256-column accumulators alternate in TMEM
 // so the top-k epilogue of tile t overlaps the MMAs of tile t+1.
-template <int KP>
+// kShare (clusters of two, QB even): the two CTAs of a cluster hold consecutive query blocks and scan the SAME gallery split.
+// Every gallery stage is fetched ONCE for the pair: each CTA loads half of the tile's rows with a multicast TMA that lands
+// in both CTAs' shared memory, and a stage is handed back only when both CTAs' MMAs have read it (multicast commit).  In the
+// small-batch regime (a few query blocks, the scan HBM-bound) this halves the gallery bytes that cross L2 -> SM and HBM:
+// the two CTAs of a split were measured to pull the gallery twice otherwise (Q = 256: 0.50 of the HBM roofline).
+template <int KP, bool kShare>
 __global__ void __launch_bounds__(KNN_THREADS, 1)
 knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
                 const KnnScanParams p) {
@@ -193,7 +198,7 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == 1) {
     if (lane == 0) {
       mbar_init(a_full, 1);
-      for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+      for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kShare ? 2 : 1); }
       for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 128); }
       fence_barrier_init();
     }
@@ -202,8 +207,10 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (kShare) cluster_sync_all();                 // both CTAs' barriers exist before anything remote touches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = kShare ? cluster_ctarank() : 0u;
 
   const int issuer = warp == 0 ? 0 : (warp >= 6 ? warp - 5 : -1);
   if (issuer >= 0) {
@@ -220,8 +227,12 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int kb = 0; kb < p.nkb; ++kb, ++it) {
           if (turn == issuer) {
             mbar_wait(&empty[s], ph ^ 1, 1);
-            mbar_arrive_expect_tx(&full[s], KNN_B_STAGE_BYTES);
-            tma_load_2d(sB + static_cast<size_t>(s) * KNN_B_STAGE_BYTES, &tmap_g, &full[s], kb * 64, row0 + t * KNN_BN);
+            mbar_arrive_expect_tx(&full[s], KNN_B_STAGE_BYTES);           // kShare: own half + the peer's half, both land here
+            if (kShare)
+              tma_load_2d_multicast(sB + static_cast<size_t>(s) * KNN_B_STAGE_BYTES + crank * (KNN_B_STAGE_BYTES / 2), &tmap_g, &full[s], kb * 64,
+                                    row0 + t * KNN_BN + static_cast<int>(crank) * (KNN_BN / 2), static_cast<uint16_t>(3));
+            else
+              tma_load_2d(sB + static_cast<size_t>(s) * KNN_B_STAGE_BYTES, &tmap_g, &full[s], kb * 64, row0 + t * KNN_BN);
           }
           if (++turn == p.n_issuers) turn = 0;
           if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -250,7 +261,8 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_f16(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[s]);      // frees the smem stage once these MMAs have read it
+          if (kShare) umma_commit_multicast(&empty[s], static_cast<uint16_t>(3));   // the stage is free once BOTH CTAs' MMAs have read it
+          else umma_commit(&empty[s]);      // frees the smem stage once these MMAs have read it
         }
         umma_commit(&tfull[buf]);      // accumulator tile complete
       }
@@ -315,6 +327,7 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (kShare) cluster_sync_all();                 // no CTA leaves while its peer can still write into it or signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -800,17 +813,26 @@ static int knn_ensure_scratch(fire_knn* h, int Q, int S, int KP) {
   return FIRE_OK;
 }
 
-template <int KP>
+template <int KP, bool kShare>
 static int knn_launch_scan(fire_knn* h, const CUtensorMap& tq, const CUtensorMap& tg, const KnnScanParams& p,
                            size_t smem_bytes, cudaStream_t st) {
   static bool attr_done[FIRE_MAX_DEVICES] = {};        // the opt-in is per device (context), not per process
   if (!attr_done[h->device]) {
-    FIRE_CUDA(cudaFuncSetAttribute(knn_scan_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FIRE_CUDA(cudaFuncSetAttribute(knn_scan_kernel<KP, kShare>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(KNN_SMEM_BUDGET + 1024)));
     attr_done[h->device] = true;
   }
-  knn_scan_kernel<KP><<<p.QB * p.S, KNN_THREADS, smem_bytes, st>>>(tq, tg, p);
-  FIRE_LAUNCH_CHECK("knn_scan_kernel");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(p.QB * p.S));
+  cfg.blockDim = dim3(KNN_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = kShare ? 1 : 0;
+  FIRE_CUDA(cudaLaunchKernelEx(&cfg, knn_scan_kernel<KP, kShare>, tq, tg, p));
   count_launch();
   return FIRE_OK;
 }
@@ -861,7 +883,10 @@ static int knn_search_impl(fire_knn* h, const float* queries, long long stored_f
   CUtensorMap tq, tg;
   rc = make_tmap_f16_2d(&tq, h->q16, static_cast<uint64_t>(QB) * KNN_BM, D, static_cast<uint64_t>(D) * 2, KNN_BM);
   if (rc != FIRE_OK) return rc;
-  rc = make_tmap_f16_2d(&tg, h->g16, static_cast<uint64_t>(n_rows), D, static_cast<uint64_t>(D) * 2, KNN_BN);
+  // gallery stages shared by CTA pairs (see knn_scan_kernel): the small-batch regime, where the scan is HBM-bound
+  bool share = QB % 2 == 0 && QB <= 8;
+  if (const char* e = getenv("FIRE_B200_KNN_SHARE")) share = QB % 2 == 0 && e[0] == '1';       // A/B experiments
+  rc = make_tmap_f16_2d(&tg, h->g16, static_cast<uint64_t>(n_rows), D, static_cast<uint64_t>(D) * 2, share ? KNN_BN / 2 : KNN_BN);
   if (rc != FIRE_OK) return rc;
 
   KnnScanParams p;
@@ -880,7 +905,8 @@ static int knn_search_impl(fire_knn* h, const float* queries, long long stored_f
   const size_t smem_bytes = 1024 + a_bytes + static_cast<size_t>(stages) * KNN_B_STAGE_BYTES + bar_bytes;
 
   FIRE_CUDA(cudaMemsetAsync(h->counters, 0, sizeof(uint32_t) * 4, st));
-  rc = KP == 16 ? knn_launch_scan<16>(h, tq, tg, p, smem_bytes, st) : knn_launch_scan<64>(h, tq, tg, p, smem_bytes, st);
+  if (share) rc = KP == 16 ? knn_launch_scan<16, true>(h, tq, tg, p, smem_bytes, st) : knn_launch_scan<64, true>(h, tq, tg, p, smem_bytes, st);
+  else rc = KP == 16 ? knn_launch_scan<16, false>(h, tq, tg, p, smem_bytes, st) : knn_launch_scan<64, false>(h, tq, tg, p, smem_bytes, st);
   if (rc != FIRE_OK) return rc;
 
   {
