@@ -546,7 +546,7 @@ def run_fire(args):
 
         def step_frames(i):
             # host: pack the crop rectangles of the 256 boxes (fire_pack_rois_host) -> ONE H2D copy -> K1 -> K2 -> top-1 -> D2H
-            d_frames, d_desc, d_boxes, d_bf = stager.submit(frames_pin, desc5, bx, bf)
+            d_frames, d_desc, d_boxes, d_bf = stager.submit(frames_pin, desc5, bx, bf, next_args=(frames_pin, desc5, bx, bf))
             f16, _, status = engine.preprocess_boxes(d_frames, d_desc, d_boxes, d_bf, _lib.PRE_REFERENCE, True, False)
             stager.release()
             eng.forward(f16, want_l2=True, out_raw=raw5, out_l2=l25)
@@ -579,6 +579,10 @@ def run_fire(args):
                                     "decisions_equal_cpu_chain": bool(np.array_equal(cpu_acc, gpu_acc)), "accepted_cpu_chain": int(cpu_acc.sum()),
                                     "accepted_gpu_chain": int(gpu_acc.sum()), "max_abs_cosine_diff": float(np.abs(gpu_d - od[:, 0]).max()),
                                     "planted_cosines": [0.9, 0.72, 0.68, 0.5]}
+        t_pack = time.perf_counter()
+        engine.pack_rois(frames_pin, desc5, bx, bf, torch.empty(stager.host[0].numel(), dtype=torch.uint8), pack_threads)
+        frames_blk["host_pack_ms"] = (time.perf_counter() - t_pack) * 1e3
+        stager.close()
         gal5.close()
         del gal5, stager
         torch.cuda.empty_cache()

@@ -398,7 +398,8 @@ __global__ void knn_rerank_kernel(const float* __restrict__ qn, const float* __r
                                   const float* __restrict__ cand_score, const uint32_t* __restrict__ cand_idx, int S,
                                   int D, int Q, int k, float slack, const float* __restrict__ q_err,
                                   const int* __restrict__ g_max_err, KnnOut out, uint32_t* __restrict__ flagged,
-                                  uint32_t* __restrict__ flagged_count) {
+                                  uint32_t* __restrict__ flagged_count, int stage_lists) {
+  extern __shared__ __align__(16) uint8_t rerank_smem[];
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (q >= Q) return;
@@ -410,6 +411,20 @@ __global__ void knn_rerank_kernel(const float* __restrict__ qn, const float* __r
 
   const float* cs = cand_score + static_cast<size_t>(q) * S * KP;
   const uint32_t* ci = cand_idx + static_cast<size_t>(q) * S * KP;
+  if (stage_lists) {
+    // The merge below pops one entry per round and then reads the winner's next entry: from global memory that is a chain
+    // of dependent ~1 us loads (16 rounds: 30 us for a single query, the whole latency of a small-batch search's tail).  The
+    // warp first copies its query's S x KP candidates into shared memory with coalesced loads.
+    const int per_q = S * KP;
+    float* ss = reinterpret_cast<float*>(rerank_smem) + static_cast<size_t>(threadIdx.x >> 5) * per_q * 2;
+    uint32_t* si = reinterpret_cast<uint32_t*>(ss + per_q);
+    for (int i = lane * 4; i < per_q; i += 128) {
+      *reinterpret_cast<float4*>(ss + i) = *reinterpret_cast<const float4*>(cs + i);
+      *reinterpret_cast<uint4*>(si + i) = *reinterpret_cast<const uint4*>(ci + i);
+    }
+    __syncwarp();
+    cs = ss; ci = si;
+  }
   auto get = [&](int l, int pos, float& key, unsigned long long& id) {
     key = -cs[l * KP + pos];                       // descending score == ascending -score
     id = ci[l * KP + pos];
@@ -910,13 +925,19 @@ static int knn_search_impl(fire_knn* h, const float* queries, long long stored_f
   if (rc != FIRE_OK) return rc;
 
   {
-    const int blocks = (Q + 7) / 8;
+    // warps (= queries) per block: as many as fit their candidate lists (S x KP x 8 bytes each) into 48 KB of shared memory
+    const size_t per_q = static_cast<size_t>(S) * KP * 8;
+    int wpb = 8;
+    while (wpb > 1 && wpb * per_q > 48 * 1024) wpb >>= 1;
+    const int stage_lists = wpb * per_q <= 48 * 1024 ? 1 : 0;
+    const size_t sm = stage_lists ? wpb * per_q : 0;
+    const int blocks = (Q + wpb - 1) / wpb;
     if (KP == 16)
-      knn_rerank_kernel<16><<<blocks, 256, 0, st>>>(h->qn32, h->g32, h->cand_score, h->cand_idx, S, D, Q, k, h->eps, h->q_err, h->g_max_err,
-                                                    out, h->flagged, h->counters);
+      knn_rerank_kernel<16><<<blocks, wpb * 32, sm, st>>>(h->qn32, h->g32, h->cand_score, h->cand_idx, S, D, Q, k, h->eps, h->q_err, h->g_max_err,
+                                                          out, h->flagged, h->counters, stage_lists);
     else
-      knn_rerank_kernel<64><<<blocks, 256, 0, st>>>(h->qn32, h->g32, h->cand_score, h->cand_idx, S, D, Q, k, h->eps, h->q_err, h->g_max_err,
-                                                    out, h->flagged, h->counters);
+      knn_rerank_kernel<64><<<blocks, wpb * 32, sm, st>>>(h->qn32, h->g32, h->cand_score, h->cand_idx, S, D, Q, k, h->eps, h->q_err, h->g_max_err,
+                                                          out, h->flagged, h->counters, stage_lists);
     FIRE_LAUNCH_CHECK("knn_rerank_kernel");
     count_launch();
   }

@@ -212,7 +212,7 @@ __device__ __forceinline__ void reference_pixel(int mode, const CropGeom& g, con
 //      row block, whatever the tap overlap.  Blocks whose span does not fit (very large boxes) read the frame directly;
 //   3. one thread finishes one network-input POSITION (the 2 x 2 pixel block of the space-to-depth layout): 4 pixels ->
 //      16 fp16 channels -> one aligned 32-byte store; a warp writes 1 KB of consecutive bytes.
-constexpr int PRE_STAGE_BYTES = 64 * 1024;
+constexpr int PRE_STAGE_BYTES = 32 * 1024;      // + 9 KB of tables: five CTAs per SM (measured round 2: the kernel is occupancy-bound at three)
 
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_reference_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict__ frame_desc,

@@ -371,7 +371,9 @@ class RoiStager:
     """Upload only what the crops read (BASELINE configs[4]): per step, the crop rectangles of all boxes are packed on the
     host into a pinned buffer (fire_pack_rois_host) and moved with ONE host->device copy on a copy stream, `depth` slots
     deep so that the upload of step i+1 runs under the kernels of step i.  `submit` returns the device arguments of
-    preprocess_boxes; results are bit-identical to uploading the whole frames."""
+    preprocess_boxes; results are bit-identical to uploading the whole frames.  `submit(..., next_args=...)` also starts
+    packing the NEXT step's rectangles on a background thread (the C call releases the GIL), so that the host-side
+    gather of step i+1 runs while the main thread enqueues the kernels of step i."""
 
     def __init__(self, max_bytes: int, depth: int = 2, device: int = 0, threads: int = 4):
         torch = _torch()
@@ -383,28 +385,61 @@ class RoiStager:
         self.ev_in = [torch.cuda.Event() for _ in range(self.depth)]
         self.ev_free = [torch.cuda.Event() for _ in range(self.depth)]
         self.last_bytes = 0
+        self._pending = None            # (thread, slot, args, result holder) of a background pack
 
-    def submit(self, frames_host, frame_desc_host, boxes_host, box_frame_host):
+    def _pack_into(self, slot: int, args, holder: dict):
+        try:
+            if self.n >= self.depth or holder.get("ahead"):
+                self.ev_in[slot].synchronize()                  # the copy out of this pinned slot (depth submits ago) has finished
+            holder["used"] = pack_rois(*args, self.host[slot], self.threads)
+        except Exception as e:                                  # re-raised by the submit that consumes this pack
+            holder["error"] = e
+
+    def submit(self, frames_host, frame_desc_host, boxes_host, box_frame_host, next_args=None):
         """-> (frames, frame_desc, boxes, box_frame) cuda tensors for preprocess_boxes, valid until `depth` later submits;
-        call `release()` once the kernels reading them are enqueued."""
+        call `release()` once the kernels reading them are enqueued.  next_args: the four arguments of the NEXT submit."""
+        import threading
         torch = _torch()
         slot = self.n % self.depth
+        args = (frames_host, frame_desc_host, boxes_host, box_frame_host)
         n = int(boxes_host.shape[0])
-        if self.n >= self.depth:
-            self.ev_in[slot].synchronize()                      # the copy out of this pinned slot (depth submits ago) has finished
-            self.copy_stream.wait_event(self.ev_free[slot])     # and the kernels that read the device slot are done
-        used = pack_rois(frames_host, frame_desc_host, boxes_host, box_frame_host, self.host[slot], self.threads)
+        holder = None
+        if self._pending is not None:
+            th, p_slot, p_args, p_holder = self._pending
+            th.join()
+            self._pending = None
+            if p_slot == slot and all(a is b for a, b in zip(p_args, args)):
+                holder = p_holder
+        if holder is None:
+            holder = {}
+            self._pack_into(slot, args, holder)
+        if "error" in holder:
+            raise holder["error"]
+        used = holder["used"]
         self.last_bytes = used
+        if self.n >= self.depth:
+            self.copy_stream.wait_event(self.ev_free[slot])     # the kernels that read the device slot are done
         with torch.cuda.stream(self.copy_stream):
             self.dev[slot][:used].copy_(self.host[slot][:used], non_blocking=True)
             self.ev_in[slot].record(self.copy_stream)
         torch.cuda.current_stream().wait_event(self.ev_in[slot])
         self._slot = slot
         self.n += 1
+        if next_args is not None:
+            nslot = self.n % self.depth
+            nh = {"ahead": self.n >= self.depth}
+            th = threading.Thread(target=self._pack_into, args=(nslot, tuple(next_args), nh), daemon=True)
+            th.start()
+            self._pending = (th, nslot, tuple(next_args), nh)
         return (self.dev[slot],) + roi_views(self.dev[slot], n)
 
     def release(self):
         self.ev_free[self._slot].record(_torch().cuda.current_stream())
+
+    def close(self):
+        if self._pending is not None:
+            self._pending[0].join()
+            self._pending = None
 
 
 def align_warp(frames, frame_desc, matrices, face_frame, swap_rb: bool = True, output: str = "uint8"):

@@ -138,10 +138,11 @@ def test_staged_loads_unaligned_frames_and_roi_upload(fire_lib, oracle_native):
     # ROI upload: same boxes through the stager, twice (both slots), bit-identical outputs
     stager = engine.RoiStager(max_bytes=8 << 20, depth=2)
     host_flat = torch.from_numpy(flat).pin_memory()
-    for _ in range(3):
-        d_frames, d_desc, d_boxes, d_bf = stager.submit(host_flat, desc, boxes, bf)
+    for it in range(5):                                                  # with and without the background pack of the next step
+        d_frames, d_desc, d_boxes, d_bf = stager.submit(host_flat, desc, boxes, bf, next_args=(host_flat, desc, boxes, bf) if it % 2 == 0 else None)
         g16, g32, gst = engine.preprocess_boxes(d_frames, d_desc, d_boxes, d_bf, _lib.PRE_REFERENCE, True, True)
         stager.release()
         torch.cuda.synchronize()
         assert torch.equal(g16, f16) and torch.equal(g32, f32) and torch.equal(gst, status)
+    stager.close()
     assert stager.last_bytes < flat.nbytes * 6                           # rectangles, not frames (boxes overlap, so not < 1x here)
