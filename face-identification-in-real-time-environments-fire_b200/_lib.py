@@ -32,6 +32,8 @@ _SIGNATURES = {
     "fire_roi_meta_bytes": (C.c_size_t, [C.c_int]),
     "fire_pack_rois_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t,
                                       C.POINTER(C.c_size_t), C.c_int]),
+    "fire_upload_rois_dma": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                       C.POINTER(C.c_size_t), C.c_void_p]),
     "fire_align_warp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
     "fire_ingest_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

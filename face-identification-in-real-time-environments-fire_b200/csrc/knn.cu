@@ -438,30 +438,41 @@ __global__ void knn_rerank_kernel(const float* __restrict__ qn, const float* __r
   };
   warp_merge_lists(S, KP, KP, get, emit);
 
-  // exact fp32 distances of the survivors
+  // exact fp32 distances of the survivors.  FOUR candidates per round, eight lanes each (a lane group reads 128 contiguous
+  // bytes of its row per load, 16 independent loads per lane): the rows are random 2 KB reads from HBM, and walking them one
+  // after the other made this loop a chain of KP dependent ~1 us round trips (20 us of a small-batch search's latency).
   const float* qv = qn + static_cast<size_t>(q) * D;
   float dist[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) dist[e] = FLT_MAX;
-  for (int r = 0; r < KP; ++r) {
-    uint32_t idx = 0;
+  const int grp = lane >> 3, gl = lane & 7;
+  for (int r0 = 0; r0 < KP; r0 += 4) {
+    const int r = r0 + grp;                          // this lane group's candidate
+    uint32_t idx = 0xFFFFFFFFu;
 #pragma unroll
     for (int e = 0; e < EPL; ++e)
-      if (e == (r >> 5)) idx = __shfl_sync(0xffffffffu, sel_idx[e], r & 31);
-    if (idx == 0xFFFFFFFFu) continue;             // warp-uniform
-    const float* gv = g32 + static_cast<size_t>(idx) * D;
+      if (e == (r0 >> 5)) idx = __shfl_sync(0xffffffffu, sel_idx[e], r & 31);     // r0 .. r0+3 live in the same slot e
     float acc = 0.f;
-    for (int c = lane * 4; c < D; c += 128) {
-      float4 a = *reinterpret_cast<const float4*>(qv + c);
-      float4 b = __ldg(reinterpret_cast<const float4*>(gv + c));
-      acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+    if (idx != 0xFFFFFFFFu) {
+      const float* gv = g32 + static_cast<size_t>(idx) * D;
+      for (int c = gl * 4; c < D; c += 32) {
+        const float4 a = *reinterpret_cast<const float4*>(qv + c);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(gv + c));
+        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((r & 31) == lane) {
+    for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);      // within the 8-lane group
+    const float dd = 1.0f - acc;
+    const float mine = (idx != 0xFFFFFFFFu && dd == dd) ? dd : FLT_MAX;       // a NaN (NaN/Inf in the query) sorts last instead of poisoning the ranking
 #pragma unroll
-      for (int e = 0; e < EPL; ++e)
-        if (e == (r >> 5)) { const float dd = 1.0f - acc; dist[e] = dd == dd ? dd : FLT_MAX; }    // a NaN (NaN/Inf in the query) sorts last instead of poisoning the ranking
+    for (int g = 0; g < 4; ++g) {                    // hand candidate r0+g's distance to the lane that owns list entry r0+g
+      const float v = __shfl_sync(0xffffffffu, mine, g * 8);
+      if (((r0 + g) & 31) == lane) {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e)
+          if (e == ((r0 + g) >> 5)) dist[e] = v;
+      }
     }
   }
 

@@ -375,11 +375,15 @@ class RoiStager:
     packing the NEXT step's rectangles on a background thread (the C call releases the GIL), so that the host-side
     gather of step i+1 runs while the main thread enqueues the kernels of step i."""
 
-    def __init__(self, max_bytes: int, depth: int = 2, device: int = 0, threads: int = 4):
+    def __init__(self, max_bytes: int, depth: int = 2, device: int = 0, threads: int = 4, mode: str = "pack", max_boxes: int = 4096):
+        """mode "pack": host gather into a pinned buffer + one copy (fire_pack_rois_host); mode "dma": the copy engine gathers,
+        one cudaMemcpy2DAsync per rectangle straight out of the PINNED frames (fire_upload_rois_dma) - no host cores needed."""
         torch = _torch()
+        assert mode in ("pack", "dma")
         self.device = torch.device("cuda", device)
-        self.depth, self.threads, self.n = max(2, depth), threads, 0
-        self.host = [torch.empty(max_bytes, dtype=torch.uint8).pin_memory() for _ in range(self.depth)]
+        self.depth, self.threads, self.n, self.mode = max(2, depth), threads, 0, mode
+        host_bytes = max_bytes if mode == "pack" else int(_lib.lib().fire_roi_meta_bytes(max_boxes))
+        self.host = [torch.empty(host_bytes, dtype=torch.uint8).pin_memory() for _ in range(self.depth)]
         self.dev = [torch.empty(max_bytes, dtype=torch.uint8, device=self.device) for _ in range(self.depth)]
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.ev_in = [torch.cuda.Event() for _ in range(self.depth)]
@@ -403,6 +407,22 @@ class RoiStager:
         slot = self.n % self.depth
         args = (frames_host, frame_desc_host, boxes_host, box_frame_host)
         n = int(boxes_host.shape[0])
+        if self.mode == "dma":
+            def addr(a):
+                return a.ctypes.data if isinstance(a, np.ndarray) else int(a.data_ptr())
+            if self.n >= self.depth:
+                self.ev_in[slot].synchronize()                  # the table copy out of this pinned slot has finished
+                self.copy_stream.wait_event(self.ev_free[slot])
+            used = C.c_size_t(0)
+            check(_lib.lib().fire_upload_rois_dma(addr(frames_host), addr(frame_desc_host), int(frame_desc_host.shape[0]), addr(boxes_host),
+                                                  addr(box_frame_host), n, _ptr(self.host[slot]), _ptr(self.dev[slot]), self.dev[slot].numel(),
+                                                  C.byref(used), int(self.copy_stream.cuda_stream)))
+            self.last_bytes = int(used.value)
+            self.ev_in[slot].record(self.copy_stream)
+            torch.cuda.current_stream().wait_event(self.ev_in[slot])
+            self._slot = slot
+            self.n += 1
+            return (self.dev[slot],) + roi_views(self.dev[slot], n)
         holder = None
         if self._pending is not None:
             th, p_slot, p_args, p_holder = self._pending

@@ -83,6 +83,14 @@ int fire_pack_rois_host(const uint8_t* host_frames, const int64_t* host_frame_de
                         const int32_t* host_boxes_xywh, const int32_t* host_box_frame, int n_boxes,
                         uint8_t* host_packed, size_t host_packed_bytes, size_t* bytes_used, int n_threads);
 
+/* The same upload with the copy engine doing the gather (no host copy): tables -> host_tables (pinned, fire_roi_meta_bytes(n)
+ * bytes, untouched until `stream` has passed this call) -> one cudaMemcpyAsync; every crop rectangle goes straight from the
+ * pinned frames to its place in dev_packed with one cudaMemcpy2DAsync.  Same device layout as fire_pack_rois_host + copy. */
+int fire_upload_rois_dma(const uint8_t* host_frames, const int64_t* host_frame_desc, int n_frames,
+                         const int32_t* host_boxes_xywh, const int32_t* host_box_frame, int n_boxes,
+                         uint8_t* host_tables, uint8_t* dev_packed, size_t dev_packed_bytes, size_t* bytes_used,
+                         fire_stream_t stream);
+
 /* Aligned crop of the enrol path: cv2.warpAffine(image, M, (160, 160)) (INTER_LINEAR, constant 0 border) bit for bit,
  * optionally followed by the reference's [:, :, ::-1]            yunet_face_detector.py:135-165 (and the MediaPipe /
  * RetinaFace twins).  matrices: double [n_faces][6], the FORWARD 2x3 matrix cv2.getAffineTransform returns (the host

@@ -145,4 +145,12 @@ def test_staged_loads_unaligned_frames_and_roi_upload(fire_lib, oracle_native):
         torch.cuda.synchronize()
         assert torch.equal(g16, f16) and torch.equal(g32, f32) and torch.equal(gst, status)
     stager.close()
+    dma = engine.RoiStager(max_bytes=8 << 20, depth=2, mode="dma")      # the copy engine gathers: one 2-D copy per rectangle
+    for _ in range(3):
+        d_frames, d_desc, d_boxes, d_bf = dma.submit(host_flat, desc, boxes, bf)
+        g16, g32, gst = engine.preprocess_boxes(d_frames, d_desc, d_boxes, d_bf, _lib.PRE_REFERENCE, True, True)
+        dma.release()
+        torch.cuda.synchronize()
+        assert torch.equal(g16, f16) and torch.equal(g32, f32) and torch.equal(gst, status)
+    assert dma.last_bytes == stager.last_bytes
     assert stager.last_bytes < flat.nbytes * 6                           # rectangles, not frames (boxes overlap, so not < 1x here)
