@@ -571,13 +571,33 @@ def run_fire(args):
                 routes[mode]["pack_threads"] = pack_threads
             roi_bytes = int(stager.last_bytes)
             del stager
+        # where one frames step spends its device time (one un-pipelined step, CUDA events between the stages)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        stager = RoiStager(max_bytes=max_roi_bytes, depth=2, device=local, threads=pack_threads, mode="pack", max_boxes=NF)
+        for rep in range(3):
+            torch.cuda.synchronize()
+            evs[0].record()
+            d_frames, d_desc, d_boxes, d_bf = stager.submit(frames_pin, desc5, bx, bf)
+            evs[1].record()
+            f16, _, status = engine.preprocess_boxes(d_frames, d_desc, d_boxes, d_bf, _lib.PRE_REFERENCE, True, False)
+            stager.release()
+            evs[2].record()
+            eng.forward(f16, want_l2=True, out_raw=raw5, out_l2=l25)
+            evs[3].record()
+            gal5.search(l25, 1, out_dist=dd5, out_ids=ii5)
+            out_d.copy_(dd5, non_blocking=True); out_i.copy_(ii5, non_blocking=True)
+            evs[4].record()
+            torch.cuda.synchronize()
+        breakdown = {"h2d_wait_ms": evs[0].elapsed_time(evs[1]), "k1_ms": evs[1].elapsed_time(evs[2]), "facenet_ms": evs[2].elapsed_time(evs[3]),
+                     "top1_and_d2h_ms": evs[3].elapsed_time(evs[4])}
+        del stager
         best = max(routes, key=lambda m: routes[m]["faces_per_s"])
         ms_step = routes[best]["ms_per_step"]
         accepted = int(((1.0 - out_d.numpy()[:, 0]) > 0.7).sum())          # strict >, face_recognition.py:462-463
         frames_blk = {"metric": "configs[4]: 1080p frames, 8 fixed boxes each -> ROI upload -> K1 -> FaceNet512 -> cosine top-1 vs 1M gallery (replicated), thr 0.7",
                       "frames_per_s": routes[best]["faces_per_s"] / PER, "faces_per_s": routes[best]["faces_per_s"],
                       "ms_per_step": ms_step, "frames_per_step_per_gpu": F, "boxes_per_frame": PER, "n_gpus": world, "upload_route": best,
-                      "upload_routes": routes,
+                      "upload_routes": routes, "one_step_device_breakdown": breakdown,
                       "h2d_bytes_per_step": roi_bytes, "h2d_GBps_per_gpu": roi_bytes / (ms_step * 1e-3) / 1e9,
                       "whole_frame_bytes_per_step": int(frames_pin.numel()),
                       "d2h_bytes_per_step": NF * 12, "accepted_faces_last_step": accepted,

@@ -164,32 +164,39 @@ __device__ __forceinline__ float pick32(const uint32_t (&r)[32], int j) {
 // One CTA = one (query block, gallery split).  The 128 x D query tile stays resident in shared
 // memory; gallery K-blocks stream through a TMA ring; two 256-column accumulators alternate in TMEM
 // so the top-k epilogue of tile t overlaps the MMAs of tile t+1.
-// kShare (clusters of two, QB even): the two CTAs of a cluster hold consecutive query blocks and scan the SAME gallery split.
-// Every gallery stage is fetched ONCE for the pair: each CTA loads half of the tile's rows with a multicast TMA that lands
-// in both CTAs' shared memory, and a stage is handed back only when both CTAs' MMAs have read it (multicast commit).  In the
-// small-batch regime (a few query blocks, the scan HBM-bound) this halves the gallery bytes that cross L2 -> SM and HBM:
-// the two CTAs of a split were measured to pull the gallery twice otherwise (Q = 256: 0.50 of the HBM roofline).
-template <int KP, bool kShare>
+// kPair (clusters of two, QB even, tcgen05 cta_group::2): the two CTAs of a cluster hold consecutive query blocks and scan the
+// SAME gallery split as ONE M = 256 MMA per K step.  Each CTA keeps its own 128 queries (A) and loads only HALF of every
+// gallery tile's rows (its half of the B operand): every SM ingests half of the gallery bytes.  With the 128 KB query tile
+// resident only ~96 KB of gallery stages fit in flight per SM, which caps the ingest of one SM at ~49 GB/s (measured); a
+// few query blocks per split are therefore bound by per-SM ingest, not by HBM (Q = 256: 0.49 of the HBM roofline with two
+// independent CTAs per split - and sharing the stages by multicast changed nothing, since every SM still ingested every
+// byte).  Only the leader (cluster rank 0) issues MMAs; completions are multicast to both CTAs' barriers; the peer's
+// otherwise idle MMA warp relays "my operands have landed" to the leader (same protocol as conv_igemm_kernel_t<true>).
+template <int KP, bool kPair>
 __global__ void __launch_bounds__(KNN_THREADS, 1)
 knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
                 const KnnScanParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int b_stage_bytes = kPair ? KNN_B_STAGE_BYTES / 2 : KNN_B_STAGE_BYTES;
   uint8_t* sA = smem;
   uint8_t* sB = smem + static_cast<size_t>(p.nkb) * KNN_A_KB_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + static_cast<size_t>(p.stages) * KNN_B_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + static_cast<size_t>(p.stages) * b_stage_bytes);
   uint64_t* a_full = bars;
   uint64_t* full = bars + 1;
   uint64_t* empty = full + p.stages;
   uint64_t* tfull = empty + p.stages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* peer_a_full = tempty + 2;             // pair mode, leader: the peer's query tile / gallery half of stage s has landed
+  uint64_t* peer_full = peer_a_full + 1;          // [stages]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_full + p.stages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x % p.QB, split = blockIdx.x / p.QB;
   const int row0 = split * p.rows_per_split;
   const int row1 = min(row0 + p.rows_per_split, p.n_rows);
   const int n_tiles = row1 > row0 ? (row1 - row0 + KNN_BN - 1) / KNN_BN : 0;
+  const uint32_t crank = kPair ? cluster_ctarank() : 0u;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -198,19 +205,25 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == 1) {
     if (lane == 0) {
       mbar_init(a_full, 1);
-      for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kShare ? 2 : 1); }
-      for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 128); }
+      mbar_init(peer_a_full, 1);
+      for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&peer_full[s], 1); }
+      // one arrival per epilogue WARP (per-thread arrivals on one barrier word serialise); pair: both CTAs' warps release the leader's
+      for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kPair ? 8 : 4); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc<512>(tmem_slot);
+    if (!kPair) tmem_alloc<512>(tmem_slot);
+  }
+  if (kPair) {                                      // barriers of both CTAs exist before anything remote touches them
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) tmem_alloc2_rt(tmem_slot, 512u);
   }
   tc_fence_before();
   __syncthreads();
-  if (kShare) cluster_sync_all();                 // both CTAs' barriers exist before anything remote touches them
+  if (kPair) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t crank = kShare ? cluster_ctarank() : 0u;
 
   const int issuer = warp == 0 ? 0 : (warp >= 6 ? warp - 5 : -1);
   if (issuer >= 0) {
@@ -227,12 +240,10 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int kb = 0; kb < p.nkb; ++kb, ++it) {
           if (turn == issuer) {
             mbar_wait(&empty[s], ph ^ 1, 1);
-            mbar_arrive_expect_tx(&full[s], KNN_B_STAGE_BYTES);           // kShare: own half + the peer's half, both land here
-            if (kShare)
-              tma_load_2d_multicast(sB + static_cast<size_t>(s) * KNN_B_STAGE_BYTES + crank * (KNN_B_STAGE_BYTES / 2), &tmap_g, &full[s], kb * 64,
-                                    row0 + t * KNN_BN + static_cast<int>(crank) * (KNN_BN / 2), static_cast<uint16_t>(3));
-            else
-              tma_load_2d(sB + static_cast<size_t>(s) * KNN_B_STAGE_BYTES, &tmap_g, &full[s], kb * 64, row0 + t * KNN_BN);
+            mbar_arrive_expect_tx(&full[s], b_stage_bytes);
+            // pair: this CTA's half of the tile's rows (the tensor map's box is 128 rows then)
+            tma_load_2d(sB + static_cast<size_t>(s) * b_stage_bytes, &tmap_g, &full[s], kb * 64,
+                        row0 + t * KNN_BN + (kPair ? static_cast<int>(crank) * (KNN_BN / 2) : 0));
           }
           if (++turn == p.n_issuers) turn = 0;
           if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -240,10 +251,22 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(KNN_BM, KNN_BN);
+    // ------------------------------------------------------------------ MMA issuer (one thread); the peer's thread is the relay
+    if (lane == 0 && crank != 0) {
+      mbar_wait(a_full, 0, 6);
+      mbar_arrive_remote_relaxed(peer_a_full, 0u);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < n_tiles; ++t)
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(&full[s], ph, 7);
+          mbar_arrive_remote_relaxed(&peer_full[s], 0u);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+    } else if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kPair ? 2 * KNN_BM : KNN_BM, KNN_BN);
       mbar_wait(a_full, 0, 2);
+      if (kPair) mbar_wait(peer_a_full, 0, 8);
       tc_fence_after();
       int it = 0;
       for (int t = 0; t < n_tiles; ++t) {
@@ -255,16 +278,18 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(&full[s], ph, 4);
+          if (kPair) mbar_wait(&peer_full[s], ph, 9);
           tc_fence_after();
           const uint32_t a0 = smem_u32(sA + static_cast<size_t>(kb) * KNN_A_KB_BYTES);
-          const uint32_t b0 = smem_u32(sB + static_cast<size_t>(s) * KNN_B_STAGE_BYTES);
+          const uint32_t b0 = smem_u32(sB + static_cast<size_t>(s) * b_stage_bytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
-          if (kShare) umma_commit_multicast(&empty[s], static_cast<uint16_t>(3));   // the stage is free once BOTH CTAs' MMAs have read it
-          else umma_commit(&empty[s]);      // frees the smem stage once these MMAs have read it
+          for (int k = 0; k < 4; ++k) {
+            if (kPair) umma_f16_2cta(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if (kPair) umma_commit_2cta(&empty[s]); else umma_commit(&empty[s]);      // frees the stage (in both CTAs) once these MMAs have read it
         }
-        umma_commit(&tfull[buf]);      // accumulator tile complete
+        if (kPair) umma_commit_2cta(&tfull[buf]); else umma_commit(&tfull[buf]);    // accumulator tile complete (each CTA reads its own 128 lanes)
       }
     }
   } else {
@@ -311,9 +336,9 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           }
         }
       }
-      __syncwarp();
       tc_fence_before();
-      mbar_arrive(&tempty[buf]);
+      __syncwarp();
+      if (lane == 0) { if (crank != 0) mbar_arrive_remote_relaxed(&tempty[buf], 0u); else mbar_arrive(&tempty[buf]); }
     }
     const size_t q = static_cast<size_t>(qb) * KNN_BM + qrow;
     float* os = p.cand_score + (q * p.S + split) * KP;
@@ -327,10 +352,10 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (kShare) cluster_sync_all();                 // no CTA leaves while its peer can still write into it or signal its barriers
+  if (kPair) cluster_sync_all();                  // no CTA leaves while its peer can still signal its barriers or the pair's MMAs run
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    if (kPair) tmem_dealloc2_rt(tmem_base, 512u); else tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -839,12 +864,12 @@ static int knn_ensure_scratch(fire_knn* h, int Q, int S, int KP) {
   return FIRE_OK;
 }
 
-template <int KP, bool kShare>
+template <int KP, bool kPair>
 static int knn_launch_scan(fire_knn* h, const CUtensorMap& tq, const CUtensorMap& tg, const KnnScanParams& p,
                            size_t smem_bytes, cudaStream_t st) {
   static bool attr_done[FIRE_MAX_DEVICES] = {};        // the opt-in is per device (context), not per process
   if (!attr_done[h->device]) {
-    FIRE_CUDA(cudaFuncSetAttribute(knn_scan_kernel<KP, kShare>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FIRE_CUDA(cudaFuncSetAttribute(knn_scan_kernel<KP, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(KNN_SMEM_BUDGET + 1024)));
     attr_done[h->device] = true;
   }
@@ -857,8 +882,8 @@ static int knn_launch_scan(fire_knn* h, const CUtensorMap& tq, const CUtensorMap
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = kShare ? 1 : 0;
-  FIRE_CUDA(cudaLaunchKernelEx(&cfg, knn_scan_kernel<KP, kShare>, tq, tg, p));
+  cfg.numAttrs = kPair ? 1 : 0;
+  FIRE_CUDA(cudaLaunchKernelEx(&cfg, knn_scan_kernel<KP, kPair>, tq, tg, p));
   count_launch();
   return FIRE_OK;
 }
@@ -909,18 +934,19 @@ static int knn_search_impl(fire_knn* h, const float* queries, long long stored_f
   CUtensorMap tq, tg;
   rc = make_tmap_f16_2d(&tq, h->q16, static_cast<uint64_t>(QB) * KNN_BM, D, static_cast<uint64_t>(D) * 2, KNN_BM);
   if (rc != FIRE_OK) return rc;
-  // gallery stages shared by CTA pairs (see knn_scan_kernel): the small-batch regime, where the scan is HBM-bound
-  bool share = QB % 2 == 0 && QB <= 8;
-  if (const char* e = getenv("FIRE_B200_KNN_SHARE")) share = QB % 2 == 0 && e[0] == '1';       // A/B experiments
-  rc = make_tmap_f16_2d(&tg, h->g16, static_cast<uint64_t>(n_rows), D, static_cast<uint64_t>(D) * 2, share ? KNN_BN / 2 : KNN_BN);
+  // CTA pairs (see knn_scan_kernel): the few-query-blocks regime, where two independent CTAs per split are bound by per-SM ingest
+  bool pair = QB % 2 == 0 && QB <= 8;
+  if (const char* e = getenv("FIRE_B200_KNN_PAIR")) pair = QB % 2 == 0 && e[0] == '1';        // A/B experiments
+  rc = make_tmap_f16_2d(&tg, h->g16, static_cast<uint64_t>(n_rows), D, static_cast<uint64_t>(D) * 2, pair ? KNN_BN / 2 : KNN_BN);
   if (rc != FIRE_OK) return rc;
 
   KnnScanParams p;
   p.nkb = nkb; p.n_rows = n_rows; p.S = S; p.rows_per_split = tiles_per_split * KNN_BN; p.QB = QB;
   const size_t a_bytes = static_cast<size_t>(nkb) * KNN_A_KB_BYTES;
-  const size_t bar_bytes = 256;
-  int stages = static_cast<int>((KNN_SMEM_BUDGET - a_bytes - bar_bytes) / KNN_B_STAGE_BYTES);
-  stages = std::max(2, std::min(stages, 6));
+  const size_t bar_bytes = 512;
+  const size_t b_stage = pair ? KNN_B_STAGE_BYTES / 2 : KNN_B_STAGE_BYTES;
+  int stages = static_cast<int>((KNN_SMEM_BUDGET - a_bytes - bar_bytes) / b_stage);
+  stages = std::max(2, std::min(stages, pair ? 12 : 6));
   p.stages = stages;
   p.n_issuers = stages % 3 == 0 ? 3 : (stages % 2 == 0 ? 2 : 1);
   if (const char* e = getenv("FIRE_B200_KNN_ISSUERS")) {            // A/B experiments only
@@ -928,10 +954,10 @@ static int knn_search_impl(fire_knn* h, const float* queries, long long stored_f
     if (j >= 1 && j <= KNN_ISSUERS && stages % j == 0) p.n_issuers = j;
   }
   p.cand_score = h->cand_score; p.cand_idx = h->cand_idx;
-  const size_t smem_bytes = 1024 + a_bytes + static_cast<size_t>(stages) * KNN_B_STAGE_BYTES + bar_bytes;
+  const size_t smem_bytes = 1024 + a_bytes + static_cast<size_t>(stages) * b_stage + bar_bytes;
 
   FIRE_CUDA(cudaMemsetAsync(h->counters, 0, sizeof(uint32_t) * 4, st));
-  if (share) rc = KP == 16 ? knn_launch_scan<16, true>(h, tq, tg, p, smem_bytes, st) : knn_launch_scan<64, true>(h, tq, tg, p, smem_bytes, st);
+  if (pair) rc = KP == 16 ? knn_launch_scan<16, true>(h, tq, tg, p, smem_bytes, st) : knn_launch_scan<64, true>(h, tq, tg, p, smem_bytes, st);
   else rc = KP == 16 ? knn_launch_scan<16, false>(h, tq, tg, p, smem_bytes, st) : knn_launch_scan<64, false>(h, tq, tg, p, smem_bytes, st);
   if (rc != FIRE_OK) return rc;
 
