@@ -305,13 +305,9 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tc_fence_after();
       const int col0 = row0 + t * KNN_BN;
       const int nvalid = min(KNN_BN, row1 - col0);
-#pragma unroll 1
-      for (int c = 0; c < KNN_BN / 32; ++c) {
-        if (c * 32 >= nvalid) break;
-        uint32_t r[32];
-        __syncwarp();                                // tcgen05.ld is warp-collective: reconverge first
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * KNN_BN + c * 32), r);
-        tmem_ld_wait(r);
+      // One 32-column chunk of this lane's query row: block maximum against the list's threshold (almost always the end of
+      // it once the list has warmed up), else the few candidates above the threshold are inserted.
+      auto consume = [&](uint32_t (&r)[32], int c) {
         const int lim = nvalid - c * 32;          // >= 32 for full chunks
         if (lim < 32) {
 #pragma unroll
@@ -334,6 +330,39 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               thr = list.worst();
             }
           }
+        }
+      };
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(buf * KNN_BN);
+      const int n_chunks = (nvalid + 31) >> 5;
+      if (KP <= 16) {
+        // tcgen05.ld has ~500 cycles of latency and the block maximum of 32 values costs ~40 instructions: walking the eight
+        // chunks one after the other left the accumulator busy for ~4 us per tile - longer than the tile's MMAs (2.1 us), so
+        // the EPILOGUE set the pace of the whole scan (round-2 ncu: tensor pipe 65 % at Q = 4096, 48 % at Q = 256).  The
+        // load of chunk c+1 is now in flight while chunk c is reduced (two register buffers).
+        uint32_t ra[32], rb[32];
+        __syncwarp();
+        tmem_ld_32x32(tbase, ra);
+#pragma unroll 1
+        for (int c = 0; c < n_chunks; c += 2) {
+          tmem_ld_wait(ra);
+          __syncwarp();
+          if (c + 1 < n_chunks) tmem_ld_32x32(tbase + static_cast<uint32_t>((c + 1) * 32), rb);
+          consume(ra, c);
+          if (c + 1 < n_chunks) {
+            tmem_ld_wait(rb);
+            __syncwarp();
+            if (c + 2 < n_chunks) tmem_ld_32x32(tbase + static_cast<uint32_t>((c + 2) * 32), ra);
+            consume(rb, c + 1);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < n_chunks; ++c) {
+          uint32_t r[32];
+          __syncwarp();                                // tcgen05.ld is warp-collective: reconverge first
+          tmem_ld_32x32(tbase + static_cast<uint32_t>(c * 32), r);
+          tmem_ld_wait(r);
+          consume(r, c);
         }
       }
       tc_fence_before();

@@ -28,6 +28,25 @@ full = KnnIndex(D, N, device=local); full.add(rows)
 fd, fi = full.search(q, k)
 torch.cuda.synchronize()
 ok = torch.equal(i, fi) and torch.equal(d, fd) and i[0, 0].item() == 17 and i[0, 1].item() == 200_000
+# the chunk-pipelined exchange (all_gather of chunk c under the scan of chunk c+1) gives the same answer
+for chunks in (1, 3):
+    d3, i3 = gal.search(q, k, chunks=chunks)
+    torch.cuda.synchronize()
+    ok = ok and torch.equal(i3, fi) and torch.equal(d3, fd)
+# a gallery that GROWS across the ranks one row at a time (hnsw_manager.py:135-143 sharded): interleaved layout, from empty;
+# early on some shard holds fewer than k rows (or none) and pads its lists
+grow = ShardedGallery(D, 64, rank, world, device=local, layout="interleaved")
+single = KnnIndex(D, 64, device=local)
+for n in range(1, 40):
+    row = rows[n - 1:n].clone()
+    assert grow.add_embedding(grow.broadcast_row(row)) == n - 1
+    single.add(row)
+    if n in (1, 2, 3, 11, 39):
+        kk = min(k, n)
+        gd, gi = grow.search(q[:9].contiguous(), kk)
+        sd, si = single.search(q[:9].contiguous(), kk)
+        torch.cuda.synchronize()
+        ok = ok and torch.equal(gi, si) and torch.equal(gd, sd)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
