@@ -166,12 +166,11 @@ __device__ __forceinline__ float pick32(const uint32_t (&r)[32], int j) {
 // so the top-k epilogue of tile t overlaps the MMAs of tile t+1.
 // kPair (clusters of two, QB even, tcgen05 cta_group::2): the two CTAs of a cluster hold consecutive query blocks and scan the
 // SAME gallery split as ONE M = 256 MMA per K step.  Each CTA keeps its own 128 queries (A) and loads only HALF of every
-// gallery tile's rows (its half of the B operand): every SM ingests half of the gallery bytes.  With the 128 KB query tile
-// resident only ~96 KB of gallery stages fit in flight per SM, which caps the ingest of one SM at ~49 GB/s (measured); a
-// few query blocks per split are therefore bound by per-SM ingest, not by HBM (Q = 256: 0.49 of the HBM roofline with two
-// independent CTAs per split - and sharing the stages by multicast changed nothing, since every SM still ingested every
-// byte).  Only the leader (cluster rank 0) issues MMAs; completions are multicast to both CTAs' barriers; the peer's
-// otherwise idle MMA warp relays "my operands have landed" to the leader (same protocol as conv_igemm_kernel_t<true>).
+// gallery tile's rows (its half of the B operand): every SM ingests half of the gallery bytes.  Only the leader (cluster rank
+// 0) issues MMAs; completions are multicast to both CTAs' barriers; the peer's otherwise idle MMA warp relays "my operands
+// have landed" to the leader (same protocol as conv_igemm_kernel_t<true>).  Bit-identical results (tests/test_gpu_knn.py), but
+// NO gain measured on the B200 in any regime - like sharing the stages of two independent CTAs by multicast TMA, tried just
+// before (round 2): the scan is not bound by gallery bytes per SM.  Kept behind FIRE_B200_KNN_PAIR=1 for that record only.
 template <int KP, bool kPair>
 __global__ void __launch_bounds__(KNN_THREADS, 1)
 knn_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
@@ -963,9 +962,10 @@ static int knn_search_impl(fire_knn* h, const float* queries, long long stored_f
   CUtensorMap tq, tg;
   rc = make_tmap_f16_2d(&tq, h->q16, static_cast<uint64_t>(QB) * KNN_BM, D, static_cast<uint64_t>(D) * 2, KNN_BM);
   if (rc != FIRE_OK) return rc;
-  // CTA pairs (see knn_scan_kernel): the few-query-blocks regime, where two independent CTAs per split are bound by per-SM ingest
-  bool pair = QB % 2 == 0 && QB <= 8;
-  if (const char* e = getenv("FIRE_B200_KNN_PAIR")) pair = QB % 2 == 0 && e[0] == '1';        // A/B experiments
+  // CTA pairs (see knn_scan_kernel) are OFF by default: measured on the B200 (profiles/r02_knn_experiments.txt) they change
+  // neither the few-query-blocks regime (Q = 256: 0.325 vs 0.327 ms) nor the large batches (Q = 4096: 3.40 vs 3.53 ms)
+  bool pair = false;
+  if (const char* e = getenv("FIRE_B200_KNN_PAIR")) pair = QB % 2 == 0 && e[0] == '1';        // A/B experiments, parity test
   rc = make_tmap_f16_2d(&tg, h->g16, static_cast<uint64_t>(n_rows), D, static_cast<uint64_t>(D) * 2, pair ? KNN_BN / 2 : KNN_BN);
   if (rc != FIRE_OK) return rc;
 

@@ -252,3 +252,21 @@ def test_knn_nan_query_writes_every_slot(fire_lib):
     assert int((i == 123456789).sum()) == 0 and int((d == 123.0).sum()) == 0
     assert bool(((i[1] == -1) | ((i[1] >= 0) & (i[1] < 500))).all())
     assert bool((i[[0, 2, 3]] >= 0).all())
+
+
+def test_knn_cta_pair_scan_is_identical(fire_lib, oracle_native, monkeypatch):
+    """The cta_group::2 instantiation of knn_scan_kernel (FIRE_B200_KNN_PAIR=1; off by default: no gain measured,
+    profiles/r02_knn_experiments.txt) returns exactly what the single-CTA kernel returns."""
+    import torch
+    from fire_b200.engine import KnnIndex
+    rng = np.random.default_rng(43)
+    g = rng.standard_normal((50000, 512), dtype=np.float32)
+    idx = KnnIndex(512, 50000); idx.add(g)
+    for Q, k in ((256, 10), (130, 1), (1024, 10), (200, 50)):
+        q = torch.from_numpy(rng.standard_normal((Q, 512), dtype=np.float32)).cuda()
+        monkeypatch.setenv("FIRE_B200_KNN_PAIR", "0")
+        d0, i0 = idx.search(q, k)
+        monkeypatch.setenv("FIRE_B200_KNN_PAIR", "1")
+        d1, i1 = idx.search(q, k)
+        torch.cuda.synchronize()
+        assert torch.equal(i0, i1) and torch.equal(d0, d1), (Q, k)
