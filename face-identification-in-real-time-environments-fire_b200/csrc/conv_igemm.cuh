@@ -54,8 +54,6 @@ constexpr int CONV_MAX_COUT = 1792;
 constexpr int CONV_PASS_COLS = 128;        // columns staged per epilogue pass
 
 constexpr int CF_RELU = 1, CF_RESIDUAL = 2, CF_OUT_F32 = 4;
-constexpr int CF_NO_TAIL_WAIT = 1 << 20;   // the store warp does not wait for its last TMA stores to COMPLETE before the CTA exits (their shared-memory
-                                           // reads are already done; the grid's completion flushes the writes for the dependent launch)
 constexpr int CF_DBG_PHASES = 1 << 19;     // with a trace buffer: per-role cycle accounting (strip kernel)
 // Work-skipping switches for timing experiments exist only in a -DFIRE_B200_SKIP_EXPERIMENTS build; in the shipped library the
 // masks are 0, the tests below fold to constants and no code path can drop a gather, a store or an MMA.
@@ -522,7 +520,7 @@ conv_igemm_kernel_t(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
           __syncwarp();
         }
       }
-      if (!(p.flags & CF_NO_TAIL_WAIT) && elect_one()) bulk_wait_all();      // stores complete before the CTA exits
+      if (elect_one()) bulk_wait_all();                         // stores complete before the CTA exits
       __syncwarp();
     }
   } else if (!p.tma_a && warp < CONV_STORE_WARP) {

@@ -386,7 +386,7 @@ conv_strip_kernel_t(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
       }
       __syncwarp();
     }
-    if (!(p.flags & CF_NO_TAIL_WAIT) && elect_one()) bulk_wait_all();      // stores complete before the CTA exits
+    if (elect_one()) bulk_wait_all();                           // stores complete before the CTA exits
     __syncwarp();
   }
 

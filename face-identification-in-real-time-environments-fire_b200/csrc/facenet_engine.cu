@@ -51,9 +51,7 @@ static_assert(sizeof(BlobOp) == 104, "op layout must match weights.OP_DT");
 // ---------------------------------------------------------------------------------------------
 // 3x3 stride-2 VALID max-pool, NHWC fp16, 8 channels (16 bytes) per thread, channel-offset store.
 __global__ void maxpool3x3s2_kernel(const __half* __restrict__ in, int in_ld, int in_coff, __half* __restrict__ out,
-                                    int out_ld, int out_coff, int B, int H, int W, int Ho, int Wo, int C, int pdl) {   // W = input row pitch
-  // programmatic dependent launch: the next layer may start its prologue now; this kernel's reads wait for the previous layer
-  if (pdl) { pdl_launch_dependents(); pdl_wait(); }
+                                    int out_ld, int out_coff, int B, int H, int W, int Ho, int Wo, int C) {   // W = input row pitch
   const int c8 = C >> 3;
   const long long total = static_cast<long long>(B) * Ho * Wo * c8;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -84,8 +82,7 @@ __global__ void maxpool3x3s2_kernel(const __half* __restrict__ in, int in_ld, in
 
 // global average pool over HW pixels (fp32 accumulation), NHWC fp16 -> [B, C] fp16
 __global__ void gap_kernel(const __half* __restrict__ in, int in_ld, int in_coff, __half* __restrict__ out, int out_ld,
-                           int B, int HW, int C, int pdl) {
-  if (pdl) { pdl_launch_dependents(); pdl_wait(); }
+                           int B, int HW, int C) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;    // one thread per (b, channel pair)
   const int c2 = C >> 1;
   if (i >= B * c2) return;
@@ -100,8 +97,7 @@ __global__ void gap_kernel(const __half* __restrict__ in, int in_ld, int in_coff
 }
 
 // rows / ||row||_2 (face_recognition.py:225-229); a zero row stays zero (the caller skips such faces)
-__global__ void l2norm_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int D, int pdl) {
-  if (pdl) pdl_wait();
+__global__ void l2norm_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int D) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= B) return;
   float s = 0.f;
@@ -232,27 +228,10 @@ struct fire_net {
   bool use_strip = true;    // FIRE_B200_STRIP=0 forces the gather path for every k x k layer (A/B experiments)
   bool trace_all = false;   // FIRE_B200_TRACE_ALL=1: forward() records every conv's timeline, synchronises and prints it
   long long* d_trace = nullptr; int trace_op = -1;   // FIRE_B200_TRACE_OP=<op index>: in-kernel timeline of that op (profile only)
-  int tail_flags = 0;     // CF_NO_TAIL_WAIT when FIRE_B200_TAIL_WAIT=0 (A/B experiment, round 2)
   int dbg_flags = 0;      // always 0 unless built with -DFIRE_B200_SKIP_EXPERIMENTS (then FIRE_B200_DBG: 1 = no gather copies, 2 = no epilogue stores, 4 = no MMA)
 };
 
 static inline int buf_wp(const BlobBuf& b) { return b.Wp > 0 ? b.Wp : b.W; }
-
-// The element-wise kernels between the tensor launches (max-pools, GAP, L2 norm) take part in the programmatic-dependent-launch
-// chain too: a plain <<<>>> launch in the middle of it made both of its neighbours wait for a full launch boundary.
-template <class... KArgs, class... Args>
-static cudaError_t launch_small(void (*kernel)(KArgs...), int blocks, int threads, cudaStream_t st, bool pdl, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(static_cast<unsigned>(blocks));
-  cfg.blockDim = dim3(static_cast<unsigned>(threads));
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
 
 static int pow2_cols(int n) {
   int c = 32;
@@ -571,7 +550,6 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
   }
   const char* pdl_env = getenv("FIRE_B200_PDL");
   net->pdl = !(pdl_env && pdl_env[0] == '0');
-  if (const char* e = getenv("FIRE_B200_TAIL_WAIT")) net->tail_flags = e[0] == '0' ? CF_NO_TAIL_WAIT : 0;
   const char* l1_env = getenv("FIRE_B200_GATHER_L1");
   net->gather_l1 = l1_env && l1_env[0] == '1';
 #ifdef FIRE_B200_SKIP_EXPERIMENTS
@@ -666,7 +644,7 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
       q.pair = r.pair ? 1 : 0;
       q.total_tiles = (r.pair ? (B + 1) / 2 : B) * r.row_blocks;          // pair mode: one scheduling unit = the same position block of two images
       q.flat = r.flat ? 1 : 0; q.Ho = o.Ho; q.d_wbox = make_fastdiv(r.Wbox);
-      q.a_stage_bytes = r.a_stage_bytes; q.stages = r.stages; q.tmem_cols = r.tmem_cols; q.flags = o.flags | net->dbg_flags | net->tail_flags;
+      q.a_stage_bytes = r.a_stage_bytes; q.stages = r.stages; q.tmem_cols = r.tmem_cols; q.flags = o.flags | net->dbg_flags;
       if (net->d_trace && !net->trace_all) q.flags |= CF_DBG_PHASES;
       q.pdl = pdl ? 1 : 0; q.box_cols = r.box_cols; q.n_acc = r.n_acc;
       // two issuing warps pay off when the main loop is long enough to be issue-bound (Conv2d_2a / 2b: 18 K steps; 1a has 4)
@@ -709,7 +687,7 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
     p.stages = r.stages; p.tma_a = r.tma_a ? 1 : (r.im2col ? 2 : 0); p.tmem_cols = r.tmem_cols;
     p.cpb = std::max(1, o.cin / 64); p.d_cpb = make_fastdiv(p.cpb);
     p.m_tiles = r.m_tiles; p.n_tiles = r.n_tiles; p.pdl = pdl ? 1 : 0;
-    p.flags |= net->dbg_flags | net->tail_flags;
+    p.flags |= net->dbg_flags;
     if (net->d_trace && !net->trace_all) p.flags |= CF_DBG_PHASES;
     p.n_res = r.n_res; p.box_cols = r.box_cols;
     p.n_issuers = r.n_issuers;
@@ -745,12 +723,13 @@ static int run_op(fire_net* net, OpRt& r, int B, const void* in, void* ws, float
   } else if (o.kind == OP_MAXPOOL) {
     const long long total = (long long)B * o.Ho * o.Wo * (o.cin / 8);
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-    FIRE_CUDA(launch_small(maxpool3x3s2_kernel, blocks, 256, st, pdl, src, sb.C, o.src_coff, static_cast<__half*>(dst), db.C, o.dst_coff, B, o.H,
-                           buf_wp(sb), o.Ho, o.Wo, o.cin, pdl ? 1 : 0));      // reads a pitched input through its pitch
+    maxpool3x3s2_kernel<<<blocks, 256, 0, st>>>(src, sb.C, o.src_coff, static_cast<__half*>(dst), db.C, o.dst_coff, B, o.H,
+                                                buf_wp(sb), o.Ho, o.Wo, o.cin);      // reads a pitched input through its pitch
+    FIRE_LAUNCH_CHECK("maxpool3x3s2_kernel");
   } else if (o.kind == OP_GAP) {
     const int n = B * (o.cin / 2);
-    FIRE_CUDA(launch_small(gap_kernel, (n + 255) / 256, 256, st, pdl, src, sb.C, o.src_coff, static_cast<__half*>(dst), db.C, B, o.H * o.W, o.cin,
-                           pdl ? 1 : 0));
+    gap_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, sb.C, o.src_coff, static_cast<__half*>(dst), db.C, B, o.H * o.W, o.cin);
+    FIRE_LAUNCH_CHECK("gap_kernel");
   } else {
     return fail(FIRE_ERR_ARG, "unknown op kind %d", o.kind);
   }
@@ -992,8 +971,8 @@ int fire_facenet_forward(fire_net_t* net, const void* in_f16, int B, float* out_
     }
   }
   if (out_l2) {
-    FIRE_CUDA(launch_small(l2norm_kernel, (B + 7) / 8, 256, st, net->pdl, static_cast<const float*>(out_raw), out_l2, B, static_cast<int>(net->hdr.D),
-                           net->pdl ? 1 : 0));
+    l2norm_kernel<<<(B + 7) / 8, 256, 0, st>>>(out_raw, out_l2, B, net->hdr.D);
+    FIRE_LAUNCH_CHECK("l2norm_kernel");
     count_launch();
   }
   if (net->trace_all) {
