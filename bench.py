@@ -379,6 +379,29 @@ def run_fire(args):
                         "by_stage_ms_serialised": {s: float(sum(m for m, l in zip(ms_ops, labels) if l.startswith(s)))
                                                    for s in ("Conv2d", "MaxPool", "Block35", "Mixed_6a", "Block17", "Mixed_7a", "Block8", "AvgPool", "Bottleneck")}}}
 
+    # ---------------- the reference's own calling pattern: one face (or a frame's handful) per encode call ------------------
+    small_batch = None
+    if rank == 0:
+        small_batch = {"metric": "FaceNet512 forward latency at small batches (K1 + K2 + L2 norm, inputs resident; the reference encodes ONE face per call, modules/encoder.py:26)"}
+        for b in (1, 8, 32):
+            xb, db_, bb, fb = dev_batches[0][:b].contiguous(), desc[:b].contiguous(), boxes[:b].contiguous(), frame_ids[:b].contiguous()
+            rb, lb = torch.empty(b, D, dtype=torch.float32, device=dev), torch.empty(b, D, dtype=torch.float32, device=dev)
+
+            def one():
+                f16_, _, _ = engine.preprocess_boxes(xb, db_, bb, fb, _lib.PRE_REFERENCE, True, False)
+                eng.forward(f16_, want_l2=True, out_raw=rb, out_l2=lb)
+            for _ in range(5):
+                one()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for _ in range(50):
+                one()
+            b_.record()
+            torch.cuda.synchronize()
+            ms_b = a_.elapsed_time(b_) / 50
+            small_batch[f"B{b}"] = {"ms_per_call": ms_b, "embeds_per_s": b / (ms_b * 1e-3)}
+        eng.forward(engine.preprocess_boxes(dev_batches[0], desc, boxes, frame_ids, _lib.PRE_REFERENCE, True, False)[0], want_l2=True, out_raw=raw, out_l2=l2)
+
     # ---------------- exact cosine top-10 ---------------------------------------------------------------
     knn = None
     if not args.no_knn:
@@ -480,8 +503,18 @@ def run_fire(args):
                     us = a.elapsed_time(b) * 1e3 / reps
                     small[f"Q{qn}"] = {"us_per_call": us, "qps": qn / (us * 1e-6), "achieved_GBps": gal_bytes / (us * 1e-6) / 1e9,
                                        "frac_of_hbm": gal_bytes / (us * 1e-6) / 1e9 / peaks["hbm_gbs"]}
+                # what a FIRE caller sees per call (hnsw_manager.py:147: one numpy query in, numpy labels / distances out, synchronous)
+                q_host = queries[:1].cpu().numpy()
+                for _ in range(5):
+                    gal.local.search(q_host, k)
+                t_h = time.perf_counter()
+                for _ in range(50):
+                    gal.local.search(q_host, k)
+                host_us = (time.perf_counter() - t_h) / 50 * 1e6
                 knn["1M_small_batch"] = {"metric": "cosine top-10 latency / QPS at small query batches, 1M x 512 gallery", "bound": "hbm",
-                                         "algorithmic_bytes_per_call": gal_bytes, "peak_GBps": peaks["hbm_gbs"], **small}
+                                         "algorithmic_bytes_per_call": gal_bytes, "peak_GBps": peaks["hbm_gbs"], **small,
+                                         "Q1_host_call": {"us_per_call": host_us, "frac_of_hbm": gal_bytes / (host_us * 1e-6) / 1e9 / peaks["hbm_gbs"],
+                                                          "note": "numpy query in, numpy result out, synchronous (the reference's calling convention); wall clock"}}
                 if rank == 0 and not args.no_cpu:
                     v, dt = cpu_reference_knn(n_total, 64, k, host_threads)
                     knn["1M"]["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": host_threads, "kind": "port",
@@ -636,7 +669,8 @@ def run_fire(args):
                 "e2e": {"value": e2e_value, "unit": "embeds/s", "h2d_bytes_per_step": BATCH * 160 * 160 * 3,
                         "d2h_bytes_per_step": BATCH * D * 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "wall_ms_per_step": wall_dev / args.steps, "sustained": sustained,
-                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity, "knn": knn, "frames": frames_blk}
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity, "encode_small_batch": small_batch, "knn": knn,
+                "frames": frames_blk}
         sys.stdout.flush()
         os.dup2(saved_stdout_fd, 1)
         print(json.dumps(line), flush=True)

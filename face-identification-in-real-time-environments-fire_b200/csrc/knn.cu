@@ -451,8 +451,8 @@ __global__ void knn_rerank_kernel(const float* __restrict__ qn, const float* __r
                                   const float* __restrict__ cand_score, const uint32_t* __restrict__ cand_idx, int S,
                                   int D, int Q, int k, float slack, const float* __restrict__ q_err,
                                   const int* __restrict__ g_max_err, KnnOut out, uint32_t* __restrict__ flagged,
-                                  uint32_t* __restrict__ flagged_count, int stage_lists) {
-  extern __shared__ __align__(16) uint8_t rerank_smem[];
+                                  uint32_t* __restrict__ flagged_count, unsigned long long* __restrict__ stats) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) stats[0] += static_cast<unsigned long long>(Q);      // queries answered by this handle
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (q >= Q) return;
@@ -464,20 +464,6 @@ __global__ void knn_rerank_kernel(const float* __restrict__ qn, const float* __r
 
   const float* cs = cand_score + static_cast<size_t>(q) * S * KP;
   const uint32_t* ci = cand_idx + static_cast<size_t>(q) * S * KP;
-  if (stage_lists) {
-    // The merge below pops one entry per round and then reads the winner's next entry: from global memory that is a chain
-    // of dependent ~1 us loads (16 rounds: 30 us for a single query, the whole latency of a small-batch search's tail).  The
-    // warp first copies its query's S x KP candidates into shared memory with coalesced loads.
-    const int per_q = S * KP;
-    float* ss = reinterpret_cast<float*>(rerank_smem) + static_cast<size_t>(threadIdx.x >> 5) * per_q * 2;
-    uint32_t* si = reinterpret_cast<uint32_t*>(ss + per_q);
-    for (int i = lane * 4; i < per_q; i += 128) {
-      *reinterpret_cast<float4*>(ss + i) = *reinterpret_cast<const float4*>(cs + i);
-      *reinterpret_cast<uint4*>(si + i) = *reinterpret_cast<const uint4*>(ci + i);
-    }
-    __syncwarp();
-    cs = ss; ci = si;
-  }
   auto get = [&](int l, int pos, float& key, unsigned long long& id) {
     key = -cs[l * KP + pos];                       // descending score == ascending -score
     id = ci[l * KP + pos];
@@ -491,41 +477,32 @@ __global__ void knn_rerank_kernel(const float* __restrict__ qn, const float* __r
   };
   warp_merge_lists(S, KP, KP, get, emit);
 
-  // exact fp32 distances of the survivors.  FOUR candidates per round, eight lanes each (a lane group reads 128 contiguous
-  // bytes of its row per load, 16 independent loads per lane): the rows are random 2 KB reads from HBM, and walking them one
-  // after the other made this loop a chain of KP dependent ~1 us round trips (20 us of a small-batch search's latency).
+  // exact fp32 distances of the survivors: one candidate per round, the whole warp on one row (512 contiguous bytes per load).
+  // (Round 2 tried four candidates per round with eight lanes each, and merging the lists from shared memory: the single-query
+  // latency did not move - it is instruction latency of one warp, ~30 us - and the 4096-query batch got slower, 48 -> 66 us.)
   const float* qv = qn + static_cast<size_t>(q) * D;
   float dist[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) dist[e] = FLT_MAX;
-  const int grp = lane >> 3, gl = lane & 7;
-  for (int r0 = 0; r0 < KP; r0 += 4) {
-    const int r = r0 + grp;                          // this lane group's candidate
-    uint32_t idx = 0xFFFFFFFFu;
+  for (int r = 0; r < KP; ++r) {
+    uint32_t idx = 0;
 #pragma unroll
     for (int e = 0; e < EPL; ++e)
-      if (e == (r0 >> 5)) idx = __shfl_sync(0xffffffffu, sel_idx[e], r & 31);     // r0 .. r0+3 live in the same slot e
+      if (e == (r >> 5)) idx = __shfl_sync(0xffffffffu, sel_idx[e], r & 31);
+    if (idx == 0xFFFFFFFFu) continue;             // warp-uniform
+    const float* gv = g32 + static_cast<size_t>(idx) * D;
     float acc = 0.f;
-    if (idx != 0xFFFFFFFFu) {
-      const float* gv = g32 + static_cast<size_t>(idx) * D;
-      for (int c = gl * 4; c < D; c += 32) {
-        const float4 a = *reinterpret_cast<const float4*>(qv + c);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(gv + c));
-        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
-      }
+    for (int c = lane * 4; c < D; c += 128) {
+      float4 a = *reinterpret_cast<const float4*>(qv + c);
+      float4 b = __ldg(reinterpret_cast<const float4*>(gv + c));
+      acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
     }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);      // within the 8-lane group
-    const float dd = 1.0f - acc;
-    const float mine = (idx != 0xFFFFFFFFu && dd == dd) ? dd : FLT_MAX;       // a NaN (NaN/Inf in the query) sorts last instead of poisoning the ranking
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((r & 31) == lane) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {                    // hand candidate r0+g's distance to the lane that owns list entry r0+g
-      const float v = __shfl_sync(0xffffffffu, mine, g * 8);
-      if (((r0 + g) & 31) == lane) {
-#pragma unroll
-        for (int e = 0; e < EPL; ++e)
-          if (e == ((r0 + g) >> 5)) dist[e] = v;
-      }
+      for (int e = 0; e < EPL; ++e)
+        if (e == (r >> 5)) { const float dd = 1.0f - acc; dist[e] = dd == dd ? dd : FLT_MAX; }    // a NaN (NaN/Inf in the query) sorts last instead of poisoning the ranking
     }
   }
 
@@ -653,10 +630,8 @@ knn_refine_kernel(const float* __restrict__ qn, const float* __restrict__ g32, c
   __shared__ ExactSmem sm;
   __shared__ float s_kth;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {               // fold this search into the handle's counters
-    stats[0] += static_cast<unsigned long long>(Q);
-    stats[1] += static_cast<unsigned long long>(counters[0]);
-  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) stats[1] += static_cast<unsigned long long>(counters[0]);     // queries whose proof failed
+  (void)Q;
   const uint32_t nf = min(counters[0], static_cast<uint32_t>(EXACT_CAP));
   for (uint32_t f = blockIdx.x; f < nf; f += gridDim.x) {
     const uint32_t q = flagged[f];
@@ -852,6 +827,9 @@ struct fire_knn {
   KnnWorkItem* work = nullptr;       // [EXACT_CAP]
   int exact_blocks = 0;
   float eps = KNN_DEFAULT_EPS;
+  // the last search's decomposition, for a deferred fallback (host path: launched only when a query was flagged)
+  int last_S = 0, last_KP = 0, last_k = 0, last_Q = 0, last_rows_per_split = 0, last_n_rows = 0;
+  uint32_t* host_flagged = nullptr;  // pinned [1]
   // staging for *_host calls
   float* stage_q = nullptr; float* stage_d = nullptr; long long* stage_i = nullptr;
   size_t stage_q_cap = 0, stage_o_cap = 0;
@@ -919,8 +897,24 @@ static int knn_launch_scan(fire_knn* h, const CUtensorMap& tq, const CUtensorMap
 // The whole search: normalise the queries, tensor-core scan, exact re-rank with proof, bounded exact fallback.
 // `stored_first` >= 0: the queries are the stored (already normalised) rows [stored_first, stored_first + Q).
 // `allow_short`: k may exceed the number of stored rows; missing entries come back as (FLT_MAX, -1) (shards of a sharded gallery).
+// refine -> exact scan -> merge -> overflow for the queries the rerank flagged (all four return at once when there are none)
+static int knn_launch_fallback(fire_knn* h, const KnnOut& out, cudaStream_t st) {
+  const int sms = device_sm_count();
+  knn_refine_kernel<<<sms, EXACT_WARPS * 32, 0, st>>>(h->qn32, h->g32, h->cand_score, h->cand_idx, h->last_S, h->last_KP, h->D, h->last_k, h->eps, h->q_err,
+                                                      h->g_max_err, h->flagged, h->counters, h->ref_dist, h->ref_idx, h->work, out, h->stats, h->last_Q);
+  knn_exact_scan_kernel<<<h->exact_blocks, EXACT_WARPS * 32, 0, st>>>(h->qn32, h->g32, h->last_n_rows, h->last_rows_per_split, h->D, h->last_k, h->work,
+                                                                      h->counters, h->part_dist, h->part_idx);
+  knn_exact_merge_kernel<<<32, 256, 0, st>>>(h->part_dist, h->part_idx, h->exact_blocks, h->last_k, h->work, h->counters, h->ref_dist, h->ref_idx, out);
+  knn_exact_overflow_kernel<<<h->exact_blocks, EXACT_WARPS * 32, 0, st>>>(h->qn32, h->g32, h->last_n_rows, h->D, h->last_k, h->flagged, h->counters, out);
+  FIRE_LAUNCH_CHECK("knn exact fallback");
+  count_launch(4);
+  return FIRE_OK;
+}
+
+// `defer_fallback`: the caller will look at the flagged count on the host (it synchronises anyway) and launch the fallback
+// only when needed - four launches less on the latency path of a single query.
 static int knn_search_impl(fire_knn* h, const float* queries, long long stored_first, int Q, int k, const KnnOut& out, bool allow_short,
-                           cudaStream_t st) {
+                           cudaStream_t st, bool defer_fallback = false) {
   if (Q <= 0) return fail(FIRE_ERR_ARG, "fire_knn_search: Q=%d", Q);
   if (k < 1 || k > 64) return fail(FIRE_ERR_UNSUPPORTED, "fire_knn_search: k=%d outside [1,64]", k);
   if (static_cast<size_t>(k) > h->count && !allow_short)
@@ -930,6 +924,7 @@ static int knn_search_impl(fire_knn* h, const float* queries, long long stored_f
     knn_fill_padding_kernel<<<static_cast<unsigned>(std::min<size_t>((n + 255) / 256, 1024)), 256, 0, st>>>(out, n);
     FIRE_LAUNCH_CHECK("knn_fill_padding_kernel");
     count_launch();
+    h->last_Q = 0;
     return FIRE_OK;
   }
   const int D = h->D, nkb = D / 64;
@@ -991,31 +986,19 @@ static int knn_search_impl(fire_knn* h, const float* queries, long long stored_f
   if (rc != FIRE_OK) return rc;
 
   {
-    // warps (= queries) per block: as many as fit their candidate lists (S x KP x 8 bytes each) into 48 KB of shared memory
-    const size_t per_q = static_cast<size_t>(S) * KP * 8;
-    int wpb = 8;
-    while (wpb > 1 && wpb * per_q > 48 * 1024) wpb >>= 1;
-    const int stage_lists = wpb * per_q <= 48 * 1024 ? 1 : 0;
-    const size_t sm = stage_lists ? wpb * per_q : 0;
-    const int blocks = (Q + wpb - 1) / wpb;
+    const int blocks = (Q + 7) / 8;
     if (KP == 16)
-      knn_rerank_kernel<16><<<blocks, wpb * 32, sm, st>>>(h->qn32, h->g32, h->cand_score, h->cand_idx, S, D, Q, k, h->eps, h->q_err, h->g_max_err,
-                                                          out, h->flagged, h->counters, stage_lists);
+      knn_rerank_kernel<16><<<blocks, 256, 0, st>>>(h->qn32, h->g32, h->cand_score, h->cand_idx, S, D, Q, k, h->eps, h->q_err, h->g_max_err,
+                                                    out, h->flagged, h->counters, h->stats);
     else
-      knn_rerank_kernel<64><<<blocks, wpb * 32, sm, st>>>(h->qn32, h->g32, h->cand_score, h->cand_idx, S, D, Q, k, h->eps, h->q_err, h->g_max_err,
-                                                          out, h->flagged, h->counters, stage_lists);
+      knn_rerank_kernel<64><<<blocks, 256, 0, st>>>(h->qn32, h->g32, h->cand_score, h->cand_idx, S, D, Q, k, h->eps, h->q_err, h->g_max_err,
+                                                    out, h->flagged, h->counters, h->stats);
     FIRE_LAUNCH_CHECK("knn_rerank_kernel");
     count_launch();
   }
-  knn_refine_kernel<<<sms, EXACT_WARPS * 32, 0, st>>>(h->qn32, h->g32, h->cand_score, h->cand_idx, S, KP, D, k, h->eps, h->q_err, h->g_max_err,
-                                                      h->flagged, h->counters, h->ref_dist, h->ref_idx, h->work, out, h->stats, Q);
-  knn_exact_scan_kernel<<<h->exact_blocks, EXACT_WARPS * 32, 0, st>>>(h->qn32, h->g32, n_rows, p.rows_per_split, D, k, h->work, h->counters,
-                                                                      h->part_dist, h->part_idx);
-  knn_exact_merge_kernel<<<32, 256, 0, st>>>(h->part_dist, h->part_idx, h->exact_blocks, k, h->work, h->counters, h->ref_dist, h->ref_idx, out);
-  knn_exact_overflow_kernel<<<h->exact_blocks, EXACT_WARPS * 32, 0, st>>>(h->qn32, h->g32, n_rows, D, k, h->flagged, h->counters, out);
-  FIRE_LAUNCH_CHECK("knn exact fallback");
-  count_launch(4);
-  return FIRE_OK;
+  h->last_S = S; h->last_KP = KP; h->last_k = k; h->last_Q = Q; h->last_rows_per_split = p.rows_per_split; h->last_n_rows = n_rows;
+  if (defer_fallback) return FIRE_OK;
+  return knn_launch_fallback(h, out, st);
 }
 
 extern "C" {
@@ -1059,6 +1042,7 @@ int fire_knn_destroy(fire_knn_t* h) {
   if (h->stage_d) cudaFreeHost(h->stage_d);
   if (h->stage_i) cudaFreeHost(h->stage_i);
   if (h->stage_rows) cudaFree(h->stage_rows);
+  if (h->host_flagged) cudaFreeHost(h->host_flagged);
   cudaFree(h->dev_q); cudaFree(h->dev_d); cudaFree(h->dev_i);
   delete h;
   return FIRE_OK;
@@ -1207,13 +1191,26 @@ int fire_knn_search_host(fire_knn_t* h, const float* host_queries, int Q, int k,
     FIRE_CUDA(cudaMalloc(&h->dev_i, sizeof(long long) * on));
     h->dev_o_cap = on;
   }
+  if (!h->host_flagged) FIRE_CUDA(cudaMallocHost(&h->host_flagged, sizeof(uint32_t)));
   memcpy(h->stage_q, host_queries, sizeof(float) * qn);
   FIRE_CUDA(cudaMemcpyAsync(h->dev_q, h->stage_q, sizeof(float) * qn, cudaMemcpyHostToDevice, nullptr));
-  int rc = fire_knn_search(h, h->dev_q, Q, k, id_offset, h->dev_d, reinterpret_cast<int64_t*>(h->dev_i), nullptr);
+  // This call returns host arrays, so it synchronises anyway: the flagged count comes back with the results and the four
+  // fallback kernels are launched only when a query's proof failed (rare) - they cost a single query ~15 us of launch latency.
+  KnnOut out{h->dev_d, h->dev_i, nullptr, id_offset, 1};
+  *h->host_flagged = 0;
+  int rc = knn_search_impl(h, h->dev_q, -1, Q, k, out, false, nullptr, true);
   if (rc != FIRE_OK) return rc;
   FIRE_CUDA(cudaMemcpyAsync(h->stage_d, h->dev_d, sizeof(float) * on, cudaMemcpyDeviceToHost, nullptr));
   FIRE_CUDA(cudaMemcpyAsync(h->stage_i, h->dev_i, sizeof(long long) * on, cudaMemcpyDeviceToHost, nullptr));
+  if (h->last_Q > 0) FIRE_CUDA(cudaMemcpyAsync(h->host_flagged, h->counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, nullptr));
   FIRE_CUDA(cudaStreamSynchronize(nullptr));
+  if (h->last_Q > 0 && *h->host_flagged > 0) {
+    rc = knn_launch_fallback(h, out, nullptr);
+    if (rc != FIRE_OK) return rc;
+    FIRE_CUDA(cudaMemcpyAsync(h->stage_d, h->dev_d, sizeof(float) * on, cudaMemcpyDeviceToHost, nullptr));
+    FIRE_CUDA(cudaMemcpyAsync(h->stage_i, h->dev_i, sizeof(long long) * on, cudaMemcpyDeviceToHost, nullptr));
+    FIRE_CUDA(cudaStreamSynchronize(nullptr));
+  }
   memcpy(host_out_dist, h->stage_d, sizeof(float) * on);
   memcpy(host_out_ids, h->stage_i, sizeof(long long) * on);
   return FIRE_OK;
