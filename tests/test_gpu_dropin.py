@@ -109,6 +109,41 @@ def test_recognise_loop_decisions_match_cpu_chain(encoder, oracle_native, tmp_pa
     assert np.array_equal(l50, ol) and np.abs(d50 - od).max() < 5e-6
 
 
+def test_bulk_similar_lists_and_shrink_on_the_gpu_index(fire_lib, oracle_native, tmp_path):
+    """SURVEY 8(f) row 3 on the real index: find_similar_all (tiled fire_knn_search_rows) == the per-row reference call, the
+    bulk shrink_db_ids merges what those lists say, and the hnswlib-image save/load round trip keeps every answer."""
+    import sqlite3
+    from fire_b200.hnsw_manager import HNSWManager
+    rng = np.random.default_rng(15)
+    D, n = 512, 700
+    centers = rng.standard_normal((60, D)).astype(np.float32)
+    vecs = [(centers[rng.integers(0, 60)] + 0.25 * rng.standard_normal(D)).astype(np.float32) * float(rng.uniform(0.5, 2)) for _ in range(n)]
+    labels = [f"person{i % 7}" if i % 5 == 0 else f"Unknown_{i:08x}" for i in range(n)]
+    conn = sqlite3.connect(str(tmp_path / "f.db")); cur = conn.cursor()
+    cur.execute("CREATE TABLE faces (id INTEGER PRIMARY KEY AUTOINCREMENT, label TEXT NOT NULL, embedding BLOB NOT NULL)")
+    mgr = HNSWManager(D, str(tmp_path / "i"), str(tmp_path / "l"), str(tmp_path / "d"), None, max_elements=1000)
+    for v, lab in zip(vecs, labels):
+        cur.execute("INSERT INTO faces (label, embedding) VALUES (?, ?)", (lab, v.tobytes()))
+        mgr.add_embedding(v, lab, cur.lastrowid)
+    conn.commit()
+    lists = mgr.find_similar_all(0.75, tile=256)
+    ora = oracle_native.BFIndexOracle(D); ora.add_items(np.stack(vecs))
+    for hid in range(0, n, 37):
+        e = mgr._get_embedding_from_db_id(mgr.hnsw_db_ids[hid], cur)
+        assert [int(x) for x in lists[hid]] == [int(x) for x in mgr.find_similar_embeddings(e, 0.75)]
+        ol, od = ora.knn_query(e, 50)
+        assert [int(x) for x in lists[hid]] == [int(l) for l, d in zip(ol[0], od[0]) if 1 - d >= 0.75]
+    before = list(mgr.hnsw_labels)
+    merges = mgr.shrink_db_ids(cur, conn, 0.75)
+    assert merges > 0 and mgr.hnsw_labels != before
+    assert [r[0] for r in cur.execute("SELECT label FROM faces ORDER BY id")] == mgr.hnsw_labels
+    mgr2 = HNSWManager(D, str(tmp_path / "i"), str(tmp_path / "l"), str(tmp_path / "d"), None, max_elements=1000)   # the hnswlib image written by unify_labels
+    assert mgr2.hnsw_labels == mgr.hnsw_labels and mgr2.hnsw_index.get_current_count() == n
+    q = rng.standard_normal((5, D)).astype(np.float32)
+    a, b = mgr.query_batch(q, k=10), mgr2.query_batch(q, k=10)
+    assert np.array_equal(a[0], b[0]) and np.abs(a[1] - b[1]).max() < 2e-7
+
+
 def test_preprocess_module_and_dropin(fire_lib):
     import sys
     import cv2
