@@ -19,6 +19,7 @@
 #include "conv_strip.cuh"
 #include "block17_fused.cuh"
 #include "block35_fused.cuh"
+#include "block8_fused.cuh"
 #include "fire_internal.h"
 
 namespace fire {
@@ -205,11 +206,23 @@ struct Fused35 {
   B35Params prm;
 };
 
+// The 1x3 -> 3x1 -> up tail of every Block8 block as one launch (block8_fused.cuh): ops first_op + 4 j + {1, 2, 3}; the
+// heads conv (first_op + 4 j) stays a conv_igemm launch.
+struct Fused8 {
+  int first_op = -1, n_blocks = 0;
+  uint8_t* d_w = nullptr;           // per block: 36 units of 12288 B (1x3, 3x1) + 7 x 12 units of 16 KB (up, by N tile)
+  float* d_bias = nullptr;          // per block: [192 | 192 | 1792] fp32
+  long long* d_trace = nullptr;     // FIRE_B200_TRACE8=1
+  B8Params prm[B8_MAX_BLOCKS];
+};
+constexpr size_t B8_W_PER_BLOCK = (size_t)B8_WMID_UNITS * B8_WMID_BYTES + (size_t)B8_NTILES * B8_WUP_UNITS * B8_UNIT;
+
 struct fire_net {
   BlobHeader hdr;
   int device = 0;          // the device that was current at fire_facenet_create; every entry point runs there
   Fused17 f17;
   Fused35 f35;
+  Fused8 f8;
   std::vector<BlobBuf> bufs;
   std::vector<OpRt> ops;
   uint8_t* d_weights = nullptr;
@@ -449,6 +462,100 @@ static int run_f35(fire_net* net, cudaStream_t st, bool pdl) {
   return FIRE_OK;
 }
 
+// ---- Block8 tail fusion ---------------------------------------------------------------------------------------------
+static bool b8_match(const std::vector<BlobOp>& ops, const std::vector<BlobBuf>& bufs, size_t i) {
+  if (i + 3 >= ops.size()) return false;
+  const BlobOp &h = ops[i], &a = ops[i + 1], &b = ops[i + 2], &u = ops[i + 3];
+  auto conv = [](const BlobOp& o, int kh, int kw, int cin, int cout, int ph, int pw) {
+    return o.kind == OP_CONV && o.kh == kh && o.kw == kw && o.stride == 1 && o.cin == cin && o.cout == cout && o.pad_h == ph && o.pad_w == pw &&
+           o.H == 3 && o.W == 3 && o.Ho == 3 && o.Wo == 3 && o.k_pad == kh * kw * cin;
+  };
+  if (!conv(h, 1, 1, B8_C, 2 * B8_MID, 0, 0) || !conv(a, 1, 3, B8_MID, B8_MID, 0, 1) || !conv(b, 3, 1, B8_MID, B8_MID, 1, 0) ||
+      !conv(u, 1, 1, 2 * B8_MID, B8_C, 0, 0)) return false;
+  if (h.flags != CF_RELU || a.flags != CF_RELU || b.flags != CF_RELU || (u.flags != (CF_RELU | CF_RESIDUAL) && u.flags != CF_RESIDUAL)) return false;
+  const BlobBuf &xb = bufs[h.src_buf], &yb = bufs[u.dst_buf], &Xb = bufs[h.dst_buf];
+  if (xb.C != B8_C || yb.C != B8_C || h.src_coff || u.dst_coff || (xb.Wp && xb.Wp != xb.W) || (yb.Wp && yb.Wp != yb.W) || (Xb.Wp && Xb.Wp != Xb.W)) return false;
+  if (u.res_buf != h.src_buf || u.res_coff) return false;
+  // X = [b1a | b0 | b1c]: 1x3 reads the first 192 heads columns, `up` reads [b0 | b1c]
+  if (a.src_buf != h.dst_buf || a.src_coff != h.dst_coff || b.src_buf != a.dst_buf || b.src_coff != a.dst_coff) return false;
+  if (u.src_buf != h.dst_buf || u.src_coff != h.dst_coff + B8_MID || b.dst_buf != h.dst_buf || b.dst_coff != h.dst_coff + 2 * B8_MID) return false;
+  return true;
+}
+static bool b8_setup(fire_net* net, const std::vector<BlobOp>& ops, const uint8_t* blob, const BlobHeader& h) {
+  Fused8& f = net->f8;
+  for (size_t i = 0; i < ops.size(); ++i) {
+    if (!b8_match(ops, net->bufs, i)) continue;
+    int n = 1;
+    while (n < B8_MAX_BLOCKS && b8_match(ops, net->bufs, i + 4 * n)) ++n;
+    f.first_op = (int)i; f.n_blocks = n;
+    break;
+  }
+  if (f.first_op < 0) return false;
+  std::vector<uint16_t> w((size_t)f.n_blocks * B8_W_PER_BLOCK / 2, 0);
+  std::vector<float> bias((size_t)f.n_blocks * B8_BIAS_PER_BLOCK);
+  for (int j = 0; j < f.n_blocks; ++j) {
+    const BlobOp* o = &ops[f.first_op + 4 * j];
+    const uint16_t* W[4];
+    for (int q = 0; q < 4; ++q) W[q] = reinterpret_cast<const uint16_t*>(blob + h.weights_off + o[q].w_off);
+    uint16_t* dst = w.data() + (size_t)j * B8_W_PER_BLOCK / 2;
+    // 1x3 then 3x1: (tap, 64-channel K-block, 32-channel half) -> [192 x 32] SWIZZLE_64B images
+    for (int q = 1; q <= 2; ++q)
+      for (int t = 0; t < 3; ++t)
+        for (int kb = 0; kb < 3; ++kb)
+          for (int half = 0; half < 2; ++half) { b35_put_sw64(dst, W[q], 3 * B8_MID, 0, B8_MID, t * B8_MID + kb * 64 + half * 32); dst += B8_WMID_BYTES / 2; }
+    // up: per N tile, (K-block, half) -> [256 x 32] SWIZZLE_64B images
+    for (int nt = 0; nt < B8_NTILES; ++nt)
+      for (int kb = 0; kb < 6; ++kb)
+        for (int half = 0; half < 2; ++half) { b35_put_sw64(dst, W[3], 2 * B8_MID, nt * B8_NT, B8_NT, kb * 64 + half * 32); dst += B8_UNIT / 2; }
+    float* bd = bias.data() + (size_t)j * B8_BIAS_PER_BLOCK;
+    memcpy(bd, blob + h.weights_off + o[1].b_off, sizeof(float) * B8_MID);
+    memcpy(bd + B8_MID, blob + h.weights_off + o[2].b_off, sizeof(float) * B8_MID);
+    memcpy(bd + 2 * B8_MID, blob + h.weights_off + o[3].b_off, sizeof(float) * B8_C);
+  }
+  if (cudaMalloc(&f.d_w, w.size() * 2) != cudaSuccess || cudaMalloc(&f.d_bias, bias.size() * 4) != cudaSuccess ||
+      cudaMemcpy(f.d_w, w.data(), w.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(f.d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaFuncSetAttribute(block8_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B8_SMEM) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(f.d_w); cudaFree(f.d_bias);
+    f.d_w = nullptr; f.d_bias = nullptr; f.first_op = -1; f.n_blocks = 0;
+    return false;
+  }
+  if (const char* e = getenv("FIRE_B200_TRACE8")) {
+    if (e[0] == '1') {
+      cudaMalloc(&f.d_trace, (size_t)B8_MAX_BLOCKS * 148 * B8_TRACE_SLOTS * 8);
+      cudaMemset(f.d_trace, 0, (size_t)B8_MAX_BLOCKS * 148 * B8_TRACE_SLOTS * 8);
+    }
+  }
+  return true;
+}
+// role of op i: -1 = not part of a fused Block8 tail, 0 = the block's heads conv (runs as itself), 1 = the op that launches
+// the fused tail (the 1x3 conv's slot), 2 = covered by that launch
+static inline int f8_role(const fire_net* net, size_t i) {
+  const Fused8& f = net->f8;
+  if (f.first_op < 0 || (int)i < f.first_op || (int)i >= f.first_op + 4 * f.n_blocks) return -1;
+  const int k = ((int)i - f.first_op) & 3;
+  return k == 0 ? 0 : k == 1 ? 1 : 2;
+}
+static int run_f8(fire_net* net, size_t i, cudaStream_t st, bool pdl) {
+  Fused8& f = net->f8;
+  B8Params& prm = f.prm[((int)i - f.first_op) >> 2];
+  prm.pdl = pdl ? 1 : 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(prm.n_groups * B8_NTILES));
+  cfg.blockDim = dim3(B8_THREADS);
+  cfg.dynamicSmemBytes = B8_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  FIRE_CUDA(cudaLaunchKernelEx(&cfg, block8_fused_kernel, prm));
+  count_launch();
+  return FIRE_OK;
+}
+
 extern "C" {
 
 int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
@@ -587,6 +694,8 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
     if (!(f17_env && f17_env[0] == '0')) b17_setup(net, ops, p, h);
     const char* f35_env = getenv("FIRE_B200_FUSE35");
     if (!(f35_env && f35_env[0] == '0')) b35_setup(net, ops, p, h);
+    const char* f8_env = getenv("FIRE_B200_FUSE8");
+    if (!(f8_env && f8_env[0] == '0')) b8_setup(net, ops, p, h);
   }
   *out = net;
   return FIRE_OK;
@@ -600,6 +709,7 @@ int fire_facenet_destroy(fire_net_t* net) {
   cudaFree(net->d_trace);
   cudaFree(net->f17.d_stream); cudaFree(net->f17.d_bias); cudaFree(net->f17.d_trace);
   cudaFree(net->f35.d_stream); cudaFree(net->f35.d_bias); cudaFree(net->f35.d_trace);
+  cudaFree(net->f8.d_w); cudaFree(net->f8.d_bias); cudaFree(net->f8.d_trace);
   delete net;
   return FIRE_OK;
 }
@@ -611,6 +721,7 @@ int fire_facenet_num_launches(const fire_net_t* net) {
   int n = (int)net->ops.size();
   if (net->f17.first_op >= 0) n -= 4 * net->f17.n_blocks - 1;
   if (net->f35.first_op >= 0) n -= 4 * net->f35.n_blocks - 1;
+  if (net->f8.first_op >= 0) n -= 2 * net->f8.n_blocks;
   return n;
 }
 double fire_facenet_flops(const fire_net_t* net) { return net ? net->flops_per_image : 0.0; }
@@ -910,6 +1021,30 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
       }
       f.prm.wstream = f.d_stream; f.prm.bias = f.d_bias; f.prm.n_blocks = f.n_blocks; f.prm.n_images = B; f.prm.trace = f.d_trace;
     }
+    if (net->f8.first_op >= 0) {
+      Fused8& f = net->f8;
+      for (int j = 0; j < f.n_blocks; ++j) {
+        const BlobOp& hop = net->ops[f.first_op + 4 * j].op;
+        const BlobOp& uop = net->ops[f.first_op + 4 * j + 3].op;
+        B8Params& q = f.prm[j];
+        const BlobBuf& Xb = net->bufs[hop.dst_buf];
+        const void* Xp = buf_ptr(net, hop.dst_buf, B, in, ws, out_raw);
+        const void* xp = buf_ptr(net, hop.src_buf, B, in, ws, out_raw);
+        const void* yp = buf_ptr(net, uop.dst_buf, B, in, ws, out_raw);
+        int rc = make_tmap_f16_nhwc(&q.hmap_nat, Xp, (uint64_t)Xb.C, 3, 3, (uint64_t)B, (uint64_t)Xb.C, 3, 64, 3, 3, B8_IMGS);
+        if (rc == FIRE_OK) rc = make_tmap_f16_nhwc(&q.hmap_ym, Xp, (uint64_t)Xb.C, 3, 3, (uint64_t)B, (uint64_t)Xb.C, 3, 64, 3, 1, B8_IMGS);
+        if (rc == FIRE_OK) rc = make_tmap_f16_nhwc(&q.xmap_ym, xp, (uint64_t)B8_C, 3, 3, (uint64_t)B, (uint64_t)B8_C, 3, 64, 3, 1, B8_IMGS);
+        if (rc == FIRE_OK) rc = make_tmap_f16_nhwc(&q.ymap_ym, yp, (uint64_t)B8_C, 3, 3, (uint64_t)B, (uint64_t)B8_C, 3, 64, 3, 1, B8_IMGS);
+        if (rc != FIRE_OK) return rc;
+        q.wmid = f.d_w + (size_t)j * B8_W_PER_BLOCK;
+        q.wup = q.wmid + (size_t)B8_WMID_UNITS * B8_WMID_BYTES;
+        q.bias = f.d_bias + (size_t)j * B8_BIAS_PER_BLOCK;
+        q.n_groups = (B + B8_IMGS - 1) / B8_IMGS;
+        q.relu = (uop.flags & CF_RELU) ? 1 : 0;
+        q.b1a_coff = hop.dst_coff; q.b0_coff = hop.dst_coff + B8_MID;
+        q.trace = f.d_trace ? f.d_trace + (size_t)j * 148 * B8_TRACE_SLOTS : nullptr;
+      }
+    }
     net->key_in = in; net->key_ws = ws; net->key_out = out_raw; net->key_B = B;
   }
   return FIRE_OK;
@@ -934,8 +1069,32 @@ int fire_facenet_forward(fire_net_t* net, const void* in_f16, int B, float* out_
       if ((int)i == net->f35.first_op) { rc = run_f35(net, st, net->pdl); if (rc != FIRE_OK) return rc; }
       continue;
     }
+    {
+      const int role = f8_role(net, i);
+      if (role == 2) continue;
+      if (role == 1) { rc = run_f8(net, i, st, net->pdl); if (rc != FIRE_OK) return rc; continue; }
+    }
     rc = run_op(net, net->ops[i], B, in_f16, workspace, out_raw, st, net->pdl);
     if (rc != FIRE_OK) return rc;
+  }
+  if (net->f8.d_trace) {
+    FIRE_CUDA(cudaStreamSynchronize(st));
+    std::vector<long long> t((size_t)B8_MAX_BLOCKS * 148 * B8_TRACE_SLOTS);
+    cudaMemcpy(t.data(), net->f8.d_trace, t.size() * 8, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "# block8_fused, ns since CTA 0 of block 1 entered.  entry | MMA warp: first operands, 1x3 issued, r2 ready, 3x1 issued, r3 ready, up issued |"
+                    " epilogue warp 2: acc1, r2 written, acc2, r3 written, accU, staged, stores done   (CTA 0; then max over CTAs of entry / stores done)\n");
+    const long long t0 = t[0];
+    for (int j = 0; j < net->f8.n_blocks; ++j) {
+      const long long* q = &t[(size_t)j * 148 * B8_TRACE_SLOTS];
+      fprintf(stderr, "  blk %d | %7lld |", j + 1, q[0] - t0);
+      for (int k = 1; k <= 6; ++k) fprintf(stderr, " %7lld", q[k] - t0);
+      fprintf(stderr, " |");
+      for (int k = 8; k <= 14; ++k) fprintf(stderr, " %7lld", q[k] - t0);
+      long long emax = 0, smax = 0;
+      const int ctas = std::min(148, net->f8.prm[j].n_groups * B8_NTILES);
+      for (int c = 0; c < ctas; ++c) { emax = std::max(emax, q[c * B8_TRACE_SLOTS]); smax = std::max(smax, q[c * B8_TRACE_SLOTS + 14]); }
+      fprintf(stderr, " | %7lld %7lld\n", emax - t0, smax - t0);
+    }
   }
   if (net->f35.d_trace) {
     FIRE_CUDA(cudaStreamSynchronize(st));
@@ -983,7 +1142,7 @@ int fire_facenet_forward(fire_net_t* net, const void* in_f16, int B, float* out_
     fprintf(stderr, "# op grid | first entry, setup, first full(max), last MMA commit(max), epilogue done(max), last exit [ns since op 0 entered] | span | gap to previous exit\n");
     for (size_t i = 0; i < net->ops.size(); ++i) {
       const OpRt& r = net->ops[i];
-      if (r.op.kind != OP_CONV || in_f17(net, i) || in_f35(net, i)) continue;
+      if (r.op.kind != OP_CONV || in_f17(net, i) || in_f35(net, i) || f8_role(net, i) >= 1) continue;
       const int grid = (int)std::min<long long>(r.strip ? (long long)B * r.row_blocks : (long long)r.m_tiles * r.n_tiles, device_sm_count());
       const long long* q = &t[i * 4096];
       long long e0 = 1ll << 62, su = 0, ff = 0, mc = 0, ed = 0, ex = 0;
@@ -1017,6 +1176,8 @@ int fire_facenet_profile(fire_net_t* net, const void* in_f16, int B, void* works
       if ((int)i == net->f17.first_op) rc = run_f17(net, B, st, false);
     } else if (in_f35(net, i)) {
       if ((int)i == net->f35.first_op) rc = run_f35(net, st, false);
+    } else if (f8_role(net, i) >= 1) {                // the fused Block8 tail is timed on the 1x3 conv's slot
+      if (f8_role(net, i) == 1) rc = run_f8(net, i, st, false);
     } else {
       rc = run_op(net, net->ops[i], B, in_f16, workspace, out_raw, st, false);   // no overlap: clean per-op times
     }
@@ -1038,6 +1199,12 @@ int fire_facenet_profile(fire_net_t* net, const void* in_f16, int B, void* works
       double sum = 0;
       for (int q = 0; q < 4 * net->f35.n_blocks; ++q) { sum += host_flops[net->f35.first_op + q]; host_flops[net->f35.first_op + q] = 0; }
       host_flops[net->f35.first_op] = sum;
+    }
+    if (host_flops && net->f8.first_op >= 0) {
+      for (int j = 0; j < net->f8.n_blocks; ++j) {
+        double* hf = host_flops + net->f8.first_op + 4 * j;
+        hf[1] += hf[2] + hf[3]; hf[2] = 0; hf[3] = 0;
+      }
     }
   }
   if (net->d_trace && rc == FIRE_OK && e == cudaSuccess) {

@@ -75,10 +75,10 @@ int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 
 
 int make_tmap_f16_nhwc(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint64_t ld_elems,
-                       uint64_t w_pitch, uint32_t box_c, uint32_t box_w, uint32_t box_h) {
+                       uint64_t w_pitch, uint32_t box_c, uint32_t box_w, uint32_t box_h, uint32_t box_n) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(FIRE_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld_elems & 7) || box_w == 0 || box_w > 256 || box_h == 0 || box_h > 256)
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld_elems & 7) || box_w == 0 || box_w > 256 || box_h == 0 || box_h > 256 || box_n == 0 || box_n > 256)
     return fail(FIRE_ERR_ARG, "NHWC tensor map: base/stride must be 16-byte aligned, box extents in [1,256]");
   CUtensorMapSwizzle sw;
   switch (box_c) {
@@ -89,7 +89,7 @@ int make_tmap_f16_nhwc(CUtensorMap* out, const void* base, uint64_t C, uint64_t 
   }
   cuuint64_t gdim[4] = {C, W, H, N};
   cuuint64_t gstride[3] = {ld_elems * 2, w_pitch * ld_elems * 2, H * w_pitch * ld_elems * 2};
-  cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+  cuuint32_t box[4] = {box_c, box_w, box_h, box_n};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

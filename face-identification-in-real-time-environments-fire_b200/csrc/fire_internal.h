@@ -39,11 +39,11 @@ int make_tmap_f16_2d_ex(CUtensorMap* out, const void* base, uint64_t rows, uint6
                         uint32_t box_cols, uint32_t box_rows);
 
 // 4-D view {C, W, H, N} of an NHWC fp16 buffer whose pixels are `ld_elems` channels apart (C <= ld_elems: a channel
-// slice); box = (box_c channels, box_w, box_h, 1 image), swizzle = box_c * 2 bytes.  Out-of-range coordinates
+// slice); box = (box_c channels, box_w, box_h, box_n images), swizzle = box_c * 2 bytes.  Out-of-range coordinates
 // (negative included) read as zero and are not written: this is how 'same' padding and ragged edges are handled.
 // `w_pitch` = pixels between image rows (>= W).
 int make_tmap_f16_nhwc(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint64_t ld_elems,
-                       uint64_t w_pitch, uint32_t box_c, uint32_t box_w, uint32_t box_h);
+                       uint64_t w_pitch, uint32_t box_c, uint32_t box_w, uint32_t box_h, uint32_t box_n = 1);
 // 3-D view {C, positions per image, N} of a buffer whose images are `positions` pixels of `ld_elems` channels: the
 // pitched position space written by flat-mode strip convs (box = box_c channels x box_pos positions x 1 image).
 int make_tmap_f16_pos3d(CUtensorMap* out, const void* base, uint64_t C, uint64_t positions, uint64_t N, uint64_t ld_elems,

@@ -195,6 +195,34 @@ def test_block35_fused_chain_matches_layer_by_layer(fire_lib, monkeypatch, B):
     assert np.abs(ra - rb).max() <= 1e-2 * np.abs(rb).max()
 
 
+@pytest.mark.parametrize("B", [1, 13, 14, 100, 256, 300])
+def test_block8_fused_tail_matches_layer_by_layer(fire_lib, monkeypatch, B):
+    """block8_fused_kernel (1x3 -> 3x1 -> up + residual of a Block8 block in one launch: a CTA owns 13 images x 256 output
+    channels, the 1x3 taps are TMA boxes shifted in x with out-of-bounds zero fill, the 3x1 taps row-shifted windows of a
+    y-major buffer, the residual one more K block) against the same plan run layer by layer (FIRE_B200_FUSE8=0:
+    conv_igemm_kernel x 3 per block).  Same fp16 operands and fp32 accumulation; the bias joins the sum in fp32 instead of
+    as an fp16 hi+lo MMA.  B = 1 / 14 / 100: ragged last image group (TMA zero fill and clipping); 300: two waves of CTAs."""
+    import torch
+    from fire_b200 import engine, weights as W
+    for D in (128, 512):
+        t = W.synthetic_weights(D, 8)
+        x = torch.from_numpy(_images(B, 19).astype(np.float32) / 255.0).cuda()
+        a = engine.FaceNetEngine(D, t)
+        ra, _ = a.encode_unit_f32(x)
+        ra2, _ = a.encode_unit_f32(x)
+        assert torch.equal(ra, ra2)                                    # deterministic
+        monkeypatch.setenv("FIRE_B200_FUSE8", "0")
+        b = engine.FaceNetEngine(D, t)
+        monkeypatch.delenv("FIRE_B200_FUSE8")
+        assert b.num_launches - a.num_launches == 12                   # 3 launches per block became one
+        rb, _ = b.encode_unit_f32(x)
+        ra, rb = ra.cpu().numpy(), rb.cpu().numpy()
+        assert np.isfinite(ra).all()
+        assert _cos(ra, rb).min() >= 0.99999
+        assert np.abs(ra - rb).max() <= 1e-2 * np.abs(rb).max()
+        a.close(); b.close()
+
+
 @pytest.mark.parametrize("B", [2, 37, 130])
 def test_im2col_tma_operand_is_bit_identical_to_gather(fire_lib, monkeypatch, B):
     """k x k layers with Cin % 64 == 0 (Conv2d_4b, Mixed_6a, Mixed_7a) fetch their A operand with im2col-mode TMA loads
@@ -292,6 +320,7 @@ def test_no_activation_saturates_fp16(fire_lib, monkeypatch):
     from fire_b200 import engine, weights as W
     monkeypatch.setenv("FIRE_B200_FUSE17", "0")
     monkeypatch.setenv("FIRE_B200_FUSE35", "0")
+    monkeypatch.setenv("FIRE_B200_FUSE8", "0")
     for D in (512, 128):
         t = W.synthetic_weights(D, 1234)
         eng = engine.FaceNetEngine(D, t, reuse_buffers=False)
