@@ -75,6 +75,8 @@ struct B8Params {
   const uint8_t* wup;       // 7 x 12 units of 16384 B
   const float* bias;        // [192 | 192 | 1792]
   int n_groups, relu, pdl, b1a_coff, b0_coff;
+  __half* gap_out;          // last block only: the global average pool of y, [n_images][gap_ld] fp16 (replaces gap_kernel); else nullptr
+  int gap_ld, n_images;
   long long* trace;         // optional: [gridDim.x][B8_TRACE_SLOTS] globaltimer stamps
 };
 
@@ -341,6 +343,39 @@ block8_fused_kernel(const __grid_constant__ B8Params p) {
       tc_fence_before();
       fence_proxy_async_smem();
       named_bar_sync(1, CONV_EPI_WARPS * 32);
+      if (p.gap_out) {
+        // global average pool of this CTA's 13 images x 256 channels, read back from the staged fp16 tiles: the same values
+        // gap_kernel would read from y, summed in the same order (p = 3 y + x) in fp32, scaled by 1/9, rounded once
+        for (int w = threadIdx.x - CONV_FIRST_EPI_WARP * 32; w < B8_IMGS * 32; w += CONV_EPI_WARPS * 32) {
+          const int img = w >> 5, pc = w & 31, g = pc >> 3, u = pc & 7;
+          if (img0 + img >= p.n_images) continue;
+          const uint32_t sg = g < 3 ? sbase + b8_data(g) : ring;
+          float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int y = 0; y < 3; ++y)
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+              const int row = B8_SLOT_ROWS * y + 3 * img + x;
+              const uint4 v = lds128(sg + static_cast<uint32_t>(row * 128 + ((u ^ (row & 7)) << 4)));
+              const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __half2 hh;
+                memcpy(&hh, &wv[e], 4);
+                const float2 f = __half22float2(hh);
+                s[2 * e] += f.x; s[2 * e + 1] += f.y;
+              }
+            }
+          const float inv = 1.0f / 9.0f;
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __half2 hh = __floats2half2_rn(s[2 * e] * inv, s[2 * e + 1] * inv);
+            memcpy(&o[e], &hh, 4);
+          }
+          st_global_v4(p.gap_out + static_cast<size_t>(img0 + img) * p.gap_ld + nt * B8_NT + g * 64 + u * 8, make_uint4(o[0], o[1], o[2], o[3]));
+        }
+      }
       if (warp == CONV_FIRST_EPI_WARP) {
         B8_TRACE(13);
         if (elect_one()) {

@@ -210,6 +210,7 @@ struct Fused35 {
 // heads conv (first_op + 4 j) stays a conv_igemm launch.
 struct Fused8 {
   int first_op = -1, n_blocks = 0;
+  int gap_op = -1;                  // index of the OP_GAP that the last block's launch also computes (-1: none)
   uint8_t* d_w = nullptr;           // per block: 36 units of 12288 B (1x3, 3x1) + 7 x 12 units of 16 KB (up, by N tile)
   float* d_bias = nullptr;          // per block: [192 | 192 | 1792] fp32
   long long* d_trace = nullptr;     // FIRE_B200_TRACE8=1
@@ -491,6 +492,14 @@ static bool b8_setup(fire_net* net, const std::vector<BlobOp>& ops, const uint8_
     break;
   }
   if (f.first_op < 0) return false;
+  {
+    // global average pool right after the last block, over the whole of its output: folded into that block's launch
+    const size_t g = (size_t)f.first_op + 4 * f.n_blocks;
+    const BlobOp& u = ops[g - 1];
+    if (g < ops.size() && ops[g].kind == OP_GAP && ops[g].src_buf == u.dst_buf && ops[g].src_coff == 0 && ops[g].cin == B8_C && ops[g].H == 3 &&
+        ops[g].W == 3 && net->bufs[ops[g].dst_buf].elt == 2 && !(getenv("FIRE_B200_FUSE_GAP") && getenv("FIRE_B200_FUSE_GAP")[0] == '0'))
+      f.gap_op = (int)g;
+  }
   std::vector<uint16_t> w((size_t)f.n_blocks * B8_W_PER_BLOCK / 2, 0);
   std::vector<float> bias((size_t)f.n_blocks * B8_BIAS_PER_BLOCK);
   for (int j = 0; j < f.n_blocks; ++j) {
@@ -518,7 +527,7 @@ static bool b8_setup(fire_net* net, const std::vector<BlobOp>& ops, const uint8_
       cudaFuncSetAttribute(block8_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B8_SMEM) != cudaSuccess) {
     cudaGetLastError();
     cudaFree(f.d_w); cudaFree(f.d_bias);
-    f.d_w = nullptr; f.d_bias = nullptr; f.first_op = -1; f.n_blocks = 0;
+    f.d_w = nullptr; f.d_bias = nullptr; f.first_op = -1; f.n_blocks = 0; f.gap_op = -1;
     return false;
   }
   if (const char* e = getenv("FIRE_B200_TRACE8")) {
@@ -721,7 +730,7 @@ int fire_facenet_num_launches(const fire_net_t* net) {
   int n = (int)net->ops.size();
   if (net->f17.first_op >= 0) n -= 4 * net->f17.n_blocks - 1;
   if (net->f35.first_op >= 0) n -= 4 * net->f35.n_blocks - 1;
-  if (net->f8.first_op >= 0) n -= 2 * net->f8.n_blocks;
+  if (net->f8.first_op >= 0) n -= 2 * net->f8.n_blocks + (net->f8.gap_op >= 0 ? 1 : 0);
   return n;
 }
 double fire_facenet_flops(const fire_net_t* net) { return net ? net->flops_per_image : 0.0; }
@@ -1043,6 +1052,12 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
         q.relu = (uop.flags & CF_RELU) ? 1 : 0;
         q.b1a_coff = hop.dst_coff; q.b0_coff = hop.dst_coff + B8_MID;
         q.trace = f.d_trace ? f.d_trace + (size_t)j * 148 * B8_TRACE_SLOTS : nullptr;
+        q.gap_out = nullptr; q.gap_ld = 0; q.n_images = B;
+        if (j == f.n_blocks - 1 && f.gap_op >= 0) {
+          const BlobOp& gop = net->ops[f.gap_op].op;
+          q.gap_out = static_cast<__half*>(buf_ptr(net, gop.dst_buf, B, in, ws, out_raw));
+          q.gap_ld = net->bufs[gop.dst_buf].C;
+        }
       }
     }
     net->key_in = in; net->key_ws = ws; net->key_out = out_raw; net->key_B = B;
@@ -1071,7 +1086,7 @@ int fire_facenet_forward(fire_net_t* net, const void* in_f16, int B, float* out_
     }
     {
       const int role = f8_role(net, i);
-      if (role == 2) continue;
+      if (role == 2 || (int)i == net->f8.gap_op) continue;
       if (role == 1) { rc = run_f8(net, i, st, net->pdl); if (rc != FIRE_OK) return rc; continue; }
     }
     rc = run_op(net, net->ops[i], B, in_f16, workspace, out_raw, st, net->pdl);
@@ -1176,7 +1191,7 @@ int fire_facenet_profile(fire_net_t* net, const void* in_f16, int B, void* works
       if ((int)i == net->f17.first_op) rc = run_f17(net, B, st, false);
     } else if (in_f35(net, i)) {
       if ((int)i == net->f35.first_op) rc = run_f35(net, st, false);
-    } else if (f8_role(net, i) >= 1) {                // the fused Block8 tail is timed on the 1x3 conv's slot
+    } else if (f8_role(net, i) >= 1 || (int)i == net->f8.gap_op) {   // the fused Block8 tail is timed on the 1x3 conv's slot
       if (f8_role(net, i) == 1) rc = run_f8(net, i, st, false);
     } else {
       rc = run_op(net, net->ops[i], B, in_f16, workspace, out_raw, st, false);   // no overlap: clean per-op times
