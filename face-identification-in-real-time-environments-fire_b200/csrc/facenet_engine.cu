@@ -37,7 +37,7 @@ struct BlobHeader {
 struct BlobBuf {
   int32_t H, W, C, elt;
   int64_t offset;
-  int32_t external, Wp;     // Wp: row pitch in pixels (0 = W); > W for the outputs of flat-mode strip convs
+  int32_t external, Wp;     // external: 1 = bound by the caller, 2 = a view of the network input; Wp: row pitch in pixels (0 = W); > W for the outputs of flat-mode strip convs
 };
 struct BlobOp {
   int32_t kind, src_buf, src_coff, dst_buf, dst_coff, res_buf, res_coff, H, W, Ho, Wo, kh, kw, stride, pad_h, pad_w, cin,
@@ -743,7 +743,7 @@ size_t fire_facenet_workspace(const fire_net_t* net, int B) {
 }  // extern "C"
 
 static void* buf_ptr(const fire_net* net, int buf, int B, const void* in, void* ws, void* out_raw) {
-  if (buf == net->hdr.in_buf) return const_cast<void*>(in);
+  if (buf == net->hdr.in_buf || net->bufs[buf].external == 2) return const_cast<void*>(in);      // 2: a pixel-pair view of the network input
   if (buf == net->hdr.out_buf) return out_raw;
   return static_cast<uint8_t*>(ws) + (size_t)net->bufs[buf].offset * (size_t)B;
 }

@@ -33,12 +33,12 @@ class FaceNetEngine:
     """K2: the Inception-ResNet-v1 conv stack (replaces the onnxruntime session, facenet_gpu.py:72,127)."""
 
     def __init__(self, D: int = 512, tensors: Optional[dict] = None, device: int = 0, fuse_siblings: bool = True,
-                 seed: int = 1234, pitched: bool = True, reuse_buffers: bool = True):
+                 seed: int = 1234, pitched: bool = True, reuse_buffers: bool = True, pair_stem: bool = True):
         torch = _torch()
         _lib.init(device)
         self.device = torch.device("cuda", device)
         self.D = D
-        self.plan = Plan(D, fuse_siblings=fuse_siblings, pitched=pitched, reuse_buffers=reuse_buffers)   # reuse_buffers=False: debug layout, every activation keeps its own memory
+        self.plan = Plan(D, fuse_siblings=fuse_siblings, pitched=pitched, reuse_buffers=reuse_buffers, pair_stem=pair_stem)   # reuse_buffers=False: debug layout, every activation keeps its own memory
         if tensors is None:
             tensors = W.synthetic_weights(D, seed)
         self.blob = W.pack(self.plan, tensors)

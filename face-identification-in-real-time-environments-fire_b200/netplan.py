@@ -95,6 +95,8 @@ class Op:
     b_off: int = 0               # byte offset of the fp32 bias
     label: str = ""
     s2d: bool = False            # first conv only: executed as a 2x2 stride-1 conv over the space-to-depth input (see Plan)
+    pair: bool = False           # executed over PIXEL PAIRS: two horizontally adjacent pixels are one position with twice the
+                                 # channels (same memory), so N doubles and the tile count halves (see Plan.pair_stem)
 
     @property
     def k_real(self) -> int:
@@ -123,7 +125,7 @@ def _pick_bn_tile(cout: int) -> int:
 
 class Plan:
     def __init__(self, D: int, fuse_siblings: bool = True, reuse_buffers: bool = True, pitched: bool = True,
-                 s2d_input: bool = True):
+                 s2d_input: bool = True, pair_stem: bool = True):
         assert D in (128, 512)
         self.D = D
         self.pitched = pitched
@@ -134,6 +136,15 @@ class Plan:
         # strip kernel runs without im2col.  The Plan keeps describing the logical 3x3/2 conv; weights.pack()
         # writes the transformed op into the blob.
         self.s2d_input = s2d_input
+        # pair_stem: Conv2d_1a and Conv2d_2a have only 32 output channels, and a tcgen05.mma costs the issuing thread the
+        # same ~100 cycles at N = 32 as at N = 64.  An NHWC row of pixels with C channels IS a row of pixel pairs with 2C
+        # channels, so the 'valid' kh x kw conv over pixels is a kh x 2 conv over pairs (output pair X = pixels 2X, 2X+1
+        # reads input pixels 2X .. 2X+kw = input pairs X, X+1) with weights [2 Cout][kh][2][2 Cin] that are the original
+        # taps shifted by the output parity (zero where the shifted tap leaves the window): a third more MMA work, a
+        # third fewer MMA instructions, half as many tiles.  Row pitches must be even (80 pixels = 40 pairs).  Like s2d
+        # this is a property of the packed blob: the Plan keeps describing the logical conv, weights.pack() emits the
+        # pair op over alias views of the same buffers.
+        self.pair_stem = pair_stem and pitched and s2d_input
         self.fuse = fuse_siblings
         self.reuse = reuse_buffers
         self.bufs: List[Buf] = []
@@ -198,9 +209,12 @@ class Plan:
         B = self._buf
         x = self.whole(self.in_buf)
         t = B(79, 79, 32, Wp=80 if self.s2d_input else 0)
-        self.conv("Conv2d_1a_3x3", x, self.whole(t), 3, 3, 2, cin_real=3, in_scale=1.0 / 255.0).s2d = self.s2d_input
+        op = self.conv("Conv2d_1a_3x3", x, self.whole(t), 3, 3, 2, cin_real=3, in_scale=1.0 / 255.0)
+        op.s2d, op.pair = self.s2d_input, self.pair_stem
         x = self.whole(t)
-        t = B(77, 77, 32, Wp=79); self.conv("Conv2d_2a_3x3", x, self.whole(t), 3, 3); x = self.whole(t)
+        t = B(77, 77, 32, Wp=80 if self.pair_stem else 79)
+        self.conv("Conv2d_2a_3x3", x, self.whole(t), 3, 3).pair = self.pair_stem
+        x = self.whole(t)
         t = B(77, 77, 64, Wp=79); self.conv("Conv2d_2b_3x3", x, self.whole(t), 3, 3, same=True); x = self.whole(t)
         t = B(38, 38, 64); self.maxpool(x, self.whole(t), "MaxPool_3a_3x3"); x = self.whole(t)
         t = B(38, 38, 80); self.conv("Conv2d_3b_1x1", x, self.whole(t)); x = self.whole(t)

@@ -199,6 +199,36 @@ def s2d_weights(Wg: np.ndarray, cin: int) -> np.ndarray:
     return out.reshape(cout, S2D_K)
 
 
+def pair_weights(Wg: np.ndarray, kh: int, kw: int, cin: int) -> np.ndarray:
+    """[cout, kh*kw*cin] (tap-major, channel-minor; stride 1, no padding) -> [2*cout, kh*kw2*2*cin] for the same conv over
+    PIXEL PAIRS (netplan.Plan.pair_stem): output row d*cout + co is output pixel 2X + d, K index ((r*kw2 + pt)*2 + e)*cin + c
+    is input pixel 2(X + pt) + e, i.e. original tap s = 2 pt + e - d (zero weights where s leaves [0, kw))."""
+    cout = Wg.shape[0]
+    w = Wg.reshape(cout, kh, kw, cin)
+    kw2 = (kw + 2) // 2                       # pixels 2X .. 2X + kw  ->  pairs X .. X + kw2 - 1
+    out = np.zeros((2, cout, kh, kw2, 2, cin), dtype=np.float32)
+    for d in range(2):
+        for pt in range(kw2):
+            for e in range(2):
+                s_ = 2 * pt + e - d
+                if 0 <= s_ < kw:
+                    out[d, :, :, pt, e, :] = w[:, :, s_, :]
+    return out.reshape(2 * cout, kh * kw2 * 2 * cin)
+
+
+def unpair_weights(Wpair: np.ndarray, kh: int, kw: int, cin: int) -> np.ndarray:
+    """Inverse of pair_weights (test tool: the plan emulator runs the logical conv); checks that the two parity blocks
+    are shifted copies of the same taps."""
+    cout = Wpair.shape[0] // 2
+    kw2 = (kw + 2) // 2
+    v = Wpair[:, :kh * kw2 * 2 * cin].reshape(2, cout, kh, kw2, 2, cin)
+    w = np.zeros((cout, kh, kw, cin), dtype=np.float32)
+    for s_ in range(kw):
+        w[:, :, s_, :] = v[0, :, :, s_ // 2, s_ % 2, :]
+    assert np.array_equal(pair_weights(w.reshape(cout, -1), kh, kw, cin), Wpair[:, :kh * kw2 * 2 * cin].astype(np.float32))
+    return w.reshape(cout, kh * kw * cin)
+
+
 def pack(plan: Plan, tensors: dict) -> bytes:
     """Serialise plan + folded bf16 weights into the blob `fire_facenet_create` parses."""
     chunks, pos = [], 0
@@ -219,22 +249,51 @@ def pack(plan: Plan, tensors: dict) -> bytes:
         if op.s2d:
             W = s2d_weights(W, op.cin)
         k_pad = S2D_K if op.s2d else op.k_pad
-        Wp = np.zeros((op.cout, k_pad), dtype=np.uint16)
+        cout = op.cout
+        if op.pair:                                        # the same conv over pixel pairs: [2 cout][kh * 2 * 2 cin]
+            kh, kw, cin = (2, 2, S2D_C) if op.s2d else (op.kh, op.kw, op.cin)
+            assert op.stride == (2 if op.s2d else 1) and op.pad_h == 0 and op.pad_w == 0 and kw in (2, 3)
+            W = pair_weights(W[:, :kh * kw * cin], kh, kw, cin)
+            b = np.concatenate([b, b])
+            cout, k_pad = 2 * cout, (W.shape[1] + 63) // 64 * 64
+        Wp = np.zeros((cout, k_pad), dtype=np.uint16)
         Wp[:, :W.shape[1]] = f32_to_f16_bits(W)
         op.w_off = put(Wp)
         op.b_off = put(b)
 
-    bufs = np.zeros(len(plan.bufs), dtype=BUF_DT)
     s2d = any(o.s2d for o in plan.ops)
+    buf_rows = []
     for i, b in enumerate(plan.bufs):
         if s2d and i == plan.in_buf:                       # the engine sees the space-to-depth tensor
-            bufs[i] = (b.H // 2, b.W // 2, S2D_C, b.elt, 0, 1, 0)
+            buf_rows.append((b.H // 2, b.W // 2, S2D_C, b.elt, 0, 1, 0))
             continue
-        bufs[i] = (b.H, b.W, b.C, b.elt, max(b.offset, 0), int(b.external), b.Wp)
+        buf_rows.append((b.H, b.W, b.C, b.elt, max(b.offset, 0), int(b.external), b.Wp))
+
+    def pair_view(i: int, w_pairs: int) -> int:
+        """Extra buffer-table entry: buffer i seen as pixel pairs (same memory; external = 2 marks a view of the network input)."""
+        H, Wd, C, elt, off, ext, Wpitch = buf_rows[i]
+        pitch = Wpitch or Wd
+        assert pitch % 2 == 0 and w_pairs <= pitch // 2, (i, pitch, w_pairs)
+        buf_rows.append((H, w_pairs, 2 * C, elt, off, 2 if ext else 0, pitch // 2))
+        return len(buf_rows) - 1
+
     ops = np.zeros(len(plan.ops), dtype=OP_DT)
     for i, o in enumerate(plan.ops):
         res_buf, res_coff = (o.res.buf, o.res.c_off) if o.res is not None else (-1, 0)
         flop_k = o.macs_per_image // (o.Ho * o.Wo * o.cout) if o.kind == OP_CONV else 0      # real MACs per output element
+        if o.pair:
+            # kh x kw over [H, W, C]  ==  kh x 2 over the pair views [H, W/2, 2C]; Wo pairs = input pairs - 1, the last
+            # input pair column is the flat tiles' spare column, whose first pixel is still a correct output
+            H, Wd, kh, cin = (o.H // 2, o.W // 2, 2, S2D_C) if o.s2d else (o.H, plan.bufs[o.src.buf].Wp or o.W, o.kh, o.cin)
+            assert o.src.c_off == 0 and o.dst.c_off == 0 and o.res is None and Wd % 2 == 0
+            wp_in = Wd // 2
+            src, dst = pair_view(o.src.buf, wp_in), pair_view(o.dst.buf, wp_in - 1)
+            assert buf_rows[dst][6] == wp_in, "pair conv: the destination pitch must equal the input width in pairs"
+            k_pad = (kh * 2 * 2 * cin + 63) // 64 * 64
+            flop_k = int(round(o.macs_per_image / (o.Ho * (wp_in - 1) * 2 * o.cout)))
+            ops[i] = (o.kind, src, 0, dst, 0, -1, 0, H, wp_in, o.Ho, wp_in - 1, kh, 2, 1, 0, 0, 2 * cin, 2 * o.cout, k_pad,
+                      o.flags, min(2 * o.cout, 256), flop_k, o.w_off, o.b_off)
+            continue
         if o.s2d:                                          # 3x3 / stride 2 over [160,160,8]  ==  2x2 / stride 1 over [80,80,16]
             ops[i] = (o.kind, o.src.buf, 0, o.dst.buf, o.dst.c_off, res_buf, res_coff, o.H // 2, o.W // 2, o.Ho, o.Wo,
                       2, 2, 1, 0, 0, S2D_C, o.cout, S2D_K, o.flags, o.bn_tile, flop_k, o.w_off, o.b_off)
@@ -242,10 +301,13 @@ def pack(plan: Plan, tensors: dict) -> bytes:
         ops[i] = (o.kind, o.src.buf, o.src.c_off, o.dst.buf, o.dst.c_off, res_buf, res_coff, o.H, o.W, o.Ho, o.Wo,
                   o.kh, o.kw, o.stride, o.pad_h, o.pad_w, o.cin, o.cout, o.k_pad if o.kind == OP_CONV else 0,
                   o.flags, o.bn_tile, flop_k, o.w_off, o.b_off)
+    bufs = np.zeros(len(buf_rows), dtype=BUF_DT)
+    for i, row in enumerate(buf_rows):
+        bufs[i] = row
     hdr = np.zeros(1, dtype=HEADER_DT)
     meta = HEADER_DT.itemsize + bufs.nbytes + ops.nbytes
     weights_off = (meta + 255) // 256 * 256
-    hdr[0] = (MAGIC, BLOB_VERSION, plan.D, len(plan.ops), len(plan.bufs), plan.workspace_bytes_per_image,
+    hdr[0] = (MAGIC, BLOB_VERSION, plan.D, len(plan.ops), len(buf_rows), plan.workspace_bytes_per_image,
               weights_off, pos, plan.in_buf, plan.out_buf)
     head = hdr.tobytes() + bufs.tobytes() + ops.tobytes()
     return head + b"\0" * (weights_off - len(head)) + b"".join(chunks)

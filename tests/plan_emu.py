@@ -51,9 +51,18 @@ def run_plan(plan: Plan, blob: bytes, x_pix_nhwc8: np.ndarray, store_f16: bool =
             src = view(op.src.buf)[..., op.src.c_off:op.src.c_off + op.src.c]
             dstv = view(op.dst.buf)
             if op.kind == OP_CONV:
+                def packed(k_real, k_pad):
+                    """this op's [cout][k_real] weights out of the blob; a pair op (netplan.Plan.pair_stem) is stored as
+                    the pixel-pair conv [2 cout][kh * 2 * 2 cin]: undo, the emulator runs the logical conv"""
+                    if not op.pair:
+                        wb = np.frombuffer(blob, dtype=np.uint16, count=op.cout * k_pad, offset=wbase + op.w_off)
+                        return W.f16_bits_to_f32(wb.reshape(op.cout, k_pad)[:, :k_real])
+                    kh, kw, cin = (2, 2, W.S2D_C) if op.s2d else (op.kh, op.kw, op.cin)
+                    kp = (kh * 2 * 2 * cin + 63) // 64 * 64
+                    wb = np.frombuffer(blob, dtype=np.uint16, count=2 * op.cout * kp, offset=wbase + op.w_off)
+                    return W.unpair_weights(W.f16_bits_to_f32(wb.reshape(2 * op.cout, kp)), kh, kw, cin)
                 if op.s2d:      # packed as the 2x2 conv over the space-to-depth input: undo, the emulator feeds NHWC8
-                    wb = np.frombuffer(blob, dtype=np.uint16, count=op.cout * W.S2D_K, offset=wbase + op.w_off)
-                    w2 = W.f16_bits_to_f32(wb.reshape(op.cout, W.S2D_K)).reshape(op.cout, 2, 2, W.S2D_C)
+                    w2 = packed(W.S2D_K, W.S2D_K).reshape(op.cout, 2, 2, W.S2D_C)
                     w3 = np.zeros((op.cout, 3, 3, op.cin), dtype=np.float32)
                     for a in range(2):
                         for b_ in range(2):
@@ -63,8 +72,7 @@ def run_plan(plan: Plan, blob: bytes, x_pix_nhwc8: np.ndarray, store_f16: bool =
                                         w3[:, 2 * a + dy, 2 * b_ + dx, :3] = w2[:, a, b_, (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3]
                     wf = w3.reshape(op.cout, -1)
                 else:
-                    wb = np.frombuffer(blob, dtype=np.uint16, count=op.cout * op.k_pad, offset=wbase + op.w_off)
-                    wf = W.f16_bits_to_f32(wb.reshape(op.cout, op.k_pad)[:, :op.k_real])
+                    wf = packed(op.k_real, op.k_pad)
                 bias = np.frombuffer(blob, dtype=np.float32, count=op.cout, offset=wbase + op.b_off)
                 k = torch.from_numpy(wf.reshape(op.cout, op.kh, op.kw, op.cin).transpose(0, 3, 1, 2).copy())
                 y = F.conv2d(src.permute(0, 3, 1, 2), k, torch.from_numpy(bias.copy()), stride=op.stride,

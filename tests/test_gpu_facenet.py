@@ -195,6 +195,31 @@ def test_block35_fused_chain_matches_layer_by_layer(fire_lib, monkeypatch, B):
     assert np.abs(ra - rb).max() <= 1e-2 * np.abs(rb).max()
 
 
+@pytest.mark.parametrize("B", [1, 3, 130])
+def test_pair_stem_matches_pixel_stem(fire_lib, B):
+    """Conv2d_1a / Conv2d_2a run over PIXEL PAIRS (netplan.Plan.pair_stem: N = 64 instead of 32, half as many tiles, the
+    weights shifted copies of the same taps) against the same strip kernel over single pixels: the stored activations of
+    both layers - every valid pixel, including column 78 of Conv2d_1a, which the pair conv produces in the flat tiles'
+    spare column - and the embeddings.  Same fp16 operands; the extra zero-weight taps add exact zeros."""
+    import torch
+    from fire_b200 import engine, weights as W
+    t = W.synthetic_weights(512, 21)
+    x = torch.from_numpy(_images(B, 23).astype(np.float32) / 255.0).cuda()
+    a = engine.FaceNetEngine(512, t, reuse_buffers=False)
+    b = engine.FaceNetEngine(512, t, reuse_buffers=False, pair_stem=False)
+    assert a.plan.pair_stem and not b.plan.pair_stem
+    xa, xb = a.ingest_unit_f32(x), b.ingest_unit_f32(x)
+    ra, _ = a.forward(xa)
+    rb, _ = b.forward(xb)
+    for i in (1, 2):                                                   # outputs of Conv2d_1a, Conv2d_2a
+        ba, bb = a.read_buffer(a.plan.ops[i - 1].dst.buf, xa), b.read_buffer(b.plan.ops[i - 1].dst.buf, xb)
+        assert ba.shape == bb.shape and ba.shape[2] in (79, 77)
+        assert np.abs(ba - bb).max() <= 2e-3 * max(1.0, np.abs(bb).max()), (i, np.abs(ba - bb).max())
+    ra, rb = ra.cpu().numpy(), rb.cpu().numpy()
+    assert _cos(ra, rb).min() >= 0.99999
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("B", [1, 13, 14, 100, 256, 300])
 def test_block8_fused_tail_matches_layer_by_layer(fire_lib, monkeypatch, B):
     """block8_fused_kernel (1x3 -> 3x1 -> up + residual of a Block8 block in one launch: a CTA owns 13 images x 256 output

@@ -68,6 +68,41 @@ def test_bf16_would_miss_the_bar(setup, monkeypatch):
     assert _cos(out, ref).min() < 0.9999
 
 
+def test_pair_weights_compute_the_same_convolution():
+    """netplan.Plan.pair_stem: a 'valid' kh x kw conv over [H, W, C] equals the kh x 2 conv with weights.pair_weights over the
+    same memory seen as pixel pairs [H, W/2, 2C] (what Conv2d_1a / 2a run as on the GPU); unpair_weights inverts it."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(0)
+    for kh, kw, cin, cout, H, Wd in ((3, 3, 8, 16, 7, 10), (2, 2, 16, 32, 6, 12)):
+        x = rng.standard_normal((2, H, Wd, cin)).astype(np.float32)
+        w = rng.standard_normal((cout, kh, kw, cin)).astype(np.float32)
+        y = F.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(w).permute(0, 3, 1, 2)).permute(0, 2, 3, 1).numpy()
+        wp = W.pair_weights(w.reshape(cout, -1), kh, kw, cin)
+        assert np.array_equal(W.unpair_weights(wp, kh, kw, cin), w.reshape(cout, -1))
+        xp = torch.from_numpy(x.reshape(2, H, Wd // 2, 2 * cin)).permute(0, 3, 1, 2)
+        kp = torch.from_numpy(wp.reshape(2 * cout, kh, 2, 2 * cin)).permute(0, 3, 1, 2)
+        yp = F.conv2d(xp, kp).permute(0, 2, 3, 1).numpy()              # [2, Ho, W/2 - 1, 2 cout]
+        yp = yp.reshape(2, yp.shape[1], -1, cout)                       # pixels 0 .. W - 3
+        n = min(y.shape[2], yp.shape[2])
+        assert n >= Wd - kw - 1 and np.allclose(y[:, :, :n], yp[:, :, :n], atol=1e-4)
+
+
+def test_pair_stem_blob_views():
+    p = Plan(512)
+    assert p.pair_stem and [o.pair for o in p.conv_ops()[:3]] == [True, True, False]
+    blob = W.pack(p, W.synthetic_weights(512, 5, calibrate=False))
+    hdr = np.frombuffer(blob, dtype=W.HEADER_DT, count=1)[0]
+    assert hdr["n_bufs"] == len(p.bufs) + 4                          # two pair views per pair op
+    bufs = np.frombuffer(blob, dtype=W.BUF_DT, count=int(hdr["n_bufs"]), offset=W.HEADER_DT.itemsize)
+    ops = np.frombuffer(blob, dtype=W.OP_DT, count=len(p.ops), offset=W.HEADER_DT.itemsize + bufs.nbytes)
+    for i in (0, 1):
+        o, s, d = ops[i], bufs[ops[i]["src_buf"]], bufs[ops[i]["dst_buf"]]
+        assert (o["kw"], o["cout"], o["W"], o["Wo"], d["Wp"], s["W"]) == (2, 64, 40, 39, 40, 40)
+        assert d["offset"] == bufs[p.ops[i].dst.buf]["offset"] and s["C"] == o["cin"] and d["C"] == 64
+    assert bufs[ops[0]["src_buf"]]["external"] == 2 and not Plan(512, pitched=False).pair_stem
+
+
 def test_blob_layout_and_tiling_constraints():
     p = Plan(128)
     blob = W.pack(p, W.synthetic_weights(128, 5, calibrate=False))
