@@ -40,7 +40,7 @@ __host__ __device__ inline StripSmem strip_smem_layout(int stages, int a_stage_b
   L.b = o;    o += static_cast<uint32_t>(nkb) * cout * 128;
   L.bias = o; o += static_cast<uint32_t>(cout) * 16;
   L.ones = o; o += CONV_BM * 16;
-  L.zero = o; o += 256 * 16;
+  L.zero = o; o += static_cast<uint32_t>(cout > CONV_BM ? cout : CONV_BM) * 16;   // K-chunk 1 of the ones [128] and bias [cout] operands
   o = (o + 1023) & ~1023u;
   L.out = o;  o += 2u * CONV_BM * cout * 2;                  // [2 buffers][cout / box_cols boxes][128 rows][box_cols * 2 bytes]
   L.bars = o; o += 512;
@@ -129,7 +129,7 @@ conv_strip_kernel_t(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
     uint4* s_bias = reinterpret_cast<uint4*>(smem + L.bias);
     for (int i = t; i < b_rows; i += CONV_EPI_WARPS * 32) s_bias[i] = __ldg(p.bias16 + rank * b_rows + i);
     if (t < CONV_BM) reinterpret_cast<uint4*>(smem + L.ones)[t] = make_uint4(0x3C003C00u, 0u, 0u, 0u);
-    reinterpret_cast<uint4*>(smem + L.zero)[t] = make_uint4(0u, 0u, 0u, 0u);
+    if (t < (p.cout > CONV_BM ? p.cout : CONV_BM)) reinterpret_cast<uint4*>(smem + L.zero)[t] = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
   }
   if (pair) {                                       // barriers of both CTAs are initialised before anything remote touches them
