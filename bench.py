@@ -317,7 +317,7 @@ def run_fire(args):
 
     # ---------------- roofline ----------------------------------------------------------------------------------------
     # Direct: the step's algorithmic FLOP (2.8353 GFLOP x 256 images) over the step's OWN device time as timed
-    # above - every launch of the step (K1, 42 tensor launches, pools, GAP, L2 norm) is charged to the tensor roofline, so this
+    # above - every launch of the step (K1, 30 tensor launches, pools, L2 norm) is charged to the tensor roofline, so this
     # is a lower bound for the convolution kernels and needs no share from a separate pass.  `families` adds the per-family
     # picture from one serialised per-op event pass (no overlap between launches: it overstates small launches) and the live
     # HBM figures of K1.
@@ -333,8 +333,8 @@ def run_fire(args):
         labels = [o.label for o in eng.plan.ops]
         pool_ms = float(sum(m for m, o in zip(ms_ops, eng.plan.ops) if o.kind != 1))
         pool_bytes = 0.0
-        for o in eng.plan.ops:
-            if o.kind != 1:
+        for m_, o in zip(ms_ops, eng.plan.ops):
+            if o.kind != 1 and m_ > 0:                     # the average pool is part of the last block8_fused launch (0 ms of its own)
                 sb, db = eng.plan.bufs[o.src.buf], eng.plan.bufs[o.dst.buf]
                 pool_bytes += BATCH * 2.0 * (o.H * (sb.Wp or sb.W) * o.cin + o.Ho * o.Wo * o.cout)
 
@@ -360,7 +360,7 @@ def run_fire(args):
         k1_boxes = k1_gbs(fr4, d4, torch.from_numpy(bx4).to(dev), torch.arange(BATCH, dtype=torch.int32, device=dev) % 8,
                           float((bx4[:, 2].astype(np.int64) * bx4[:, 3] * 3).sum() + BATCH * out_bytes))
         del fr4
-        roofline = {"kernel": "the step's tensor launches: conv_igemm + conv_strip + block35_fused + block17_fused "
+        roofline = {"kernel": "the step's tensor launches: conv_igemm + conv_strip + block35_fused + block17_fused + block8_fused "
                               f"({int(conv.sum())} launches for the plan's 100 convs), timed as the whole step",
                     "bound": "tensor", "achieved": achieved, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["tensor_tflops"], "frac_of_burst_peak": achieved / peaks["tensor_burst"],

@@ -242,6 +242,12 @@ struct fire_net {
   bool use_strip = true;    // FIRE_B200_STRIP=0 forces the gather path for every k x k layer (A/B experiments)
   bool trace_all = false;   // FIRE_B200_TRACE_ALL=1: forward() records every conv's timeline, synchronises and prints it
   long long* d_trace = nullptr; int trace_op = -1;   // FIRE_B200_TRACE_OP=<op index>: in-kernel timeline of that op (profile only)
+  // Max-pools whose input was produced several ops earlier (the pool branches of Mixed_6a / Mixed_7a) run on a side stream,
+  // concurrently with the branch convolutions that read the same tensor (FIRE_B200_SIDE_POOLS=0: in plan order)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::vector<int> hoist_at;   // per op: index of the max-pool to launch on the side stream just before this op (-1: none)
+  std::vector<char> hoisted;   // per op: this max-pool is launched early (skip it at its own position, join after it)
   int dbg_flags = 0;      // always 0 unless built with -DFIRE_B200_SKIP_EXPERIMENTS (then FIRE_B200_DBG: 1 = no gather copies, 2 = no epilogue stores, 4 = no MMA)
 };
 
@@ -706,6 +712,33 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
     const char* f8_env = getenv("FIRE_B200_FUSE8");
     if (!(f8_env && f8_env[0] == '0')) b8_setup(net, ops, p, h);
   }
+  {
+    net->hoist_at.assign(ops.size(), -1);
+    net->hoisted.assign(ops.size(), 0);
+    const char* sp = getenv("FIRE_B200_SIDE_POOLS");
+    if (!(sp && sp[0] == '0') && cudaStreamCreateWithFlags(&net->side, cudaStreamNonBlocking) == cudaSuccess &&
+        cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming) == cudaSuccess) {
+      for (size_t i = 0; i < ops.size(); ++i) {
+        if (ops[i].kind != OP_MAXPOOL) continue;
+        int prod = -1;                                   // last op before i that writes the pool's input
+        for (int j = (int)i - 1; j >= 0; --j) if (ops[j].dst_buf == ops[i].src_buf) { prod = j; break; }
+        if (prod < 0 || prod + 1 >= (int)i) continue;    // input of the net / produced by the previous op: nothing to overlap with
+        bool ok = i + 1 < ops.size();
+        for (int j = prod + 1; j < (int)i && ok; ++j) {  // the ops it overtakes must not touch its output slice
+          const bool same_buf_w = ops[j].dst_buf == ops[i].dst_buf, same_buf_r = ops[j].src_buf == ops[i].dst_buf || ops[j].res_buf == ops[i].dst_buf;
+          const int lo = ops[i].dst_coff, hi = lo + ops[i].cout;
+          if (same_buf_w && ops[j].dst_coff < hi && ops[j].dst_coff + ops[j].cout > lo) ok = false;
+          if (same_buf_r) ok = false;
+        }
+        if (!ok || net->hoist_at[prod + 1] >= 0) continue;
+        net->hoist_at[prod + 1] = (int)i;
+        net->hoisted[i] = 1;
+      }
+    } else {
+      cudaGetLastError();
+    }
+  }
   *out = net;
   return FIRE_OK;
 }
@@ -719,6 +752,9 @@ int fire_facenet_destroy(fire_net_t* net) {
   cudaFree(net->f17.d_stream); cudaFree(net->f17.d_bias); cudaFree(net->f17.d_trace);
   cudaFree(net->f35.d_stream); cudaFree(net->f35.d_bias); cudaFree(net->f35.d_trace);
   cudaFree(net->f8.d_w); cudaFree(net->f8.d_bias); cudaFree(net->f8.d_trace);
+  if (net->ev_fork) cudaEventDestroy(net->ev_fork);
+  if (net->ev_join) cudaEventDestroy(net->ev_join);
+  if (net->side) cudaStreamDestroy(net->side);
   delete net;
   return FIRE_OK;
 }
@@ -1077,7 +1113,21 @@ int fire_facenet_forward(fire_net_t* net, const void* in_f16, int B, float* out_
   rc = prepare(net, in_f16, B, out_raw, workspace, ws_bytes);
   if (rc != FIRE_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  bool join_pending = false;
   for (size_t i = 0; i < net->ops.size(); ++i) {
+    if (net->hoist_at[i] >= 0) {
+      // everything launched so far (the producer of the pool's input included) -> fork; the pool runs beside the next convs
+      FIRE_CUDA(cudaEventRecord(net->ev_fork, st));
+      FIRE_CUDA(cudaStreamWaitEvent(net->side, net->ev_fork, 0));
+      rc = run_op(net, net->ops[net->hoist_at[i]], B, in_f16, workspace, out_raw, net->side, false);
+      if (rc != FIRE_OK) return rc;
+      FIRE_CUDA(cudaEventRecord(net->ev_join, net->side));
+      join_pending = true;
+    }
+    if (net->hoisted[i]) {                              // its consumers come next: join here
+      if (join_pending) { FIRE_CUDA(cudaStreamWaitEvent(st, net->ev_join, 0)); join_pending = false; }
+      continue;
+    }
     if (in_f17(net, i)) {
       if ((int)i == net->f17.first_op) { rc = run_f17(net, B, st, net->pdl); if (rc != FIRE_OK) return rc; }
       continue;
