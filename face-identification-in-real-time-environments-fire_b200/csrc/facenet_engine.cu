@@ -950,8 +950,6 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
           r.n_acc = std::min(STRIP_MAX_ACC, 512 / pow2_cols(o.cout));          // accumulators side by side in TMEM
           if (const char* e = getenv("FIRE_B200_STRIP_ACC")) r.n_acc = std::max(2, std::min(r.n_acc, atoi(e)));   // A/B experiments (power of two)
           while (r.n_acc > 2 && r.n_acc / 2 > r.stages) r.n_acc >>= 1;
-          // FIRE_B200_STRIP_GROUP=1 (experiment): a group of n_acc / 2 tiles may take at most HALF of the ring, so the next group's patches are in flight
-          if (const char* e = getenv("FIRE_B200_STRIP_GROUP")) if (e[0] == '1') while (r.n_acc > 2 && r.n_acc / 2 > r.stages / 2) r.n_acc >>= 1;
           // Two MMA-issuing warps (conv_strip.cuh) each wait only for their own tiles' patches: tile t is issued by warp t % 2
           // and lives in stage t % stages, so the ring depth must be EVEN - then a stage always belongs to the same warp and no
           // warp ever skips a fill of a barrier it waits on (mbarrier waits are by phase parity; see block35_fused.cuh).
