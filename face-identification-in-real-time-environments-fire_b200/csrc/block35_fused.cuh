@@ -63,8 +63,28 @@ struct B35Params {
   const uint8_t* wstream;                 // n_blocks x 19 units of 16 KB
   const float* bias;                      // n_blocks x 448
   int n_blocks, n_images, pdl;
+  int* flags;                             // [n_blocks][n_images]: launch number (epoch) of the last launch that wrote block j's y of image i
+  int epoch, balance;                     // balance = 0: a CTA takes whole images through all blocks (no flags)
   long long* trace;
 };
+
+// Work order.  One TASK = one block of one image (~25 us).  Tasks are numbered block-major, t = j * n_images + img, and CTA w
+// takes t = w, w + G, w + 2G, ...: with n_images <= G (or a multiple of G) that is "CTA w owns image w" and a block's input is
+// the y this CTA has just written (y_done, CTA-local); otherwise - 256 images on 148 SMs - the chain of an image wanders over
+// CTAs and a block's input is published through a per-(block, image) flag (release / acquire at gpu scope).  The predecessor
+// task t - n_images always belongs to an EARLIER round of some CTA, CTAs walk their tasks in increasing order and the grid is
+// co-resident, so nothing can wait in a circle; 1280 tasks then take ceil(1280 / 148) = 9 rounds instead of 2 x 5.
+__device__ __forceinline__ int b35_ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void b35_wait_flag(const int* f, int epoch, int tag) {
+  const long long t0 = clock64();
+  while (b35_ld_acquire(f) - epoch < 0) {
+    if (clock64() - t0 > FIRE_WATCHDOG_CYCLES) { printf("fire_b200: block35 flag watchdog (tag %d, block %d)\n", tag, blockIdx.x); __trap(); }
+  }
+}
 
 // ring unit u of a block: x tile or weight unit, and its size
 __device__ __forceinline__ bool b35_is_x(int u) { return u < 16 && (u & 3) != 0; }
@@ -130,19 +150,38 @@ block35_fused_kernel(const __grid_constant__ B35Params p) {
 
   const uint32_t p12 = sbase + B35_P12, au0 = sbase + B35_AU0, au1 = sbase + B35_AU1, ring = sbase + B35_RING;
   const int issuer = warp == 0 ? 0 : warp == 10 ? 1 : -1;
+  // the previous block of a task's image was this CTA's previous task (CTA-local hand-over) unless the chains wander
+  const bool local_chain = !p.balance || (p.n_images % static_cast<int>(gridDim.x)) == 0;
+  // k-th task of this CTA -> (block j, image img); false when the CTA has no k-th task.  Balanced: t = w + G k in block-major
+  // numbering; otherwise the CTA owns images w, w + G, ... and takes each through all blocks.
+  auto task_of = [&](int k, int& j, int& img) {
+    if (!local_chain) {
+      const int t = static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x);
+      j = t / p.n_images; img = t - j * p.n_images;
+      return t < p.n_blocks * p.n_images;
+    }
+    const int q = k / p.n_blocks;
+    j = k - q * p.n_blocks; img = static_cast<int>(blockIdx.x) + q * static_cast<int>(gridDim.x);
+    return img < p.n_images;
+  };
 
   if (issuer >= 0) {
     // ---------------------------------------------------------------- producers: x tiles (TMA) and the weight stream (bulk copies)
     if (p.pdl) pdl_wait();
     int slot = 0, blk = 0;
     uint32_t ph = 0, gu = 0;
-    for (int img = blockIdx.x; img < p.n_images; img += gridDim.x) {
-      for (int j = 0; j < p.n_blocks; ++j, ++blk) {
-        bool gated = j == 0;                                    // x_j of blocks 1.. is the y this CTA has just written
+    for (int j, img; task_of(blk, j, img); ++blk) {
+      {
+        bool gated = j == 0;                                    // x_j of blocks 1.. is the y of block j - 1: this CTA's previous task, or published by flag
         for (int u = 0; u < B35_UNITS_PER_BLOCK; ++u, ++gu) {
           if ((gu & 1) == static_cast<uint32_t>(issuer)) {
             const bool is_x = b35_is_x(u);
-            if (is_x && !gated) { mbar_wait(y_done, (blk - 1) & 1, 61); fence_proxy_async_all(); gated = true; }
+            if (is_x && !gated) {
+              if (local_chain) mbar_wait(y_done, (blk - 1) & 1, 61);
+              else b35_wait_flag(p.flags + static_cast<size_t>(j - 1) * p.n_images + img, p.epoch, 61);
+              fence_proxy_async_all();
+              gated = true;
+            }
             mbar_wait(&empty[slot], ph ^ 1, 62);
             if (elect_one()) {
               if (is_x) {
@@ -186,8 +225,8 @@ block35_fused_kernel(const __grid_constant__ B35Params p) {
       if (elect_one()) umma_commit(&empty[slot]);
       __syncwarp();
     };
-    for (int img = blockIdx.x; img < p.n_images; img += gridDim.x) {
-      for (int j = 0; j < p.n_blocks; ++j, ++blk) {
+    for (int j, img; task_of(blk, j, img); ++blk) {
+      {
         const uint32_t bpar = blk & 1;
         // ---- H: D[mt] (TMEM columns 128 mt .. +95) = x[mt] * Wh^T
         if (blk > 0) { mbar_wait(&accU_empty[0], 1, 63); mbar_wait(&accU_empty[1], (blk - 1) & 1, 64); }   // the previous `up` has left TMEM
@@ -332,17 +371,20 @@ block35_fused_kernel(const __grid_constant__ B35Params p) {
     if (et < B35_BIAS_PER_BLOCK / 4) nb = __ldg(reinterpret_cast<const float4*>(p.bias) + et);
     if (p.pdl) pdl_wait();
     int blk = 0;
-    for (int img = blockIdx.x; img < p.n_images; img += gridDim.x) {
-      for (int j = 0; j < p.n_blocks; ++j, ++blk) {
+    for (int j, img; task_of(blk, j, img); ++blk) {              // (the first task of every CTA is in block 0: nb above)
+      {
         const uint32_t bpar = blk & 1;
         // bias table: every warp is done with the previous block's values (first barrier), 112 threads store the float4 they
-        // requested one block ago, and request the next block's
+        // requested one task ago, and request the next task's
         named_bar_sync(1, CONV_EPI_WARPS * 32);
         if (et < B35_BIAS_PER_BLOCK / 4)
           sts128(et < 48 ? bias_hc + et * 16 : bias_up + (et - 48) * 16, make_uint4(__float_as_uint(nb.x), __float_as_uint(nb.y), __float_as_uint(nb.z), __float_as_uint(nb.w)));
         named_bar_sync(1, CONV_EPI_WARPS * 32);
         if (et < B35_BIAS_PER_BLOCK / 4)
-          nb = __ldg(reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(j + 1 < p.n_blocks ? j + 1 : 0) * B35_BIAS_PER_BLOCK) + et);
+          {
+            int jn, in_;
+            nb = __ldg(reinterpret_cast<const float4*>(p.bias + static_cast<size_t>(task_of(blk + 1, jn, in_) ? jn : 0) * B35_BIAS_PER_BLOCK) + et);
+          }
         uint32_t a[16], b[16];
         uint4 lo, hi;
         // ---- H: natural rows.  Chunks 0-3 (b1a | b2a) -> P12 row q, chunks 4, 5 (b0) -> AU0 row m; this half takes 3 chunks
@@ -432,6 +474,7 @@ block35_fused_kernel(const __grid_constant__ B35Params p) {
         // ---- up: + bias + x, ReLU -> y.  Per M tile this warp takes the 64-column groups g = h (mod 2), 32 columns at a time:
         // residual rows arrive in the coalesced mapping (4 lanes = one 64-byte row piece), are transposed through the 2 KB
         // scratch to "thread = row", combined, and go back the same way.
+        if (!local_chain && j > 0) b35_wait_flag(p.flags + static_cast<size_t>(j - 1) * p.n_images + img, p.epoch, 80);   // the residual x_j came from another CTA
         const __half* xg = p.xptr[j] + static_cast<size_t>(img) * B35_POS * B35_C + pc * 8;
         __half* yg = const_cast<__half*>(p.xptr[j + 1]) + static_cast<size_t>(img) * B35_POS * B35_C + pc * 8;
         const uint32_t sc_own = scr + static_cast<uint32_t>(lane * 64), own_swz = (lane >> 1) & 3;
@@ -507,6 +550,14 @@ block35_fused_kernel(const __grid_constant__ B35Params p) {
         fence_proxy_async_all();                                // generic-proxy writes of y -> the TMA loads of the next block's H
         __syncwarp();
         if (lane == 0) mbar_arrive(y_done);
+        if (!local_chain && warp == CONV_FIRST_EPI_WARP) {     // all eight warps have stored their share of y: publish it
+          mbar_wait(y_done, bpar, 81);
+          if (lane == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.flags + static_cast<size_t>(j) * p.n_images + img), "r"(p.epoch) : "memory");
+          }
+          __syncwarp();
+        }
         if (warp == CONV_FIRST_EPI_WARP) B35_TRACE(18);
       }
     }

@@ -203,6 +203,9 @@ struct Fused35 {
   uint8_t* d_stream = nullptr;      // n_blocks x 19 units of 16 KB
   float* d_bias = nullptr;          // n_blocks x 448 fp32
   long long* d_trace = nullptr;     // FIRE_B200_TRACE35=1
+  int* d_flags = nullptr;           // [n_blocks][flags_cap]: epoch of the last published y of (block, image) - balanced schedule only
+  int flags_cap = 0, epoch = 0;
+  bool balance = true;              // FIRE_B200_B35_BALANCE=0: a CTA takes whole images through all blocks
   B35Params prm;
 };
 
@@ -440,6 +443,7 @@ static bool b35_setup(fire_net* net, const std::vector<BlobOp>& ops, const uint8
     f.d_stream = nullptr; f.d_bias = nullptr; f.first_op = -1; f.n_blocks = 0;
     return false;
   }
+  if (const char* e = getenv("FIRE_B200_B35_BALANCE")) f.balance = e[0] != '0';
   if (const char* e = getenv("FIRE_B200_TRACE35")) {
     if (e[0] == '1') {
       cudaMalloc(&f.d_trace, (size_t)148 * 16 * 24 * 8);
@@ -454,6 +458,7 @@ static inline bool in_f35(const fire_net* net, size_t i) {
 static int run_f35(fire_net* net, cudaStream_t st, bool pdl) {
   Fused35& f = net->f35;
   f.prm.pdl = pdl ? 1 : 0;
+  f.prm.epoch = ++f.epoch;                           // the flags only ever grow: no reset between launches
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)std::min(f.prm.n_images, device_sm_count()));
   cfg.blockDim = dim3(B35_THREADS);
@@ -750,7 +755,7 @@ int fire_facenet_destroy(fire_net_t* net) {
   cudaFree(net->d_bias16);
   cudaFree(net->d_trace);
   cudaFree(net->f17.d_stream); cudaFree(net->f17.d_bias); cudaFree(net->f17.d_trace);
-  cudaFree(net->f35.d_stream); cudaFree(net->f35.d_bias); cudaFree(net->f35.d_trace);
+  cudaFree(net->f35.d_stream); cudaFree(net->f35.d_bias); cudaFree(net->f35.d_trace); cudaFree(net->f35.d_flags);
   cudaFree(net->f8.d_w); cudaFree(net->f8.d_bias); cudaFree(net->f8.d_trace);
   if (net->ev_fork) cudaEventDestroy(net->ev_fork);
   if (net->ev_join) cudaEventDestroy(net->ev_join);
@@ -1065,6 +1070,14 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
         if (rc != FIRE_OK) return rc;
       }
       f.prm.wstream = f.d_stream; f.prm.bias = f.d_bias; f.prm.n_blocks = f.n_blocks; f.prm.n_images = B; f.prm.trace = f.d_trace;
+      if (f.balance && B > f.flags_cap) {
+        cudaFree(f.d_flags);
+        f.d_flags = nullptr; f.flags_cap = 0;
+        if (cudaMalloc(&f.d_flags, sizeof(int) * (size_t)f.n_blocks * B) != cudaSuccess) { cudaGetLastError(); return fail(FIRE_ERR_CUDA, "block35 flags: out of device memory"); }
+        FIRE_CUDA(cudaMemset(f.d_flags, 0, sizeof(int) * (size_t)f.n_blocks * B));
+        f.flags_cap = B; f.epoch = 0;
+      }
+      f.prm.flags = f.d_flags; f.prm.balance = f.balance ? 1 : 0;
     }
     if (net->f8.first_op >= 0) {
       Fused8& f = net->f8;

@@ -185,6 +185,13 @@ def test_block35_fused_chain_matches_layer_by_layer(fire_lib, monkeypatch, B):
     ra, _ = a.encode_unit_f32(x)
     ra2, _ = a.encode_unit_f32(x)
     assert torch.equal(ra, ra2)
+    if B > 148:                                                    # the balanced task order (chains wander over CTAs, per-(block, image)
+        monkeypatch.setenv("FIRE_B200_B35_BALANCE", "0")           # flags) against "a CTA owns whole images": same arithmetic
+        c = engine.FaceNetEngine(128, t)
+        monkeypatch.delenv("FIRE_B200_B35_BALANCE")
+        rc, _ = c.encode_unit_f32(x)
+        assert torch.equal(ra, rc)
+        c.close()
     monkeypatch.setenv("FIRE_B200_FUSE35", "0")
     b = engine.FaceNetEngine(128, t)
     assert b.num_launches - a.num_launches == 19                   # 20 conv launches became one
