@@ -255,6 +255,26 @@ def test_block8_fused_tail_matches_layer_by_layer(fire_lib, monkeypatch, B):
         a.close(); b.close()
 
 
+@pytest.mark.parametrize("B", [149, 256, 300])
+def test_repeated_forwards_are_bit_identical(fire_lib, B):
+    """Stress for the cross-CTA hand-overs (block35_fused's wandering chains publish y through release / acquire flags; the
+    flags carry the launch number and are never reset): 60 back-to-back forwards, alternating with a second batch so every
+    buffer is overwritten in between, must reproduce the first result bit for bit."""
+    import torch
+    from fire_b200 import engine, weights as W
+    eng = engine.FaceNetEngine(512, W.synthetic_weights(512, 3, calibrate=False))
+    xa = eng.ingest_unit_f32(torch.from_numpy(_images(B, 41).astype(np.float32) / 255.0).cuda())
+    xb = eng.ingest_unit_f32(torch.from_numpy(_images(B, 42).astype(np.float32) / 255.0).cuda())
+    ra, _ = eng.forward(xa)
+    rb, _ = eng.forward(xb)
+    ra, rb = ra.clone(), rb.clone()
+    assert torch.isfinite(ra).all() and not torch.equal(ra, rb)
+    for i in range(60):
+        r, _ = eng.forward(xa if i % 2 == 0 else xb)
+        assert torch.equal(r, ra if i % 2 == 0 else rb), i
+    eng.close()
+
+
 @pytest.mark.parametrize("B", [2, 37, 130])
 def test_im2col_tma_operand_is_bit_identical_to_gather(fire_lib, monkeypatch, B):
     """k x k layers with Cin % 64 == 0 (Conv2d_4b, Mixed_6a, Mixed_7a) fetch their A operand with im2col-mode TMA loads
