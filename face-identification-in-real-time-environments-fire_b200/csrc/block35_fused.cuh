@@ -81,7 +81,7 @@ __device__ __forceinline__ int b35_ld_acquire(const int* p) {
 }
 __device__ __forceinline__ void b35_wait_flag(const int* f, int epoch, int tag) {
   const long long t0 = clock64();
-  while (b35_ld_acquire(f) - epoch < 0) {
+  while (static_cast<int>(static_cast<uint32_t>(b35_ld_acquire(f)) - static_cast<uint32_t>(epoch)) < 0) {     // wrap-safe: launch numbers only grow
     if (clock64() - t0 > FIRE_WATCHDOG_CYCLES) { printf("fire_b200: block35 flag watchdog (tag %d, block %d)\n", tag, blockIdx.x); __trap(); }
   }
 }

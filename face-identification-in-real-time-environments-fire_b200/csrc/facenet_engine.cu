@@ -458,7 +458,8 @@ static inline bool in_f35(const fire_net* net, size_t i) {
 static int run_f35(fire_net* net, cudaStream_t st, bool pdl) {
   Fused35& f = net->f35;
   f.prm.pdl = pdl ? 1 : 0;
-  f.prm.epoch = ++f.epoch;                           // the flags only ever grow: no reset between launches
+  f.epoch = (int)((unsigned)f.epoch + 1u);            // launch number (wraps; the kernel compares differences): the flags are never reset
+  f.prm.epoch = f.epoch;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)std::min(f.prm.n_images, device_sm_count()));
   cfg.blockDim = dim3(B35_THREADS);
