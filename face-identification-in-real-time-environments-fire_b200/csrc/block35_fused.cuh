@@ -5,7 +5,9 @@
 //     y  = relu(x + 0.17 * (conv1x1 96->256 ([b0 | b1 | b2]) + bias))                        (cbr = conv + BN + ReLU, 'same')
 // The engine's plan runs this as four launches per block (heads 256->96, the two first 3x3 as one block-diagonal 64->64
 // conv, the second 3x3 of branch 2, up): 20 launches of ~14 us for 70 GFLOP.  No convolution mixes images, so ONE CTA
-// can take an image through all five blocks with every intermediate in shared memory (same idea as block17_fused.cuh).
+// can take an image through a whole block with every intermediate in shared memory (same idea as block17_fused.cuh); only
+// the block's input x and output y live in memory.  Which CTA runs which (block, image) is a scheduling question: see
+// "Work order" below (round 2: balanced over the SMs, an image's chain wanders from CTA to CTA through flags).
 //
 // Geometry.  The 3 x 3 'same' convs run on a PITCHED, zero-bordered copy of the image: position (y, x) lives in row
 // q = (y + 1) * 18 + (x + 1) of region P12 (pitch 18 = 17 + one shared zero column; one zero row above and below).

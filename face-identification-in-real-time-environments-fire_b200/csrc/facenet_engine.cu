@@ -5,9 +5,10 @@
 // the op list, the buffer table (per-image offsets into one workspace arena, live ranges already
 // resolved) and the BN-folded fp16 weights; this file uploads the weights once, builds their TMA
 // descriptors once, and on every forward() enqueues one kernel per op on the caller's stream:
-//   conv_igemm_kernel_t x 37 (single CTAs, or CTA pairs with cta_group::2 where the tile pairs fill the GPU) + conv_strip_kernel_t x 3
-//   + block35_fused_kernel x 1 + block17_fused_kernel x 1 (tcgen05; the fused kernels run the 20 / 40 convs of the five Block35 /
-//   ten Block17 blocks), maxpool3x3s2_kernel x 3,  gap_kernel x 1,  l2norm_kernel x 1.
+//   conv_igemm_kernel_t x 19 (single CTAs, or CTA pairs with cta_group::2 where the tile pairs fill the GPU) + conv_strip_kernel_t x 3
+//   + block35_fused_kernel x 1 + block17_fused_kernel x 1 + block8_fused_kernel x 6 (tcgen05; the fused kernels run the 20 / 40 convs
+//   of the five Block35 / ten Block17 blocks and the 1x3 -> 3x1 -> up tail of every Block8 block, the last one also the average pool),
+//   maxpool3x3s2_kernel x 3 (the two pool branches on a side stream),  l2norm_kernel x 1.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
