@@ -21,6 +21,7 @@
 #include "block17_fused.cuh"
 #include "block35_fused.cuh"
 #include "block8_fused.cuh"
+#include "pool_conv_fused.cuh"
 #include "fire_internal.h"
 
 namespace fire {
@@ -222,12 +223,20 @@ struct Fused8 {
 };
 constexpr size_t B8_W_PER_BLOCK = (size_t)B8_WMID_UNITS * B8_WMID_BYTES + (size_t)B8_NTILES * B8_WUP_UNITS * B8_UNIT;
 
+// MaxPool_3a + Conv2d_3b as one launch (pool_conv_fused.cuh): ops pool_op and pool_op + 1.
+struct FusedPoolConv {
+  int pool_op = -1;
+  float* d_bias = nullptr;          // [80] fp32
+  PoolConvParams prm;
+};
+
 struct fire_net {
   BlobHeader hdr;
   int device = 0;          // the device that was current at fire_facenet_create; every entry point runs there
   Fused17 f17;
   Fused35 f35;
   Fused8 f8;
+  FusedPoolConv fpc;
   std::vector<BlobBuf> bufs;
   std::vector<OpRt> ops;
   uint8_t* d_weights = nullptr;
@@ -578,6 +587,53 @@ static int run_f8(fire_net* net, size_t i, cudaStream_t st, bool pdl) {
   return FIRE_OK;
 }
 
+// ---- stem max-pool + 1x1 conv fusion ---------------------------------------------------------------------------------
+static bool pc_setup(fire_net* net, const std::vector<BlobOp>& ops, const uint8_t* blob, const BlobHeader& h) {
+  FusedPoolConv& f = net->fpc;
+  for (size_t i = 0; i + 1 < ops.size(); ++i) {
+    const BlobOp &po = ops[i], &co = ops[i + 1];
+    if (po.kind != OP_MAXPOOL || po.cin != PC_CIN || po.H != PC_IN || po.W != PC_IN || po.Ho != PC_OUT || po.Wo != PC_OUT || po.src_coff || po.dst_coff) continue;
+    if (co.kind != OP_CONV || co.kh != 1 || co.kw != 1 || co.stride != 1 || co.cin != PC_CIN || co.cout != PC_COUT || co.k_pad != PC_CIN ||
+        co.flags != CF_RELU || co.src_buf != po.dst_buf || co.src_coff || co.dst_coff) continue;
+    const BlobBuf &sb = net->bufs[po.src_buf], &pb = net->bufs[po.dst_buf], &db = net->bufs[co.dst_buf];
+    if (sb.C != PC_CIN || pb.C != PC_CIN || db.C != PC_COUT || (db.Wp && db.Wp != db.W) || sb.external || db.external) continue;
+    bool other_reader = false;                          // the pooled tensor must have no other consumer: it is never written
+    for (size_t j = 0; j < ops.size(); ++j)
+      if (j != i + 1 && (ops[j].src_buf == po.dst_buf || ops[j].res_buf == po.dst_buf)) other_reader = true;
+    if (other_reader) continue;
+    f.pool_op = (int)i;
+    break;
+  }
+  if (f.pool_op < 0) return false;
+  const BlobOp& co = ops[f.pool_op + 1];
+  if (cudaMalloc(&f.d_bias, sizeof(float) * PC_COUT) != cudaSuccess ||
+      cudaMemcpy(f.d_bias, blob + h.weights_off + co.b_off, sizeof(float) * PC_COUT, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaFuncSetAttribute(pool_conv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(f.d_bias);
+    f.d_bias = nullptr; f.pool_op = -1;
+    return false;
+  }
+  return true;
+}
+static int run_pc(fire_net* net, cudaStream_t st, bool pdl) {
+  FusedPoolConv& f = net->fpc;
+  f.prm.pdl = pdl ? 1 : 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)std::min(f.prm.n_images * PC_ROW_BLOCKS, device_sm_count()));
+  cfg.blockDim = dim3(PC_THREADS);
+  cfg.dynamicSmemBytes = PC_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  FIRE_CUDA(cudaLaunchKernelEx(&cfg, pool_conv_fused_kernel, f.prm));
+  count_launch();
+  return FIRE_OK;
+}
+
 extern "C" {
 
 int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
@@ -718,6 +774,8 @@ int fire_facenet_create(const void* host_blob, size_t bytes, fire_net_t** out) {
     if (!(f35_env && f35_env[0] == '0')) b35_setup(net, ops, p, h);
     const char* f8_env = getenv("FIRE_B200_FUSE8");
     if (!(f8_env && f8_env[0] == '0')) b8_setup(net, ops, p, h);
+    const char* fp_env = getenv("FIRE_B200_FUSE_POOL");
+    if (!(fp_env && fp_env[0] == '0')) pc_setup(net, ops, p, h);
   }
   {
     net->hoist_at.assign(ops.size(), -1);
@@ -759,6 +817,7 @@ int fire_facenet_destroy(fire_net_t* net) {
   cudaFree(net->f17.d_stream); cudaFree(net->f17.d_bias); cudaFree(net->f17.d_trace);
   cudaFree(net->f35.d_stream); cudaFree(net->f35.d_bias); cudaFree(net->f35.d_trace); cudaFree(net->f35.d_flags);
   cudaFree(net->f8.d_w); cudaFree(net->f8.d_bias); cudaFree(net->f8.d_trace);
+  cudaFree(net->fpc.d_bias);
   if (net->ev_fork) cudaEventDestroy(net->ev_fork);
   if (net->ev_join) cudaEventDestroy(net->ev_join);
   if (net->side) cudaStreamDestroy(net->side);
@@ -774,6 +833,7 @@ int fire_facenet_num_launches(const fire_net_t* net) {
   if (net->f17.first_op >= 0) n -= 4 * net->f17.n_blocks - 1;
   if (net->f35.first_op >= 0) n -= 4 * net->f35.n_blocks - 1;
   if (net->f8.first_op >= 0) n -= 2 * net->f8.n_blocks + (net->f8.gap_op >= 0 ? 1 : 0);
+  if (net->fpc.pool_op >= 0) n -= 1;
   return n;
 }
 double fire_facenet_flops(const fire_net_t* net) { return net ? net->flops_per_image : 0.0; }
@@ -1081,6 +1141,20 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
       }
       f.prm.flags = f.d_flags; f.prm.balance = f.balance ? 1 : 0;
     }
+    if (net->fpc.pool_op >= 0) {
+      FusedPoolConv& f = net->fpc;
+      const BlobOp& po = net->ops[f.pool_op].op;
+      const BlobOp& co = net->ops[f.pool_op + 1].op;
+      const BlobBuf& sb = net->bufs[po.src_buf];
+      const void* xp = buf_ptr(net, po.src_buf, B, in, ws, out_raw);
+      const void* yp = buf_ptr(net, co.dst_buf, B, in, ws, out_raw);
+      int rc = make_tmap_f16_nhwc(&f.prm.in_map, xp, PC_CIN, PC_IN, PC_IN, (uint64_t)B, (uint64_t)sb.C, (uint64_t)buf_wp(sb), PC_CIN, PC_IN, PC_IN_ROWS);
+      if (rc == FIRE_OK) rc = make_tmap_f16_2d(&f.prm.w_map, net->d_weights + co.w_off, PC_COUT, PC_CIN, PC_CIN * 2, PC_COUT);
+      if (rc == FIRE_OK) rc = make_tmap_f16_pos3d(&f.prm.out_a, yp, PC_COUT, (uint64_t)PC_OUT * PC_OUT, (uint64_t)B, PC_COUT, 64, PC_POS);
+      if (rc == FIRE_OK) rc = make_tmap_f16_pos3d(&f.prm.out_b, yp, PC_COUT, (uint64_t)PC_OUT * PC_OUT, (uint64_t)B, PC_COUT, 16, PC_POS);
+      if (rc != FIRE_OK) return rc;
+      f.prm.bias = f.d_bias; f.prm.n_images = B;
+    }
     if (net->f8.first_op >= 0) {
       Fused8& f = net->f8;
       for (int j = 0; j < f.n_blocks; ++j) {
@@ -1147,6 +1221,10 @@ int fire_facenet_forward(fire_net_t* net, const void* in_f16, int B, float* out_
     }
     if (in_f35(net, i)) {
       if ((int)i == net->f35.first_op) { rc = run_f35(net, st, net->pdl); if (rc != FIRE_OK) return rc; }
+      continue;
+    }
+    if (net->fpc.pool_op >= 0 && ((int)i == net->fpc.pool_op || (int)i == net->fpc.pool_op + 1)) {
+      if ((int)i == net->fpc.pool_op + 1) { rc = run_pc(net, st, net->pdl); if (rc != FIRE_OK) return rc; }
       continue;
     }
     {
@@ -1256,6 +1334,8 @@ int fire_facenet_profile(fire_net_t* net, const void* in_f16, int B, void* works
       if ((int)i == net->f17.first_op) rc = run_f17(net, B, st, false);
     } else if (in_f35(net, i)) {
       if ((int)i == net->f35.first_op) rc = run_f35(net, st, false);
+    } else if (net->fpc.pool_op >= 0 && ((int)i == net->fpc.pool_op || (int)i == net->fpc.pool_op + 1)) {   // timed on the conv's slot
+      if ((int)i == net->fpc.pool_op + 1) rc = run_pc(net, st, false);
     } else if (f8_role(net, i) >= 1 || (int)i == net->f8.gap_op) {   // the fused Block8 tail is timed on the 1x3 conv's slot
       if (f8_role(net, i) == 1) rc = run_f8(net, i, st, false);
     } else {

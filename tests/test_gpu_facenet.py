@@ -227,6 +227,34 @@ def test_pair_stem_matches_pixel_stem(fire_lib, B):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("B", [1, 12, 150])
+def test_pool_conv_fused_matches_two_launches(fire_lib, monkeypatch, B):
+    """pool_conv_fused_kernel (MaxPool_3a + Conv2d_3b in one launch: the TMA brings seven input rows per tile, eight warps
+    reduce the 3 x 3 / 2 windows from shared memory into the MMA operand, so the pooled tensor never exists in memory) against
+    maxpool3x3s2_kernel + conv_igemm_kernel (FIRE_B200_FUSE_POOL=0): the stored output of Conv2d_3b - every position, including
+    the two-row last tile of an image - and the embeddings.  The max is exact; the bias joins the sum in fp32 here and as an fp16
+    hi + lo MMA there."""
+    import torch
+    from fire_b200 import engine, weights as W
+    t = W.synthetic_weights(512, 27)
+    x = torch.from_numpy(_images(B, 29).astype(np.float32) / 255.0).cuda()
+    a = engine.FaceNetEngine(512, t, reuse_buffers=False)
+    monkeypatch.setenv("FIRE_B200_FUSE_POOL", "0")
+    b = engine.FaceNetEngine(512, t, reuse_buffers=False)
+    monkeypatch.delenv("FIRE_B200_FUSE_POOL")
+    assert b.num_launches - a.num_launches == 1
+    xa, xb = a.ingest_unit_f32(x), b.ingest_unit_f32(x)
+    ra, _ = a.forward(xa)
+    rb, _ = b.forward(xb)
+    i3b = next(i for i, o in enumerate(a.plan.ops) if o.label == "Conv2d_3b_1x1")
+    ba, bb = a.read_buffer(a.plan.ops[i3b].dst.buf, xa), b.read_buffer(b.plan.ops[i3b].dst.buf, xb)
+    assert ba.shape == bb.shape == (B, 38, 38, 80)
+    assert np.abs(ba - bb).max() <= 2e-3 * max(1.0, np.abs(bb).max()), np.abs(ba - bb).max()
+    ra, rb = ra.cpu().numpy(), rb.cpu().numpy()
+    assert np.isfinite(ra).all() and _cos(ra, rb).min() >= 0.99999
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("B", [1, 13, 14, 100, 256, 300])
 def test_block8_fused_tail_matches_layer_by_layer(fire_lib, monkeypatch, B):
     """block8_fused_kernel (1x3 -> 3x1 -> up + residual of a Block8 block in one launch: a CTA owns 13 images x 256 output
@@ -373,6 +401,7 @@ def test_no_activation_saturates_fp16(fire_lib, monkeypatch):
     monkeypatch.setenv("FIRE_B200_FUSE17", "0")
     monkeypatch.setenv("FIRE_B200_FUSE35", "0")
     monkeypatch.setenv("FIRE_B200_FUSE8", "0")
+    monkeypatch.setenv("FIRE_B200_FUSE_POOL", "0")
     for D in (512, 128):
         t = W.synthetic_weights(D, 1234)
         eng = engine.FaceNetEngine(D, t, reuse_buffers=False)
