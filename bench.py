@@ -317,7 +317,7 @@ def run_fire(args):
 
     # ---------------- roofline ----------------------------------------------------------------------------------------
     # Direct: the step's algorithmic FLOP (2.8353 GFLOP x 256 images) over the step's OWN device time as timed
-    # above - every launch of the step (K1, 30 tensor launches, pools, L2 norm) is charged to the tensor roofline, so this
+    # above - every launch of the step (K1, 30 tensor launches, 2 max-pools, L2 norm) is charged to the tensor roofline, so this
     # is a lower bound for the convolution kernels and needs no share from a separate pass.  `families` adds the per-family
     # picture from one serialised per-op event pass (no overlap between launches: it overstates small launches) and the live
     # HBM figures of K1.
@@ -360,7 +360,7 @@ def run_fire(args):
         k1_boxes = k1_gbs(fr4, d4, torch.from_numpy(bx4).to(dev), torch.arange(BATCH, dtype=torch.int32, device=dev) % 8,
                           float((bx4[:, 2].astype(np.int64) * bx4[:, 3] * 3).sum() + BATCH * out_bytes))
         del fr4
-        roofline = {"kernel": "the step's tensor launches: conv_igemm + conv_strip + block35_fused + block17_fused + block8_fused "
+        roofline = {"kernel": "the step's tensor launches: conv_igemm + conv_strip + block35_fused + block17_fused + block8_fused + pool_conv_fused "
                               f"({int(conv.sum())} launches for the plan's 100 convs), timed as the whole step",
                     "bound": "tensor", "achieved": achieved, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["tensor_tflops"], "frac_of_burst_peak": achieved / peaks["tensor_burst"],

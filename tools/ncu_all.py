@@ -1,7 +1,7 @@
 """One pass over every kernel family of the hot path, for `ncu --set full` (profiles/r02_ncu_*): no warm-up, every workload once.
 
     K1   preprocess_reference_kernel: 256 x 160x160 crops (copy case) and 256 configs[4]-sized boxes out of 1080p frames
-    K2   one FaceNet512 forward at B=256 (30 tensor launches + pools + L2 norm)
+    K2   one FaceNet512 forward at B=256 (30 tensor launches + 2 max-pools + L2 norm)
     K3   exact top-10 over 1M x 512: Q = 4096 (tensor-bound) and Q = 1, 32, 256 (HBM-bound small batches)
 
     python tools/ncu_all.py && ncu --set full --clock-control none -o gpurun_out/r02_full python tools/ncu_all.py

@@ -45,11 +45,11 @@ def full_summary(path):
                         tensor_pct=val(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
                         warps_pct=val(r, "sm__warps_active.avg.pct_of_peak_sustained_active")))
     ours = [o for o in out if not o["kernel"].startswith(("at::", "<unnamed>"))]           # drop torch's setup kernels (randn, arange)
-    # launch order of tools/ncu_all.py: K1 boxes, K1 copy, 34 forward launches (+ L2 norm), enrol, then 4 searches of 7 kernels.
+    # launch order of tools/ncu_all.py: K1 boxes, K1 copy, 33 forward launches (+ L2 norm), enrol, then 4 searches of 7 kernels.
     # The two pool branches are launched (on the side stream) BEFORE the convolutions they run beside.
     assert ours[0]["kernel"].startswith("preprocess_reference") and ours[1]["kernel"].startswith("preprocess_reference"), ours[0]
     labels = {0: "K1 configs[4]-sized boxes (256 boxes, 48..400 px, from 1080p frames)", 1: "K1 256 x 160x160 crops (copy case)"}
-    fwd = ["Conv2d_1a (s2d 2x2)", "Conv2d_2a", "Conv2d_2b", "MaxPool_3a", "Conv2d_3b", "Conv2d_4a", "Conv2d_4b", "Block35 x5 (fused chain)",
+    fwd = ["Conv2d_1a (s2d 2x2, pixel pairs)", "Conv2d_2a (pixel pairs)", "Conv2d_2b", "MaxPool_3a + Conv2d_3b (one launch)", "Conv2d_4a", "Conv2d_4b", "Block35 x5 (fused chain)",
            "Mixed_6a pool", "Mixed_6a b0 3x3/2", "Mixed_6a b1 1x1", "Mixed_6a b1 3x3", "Mixed_6a b1 3x3/2", "Block17 x10 (fused chain)",
            "Mixed_7a pool", "Mixed_7a heads", "Mixed_7a b0 3x3/2", "Mixed_7a b1 3x3/2", "Mixed_7a b2 3x3", "Mixed_7a b2 3x3/2"]
     fwd += [f"Block8_{b + 1} {n}" for b in range(6) for n in ("heads", "1x3 + 3x1 + up" + (" + average pool" if b == 5 else ""))] + ["Bottleneck", "L2 norm"]
@@ -74,14 +74,14 @@ def full_summary(path):
     with open(os.path.join(ROOT, "profiles", "r02_ncu_full_summary.txt"), "w") as f:
         f.write("\n".join(lines) + "\n")
     by = {labels.get(i, str(i)): o for i, o in enumerate(ours)}
-    tensor = [o for i, o in enumerate(ours) if 2 <= i < base and any(s in o["kernel"] for s in ("conv_strip", "conv_igemm", "block35", "block17", "block8"))]
+    tensor = [o for i, o in enumerate(ours) if 2 <= i < base and any(s in o["kernel"] for s in ("conv_strip", "conv_igemm", "block35", "block17", "block8", "pool_conv"))]
     tot = sum(o["rd"] + o["wr"] for o in tensor)
     traffic = {"source": "ncu --set full --clock-control none, python tools/ncu_all.py (one launch of every kernel; cold caches: ncu flushes L2 between "
                          "replays, so these are upper bounds for the warm step), profiles/r02_ncu_full_summary.txt",
                "conv_family_launches": len(tensor), "conv_family_dram_bytes_per_step": tot, "conv_family_dram_bytes_per_launch_avg": tot / len(tensor),
                "conv_family_us_serialised_cold": sum(o["us"] for o in tensor),
                "k1_copy_case_dram_bytes": by[labels[1]]["rd"] + by[labels[1]]["wr"], "k1_configs4_boxes_dram_bytes": by[labels[0]]["rd"] + by[labels[0]]["wr"],
-               "maxpool_3a_dram_bytes": by["MaxPool_3a"]["rd"] + by["MaxPool_3a"]["wr"],
+               "maxpool_3a_conv2d_3b_dram_bytes": by["MaxPool_3a + Conv2d_3b (one launch)"]["rd"] + by["MaxPool_3a + Conv2d_3b (one launch)"]["wr"],
                "knn_scan_dram_bytes_per_launch": by["kNN Q=4096: scan"]["rd"] + by["kNN Q=4096: scan"]["wr"],
                "knn_scan_q1_dram_bytes": by["kNN Q=1: scan"]["rd"] + by["kNN Q=1: scan"]["wr"],
                "knn_scan_q32_dram_bytes": by["kNN Q=32: scan"]["rd"] + by["kNN Q=32: scan"]["wr"],
@@ -107,13 +107,13 @@ def launch_shares(path):
         d[1] += v
     tot = sum(vals[s0:s1])
     out = ["# ncu --metrics gpu__time_duration.sum --clock-control none -c 400: `python bench.py --steps 2 --warmup 3 --no-knn --no-frames --no-cpu --no-sustained`",
-           f"# the two TIMED steps of that command (launches {s0}..{s1 - 1} of the capture; {(s1 - s0) // 2} launches per step: K1 + 30 tensor launches + 3 max-pools + L2 norm).",
+           f"# the two TIMED steps of that command (launches {s0}..{s1 - 1} of the capture; {(s1 - s0) // 2} launches per step: K1 + 30 tensor launches + 2 max-pools + L2 norm).",
            f"# Cold-cache, serialised per-launch times: compare SHARES, not absolutes.  unit: ns, summed over the two steps ({tot / 2 / 1000:.1f} us per step under ncu).",
            "# Full list: profiles/r02_ncu_launches_bench.csv"]
     for n, (c, v) in sorted(fam.items(), key=lambda kv: -kv[1][1]):
         out.append(f"{n:40s} launches {c // 2:3d}/step  total {v:12.1f}  share {v / tot:6.3f}")
-    tens = sum(v for n, (c, v) in fam.items() if any(s in n for s in ("conv_", "block")))
-    out.append(f"# tensor-kernel family (conv_igemm + conv_strip + block35_fused + block17_fused + block8_fused): share {tens / tot:.3f} of the step under ncu")
+    tens = sum(v for n, (c, v) in fam.items() if any(s in n for s in ("conv_", "block")))       # pool_conv_fused_kernel included
+    out.append(f"# tensor-kernel family (conv_igemm + conv_strip + block35_fused + block17_fused + block8_fused + pool_conv_fused): share {tens / tot:.3f} of the step under ncu")
     with open(os.path.join(ROOT, "profiles", "r02_ncu_launch_shares.txt"), "w") as f:
         f.write("\n".join(out) + "\n")
     shutil.copy(path, os.path.join(ROOT, "profiles", "r02_ncu_launches_bench.csv"))
