@@ -33,10 +33,12 @@ constexpr int STRIP_MAX_ACC = 8;                             // TMEM accumulator
 struct StripSmem {
   uint32_t a, b, bias, ones, zero, out, bars, total;
 };
+// The patch ring comes LAST and its stages are only as aligned as the operand swizzle needs (1024 B for 128-byte rows, 256 B for the
+// 64- / 32-byte rows of the Cin = 32 / 16 layers: the swizzle is a function of ABSOLUTE shared-memory address bits, for the TMA's writes
+// as for the UMMA's reads, so a stage may start at any multiple of the row size): Conv2d_2b gets six stages instead of four that way.
 __host__ __device__ inline StripSmem strip_smem_layout(int stages, int a_stage_bytes, int nkb, int cout) {
   StripSmem L;
   uint32_t o = 0;
-  L.a = o;    o += static_cast<uint32_t>(stages) * a_stage_bytes;
   L.b = o;    o += static_cast<uint32_t>(nkb) * cout * 128;
   L.bias = o; o += static_cast<uint32_t>(cout) * 16;
   L.ones = o; o += CONV_BM * 16;
@@ -44,6 +46,8 @@ __host__ __device__ inline StripSmem strip_smem_layout(int stages, int a_stage_b
   o = (o + 1023) & ~1023u;
   L.out = o;  o += 2u * CONV_BM * cout * 2;                  // [2 buffers][cout / box_cols boxes][128 rows][box_cols * 2 bytes]
   L.bars = o; o += 512;
+  if ((a_stage_bytes & 1023) == 0) o = (o + 1023) & ~1023u;
+  L.a = o;    o += static_cast<uint32_t>(stages) * a_stage_bytes;
   L.total = o;
   return L;
 }

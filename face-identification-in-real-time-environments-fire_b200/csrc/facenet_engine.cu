@@ -1005,6 +1005,15 @@ static int prepare(fire_net* net, const void* in, int B, float* out_raw, void* w
             rows_alloc = std::max(r.Hbox * wbox, CONV_BM + (o.kh - 1) * wbox + o.kw - 1);
           }
           r.a_stage_bytes = (rows_alloc * o.cin * 2 + 1023) / 1024 * 1024;
+          if (o.cin < 64) {
+            // 64- / 32-byte operand rows: a stage only needs 256-byte alignment (strip_smem_layout); take it when it buys ring depth
+            const int tight = (rows_alloc * o.cin * 2 + 255) / 256 * 256;
+            auto depth = [&](int bytes) {
+              int st = (int)std::min<size_t>(8, (232448 - (strip_smem_layout(0, bytes, o.k_pad / 64, o.cout).total + 1024)) / bytes);
+              return st > 2 ? st & ~1 : st;
+            };
+            if (depth(tight) > depth(r.a_stage_bytes)) r.a_stage_bytes = tight;
+          }
           r.bn_tile = 0;                       // force a fresh weight map below
           // CTA pairs for the issue-bound layers (>= 8 K steps per tile, two accumulators per warp): cout / 2 weight rows per CTA
           r.pair = net->strip_pair && r.flat && B >= 2 && o.cout % 32 == 0 && o.kh * o.kw * o.cin / 16 >= 8 && (sms & ~1) >= 2;
