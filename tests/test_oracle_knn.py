@@ -58,6 +58,26 @@ def test_against_float64_bruteforce(oracle_native, D, k):
     assert np.array_equal(one, labels)                               # threading over queries does not change results
 
 
+@pytest.mark.parametrize("D,k", [(128, 10), (512, 50)])
+def test_against_scikit_learn_bruteforce(oracle_native, D, k):
+    """An executor the builder did not write: scikit-learn's exact cosine search (`NearestNeighbors(algorithm="brute",
+    metric="cosine")`, distance = 1 - cos like hnswlib's cosine space).  It pins the semantics - which rows, in which order, at
+    which distance - not hnswlib's summation order (that wheel is not installable here)."""
+    sk = pytest.importorskip("sklearn.neighbors")
+    rng = np.random.default_rng(1000 + D)
+    g = rng.standard_normal((4000, D)).astype(np.float32) * 2
+    q = rng.standard_normal((64, D)).astype(np.float32)
+    ora = oracle_native.BFIndexOracle(D)
+    ora.add_items(g)
+    labels, dist = ora.knn_query(q, k, num_threads=4)
+    nn = sk.NearestNeighbors(n_neighbors=k, algorithm="brute", metric="cosine").fit(g.astype(np.float64))
+    d_sk, i_sk = nn.kneighbors(q.astype(np.float64))
+    assert np.abs(d_sk - dist).max() < 2e-6
+    assert (labels.astype(np.int64) != i_sk).mean() < 0.01           # only fp32-vs-fp64 near-ties may differ
+    gap_ok = np.abs(np.take_along_axis(d_sk, np.argsort(d_sk, 1), 1) - d_sk).max() == 0   # scikit-learn returns ascending distances too
+    assert gap_ok
+
+
 def test_normalize_formula(oracle_native):
     x = np.array([[3.0, 4.0] + [0.0] * 14], np.float32)
     y = oracle_native.normalize(x)
