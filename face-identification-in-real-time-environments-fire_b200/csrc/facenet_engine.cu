@@ -208,6 +208,7 @@ struct Fused35 {
   int* d_flags = nullptr;           // [n_blocks][flags_cap]: epoch of the last published y of (block, image) - balanced schedule only
   int flags_cap = 0, epoch = 0;
   bool balance = true;              // FIRE_B200_B35_BALANCE=0: a CTA takes whole images through all blocks
+  bool coop = true;                 // cooperative launch when the chains wander: the grid only starts when all of it can be resident (FIRE_B200_B35_COOP=0: plain launch)
   B35Params prm;
 };
 
@@ -454,6 +455,7 @@ static bool b35_setup(fire_net* net, const std::vector<BlobOp>& ops, const uint8
     return false;
   }
   if (const char* e = getenv("FIRE_B200_B35_BALANCE")) f.balance = e[0] != '0';
+  if (const char* e = getenv("FIRE_B200_B35_COOP")) f.coop = e[0] != '0';
   if (const char* e = getenv("FIRE_B200_TRACE35")) {
     if (e[0] == '1') {
       cudaMalloc(&f.d_trace, (size_t)148 * 16 * 24 * 8);
@@ -475,12 +477,31 @@ static int run_f35(fire_net* net, cudaStream_t st, bool pdl) {
   cfg.blockDim = dim3(B35_THREADS);
   cfg.dynamicSmemBytes = B35_SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  // Wandering chains wait on flags written by other CTAs of this grid: ask for a COOPERATIVE launch, which only starts the grid
+  // when all of its CTAs can be resident at once (measured cost: 0.8 us per forward; FIRE_B200_B35_COOP=0 turns it off)
+  const bool wander = f.balance && (f.prm.n_images % (int)cfg.gridDim.x) != 0;
+  if (wander && f.coop) {
+    attr[na].id = cudaLaunchAttributeCooperative;
+    attr[na].val.cooperative = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  FIRE_CUDA(cudaLaunchKernelEx(&cfg, block35_fused_kernel, f.prm));
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, block35_fused_kernel, f.prm);
+  if (e != cudaSuccess && wander && f.coop) {            // not launchable that way here: plain launch from now on
+    cudaGetLastError();
+    f.coop = false;
+    cfg.numAttrs = pdl ? 1 : 0;
+    e = cudaLaunchKernelEx(&cfg, block35_fused_kernel, f.prm);
+  }
+  if (e != cudaSuccess) return fail(FIRE_ERR_CUDA, "launch of block35_fused_kernel failed: %s", cudaGetErrorString(e));
   count_launch();
   return FIRE_OK;
 }
