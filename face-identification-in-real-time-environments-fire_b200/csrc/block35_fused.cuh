@@ -75,7 +75,8 @@ struct B35Params {
 // the y this CTA has just written (y_done, CTA-local); otherwise - 256 images on 148 SMs - the chain of an image wanders over
 // CTAs and a block's input is published through a per-(block, image) flag (release / acquire at gpu scope).  The predecessor
 // task t - n_images always belongs to an EARLIER round of some CTA, CTAs walk their tasks in increasing order and the grid is
-// co-resident, so nothing can wait in a circle; 1280 tasks then take ceil(1280 / 148) = 9 rounds instead of 2 x 5.
+// co-resident (the host launches this case cooperatively: the grid only starts when all of it fits at once), so nothing can
+// wait in a circle; 1280 tasks then take ceil(1280 / 148) = 9 rounds instead of 2 x 5.
 __device__ __forceinline__ int b35_ld_acquire(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
